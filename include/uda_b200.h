@@ -1,0 +1,188 @@
+/* uda_b200 — C ABI of the B200-native (sm_100a) segmentation-training hot path.
+ *
+ * Drop-in boundary for bempt/uda_aerial_semantic_segmentation_research (a pure-Python PyTorch repo
+ * with NO native/FFI layer of its own: SURVEY.md 8b).  Each entry point below replaces the ATen /
+ * cuDNN library calls the reference reaches through the cited Python call site; the Python shims in
+ * uda_aerial_semantic_segmentation_research_b200/ bind them with ctypes (INTEGRATION.md shows the
+ * stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every buffer is BORROWED device memory owned by the caller
+ *     (torch caching allocator); kernels never allocate or free; scratch is an explicit
+ *     `workspace` argument whose size is documented per call;
+ *   - `stream` is a cudaStream_t (pass torch.cuda.current_stream().cuda_stream); no internal
+ *     synchronisation; safe under CUDA-graph capture;
+ *   - return 0 on success or a negative UDA_ERR_* code; uda_last_error() returns the
+ *     thread-local message; arguments are validated BEFORE any launch; there is no CPU fallback;
+ *   - dtype codes: UDA_F32 / UDA_BF16 for activations and logits, UDA_I64 / UDA_U8 for index maps;
+ *   - activations inside the network are NHWC ([B,H,W,C], C innermost); logits / losses use the
+ *     reference's NCHW ([B,C,H,W]) edge layout; conv weights are OHWI ([Cout][KH][KW][Cin]),
+ *     the physical layout of a torch channels_last parameter of logical shape [Cout,Cin,KH,KW].
+ */
+#ifndef UDA_B200_H_
+#define UDA_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UDA_OK 0
+#define UDA_ERR_BAD_ARG (-1)
+#define UDA_ERR_UNSUPPORTED (-2)
+#define UDA_ERR_CUDA (-3)
+
+#define UDA_F32 0
+#define UDA_BF16 1
+#define UDA_I64 2
+#define UDA_U8 3
+
+/* library */
+const char* uda_last_error(void);
+int uda_abi_version(void);
+/* 1 if the current device is sm_100 (B200) and the tcgen05 kernels can run, else 0 */
+int uda_device_supported(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Loss path (fused loss + logit gradient).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Segmentation loss:  total = out_scale * (w_ce * CE_term + w_dice * Dice_term), gradient wrt logits.
+ *   ce_mode 0: no CE term; 1: nn.CrossEntropyLoss (reference src/models/train.py:208,342;
+ *   adversarial_trainer.py:105) mean over non-ignored pixels, optional class weights;
+ *   2: focal(weighted CE) of WeightedSegmentationLoss.focal_loss (src/models/losses.py:176-187).
+ *   use_dice: DiceLoss.forward (src/models/losses.py:118-152) on index targets, or on
+ *   `soft_target` ([B,C,HW] float one-hot/soft, as losses.py:134 accepts) when non-NULL.
+ *   logits/grad: [B,C,HW] contiguous, `dtype`; target: int64 [B,HW]; class_weights: float[C] or NULL.
+ *   out4 (device float[4]) = {CE term, Dice term, total, #out-of-range targets}.
+ *   Single pass when use_dice == 0, two passes (sums, then gradient) otherwise.
+ *   workspace: uda_seg_loss_workspace_bytes(B, C), 8-byte aligned. */
+size_t uda_seg_loss_workspace_bytes(int B, int C);
+int uda_seg_loss_fwd_bwd(const void* logits, int dtype, const long long* target, const float* soft_target,
+                         const float* class_weights, void* grad, float* out4, void* workspace, int B, int C,
+                         long long HW, int ce_mode, int use_dice, float alpha, float gamma, int mean_reduction,
+                         long long ignore_index, float smooth, float w_ce, float w_dice, float out_scale,
+                         void* stream);
+
+/* x[i] *= *dev_scalar, skipped entirely when *dev_scalar == 1 (autograd grad_output hook). */
+int uda_scale_by_device_scalar(void* x, int dtype, long long n, const float* dev_scalar, void* stream);
+
+/* ConsistencyLoss.forward (src/models/losses.py:62-90): out1[0] = out_scale * symmetric KL
+ * (temperature, 'batchmean'); grad1/grad2 = d/dz1, d/dz2.  workspace: 8 bytes. */
+int uda_consistency_fwd_bwd(const void* z1, const void* z2, int dtype, void* grad1, void* grad2, float* out1,
+                            void* workspace, int B, int C, long long HW, float temperature, float out_scale,
+                            void* stream);
+
+/* Target-domain entropy minimisation (north-star extension):
+ * out1[0] = out_scale * mean_px(-sum_c p log p).  workspace: 8 bytes. */
+int uda_entropy_fwd_bwd(const void* z, int dtype, void* grad, float* out1, void* workspace, int B, int C,
+                        long long HW, float out_scale, void* stream);
+
+/* nn.BCEWithLogitsLoss() against a constant label (AdversarialLoss, src/models/losses.py:16-51):
+ * out1[0] (+)= scale * mean BCE(x, label); grad (nullable) = d/dx. */
+int uda_bce_logits_fwd_bwd(const float* x, float* grad, float* out1, long long n, float label, float scale,
+                           int accumulate, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Prediction / evaluation (integer results, bit-exact).
+ * ------------------------------------------------------------------------------------------- */
+
+/* outputs.argmax(dim=1) (src/models/predict.py:129, src/models/train.py:227) fused with
+ * SegmentationMetrics._fast_hist (src/analysis/metrics.py:17-27).  logits [B,C,HW]; target int64
+ * [B,HW] or NULL; mask_i64 / mask_u8 / hist ([C,C] int64, rows=true, cols=pred) each nullable. */
+int uda_argmax_confmat(const void* logits, int dtype, const long long* target, long long* mask_i64,
+                       unsigned char* mask_u8, long long* hist, int B, int C, long long HW,
+                       long long ignore_index, int has_ignore, int zero_hist, void* stream);
+
+/* SegmentationMetrics._fast_hist on two index maps (pred int64 or uint8). bad_count (nullable)
+ * receives the number of predictions outside [0,C). */
+int uda_confmat(const void* pred, int pred_dtype, const long long* target, long long* hist, long long* bad_count,
+                long long n, int C, long long ignore_index, int has_ignore, int zero_hist, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * U-Net / discriminator layers (replace aten::_convolution, batch_norm, relu, max_pool2d,
+ * upsample_nearest2d + cat reached from smp.Unet — src/models/train.py:572-577 — and
+ * DomainDiscriminator — src/models/discriminator.py:15-55).
+ * ------------------------------------------------------------------------------------------- */
+int uda_nchw_f32_to_nhwc(const float* src, void* dst, int dtype, int B, int C, int Cpad, long long HW, void* stream);
+int uda_nhwc_to_nchw_f32(const void* src, int dtype, float* dst, int B, int C, int Cpad, long long HW, void* stream);
+int uda_cast_f32(const float* src, void* dst, int dtype, long long n, void* stream);
+
+/* Generic FP32-pipe implicit GEMM (any k/stride/pad/channels; fp32 parity mode and odd shapes). */
+int uda_conv2d_direct_fwd(const void* x, int dtype, const void* w, int w_dtype, const float* bias, void* y_nhwc,
+                          float* y_nchw_f32, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride,
+                          int pad, void* stream);
+/* dgrad: dx = conv_transpose(dy, w) (+ addend: same shape as dx, may alias dx — gradient accumulation
+ * for tensors with several consumers: residual identity, encoder skip connections) */
+int uda_conv2d_direct_dgrad(const void* dy, int dtype, const void* w, int w_dtype, const void* addend, void* dx,
+                            int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, void* stream);
+int uda_conv2d_direct_wgrad(const void* dy, const void* x, int dtype, float* dw, int B, int H, int W, int Cin,
+                            int Cout, int KH, int KW, int stride, int pad, void* stream);
+
+/* tcgen05 / TMEM / TMA implicit-GEMM convolution (bf16 NHWC in, fp32 accumulate).
+ * uda_conv2d_tc_supported returns 1 when the shape is covered (else use the direct kernels).
+ *   op 0: fwd   y = conv(x, w)                    x [B,H,W,Cin]  w OHWI bf16  y [B,Ho,Wo,Cout]
+ *   op 1: dgrad dx = conv_transpose(dy, w)
+ *   op 2: wgrad dw += dy^T * im2col(x)            dw fp32 OHWI
+ * Epilogue (fwd): optional bias[Cout]; optional fp32 NCHW second output (logits edge);
+ * optional per-channel sum / sum-of-squares accumulation (BatchNorm batch statistics, double[2*Cout]). */
+int uda_conv2d_tc_supported(int op, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad);
+int uda_conv2d_tc_fwd(const void* x, const void* w, const float* bias, void* y_nhwc, float* y_nchw_f32,
+                      double* bn_sums, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                      void* stream);
+int uda_conv2d_tc_dgrad(const void* dy, const void* w, const void* addend, void* dx, int B, int H, int W, int Cin,
+                        int Cout, int KH, int KW, int stride, int pad, void* stream);
+int uda_conv2d_tc_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, int KH,
+                        int KW, int stride, int pad, void* stream);
+
+/* BatchNorm2d (train: batch statistics; eps 1e-5, momentum 0.1 in the reference's graph).
+ * x [M,C] NHWC rows.  uda_bn_stats: workspace 2*C doubles; writes mean/rstd/scale/shift (float[C])
+ * and updates running statistics when non-NULL.  uda_bn_apply: y = act(x*scale+shift (+residual)),
+ * slope 1 = identity, 0 = ReLU, 0.2 = LeakyReLU.  uda_bn_bwd: workspace 2*C doubles + 3*C floats;
+ * `a` = saved post-activation output (NULL for identity activation); dres (nullable) receives the
+ * activation-masked gradient of the residual branch. */
+int uda_bn_stats(const void* x, int dtype, long long M, int C, const float* gamma, const float* beta,
+                 float* running_mean, float* running_var, float* mean, float* rstd, float* scale, float* shift,
+                 float eps, float momentum, void* workspace, void* stream);
+int uda_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                       float* scale, float* shift, int C, float eps, void* stream);
+int uda_bn_apply(const void* x, const void* residual, void* y, int dtype, const float* scale, const float* shift,
+                 long long M, int C, float slope, void* stream);
+int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtype, const float* gamma, const float* mean,
+               const float* rstd, void* dx, void* dres, int dres_accumulate, float* dgamma, float* dbeta,
+               int param_accumulate, long long M, int C, float slope, void* workspace, void* stream);
+int uda_act_bwd(const void* dy, const void* a, void* dx, int dtype, long long n, float slope, void* stream);
+int uda_bias_act(const void* x, const float* bias, void* y, int dtype, long long M, int C, float slope, void* stream);
+int uda_colsum(const void* x, int dtype, float* out, long long M, int C, float scale, int accumulate,
+               void* workspace, void* stream);
+
+int uda_maxpool3x3s2_fwd(const void* x, void* y, unsigned char* idx, int dtype, int B, int H, int W, int C,
+                         void* stream);
+int uda_maxpool3x3s2_bwd(const void* dy, const unsigned char* idx, const void* addend, void* dx, int dtype, int B,
+                         int H, int W, int C, void* stream);
+/* nearest x2 upsample of x [B,H/2,W/2,C1] concatenated with skip [B,H,W,C2] (C2 may be 0) */
+int uda_upsample2x_concat_fwd(const void* x, const void* skip, void* out, int dtype, int B, int H, int W, int C1,
+                              int C2, void* stream);
+int uda_upsample2x_concat_bwd(const void* dout, void* dx, void* dskip, int dtype, int B, int H, int W, int C1,
+                              int C2, void* stream);
+/* discriminator classifier: AdaptiveAvgPool2d(1) + Linear(C,1) + Sigmoid (discriminator.py:37-42) */
+int uda_gap_linear_sigmoid_fwd(const void* x, int dtype, const float* w, const float* bias, float* pooled,
+                               float* out, int B, long long HW, int C, void* stream);
+int uda_gap_linear_sigmoid_bwd(const float* dout, const float* y, const float* pooled, const float* w, float* dw,
+                               float* dbias, void* dx, int dtype, int B, long long HW, int C, int accumulate,
+                               void* stream);
+
+/* Optimizer: torch.optim.Adam semantics over a flat fp32 buffer
+ * (src/models/train.py:461), optional bf16 shadow refresh, optional device-side clip coefficient
+ * from uda_grad_clip_coef (clip_grad_norm_, src/models/unsupervised_trainer.py:144; workspace 8 bytes). */
+int uda_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, float lr,
+                  float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                  const float* dev_clip_coef, void* stream);
+int uda_grad_clip_coef(const float* g, long long n, float max_norm, float pre_scale, float* coef, float* norm_out,
+                       void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UDA_B200_H_ */

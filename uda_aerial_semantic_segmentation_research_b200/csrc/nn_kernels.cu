@@ -1,0 +1,924 @@
+// HBM-bound layer kernels around the convolutions (all activations NHWC, fp32 or bf16):
+//   layout conversion NCHW fp32 <-> NHWC T, BatchNorm (batch statistics / apply / backward),
+//   max-pool 3x3 s2 p1, nearest x2 upsample + skip concat, global average pool, fused Adam.
+//
+// Reference semantics: the U-Net the reference builds with smp.Unet (src/models/train.py:572-577) —
+// BatchNorm2d eps=1e-5, momentum=0.1, ReLU, MaxPool2d(3,2,1), nearest x2 upsample + channel concat
+//  — and the discriminator's BatchNorm + LeakyReLU(0.2) + AdaptiveAvgPool
+// (src/models/discriminator.py:15-42); torch.optim.Adam defaults (src/models/train.py:461).
+#include "common.cuh"
+
+namespace uda {
+namespace {
+
+constexpr int kThreads = 256;
+
+inline unsigned grid_for(long long work_items, int per_sm = 8) {
+  long long blocks = (work_items + kThreads - 1) / kThreads;
+  long long cap = (long long)num_sms() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (unsigned)blocks;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Layout: per image, transpose a [C][HW] fp32 matrix <-> [HW][Cpad] T matrix through a 32x33 tile.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int Cpad,
+                                    long long HW) {
+  __shared__ float tile[32][33];
+  const long long b = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const float* s = src + b * C * HW;
+  T* d = dst + b * HW * Cpad;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i;
+    long long p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? s[(long long)c * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    long long p = p0 + i;
+    int c = c0 + threadIdx.x;
+    if (p < HW && c < Cpad) d[p * Cpad + c] = from_f<T>(tile[threadIdx.x][i]);
+  }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int Cpad,
+                                    long long HW) {
+  __shared__ float tile[32][33];
+  const long long b = blockIdx.z;
+  const long long p0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const T* s = src + b * HW * Cpad;
+  float* d = dst + b * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    long long p = p0 + i;
+    int c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < HW && c < C) ? to_f(s[p * Cpad + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int c = c0 + i;
+    long long p = p0 + threadIdx.x;
+    if (c < C && p < HW) d[(long long)c * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+template <typename T>
+__global__ void cast_f32_kernel(const float* __restrict__ src, T* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    dst[i] = from_f<T>(src[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// BatchNorm.  x is [M][C] (M = B*H*W rows, C innermost).  VEC channels per thread.
+// ---------------------------------------------------------------------------------------------
+// sums[c] += sum_rows x, sums[C+c] += sum_rows x^2   (double accumulators, zeroed by the host)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+bn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, long long M, int C) {
+  extern __shared__ float sh[];  // [groups][C][2]
+  const int cv = C / VEC;                // channel vectors per row
+  const int groups = blockDim.x / cv;    // row groups per block (host guarantees >= 1)
+  const int g = threadIdx.x / cv, v = threadIdx.x % cv;
+  float s1[VEC], s2[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  if (g < groups) {
+    for (long long r = (long long)blockIdx.x * groups + g; r < M; r += (long long)gridDim.x * groups) {
+      float xv[VEC];
+      ld_vec<VEC>(x + r * C + v * VEC, xv);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) { s1[j] += xv[j]; s2[j] += xv[j] * xv[j]; }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      sh[(g * C + v * VEC + j) * 2 + 0] = s1[j];
+      sh[(g * C + v * VEC + j) * 2 + 1] = s2[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    int c = i >> 1, k = i & 1;
+    double a = 0.0;
+    for (int gg = 0; gg < groups; ++gg) a += (double)sh[(gg * C + c) * 2 + k];
+    atomicAdd(sums + k * C + c, a);
+  }
+}
+
+// mean/var -> scale/shift (+ running statistics update, momentum, unbiased running var)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ running_mean,
+                                   float* __restrict__ running_var, float* __restrict__ mean_out,
+                                   float* __restrict__ rstd_out, float* __restrict__ scale_out,
+                                   float* __restrict__ shift_out, long long M, int C, float eps, float momentum) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mean = sums[c] / (double)M;
+  double var = sums[C + c] / (double)M - mean * mean;
+  if (var < 0.0) var = 0.0;
+  double rstd = 1.0 / sqrt(var + (double)eps);
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  mean_out[c] = (float)mean;
+  rstd_out[c] = (float)rstd;
+  scale_out[c] = (float)((double)g * rstd);
+  shift_out[c] = (float)((double)b - mean * (double)g * rstd);
+  if (running_mean) {
+    double unb = (M > 1) ? var * (double)M / (double)(M - 1) : var;
+    running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
+    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unb);
+  }
+}
+
+// eval mode: scale/shift from running statistics
+__global__ void bn_eval_coeffs_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                      const float* __restrict__ running_mean, const float* __restrict__ running_var,
+                                      float* __restrict__ scale_out, float* __restrict__ shift_out, int C, float eps) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float rstd = rsqrtf(running_var[c] + eps);
+  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
+  scale_out[c] = g * rstd;
+  shift_out[c] = b - running_mean[c] * g * rstd;
+}
+
+__device__ __forceinline__ float act_fwd(float v, float slope) { return v > 0.f ? v : v * slope; }
+
+// y = act(x*scale[c] + shift[c] (+ residual)),  act: slope=1 -> identity, 0 -> ReLU, 0.2 -> LeakyReLU
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
+                const float* __restrict__ scale, const float* __restrict__ shift, long long n, int C, float slope) {
+  const long long nv = n / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i * VEC) % C);
+    float xv[VEC], rv[VEC], sc[VEC], sf[VEC];
+    ld_vec<VEC>(x + i * VEC, xv);
+    if (residual) ld_vec<VEC>(residual + i * VEC, rv);
+    ld_vec<VEC>(scale + c, sc);
+    ld_vec<VEC>(shift + c, sf);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float v = xv[j] * sc[j] + sf[j];
+      if (residual) v += rv[j];
+      xv[j] = act_fwd(v, slope);
+    }
+    st_vec<VEC>(y + i * VEC, xv);
+  }
+}
+
+// Backward reduce: g = dy * act'(a);  sums[c] += sum g,  sums[C+c] += sum g * xhat,
+// xhat = (x - mean) * rstd.  `a` is the saved post-activation output (sign decides act').
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ a,
+                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                     double* __restrict__ sums, long long M, int C, float slope) {
+  extern __shared__ float sh[];
+  const int cv = C / VEC;
+  const int groups = blockDim.x / cv;
+  const int g = threadIdx.x / cv, v = threadIdx.x % cv;
+  float s1[VEC], s2[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  if (g < groups) {
+    float mu[VEC], rs[VEC];
+    ld_vec<VEC>(mean + v * VEC, mu);
+    ld_vec<VEC>(rstd + v * VEC, rs);
+    for (long long r = (long long)blockIdx.x * groups + g; r < M; r += (long long)gridDim.x * groups) {
+      float dv[VEC], xv[VEC], av[VEC];
+      ld_vec<VEC>(dy + r * C + v * VEC, dv);
+      ld_vec<VEC>(x + r * C + v * VEC, xv);
+      if (a) ld_vec<VEC>(a + r * C + v * VEC, av);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        float gg = dv[j];
+        if (a) gg *= (av[j] > 0.f) ? 1.f : slope;
+        s1[j] += gg;
+        s2[j] += gg * (xv[j] - mu[j]) * rs[j];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      sh[(g * C + v * VEC + j) * 2 + 0] = s1[j];
+      sh[(g * C + v * VEC + j) * 2 + 1] = s2[j];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    int c = i >> 1, k = i & 1;
+    double acc = 0.0;
+    for (int gg = 0; gg < groups; ++gg) acc += (double)sh[(gg * C + c) * 2 + k];
+    atomicAdd(sums + k * C + c, acc);
+  }
+}
+
+// dgamma = sums[C+c], dbeta = sums[c] (accumulated into fp32 grads), and the per-channel
+// coefficients of the apply pass:  dx = k0*g - k1 - k2*xhat
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
+                                       const float* __restrict__ rstd, float* __restrict__ dgamma,
+                                       float* __restrict__ dbeta, float* __restrict__ coef, long long M, int C,
+                                       int accumulate) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s1 = sums[c], s2 = sums[C + c];
+  float g = gamma ? gamma[c] : 1.f;
+  double k0 = (double)g * (double)rstd[c];
+  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s2;
+  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s1;
+  coef[c] = (float)k0;
+  coef[C + c] = (float)(k0 * s1 / (double)M);
+  coef[2 * C + c] = (float)(k0 * s2 / (double)M);
+}
+
+// dx = k0*g - k1 - k2*xhat ;  optionally d_residual (+)= g  (identity branch of a residual block)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ a,
+                    const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ coef, T* __restrict__ dx, T* __restrict__ dres, int dres_accumulate,
+                    long long n, int C, float slope) {
+  const long long nv = n / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i * VEC) % C);
+    float dv[VEC], xv[VEC], av[VEC], mu[VEC], rs[VEC], k0[VEC], k1[VEC], k2[VEC], ov[VEC], rv[VEC];
+    ld_vec<VEC>(dy + i * VEC, dv);
+    ld_vec<VEC>(x + i * VEC, xv);
+    if (a) ld_vec<VEC>(a + i * VEC, av);
+    ld_vec<VEC>(mean + c, mu);
+    ld_vec<VEC>(rstd + c, rs);
+    ld_vec<VEC>(coef + c, k0);
+    ld_vec<VEC>(coef + C + c, k1);
+    ld_vec<VEC>(coef + 2 * C + c, k2);
+    if (dres && dres_accumulate) ld_vec<VEC>(dres + i * VEC, rv);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      float g = dv[j];
+      if (a) g *= (av[j] > 0.f) ? 1.f : slope;
+      ov[j] = k0[j] * g - k1[j] - k2[j] * (xv[j] - mu[j]) * rs[j];
+      dv[j] = (dres && dres_accumulate) ? rv[j] + g : g;
+    }
+    st_vec<VEC>(dx + i * VEC, ov);
+    if (dres) st_vec<VEC>(dres + i * VEC, dv);
+  }
+}
+
+// Plain activation backward (no BN): dx = dy * act'(a)     (discriminator layer 1: conv + LeakyReLU)
+template <typename T, int VEC>
+__global__ void act_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ a, T* __restrict__ dx,
+                               long long n, float slope) {
+  const long long nv = n / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    float dv[VEC], av[VEC];
+    ld_vec<VEC>(dy + i * VEC, dv);
+    ld_vec<VEC>(a + i * VEC, av);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) dv[j] *= (av[j] > 0.f) ? 1.f : slope;
+    st_vec<VEC>(dx + i * VEC, dv);
+  }
+}
+
+// y = act(x + bias[c])  (in place allowed)
+template <typename T, int VEC>
+__global__ void bias_act_kernel(const T* __restrict__ x, const float* __restrict__ bias, T* __restrict__ y,
+                                long long n, int C, float slope) {
+  const long long nv = n / VEC;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i * VEC) % C);
+    float xv[VEC], bv[VEC];
+    ld_vec<VEC>(x + i * VEC, xv);
+    if (bias) ld_vec<VEC>(bias + c, bv);
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) xv[j] = act_fwd(xv[j] + (bias ? bv[j] : 0.f), slope);
+    st_vec<VEC>(y + i * VEC, xv);
+  }
+}
+
+// out[c] (+)= sum_rows x[r][c]      (bias gradients; global-average-pool backward helper)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+colsum_kernel(const T* __restrict__ x, double* __restrict__ sums, long long M, int C) {
+  extern __shared__ float sh[];
+  const int cv = C / VEC;
+  const int groups = blockDim.x / cv;
+  const int g = threadIdx.x / cv, v = threadIdx.x % cv;
+  float s1[VEC];
+#pragma unroll
+  for (int j = 0; j < VEC; ++j) s1[j] = 0.f;
+  if (g < groups) {
+    for (long long r = (long long)blockIdx.x * groups + g; r < M; r += (long long)gridDim.x * groups) {
+      float xv[VEC];
+      ld_vec<VEC>(x + r * C + v * VEC, xv);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) s1[j] += xv[j];
+    }
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) sh[g * C + v * VEC + j] = s1[j];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double acc = 0.0;
+    for (int gg = 0; gg < groups; ++gg) acc += (double)sh[gg * C + c];
+    atomicAdd(sums + c, acc);
+  }
+}
+__global__ void sums_to_f32_kernel(const double* __restrict__ sums, float* __restrict__ out, int n, float scale,
+                                   int accumulate) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (accumulate ? out[i] : 0.f) + (float)(sums[i] * (double)scale);
+}
+
+// ---------------------------------------------------------------------------------------------
+// MaxPool 3x3 stride 2 pad 1 (NHWC).  idx stores the winning tap (kh*3+kw), first max in scan order
+// and NaN-propagating like torch.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ idx, int B, int H,
+                   int W, int C, int Ho, int Wo) {
+  const int cv = C / VEC;
+  const long long total = (long long)B * Ho * Wo * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long p = i / cv;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float best[VEC];
+    int bi[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { best[j] = -INFINITY; bi[j] = -1; }
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int h = ho * 2 - 1 + kh;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int w = wo * 2 - 1 + kw;
+        if (w < 0 || w >= W) continue;
+        float xv[VEC];
+        ld_vec<VEC>(x + (((long long)b * H + h) * W + w) * C + v * VEC, xv);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          // at::max_pool2d: index starts at the first valid tap; (val > max) || isnan(val) replaces
+          if (bi[j] < 0) bi[j] = kh * 3 + kw;
+          if ((xv[j] > best[j]) || (xv[j] != xv[j])) { best[j] = xv[j]; bi[j] = kh * 3 + kw; }
+        }
+      }
+    }
+    const long long o = (((long long)b * Ho + ho) * Wo + wo) * C + v * VEC;
+    st_vec<VEC>(y + o, best);
+    if (idx) {
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) idx[o + j] = (unsigned char)bi[j];
+    }
+  }
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+maxpool_bwd_kernel(const T* __restrict__ dy, const unsigned char* __restrict__ idx, const T* addend, T* dx, int B,
+                   int H, int W, int C, int Ho, int Wo) {
+  const int cv = C / VEC;
+  const long long total = (long long)B * H * W * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    long long p = i / cv;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H);
+    const int b = (int)(p / H);
+    float acc[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+    if (addend) ld_vec<VEC>(addend + i * VEC, acc);  // may alias dx (same elements, same thread)
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int t = h + 1 - kh;
+      if (t < 0 || (t & 1)) continue;
+      const int ho = t >> 1;
+      if (ho >= Ho) continue;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int s = w + 1 - kw;
+        if (s < 0 || (s & 1)) continue;
+        const int wo = s >> 1;
+        if (wo >= Wo) continue;
+        const long long o = (((long long)b * Ho + ho) * Wo + wo) * C + v * VEC;
+        float dv[VEC];
+        ld_vec<VEC>(dy + o, dv);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j)
+          if (idx[o + j] == kh * 3 + kw) acc[j] += dv[j];
+      }
+    }
+    st_vec<VEC>(dx + i * VEC, acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoder operand: out[b,h,w,:] = concat(x[b,h/2,w/2,:C1], skip[b,h,w,:C2])  (nearest x2)
+// ---------------------------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+upcat_fwd_kernel(const T* __restrict__ x, const T* __restrict__ skip, T* __restrict__ out, int B, int H, int W,
+                 int C1, int C2) {
+  const int Ct = C1 + C2, cv = Ct / VEC;
+  const long long total = (long long)B * H * W * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv) * VEC;
+    long long p = i / cv;
+    const int w = (int)(p % W); p /= W;
+    const int h = (int)(p % H);
+    const int b = (int)(p / H);
+    float v[VEC];
+    if (c < C1) ld_vec<VEC>(x + (((long long)b * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1)) * C1 + c, v);
+    else ld_vec<VEC>(skip + (((long long)b * H + h) * W + w) * C2 + (c - C1), v);
+    st_vec<VEC>(out + i * VEC, v);
+  }
+}
+// dx[b,h2,w2,c] = sum of the 2x2 children of dout[..., c<C1];  dskip = dout[..., C1:]
+template <typename T, int VEC>
+__global__ void __launch_bounds__(kThreads)
+upcat_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dx, T* __restrict__ dskip, int B, int H, int W,
+                 int C1, int C2) {
+  const int Ct = C1 + C2;
+  const int cv1 = C1 / VEC, cv2 = C2 / VEC;
+  const long long n1 = (long long)B * (H / 2) * (W / 2) * cv1;
+  const long long n2 = (long long)B * H * W * cv2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2;
+       i += (long long)gridDim.x * blockDim.x) {
+    if (i < n1) {
+      const int c = (int)(i % cv1) * VEC;
+      long long p = i / cv1;
+      const int w2 = (int)(p % (W / 2)); p /= (W / 2);
+      const int h2 = (int)(p % (H / 2));
+      const int b = (int)(p / (H / 2));
+      float acc[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+#pragma unroll
+      for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+        for (int dw = 0; dw < 2; ++dw) {
+          float v[VEC];
+          ld_vec<VEC>(dout + (((long long)b * H + 2 * h2 + dh) * W + 2 * w2 + dw) * Ct + c, v);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) acc[j] += v[j];
+        }
+      st_vec<VEC>(dx + i * VEC, acc);
+    } else {
+      const long long k = i - n1;
+      const int c = (int)(k % cv2) * VEC;
+      const long long p = k / cv2;
+      float v[VEC];
+      ld_vec<VEC>(dout + p * Ct + C1 + c, v);
+      st_vec<VEC>(dskip + k * VEC, v);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Discriminator tail: global average pool + Linear(C,1) + sigmoid, and its backward.
+// ---------------------------------------------------------------------------------------------
+// One CTA per image: out[b] = sigmoid(bias + sum_c w[c] * mean_hw x[b,hw,c]);  pooled[b][c] saved.
+template <typename T>
+__global__ void gap_linear_sigmoid_kernel(const T* __restrict__ x, const float* __restrict__ w,
+                                          const float* __restrict__ bias, float* __restrict__ pooled,
+                                          float* __restrict__ out, long long HW, int C) {
+  __shared__ float red[32];
+  const int b = blockIdx.x;
+  const T* xb = x + (long long)b * HW * C;
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s = 0.f;
+    for (long long p = 0; p < HW; ++p) s += to_f(xb[p * C + c]);
+    s /= (float)HW;
+    pooled[(long long)b * C + c] = s;
+    dot += s * w[c];
+  }
+  float v[1] = {dot}, o[1];
+  block_sum<1>(v, red, o);
+  if (threadIdx.x == 0) out[b] = 1.f / (1.f + expf(-(o[0] + bias[0])));
+}
+// dz = dout*y*(1-y); dw[c] += sum_b dz_b pooled[b][c]; dbias += sum dz; dx[b,hw,c] = dz_b*w[c]/HW
+template <typename T>
+__global__ void gap_linear_sigmoid_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ y,
+                                              const float* __restrict__ pooled, const float* __restrict__ w,
+                                              float* __restrict__ dw, float* __restrict__ dbias,
+                                              T* __restrict__ dx, int B, long long HW, int C, int accumulate) {
+  // grid.x = B (dx), plus block 0 also produces dw/dbias
+  const int b = blockIdx.x;
+  const float dz = dout[b] * y[b] * (1.f - y[b]);
+  T* dxb = dx + (long long)b * HW * C;
+  const float k = dz / (float)HW;
+  for (long long i = threadIdx.x; i < HW * C; i += blockDim.x) dxb[i] = from_f<T>(k * w[i % C]);
+  if (b == 0) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float s = 0.f;
+      for (int bb = 0; bb < B; ++bb) s += dout[bb] * y[bb] * (1.f - y[bb]) * pooled[(long long)bb * C + c];
+      dw[c] = (accumulate ? dw[c] : 0.f) + s;
+    }
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int bb = 0; bb < B; ++bb) s += dout[bb] * y[bb] * (1.f - y[bb]);
+      dbias[0] = (accumulate ? dbias[0] : 0.f) + s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused Adam over a flat fp32 parameter buffer (torch.optim.Adam defaults semantics, no amsgrad);
+// also refreshes the bf16 shadow copy the tensor-core convolutions read.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            bf16* __restrict__ shadow, long long n, float lr, float beta1, float beta2, float eps,
+            float weight_decay, float bc1, float bc2_sqrt, float grad_scale, const float* __restrict__ dev_clip) {
+  const float clip = dev_clip ? *dev_clip : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i] * grad_scale * clip;
+    float pi = p[i];
+    if (weight_decay != 0.f) gi += weight_decay * pi;
+    float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    m[i] = mi; v[i] = vi;
+    // torch: denom = sqrt(v)/sqrt(bc2) + eps ; p -= (lr/bc1) * m / denom
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    pi -= (lr / bc1) * mi / denom;
+    p[i] = pi;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pi);
+  }
+}
+
+// sum of squares of a flat fp32 buffer -> out[0] (double); clip coefficient kernel for clip_grad_norm_
+__global__ void __launch_bounds__(kThreads) sumsq_kernel(const float* __restrict__ x, double* __restrict__ out, long long n) {
+  __shared__ float red[32];
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) { float t = x[i]; s += t * t; }
+  float v[1] = {s}, o[1];
+  block_sum<1>(v, red, o);
+  if (threadIdx.x == 0) atomicAdd(out, (double)o[0]);
+}
+// clip_grad_norm_ (src/models/unsupervised_trainer.py:144): coef = min(1, max_norm/(norm+1e-6))
+__global__ void clip_coef_kernel(const double* __restrict__ sumsq, float* __restrict__ coef, float* __restrict__ norm_out,
+                                 float max_norm, float pre_scale) {
+  if (threadIdx.x == 0) {
+    float norm = sqrtf((float)*sumsq) * pre_scale;
+    float c = max_norm / (norm + 1e-6f);
+    coef[0] = c < 1.f ? c : 1.f;
+    if (norm_out) norm_out[0] = norm;
+  }
+}
+
+}  // namespace
+}  // namespace uda
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace uda;
+
+#define UDA_DT(dtype, FN, ...)                                                   \
+  do {                                                                           \
+    if ((dtype) == UDA_BF16) { FN(bf16, __VA_ARGS__); }                          \
+    else if ((dtype) == UDA_F32) { FN(float, __VA_ARGS__); }                     \
+    else return set_error(UDA_ERR_BAD_ARG, "unsupported dtype %d", (dtype));     \
+  } while (0)
+
+static inline int vec_for(int dtype, int C, const void* a, const void* b = nullptr, const void* c = nullptr,
+                          const void* d = nullptr) {
+  // widest channel vector (16 bytes) every pointer and C allow
+  int v = dtype == UDA_BF16 ? 8 : 4;
+  const size_t es = dtype == UDA_BF16 ? 2 : 4;
+  auto ok = [&](int vv) {
+    if (C % vv) return false;
+    const void* ps[4] = {a, b, c, d};
+    for (auto p : ps)
+      if (p && reinterpret_cast<uintptr_t>(p) % (vv * es)) return false;
+    return true;
+  };
+  while (v > 1 && !ok(v)) v >>= 1;
+  return v;
+}
+
+extern "C" int uda_nchw_f32_to_nhwc(const float* src, void* dst, int dtype, int B, int C, int Cpad,
+                                    long long HW, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(src && dst && B > 0 && C > 0 && Cpad >= C && HW > 0, UDA_ERR_BAD_ARG, "nchw_to_nhwc: bad argument");
+  dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((Cpad + 31) / 32), (unsigned)B), block(32, 8);
+  UDA_REQUIRE(B <= 65535 && grid.y <= 65535, UDA_ERR_UNSUPPORTED, "nchw_to_nhwc: shape too large");
+#define K(T, ...) nchw_to_nhwc_kernel<T><<<grid, block, 0, st>>>(src, (T*)dst, C, Cpad, HW)
+  UDA_DT(dtype, K, 0);
+#undef K
+  UDA_LAUNCH_OK("nchw_to_nhwc_kernel");
+  return UDA_OK;
+}
+
+extern "C" int uda_nhwc_to_nchw_f32(const void* src, int dtype, float* dst, int B, int C, int Cpad,
+                                    long long HW, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(src && dst && B > 0 && C > 0 && Cpad >= C && HW > 0, UDA_ERR_BAD_ARG, "nhwc_to_nchw: bad argument");
+  dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((C + 31) / 32), (unsigned)B), block(32, 8);
+  UDA_REQUIRE(B <= 65535 && grid.y <= 65535, UDA_ERR_UNSUPPORTED, "nhwc_to_nchw: shape too large");
+#define K(T, ...) nhwc_to_nchw_kernel<T><<<grid, block, 0, st>>>((const T*)src, dst, C, Cpad, HW)
+  UDA_DT(dtype, K, 0);
+#undef K
+  UDA_LAUNCH_OK("nhwc_to_nchw_kernel");
+  return UDA_OK;
+}
+
+extern "C" int uda_cast_f32(const float* src, void* dst, int dtype, long long n, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(src && dst && n >= 0, UDA_ERR_BAD_ARG, "cast: bad argument");
+  if (n == 0) return UDA_OK;
+#define K(T, ...) cast_f32_kernel<T><<<grid_for(n), kThreads, 0, st>>>(src, (T*)dst, n)
+  UDA_DT(dtype, K, 0);
+#undef K
+  UDA_LAUNCH_OK("cast_f32_kernel");
+  return UDA_OK;
+}
+
+// workspace: 2*C doubles
+extern "C" int uda_bn_stats(const void* x, int dtype, long long M, int C, const float* gamma, const float* beta,
+                            float* running_mean, float* running_var, float* mean, float* rstd, float* scale,
+                            float* shift, float eps, float momentum, void* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(x && mean && rstd && scale && shift && workspace, UDA_ERR_BAD_ARG, "bn_stats: null pointer");
+  UDA_REQUIRE(M > 0 && C > 0 && C <= 4096, UDA_ERR_BAD_ARG, "bn_stats: bad shape M=%lld C=%d", M, C);
+  double* sums = (double*)workspace;
+  UDA_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st));
+  int vec = vec_for(dtype, C, x);
+  while (C / vec > kThreads) vec *= 2;  // at least one row group per CTA
+  UDA_REQUIRE(C % vec == 0 && vec <= 8, UDA_ERR_UNSUPPORTED, "bn_stats: C=%d not supported", C);
+  const int groups = kThreads / (C / vec);
+  long long blocks = (M + groups - 1) / groups;
+  long long cap = (long long)num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  size_t smem = (size_t)groups * C * 2 * sizeof(float);
+  UDA_REQUIRE(smem <= 48 * 1024, UDA_ERR_UNSUPPORTED, "bn_stats: C=%d needs too much shared memory", C);
+#define K(T, V) bn_stats_kernel<T, V><<<(unsigned)blocks, kThreads, smem, st>>>((const T*)x, sums, M, C)
+#define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
+  UDA_DT(dtype, KV, 0);
+#undef KV
+#undef K
+  UDA_LAUNCH_OK("bn_stats_kernel");
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, gamma, beta, running_mean, running_var, mean, rstd,
+                                                      scale, shift, M, C, eps, momentum);
+  UDA_LAUNCH_OK("bn_finalize_kernel");
+  return UDA_OK;
+}
+
+extern "C" int uda_bn_eval_coeffs(const float* gamma, const float* beta, const float* running_mean,
+                                  const float* running_var, float* scale, float* shift, int C, float eps,
+                                  void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(running_mean && running_var && scale && shift && C > 0, UDA_ERR_BAD_ARG, "bn_eval_coeffs: bad argument");
+  bn_eval_coeffs_kernel<<<(C + 127) / 128, 128, 0, st>>>(gamma, beta, running_mean, running_var, scale, shift, C, eps);
+  UDA_LAUNCH_OK("bn_eval_coeffs_kernel");
+  return UDA_OK;
+}
+
+extern "C" int uda_bn_apply(const void* x, const void* residual, void* y, int dtype, const float* scale,
+                            const float* shift, long long M, int C, float slope, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(x && y && scale && shift && M > 0 && C > 0, UDA_ERR_BAD_ARG, "bn_apply: bad argument");
+  int vec = vec_for(dtype, C, x, residual, y);
+  if (reinterpret_cast<uintptr_t>(scale) % 16 || reinterpret_cast<uintptr_t>(shift) % 16) vec = 1;
+  const long long n = M * C;
+#define K(T, V) bn_apply_kernel<T, V><<<grid_for(n / V), kThreads, 0, st>>>((const T*)x, (const T*)residual, (T*)y, scale, shift, n, C, slope)
+#define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
+  UDA_DT(dtype, KV, 0);
+#undef KV
+#undef K
+  UDA_LAUNCH_OK("bn_apply_kernel");
+  return UDA_OK;
+}
+
+// workspace: 2*C doubles + 3*C floats
+extern "C" int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtype, const float* gamma,
+                          const float* mean, const float* rstd, void* dx, void* dres, int dres_accumulate,
+                          float* dgamma, float* dbeta, int param_accumulate, long long M, int C, float slope,
+                          void* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(dy && x && mean && rstd && dx && workspace, UDA_ERR_BAD_ARG, "bn_bwd: null pointer");
+  UDA_REQUIRE(M > 0 && C > 0 && C <= 4096, UDA_ERR_BAD_ARG, "bn_bwd: bad shape");
+  double* sums = (double*)workspace;
+  float* coef = (float*)(sums + 2 * C);
+  UDA_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st));
+  int vec = vec_for(dtype, C, dy, x, a, dx);
+  if (dres) vec = vec < vec_for(dtype, C, dres) ? vec : vec_for(dtype, C, dres);
+  if (vec > 1 && (reinterpret_cast<uintptr_t>(mean) % 16 || reinterpret_cast<uintptr_t>(rstd) % 16 ||
+                  reinterpret_cast<uintptr_t>(coef) % 16 || C % 4)) vec = 1;
+  const int rvec = vec;
+  UDA_REQUIRE(C / rvec <= kThreads, UDA_ERR_UNSUPPORTED, "bn_bwd: C=%d not supported", C);
+  const int groups = kThreads / (C / rvec);
+  long long blocks = (M + groups - 1) / groups;
+  long long cap = (long long)num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  size_t smem = (size_t)groups * C * 2 * sizeof(float);
+  UDA_REQUIRE(smem <= 48 * 1024, UDA_ERR_UNSUPPORTED, "bn_bwd: C=%d needs too much shared memory", C);
+#define K(T, V) bn_bwd_reduce_kernel<T, V><<<(unsigned)blocks, kThreads, smem, st>>>((const T*)dy, (const T*)x, (const T*)a, mean, rstd, sums, M, C, slope)
+#define KV(T, ...) do { if (rvec == 8) K(T, 8); else if (rvec == 4) K(T, 4); else if (rvec == 2) K(T, 2); else K(T, 1); } while (0)
+  UDA_DT(dtype, KV, 0);
+#undef KV
+#undef K
+  UDA_LAUNCH_OK("bn_bwd_reduce_kernel");
+  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, gamma, rstd, dgamma, dbeta, coef, M, C, param_accumulate);
+  UDA_LAUNCH_OK("bn_bwd_finalize_kernel");
+  const long long n = M * C;
+#define K(T, V) bn_bwd_apply_kernel<T, V><<<grid_for(n / V), kThreads, 0, st>>>((const T*)dy, (const T*)x, (const T*)a, mean, rstd, coef, (T*)dx, (T*)dres, dres_accumulate, n, C, slope)
+#define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
+  UDA_DT(dtype, KV, 0);
+#undef KV
+#undef K
+  UDA_LAUNCH_OK("bn_bwd_apply_kernel");
+  return UDA_OK;
+}
+
+extern "C" int uda_act_bwd(const void* dy, const void* a, void* dx, int dtype, long long n, float slope, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(dy && a && dx && n > 0, UDA_ERR_BAD_ARG, "act_bwd: bad argument");
+  int vec = vec_for(dtype, (int)(n % 8 == 0 ? 8 : 1), dy, a, dx);
+#define K(T, V) act_bwd_kernel<T, V><<<grid_for(n / V), kThreads, 0, st>>>((const T*)dy, (const T*)a, (T*)dx, n, slope)
+#define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
+  UDA_DT(dtype, KV, 0);
+#undef KV
+#undef K
+  UDA_LAUNCH_OK("act_bwd_kernel");
+  return UDA_OK;
+}
+
+extern "C" int uda_bias_act(const void* x, const float* bias, void* y, int dtype, long long M, int C, float slope,
+                            void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(x && y && M > 0 && C > 0, UDA_ERR_BAD_ARG, "bias_act: bad argument");
+  int vec = vec_for(dtype, C, x, y);
+  if (vec > 1 && bias && (reinterpret_cast<uintptr_t>(bias) % 16 || C % 4)) vec = 1;
+  const long long n = M * C;
+#define K(T, V) bias_act_kernel<T, V><<<grid_for(n / V), kThreads, 0, st>>>((const T*)x, bias, (T*)y, n, C, slope)
+#define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
+  UDA_DT(dtype, KV, 0);
+#undef KV
+#undef K
+  UDA_LAUNCH_OK("bias_act_kernel");
+  return UDA_OK;
+}
+
+// out[c] (+)= scale * sum_rows x[r][c];  workspace: C doubles
+extern "C" int uda_colsum(const void* x, int dtype, float* out, long long M, int C, float scale, int accumulate,
+                          void* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(x && out && workspace && M > 0 && C > 0 && C <= 4096, UDA_ERR_BAD_ARG, "colsum: bad argument");
+  double* sums = (double*)workspace;
+  UDA_CUDA_OK(cudaMemsetAsync(sums, 0, C * sizeof(double), st));
+  int vec = vec_for(dtype, C, x);
+  while (C / vec > kThreads) vec *= 2;
+  UDA_REQUIRE(C % vec == 0 && vec <= 8, UDA_ERR_UNSUPPORTED, "colsum: C=%d not supported", C);
+  const int groups = kThreads / (C / vec);
+  long long blocks = (M + groups - 1) / groups;
+  long long cap = (long long)num_sms() * 4;
+  if (blocks > cap) blocks = cap;
+  size_t smem = (size_t)groups * C * sizeof(float);
+#define K(T, V) colsum_kernel<T, V><<<(unsigned)blocks, kThreads, smem, st>>>((const T*)x, sums, M, C)
+#define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
+  UDA_DT(dtype, KV, 0);
+#undef KV
+#undef K
+  UDA_LAUNCH_OK("colsum_kernel");
+  sums_to_f32_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, out, C, scale, accumulate);
+  UDA_LAUNCH_OK("sums_to_f32_kernel");
+  return UDA_OK;
+}
+
+extern "C" int uda_maxpool3x3s2_fwd(const void* x, void* y, unsigned char* idx, int dtype, int B, int H, int W,
+                                    int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(x && y && B > 0 && H > 0 && W > 0 && C > 0, UDA_ERR_BAD_ARG, "maxpool_fwd: bad argument");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  int vec = vec_for(dtype, C, x, y);
+  const long long total = (long long)B * Ho * Wo * (C / vec);
+#define K(T, V) maxpool_fwd_kernel<T, V><<<grid_for(total), kThreads, 0, st>>>((const T*)x, (T*)y, idx, B, H, W, C, Ho, Wo)
+#define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
+  UDA_DT(dtype, KV, 0);
+#undef KV
+#undef K
+  UDA_LAUNCH_OK("maxpool_fwd_kernel");
+  return UDA_OK;
+}
+
+extern "C" int uda_maxpool3x3s2_bwd(const void* dy, const unsigned char* idx, const void* addend, void* dx, int dtype,
+                                    int B, int H, int W, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(dy && idx && dx && B > 0 && H > 0 && W > 0 && C > 0, UDA_ERR_BAD_ARG, "maxpool_bwd: bad argument");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  int vec = vec_for(dtype, C, dy, dx, addend);
+  const long long total = (long long)B * H * W * (C / vec);
+#define K(T, V) maxpool_bwd_kernel<T, V><<<grid_for(total), kThreads, 0, st>>>((const T*)dy, idx, (const T*)addend, (T*)dx, B, H, W, C, Ho, Wo)
+#define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
+  UDA_DT(dtype, KV, 0);
+#undef KV
+#undef K
+  UDA_LAUNCH_OK("maxpool_bwd_kernel");
+  return UDA_OK;
+}
+
+// H, W are the OUTPUT (upsampled) spatial size; x is [B,H/2,W/2,C1], skip [B,H,W,C2] (C2 may be 0)
+extern "C" int uda_upsample2x_concat_fwd(const void* x, const void* skip, void* out, int dtype, int B, int H, int W,
+                                         int C1, int C2, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(x && out && (skip || C2 == 0) && B > 0 && H > 0 && W > 0 && C1 > 0 && C2 >= 0, UDA_ERR_BAD_ARG,
+              "upcat_fwd: bad argument");
+  UDA_REQUIRE(H % 2 == 0 && W % 2 == 0, UDA_ERR_BAD_ARG, "upcat_fwd: output size must be even");
+  int vec = vec_for(dtype, C1, x, out);
+  if (C2) { int v2 = vec_for(dtype, C2, skip); vec = vec < v2 ? vec : v2; }
+  const long long total = (long long)B * H * W * ((C1 + C2) / vec);
+#define K(T, V) upcat_fwd_kernel<T, V><<<grid_for(total), kThreads, 0, st>>>((const T*)x, (const T*)skip, (T*)out, B, H, W, C1, C2)
+#define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
+  UDA_DT(dtype, KV, 0);
+#undef KV
+#undef K
+  UDA_LAUNCH_OK("upcat_fwd_kernel");
+  return UDA_OK;
+}
+
+extern "C" int uda_upsample2x_concat_bwd(const void* dout, void* dx, void* dskip, int dtype, int B, int H, int W,
+                                         int C1, int C2, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(dout && dx && (dskip || C2 == 0) && B > 0 && H > 0 && W > 0 && C1 > 0 && C2 >= 0, UDA_ERR_BAD_ARG,
+              "upcat_bwd: bad argument");
+  int vec = vec_for(dtype, C1, dout, dx);
+  if (C2) { int v2 = vec_for(dtype, C2, dskip); vec = vec < v2 ? vec : v2; }
+  const long long total = (long long)B * (H / 2) * (W / 2) * (C1 / vec) + (long long)B * H * W * (C2 / vec);
+#define K(T, V) upcat_bwd_kernel<T, V><<<grid_for(total), kThreads, 0, st>>>((const T*)dout, (T*)dx, (T*)dskip, B, H, W, C1, C2)
+#define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
+  UDA_DT(dtype, KV, 0);
+#undef KV
+#undef K
+  UDA_LAUNCH_OK("upcat_bwd_kernel");
+  return UDA_OK;
+}
+
+extern "C" int uda_gap_linear_sigmoid_fwd(const void* x, int dtype, const float* w, const float* bias, float* pooled,
+                                          float* out, int B, long long HW, int C, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(x && w && bias && pooled && out && B > 0 && HW > 0 && C > 0, UDA_ERR_BAD_ARG, "gap_linear: bad argument");
+#define K(T, ...) gap_linear_sigmoid_kernel<T><<<B, 256, 0, st>>>((const T*)x, w, bias, pooled, out, HW, C)
+  UDA_DT(dtype, K, 0);
+#undef K
+  UDA_LAUNCH_OK("gap_linear_sigmoid_kernel");
+  return UDA_OK;
+}
+
+extern "C" int uda_gap_linear_sigmoid_bwd(const float* dout, const float* y, const float* pooled, const float* w,
+                                          float* dw, float* dbias, void* dx, int dtype, int B, long long HW, int C,
+                                          int accumulate, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(dout && y && pooled && w && dw && dbias && dx && B > 0, UDA_ERR_BAD_ARG, "gap_linear_bwd: bad argument");
+#define K(T, ...) gap_linear_sigmoid_bwd_kernel<T><<<B, 256, 0, st>>>(dout, y, pooled, w, dw, dbias, (T*)dx, B, HW, C, accumulate)
+  UDA_DT(dtype, K, 0);
+#undef K
+  UDA_LAUNCH_OK("gap_linear_sigmoid_bwd_kernel");
+  return UDA_OK;
+}
+
+extern "C" int uda_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, float lr,
+                             float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                             const float* dev_clip_coef, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(p && g && m && v && n >= 0 && step >= 1, UDA_ERR_BAD_ARG, "adam: bad argument");
+  if (n == 0) return UDA_OK;
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  adam_kernel<<<grid_for(n), kThreads, 0, st>>>(p, g, m, v, (bf16*)bf16_shadow, n, lr, beta1, beta2, eps,
+                                                weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale, dev_clip_coef);
+  UDA_LAUNCH_OK("adam_kernel");
+  return UDA_OK;
+}
+
+// coef[0] = min(1, max_norm / (pre_scale*||g||_2 + 1e-6)); norm_out[0] = pre_scale*||g||_2.  workspace: 1 double
+extern "C" int uda_grad_clip_coef(const float* g, long long n, float max_norm, float pre_scale, float* coef,
+                                  float* norm_out, void* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(g && coef && workspace && n > 0, UDA_ERR_BAD_ARG, "grad_clip: bad argument");
+  double* acc = (double*)workspace;
+  UDA_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double), st));
+  sumsq_kernel<<<grid_for(n, 4), kThreads, 0, st>>>(g, acc, n);
+  UDA_LAUNCH_OK("sumsq_kernel");
+  clip_coef_kernel<<<1, 32, 0, st>>>(acc, coef, norm_out, max_norm, pre_scale);
+  UDA_LAUNCH_OK("clip_coef_kernel");
+  return UDA_OK;
+}

@@ -1,0 +1,288 @@
+"""Layer engine: NHWC forward / manual backward of the conv-BN-activation networks on the CUDA kernels.
+
+The reference reaches these layers through ``nn.Module`` calls into ATen/cuDNN; here a
+network forward is a straight-line sequence of C-ABI launches (``ops``) recorded on a small tape, and
+the backward replays the tape in reverse.  One ``torch.autograd.Function`` per network (see
+``unet.py`` / ``discriminator.py``) makes the whole thing a single autograd node, so the reference's
+``loss.backward(); optimizer.step()`` call sites work unchanged.
+
+Gradient accumulation for tensors with several consumers (residual identity, encoder skips) is
+folded into the consumer kernels through their ``addend`` argument instead of separate add passes.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class Var:
+    """An activation (NHWC tensor) plus its gradient slot on the tape."""
+    __slots__ = ("t", "g")
+
+    def __init__(self, t):
+        self.t = t
+        self.g = None
+
+
+class Tape:
+    def __init__(self):
+        self.fns = []
+
+    def push(self, fn):
+        self.fns.append(fn)
+
+    def backward(self):
+        for fn in reversed(self.fns):
+            fn()
+        self.fns = []
+
+
+class ConvParams(nn.Module):
+    """Parameter holder with ``nn.Conv2d``'s state_dict keys (``weight`` [O,I,KH,KW], ``bias``).
+
+    The weight is stored channels_last, i.e. physically OHWI — the layout the kernels read.
+    Forward is executed by the fused engine, never through cuDNN.
+    """
+
+    def __init__(self, cin, cout, k, stride=1, padding=0, bias=False):
+        super().__init__()
+        self.in_channels, self.out_channels = cin, cout
+        self.kernel_size, self.stride, self.padding = k, stride, padding
+        w = torch.empty(cout, cin, k, k).contiguous(memory_format=torch.channels_last)
+        self.weight = nn.Parameter(w)
+        self.bias = nn.Parameter(torch.zeros(cout)) if bias else None
+
+    def forward(self, *a, **k):
+        raise RuntimeError("ConvParams is executed by the uda_b200 engine (call the owning network)")
+
+    def extra_repr(self):
+        return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, "
+                f"stride={self.stride}, padding={self.padding}, bias={self.bias is not None}")
+
+
+class BNParams(nn.Module):
+    """Parameter/buffer holder with ``nn.BatchNorm2d``'s state_dict keys (eps 1e-5, momentum 0.1)."""
+
+    def __init__(self, c, eps=1e-5, momentum=0.1):
+        super().__init__()
+        self.num_features, self.eps, self.momentum = c, eps, momentum
+        self.weight = nn.Parameter(torch.ones(c))
+        self.bias = nn.Parameter(torch.zeros(c))
+        self.register_buffer("running_mean", torch.zeros(c))
+        self.register_buffer("running_var", torch.ones(c))
+        self.register_buffer("num_batches_tracked", torch.tensor(0, dtype=torch.long))
+
+    def forward(self, *a, **k):
+        raise RuntimeError("BNParams is executed by the uda_b200 engine (call the owning network)")
+
+    def extra_repr(self):
+        return f"{self.num_features}, eps={self.eps}, momentum={self.momentum}"
+
+
+class LinearParams(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.in_features, self.out_features = cin, cout
+        self.weight = nn.Parameter(torch.empty(cout, cin))
+        self.bias = nn.Parameter(torch.zeros(cout))
+
+    def forward(self, *a, **k):
+        raise RuntimeError("LinearParams is executed by the uda_b200 engine (call the owning network)")
+
+
+class ParamStore:
+    """Flat fp32 parameter buffer (+ bf16 shadow) and per-backward flat gradient buffer of a network.
+
+    ``nn.Parameter`` objects stay the public handles (state_dict / optimizers / DDP see them), but
+    their storage is re-pointed into one contiguous fp32 buffer so that the bf16 shadow refresh, the
+    fused Adam and the gradient all-reduce are single launches over one range.
+    """
+
+    def __init__(self, module):
+        self.module = module
+        self.params = [p for p in module.parameters()]
+        self.offsets = {}
+        off = 0
+        for p in self.params:
+            self.offsets[id(p)] = off
+            off += (p.numel() + 3) // 4 * 4  # keep every slice 16-byte aligned
+        self.total = off
+        self.flat = None
+        self.shadow = None
+        self.shadow_version = None
+        self.grad = None
+
+    # -- parameters -------------------------------------------------------------------------
+    def _view_like(self, flat, p):
+        off = self.offsets[id(p)]
+        seg = flat[off:off + p.numel()]
+        if p.dim() == 4:
+            O, I, KH, KW = p.shape
+            return seg.view(O, KH, KW, I).permute(0, 3, 1, 2)  # logical OIHW, physical OHWI
+        return seg.view(p.shape)
+
+    def ensure_flat(self, device):
+        if self.flat is not None and self.flat.device == device:
+            base = self.flat.data_ptr()
+            ok = all(p.data_ptr() == base + 4 * self.offsets[id(p)] for p in self.params)
+            if ok:
+                return
+        flat = torch.zeros(self.total, dtype=torch.float32, device=device)
+        with torch.no_grad():
+            for p in self.params:
+                v = self._view_like(flat, p)
+                v.copy_(p.detach().to(device))
+                p.data = v
+        self.flat = flat
+        self.shadow = torch.empty(self.total, dtype=torch.bfloat16, device=device)
+        self.shadow_version = None
+
+    def refresh_shadow(self, force=False):
+        ver = self.flat._version
+        if force or self.shadow_version != ver:
+            ops.cast_f32(self.flat, self.shadow)
+            self.shadow_version = ver
+
+    def mark_shadow_fresh(self):
+        self.shadow_version = self.flat._version
+
+    def w(self, p, dtype):
+        """OHWI kernel view of conv weight ``p`` in ``dtype`` (bf16 -> shadow copy)."""
+        off = self.offsets[id(p)]
+        O, I, KH, KW = p.shape
+        src = self.shadow if dtype == torch.bfloat16 else self.flat
+        return src[off:off + p.numel()].view(O, KH, KW, I)
+
+    # -- gradients --------------------------------------------------------------------------
+    def new_grad(self):
+        self.grad = torch.zeros(self.total, dtype=torch.float32, device=self.flat.device)
+        return self.grad
+
+    def g(self, p):
+        off = self.offsets[id(p)]
+        seg = self.grad[off:off + p.numel()]
+        if p.dim() == 4:
+            O, I, KH, KW = p.shape
+            return seg.view(O, KH, KW, I)
+        return seg.view(p.shape)
+
+    def grad_views(self):
+        """Gradients shaped like the parameters (zero-copy views of the flat buffer)."""
+        return [self._view_like(self.grad, p) for p in self.params]
+
+
+class Ctx:
+    """Per-forward execution context."""
+
+    def __init__(self, store, dtype, training, tape):
+        self.store, self.dtype, self.training, self.tape = store, dtype, training, tape
+        self.grad_ready = None  # optional callback(offset) fired when grads >= offset are final (DDP overlap)
+
+
+# ------------------------------------------------------------------------------------------------
+# tape ops
+# ------------------------------------------------------------------------------------------------
+def conv(ctx, xin, cp, nchw_out=False):
+    """y = conv(x) (+bias).  Returns Var (NHWC) or, with nchw_out, a raw fp32 NCHW tensor + grad hook."""
+    st = ctx.store
+    w = st.w(cp.weight, ctx.dtype)
+    y = ops.conv_fwd(xin.t, w, cp.bias, cp.stride, cp.padding, nchw_out=nchw_out)
+    out = Var(y)
+    if ctx.tape is not None:
+        def bwd():
+            dy = out.g
+            out.g = None
+            if dy is None:
+                return
+            if cp.bias is not None:
+                ops.colsum(dy, st.g(cp.bias))
+            ops.conv_wgrad(dy, xin.t, st.g(cp.weight), cp.stride, cp.padding)
+            if xin.g is not False:  # False marks "no gradient needed" (network input)
+                xin.g = ops.conv_dgrad(dy, w, xin.t.shape, cp.stride, cp.padding, addend=xin.g)
+            if ctx.grad_ready is not None:
+                ctx.grad_ready(st.offsets[id(cp.weight)])
+        ctx.tape.push(bwd)
+    return out
+
+
+def bn_act(ctx, zin, bn, slope=0.0, residual=None):
+    """a = act(BN(z) (+ residual)); train mode uses batch statistics and updates the running ones."""
+    st = ctx.store
+    if ctx.training:
+        mean, rstd, scale, shift = ops.bn_stats(zin.t, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                                bn.eps, bn.momentum)
+        bn.num_batches_tracked += 1
+    else:
+        scale, shift = ops.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+        mean = rstd = None
+    a = ops.bn_apply(zin.t, scale, shift, residual.t if residual is not None else None, slope)
+    out = Var(a)
+    if ctx.tape is not None:
+        if not ctx.training:
+            raise RuntimeError("uda_b200: backward through eval-mode BatchNorm is not supported "
+                               "(the reference never trains in eval mode)")
+
+        def bwd():
+            da = out.g
+            out.g = None
+            if da is None:
+                return
+            dres = None
+            acc = False
+            if residual is not None:
+                if residual.g is None:
+                    dres = torch.empty_like(residual.t)
+                else:
+                    dres, acc = residual.g, True
+            zin.g = ops.bn_bwd(da, zin.t, a if slope != 1.0 else None, bn.weight, mean, rstd, slope,
+                               st.g(bn.weight), st.g(bn.bias), dres=dres, dres_accumulate=acc)
+            if residual is not None:
+                residual.g = dres
+        ctx.tape.push(bwd)
+    return out
+
+
+def bias_act(ctx, zin, slope):
+    """a = act(z) for a conv whose bias was already added in its epilogue (discriminator layer 1)."""
+    a = ops.bias_act(zin.t, None, slope)
+    out = Var(a)
+    if ctx.tape is not None:
+        def bwd():
+            if out.g is not None:
+                zin.g = ops.act_bwd(out.g, a, slope)
+            out.g = None
+        ctx.tape.push(bwd)
+    return out
+
+
+def maxpool(ctx, xin):
+    y, idx = ops.maxpool_fwd(xin.t)
+    out = Var(y)
+    if ctx.tape is not None:
+        def bwd():
+            if out.g is not None:
+                xin.g = ops.maxpool_bwd(out.g, idx, xin.t.shape, addend=xin.g)
+            out.g = None
+        ctx.tape.push(bwd)
+    return out
+
+
+def upcat(ctx, xin, skip):
+    y = ops.upcat_fwd(xin.t, skip.t if skip is not None else None)
+    out = Var(y)
+    if ctx.tape is not None:
+        C1 = xin.t.shape[-1]
+        C2 = skip.t.shape[-1] if skip is not None else 0
+
+        def bwd():
+            if out.g is None:
+                return
+            dx, dskip = ops.upcat_bwd(out.g, C1, C2)
+            out.g = None
+            if xin.g is not None or (skip is not None and skip.g is not None):
+                raise RuntimeError("upcat: inputs are expected to have no earlier gradient on the tape")
+            xin.g = dx
+            if skip is not None:
+                skip.g = dskip
+        ctx.tape.push(bwd)
+    return out

@@ -1,0 +1,460 @@
+"""Thin tensor-level wrappers over the C ABI (``include/uda_b200.h``).
+
+Every function validates device / dtype / contiguity, allocates outputs through the torch caching
+allocator, and launches on the current torch CUDA stream.  No function here computes anything in
+PyTorch: if the CUDA library is missing the call raises (``_lib.UdaError``).
+
+Activations are NHWC tensors ``[B,H,W,C]`` (fp32 or bf16); conv weights are OHWI tensors
+``[Cout,KH,KW,Cin]`` (the physical layout of a channels_last parameter).
+"""
+import os
+import torch
+
+from . import _lib
+from ._lib import call, ptr, ll, ci, F32, BF16, I64, U8
+
+_WS = {}
+#: set to "0" to force the FP32-pipe direct convolution everywhere (debug / A-B comparison)
+USE_TC = os.environ.get("UDA_B200_USE_TC", "1") != "0"
+#: counts launches issued through this module (bench.py reports it as gpu_launches)
+LAUNCHES = 0
+
+
+def _count(n=1):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+def _stream():
+    import ctypes
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def dt(t):
+    if t.dtype == torch.float32:
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise TypeError(f"unsupported activation dtype {t.dtype} (float32 or bfloat16)")
+
+
+def _chk(t, name, dtype=None):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise _lib.UdaError(f"{name}: expected a CUDA tensor (the uda_b200 hot path has no CPU fallback)")
+    if not t.is_contiguous():
+        raise _lib.UdaError(f"{name}: tensor must be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise TypeError(f"{name}: expected dtype {dtype}, got {t.dtype}")
+    return t
+
+
+def workspace(nbytes, device):
+    """Stream-ordered scratch (re-used by consecutive launches on the same stream)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _WS[key] = ws
+    return ws
+
+
+# ------------------------------------------------------------------------------------------------
+# layout
+# ------------------------------------------------------------------------------------------------
+def nchw_to_nhwc(x, dtype, cpad=None):
+    _chk(x, "nchw_to_nhwc.x", torch.float32)
+    B, C, H, W = x.shape
+    cpad = cpad or C
+    out = torch.empty((B, H, W, cpad), dtype=dtype, device=x.device)
+    call("nchw_f32_to_nhwc", ptr(x), ptr(out), ci(dt(out)), ci(B), ci(C), ci(cpad), ll(H * W), _stream())
+    _count()
+    return out
+
+
+def nhwc_to_nchw(x, C=None):
+    _chk(x, "nhwc_to_nchw.x")
+    B, H, W, cpad = x.shape
+    C = C or cpad
+    out = torch.empty((B, C, H, W), dtype=torch.float32, device=x.device)
+    call("nhwc_to_nchw_f32", ptr(x), ci(dt(x)), ptr(out), ci(B), ci(C), ci(cpad), ll(H * W), _stream())
+    _count()
+    return out
+
+
+def cast_f32(src, dst):
+    _chk(src, "cast.src", torch.float32)
+    _chk(dst, "cast.dst")
+    assert src.numel() == dst.numel()
+    call("cast_f32", ptr(src), ptr(dst), ci(dt(dst)), ll(src.numel()), _stream())
+    _count()
+    return dst
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution
+# ------------------------------------------------------------------------------------------------
+def _geom(x_shape, w_shape, stride, pad):
+    B, H, W, Cin = x_shape
+    Cout, KH, KW, Cin_w = w_shape
+    if Cin != Cin_w:
+        raise _lib.UdaError(f"conv: input has {Cin} channels, weight expects {Cin_w}")
+    Ho = (H + 2 * pad - KH) // stride + 1
+    Wo = (W + 2 * pad - KW) // stride + 1
+    return B, H, W, Cin, Cout, KH, KW, Ho, Wo
+
+
+def tc_supported(op, B, H, W, Cin, Cout, KH, KW, stride, pad):
+    if not USE_TC:
+        return False
+    return bool(_lib.lib().uda_conv2d_tc_supported(ci(op), ci(B), ci(H), ci(W), ci(Cin), ci(Cout), ci(KH), ci(KW),
+                                                    ci(stride), ci(pad)))
+
+
+def conv_fwd(x, w, bias=None, stride=1, pad=1, nchw_out=False, bn_sums=None, force_direct=False):
+    """y = conv2d(x, w) (+bias).  Returns NHWC ``y`` (dtype of x) or, with ``nchw_out``, fp32 NCHW."""
+    _chk(x, "conv_fwd.x"); _chk(w, "conv_fwd.w")
+    B, H, W, Cin, Cout, KH, KW, Ho, Wo = _geom(x.shape, w.shape, stride, pad)
+    y_nhwc = None if nchw_out else torch.empty((B, Ho, Wo, Cout), dtype=x.dtype, device=x.device)
+    y_nchw = torch.empty((B, Cout, Ho, Wo), dtype=torch.float32, device=x.device) if nchw_out else None
+    if bias is not None:
+        _chk(bias, "conv_fwd.bias", torch.float32)
+    use_tc = (not force_direct and x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+              and tc_supported(0, B, H, W, Cin, Cout, KH, KW, stride, pad))
+    if use_tc:
+        call("conv2d_tc_fwd", ptr(x), ptr(w), ptr(bias), ptr(y_nhwc), ptr(y_nchw), ptr(bn_sums), ci(B), ci(H), ci(W),
+             ci(Cin), ci(Cout), ci(KH), ci(KW), ci(stride), ci(pad), _stream())
+    else:
+        if bn_sums is not None:
+            raise _lib.UdaError("conv_fwd: fused BN statistics need the tensor-core path")
+        call("conv2d_direct_fwd", ptr(x), ci(dt(x)), ptr(w), ci(dt(w)), ptr(bias), ptr(y_nhwc), ptr(y_nchw), ci(B),
+             ci(H), ci(W), ci(Cin), ci(Cout), ci(KH), ci(KW), ci(stride), ci(pad), _stream())
+    _count()
+    return y_nchw if nchw_out else y_nhwc
+
+
+def conv_dgrad(dy, w, x_shape, stride=1, pad=1, addend=None, force_direct=False):
+    """dx = conv_transpose(dy, w) (+ addend, accumulated in place into ``addend``'s buffer when given)."""
+    _chk(dy, "conv_dgrad.dy"); _chk(w, "conv_dgrad.w")
+    B, H, W, Cin, Cout, KH, KW, Ho, Wo = _geom(x_shape, w.shape, stride, pad)
+    if tuple(dy.shape) != (B, Ho, Wo, Cout):
+        raise _lib.UdaError(f"conv_dgrad: dy shape {tuple(dy.shape)} != {(B, Ho, Wo, Cout)}")
+    if addend is not None:
+        _chk(addend, "conv_dgrad.addend", dy.dtype)
+        if tuple(addend.shape) != (B, H, W, Cin):
+            raise _lib.UdaError("conv_dgrad: addend shape mismatch")
+        dx = addend
+    else:
+        dx = torch.empty((B, H, W, Cin), dtype=dy.dtype, device=dy.device)
+    use_tc = (not force_direct and dy.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+              and tc_supported(1, B, H, W, Cin, Cout, KH, KW, stride, pad))
+    if use_tc:
+        call("conv2d_tc_dgrad", ptr(dy), ptr(w), ptr(addend), ptr(dx), ci(B), ci(H), ci(W), ci(Cin), ci(Cout), ci(KH), ci(KW),
+             ci(stride), ci(pad), _stream())
+    else:
+        call("conv2d_direct_dgrad", ptr(dy), ci(dt(dy)), ptr(w), ci(dt(w)), ptr(addend), ptr(dx), ci(B), ci(H), ci(W), ci(Cin),
+             ci(Cout), ci(KH), ci(KW), ci(stride), ci(pad), _stream())
+    _count()
+    return dx
+
+
+def conv_wgrad(dy, x, dw, stride=1, pad=1, force_direct=False):
+    """dw (fp32 OHWI) += dy^T * im2col(x)."""
+    _chk(dy, "conv_wgrad.dy"); _chk(x, "conv_wgrad.x"); _chk(dw, "conv_wgrad.dw", torch.float32)
+    B, H, W, Cin, Cout, KH, KW, Ho, Wo = _geom(x.shape, dw.shape, stride, pad)
+    if tuple(dy.shape) != (B, Ho, Wo, Cout) or dy.dtype != x.dtype:
+        raise _lib.UdaError("conv_wgrad: dy/x mismatch")
+    use_tc = (not force_direct and x.dtype == torch.bfloat16
+              and tc_supported(2, B, H, W, Cin, Cout, KH, KW, stride, pad))
+    if use_tc:
+        call("conv2d_tc_wgrad", ptr(dy), ptr(x), ptr(dw), ci(B), ci(H), ci(W), ci(Cin), ci(Cout), ci(KH), ci(KW),
+             ci(stride), ci(pad), _stream())
+    else:
+        call("conv2d_direct_wgrad", ptr(dy), ptr(x), ci(dt(x)), ptr(dw), ci(B), ci(H), ci(W), ci(Cin), ci(Cout),
+             ci(KH), ci(KW), ci(stride), ci(pad), _stream())
+    _count()
+    return dw
+
+
+# ------------------------------------------------------------------------------------------------
+# batch norm / activations / pooling / concat
+# ------------------------------------------------------------------------------------------------
+def bn_stats(x, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1):
+    """Batch statistics of NHWC x -> (mean, rstd, scale, shift) fp32 [C]; updates running stats in place."""
+    _chk(x, "bn_stats.x")
+    C = x.shape[-1]
+    M = x.numel() // C
+    st = torch.empty((4, C), dtype=torch.float32, device=x.device)
+    ws = workspace(2 * C * 8, x.device)
+    call("bn_stats", ptr(x), ci(dt(x)), ll(M), ci(C), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+         ptr(st[0]), ptr(st[1]), ptr(st[2]), ptr(st[3]), float(eps), float(momentum), ptr(ws), _stream())
+    _count(2)
+    return st[0], st[1], st[2], st[3]
+
+
+def bn_eval_coeffs(gamma, beta, running_mean, running_var, eps=1e-5):
+    C = running_mean.numel()
+    st = torch.empty((2, C), dtype=torch.float32, device=running_mean.device)
+    call("bn_eval_coeffs", ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(st[0]), ptr(st[1]), ci(C),
+         float(eps), _stream())
+    _count()
+    return st[0], st[1]
+
+
+def bn_apply(x, scale, shift, residual=None, slope=0.0, out=None):
+    _chk(x, "bn_apply.x")
+    C = x.shape[-1]
+    y = torch.empty_like(x) if out is None else out
+    if residual is not None:
+        _chk(residual, "bn_apply.residual", x.dtype)
+    call("bn_apply", ptr(x), ptr(residual), ptr(y), ci(dt(x)), ptr(scale), ptr(shift), ll(x.numel() // C), ci(C),
+         float(slope), _stream())
+    _count()
+    return y
+
+
+def bn_bwd(dy, x, a, gamma, mean, rstd, slope, dgamma, dbeta, dres=None, dres_accumulate=False,
+           param_accumulate=True):
+    """BatchNorm(+activation) backward.  Returns dx; accumulates dgamma/dbeta; fills/accumulates dres."""
+    _chk(dy, "bn_bwd.dy"); _chk(x, "bn_bwd.x", dy.dtype)
+    C = x.shape[-1]
+    M = x.numel() // C
+    dx = torch.empty_like(x)
+    ws = workspace(2 * C * 8 + 3 * C * 4, x.device)
+    call("bn_bwd", ptr(dy), ptr(x), ptr(a), ci(dt(x)), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx), ptr(dres),
+         ci(1 if dres_accumulate else 0), ptr(dgamma), ptr(dbeta), ci(1 if param_accumulate else 0), ll(M), ci(C),
+         float(slope), ptr(ws), _stream())
+    _count(3)
+    return dx
+
+
+def act_bwd(dy, a, slope):
+    dx = torch.empty_like(dy)
+    call("act_bwd", ptr(dy), ptr(a), ptr(dx), ci(dt(dy)), ll(dy.numel()), float(slope), _stream())
+    _count()
+    return dx
+
+
+def bias_act(x, bias, slope, out=None):
+    C = x.shape[-1]
+    y = torch.empty_like(x) if out is None else out
+    call("bias_act", ptr(x), ptr(bias), ptr(y), ci(dt(x)), ll(x.numel() // C), ci(C), float(slope), _stream())
+    _count()
+    return y
+
+
+def colsum(x, out, scale=1.0, accumulate=True):
+    C = x.shape[-1]
+    ws = workspace(C * 8, x.device)
+    call("colsum", ptr(x), ci(dt(x)), ptr(out), ll(x.numel() // C), ci(C), float(scale), ci(1 if accumulate else 0),
+         ptr(ws), _stream())
+    _count(2)
+    return out
+
+
+def maxpool_fwd(x):
+    B, H, W, C = x.shape
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    y = torch.empty((B, Ho, Wo, C), dtype=x.dtype, device=x.device)
+    idx = torch.empty((B, Ho, Wo, C), dtype=torch.uint8, device=x.device)
+    call("maxpool3x3s2_fwd", ptr(x), ptr(y), ptr(idx), ci(dt(x)), ci(B), ci(H), ci(W), ci(C), _stream())
+    _count()
+    return y, idx
+
+
+def maxpool_bwd(dy, idx, x_shape, addend=None):
+    B, H, W, C = x_shape
+    dx = addend if addend is not None else torch.empty((B, H, W, C), dtype=dy.dtype, device=dy.device)
+    call("maxpool3x3s2_bwd", ptr(dy), ptr(idx), ptr(addend), ptr(dx), ci(dt(dy)), ci(B), ci(H), ci(W), ci(C), _stream())
+    _count()
+    return dx
+
+
+def upcat_fwd(x, skip=None):
+    B, H2, W2, C1 = x.shape
+    C2 = skip.shape[-1] if skip is not None else 0
+    out = torch.empty((B, 2 * H2, 2 * W2, C1 + C2), dtype=x.dtype, device=x.device)
+    call("upsample2x_concat_fwd", ptr(x), ptr(skip), ptr(out), ci(dt(x)), ci(B), ci(2 * H2), ci(2 * W2), ci(C1),
+         ci(C2), _stream())
+    _count()
+    return out
+
+
+def upcat_bwd(dout, C1, C2):
+    B, H, W, Ct = dout.shape
+    assert Ct == C1 + C2
+    dx = torch.empty((B, H // 2, W // 2, C1), dtype=dout.dtype, device=dout.device)
+    dskip = torch.empty((B, H, W, C2), dtype=dout.dtype, device=dout.device) if C2 else None
+    call("upsample2x_concat_bwd", ptr(dout), ptr(dx), ptr(dskip), ci(dt(dout)), ci(B), ci(H), ci(W), ci(C1), ci(C2),
+         _stream())
+    _count()
+    return dx, dskip
+
+
+def gap_linear_sigmoid_fwd(x, w, b):
+    B, H, W, C = x.shape
+    pooled = torch.empty((B, C), dtype=torch.float32, device=x.device)
+    y = torch.empty((B, 1), dtype=torch.float32, device=x.device)
+    call("gap_linear_sigmoid_fwd", ptr(x), ci(dt(x)), ptr(w), ptr(b), ptr(pooled), ptr(y), ci(B), ll(H * W), ci(C),
+         _stream())
+    _count()
+    return y, pooled
+
+
+def gap_linear_sigmoid_bwd(dout, y, pooled, w, dw, db, x_shape, dtype, accumulate=True):
+    B, H, W, C = x_shape
+    dx = torch.empty((B, H, W, C), dtype=dtype, device=dout.device)
+    call("gap_linear_sigmoid_bwd", ptr(dout), ptr(y), ptr(pooled), ptr(w), ptr(dw), ptr(db), ptr(dx), ci(dt(dx)),
+         ci(B), ll(H * W), ci(C), ci(1 if accumulate else 0), _stream())
+    _count()
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer
+# ------------------------------------------------------------------------------------------------
+def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, clip_coef=None):
+    for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
+        _chk(t, "adam." + n, torch.float32)
+    call("adam_step", ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), ll(p.numel()), float(lr), float(beta1),
+         float(beta2), float(eps), float(weight_decay), ci(step), float(grad_scale), ptr(clip_coef), _stream())
+    _count()
+
+
+def grad_clip_coef(g, max_norm, pre_scale=1.0):
+    """Returns (coef[1], norm[1]) device tensors: coef = min(1, max_norm/(pre_scale*||g||+1e-6))."""
+    out = torch.empty(2, dtype=torch.float32, device=g.device)
+    ws = workspace(8, g.device)
+    call("grad_clip_coef", ptr(g), ll(g.numel()), float(max_norm), float(pre_scale), ptr(out[0:1]), ptr(out[1:2]),
+         ptr(ws), _stream())
+    _count(2)
+    return out[0:1], out[1:2]
+
+
+# ------------------------------------------------------------------------------------------------
+# losses / evaluation  (NCHW edge layout)
+# ------------------------------------------------------------------------------------------------
+CE_NONE, CE_PLAIN, CE_FOCAL = 0, 1, 2
+
+
+def seg_loss(logits, target=None, soft_target=None, class_weights=None, ce_mode=CE_PLAIN, use_dice=False,
+             alpha=0.25, gamma=2.0, mean=True, ignore_index=-100, smooth=1.0, w_ce=1.0, w_dice=1.0, out_scale=1.0):
+    """Fused segmentation loss + gradient.  Returns (out4, grad): out4 = [ce, dice, total, n_bad]."""
+    _chk(logits, "seg_loss.logits")
+    B, C = logits.shape[:2]
+    HW = logits.numel() // (B * C)
+    if target is not None:
+        _chk(target, "seg_loss.target", torch.int64)
+        if target.numel() != B * HW:
+            raise _lib.UdaError(f"seg_loss: target has {target.numel()} elements, expected {B * HW}")
+    if soft_target is not None:
+        _chk(soft_target, "seg_loss.soft_target", torch.float32)
+        if soft_target.numel() != logits.numel():
+            raise _lib.UdaError("seg_loss: soft target shape mismatch")
+    if class_weights is not None:
+        _chk(class_weights, "seg_loss.class_weights", torch.float32)
+    grad = torch.empty_like(logits)
+    out4 = torch.empty(4, dtype=torch.float32, device=logits.device)
+    nbytes = _lib.lib().uda_seg_loss_workspace_bytes(ci(B), ci(C))
+    ws = workspace(nbytes, logits.device)
+    call("seg_loss_fwd_bwd", ptr(logits), ci(dt(logits)), ptr(target), ptr(soft_target), ptr(class_weights),
+         ptr(grad), ptr(out4), ptr(ws), ci(B), ci(C), ll(HW), ci(ce_mode), ci(1 if use_dice else 0), float(alpha),
+         float(gamma), ci(1 if mean else 0), ll(ignore_index), float(smooth), float(w_ce), float(w_dice),
+         float(out_scale), _stream())
+    _count(4)
+    return out4, grad
+
+
+def scale_by_device_scalar(x, scalar):
+    call("scale_by_device_scalar", ptr(x), ci(dt(x)), ll(x.numel()), ptr(scalar), _stream())
+    _count()
+    return x
+
+
+def consistency(z1, z2, temperature=0.5, out_scale=1.0):
+    _chk(z1, "consistency.z1"); _chk(z2, "consistency.z2", z1.dtype)
+    if z1.shape != z2.shape:
+        raise _lib.UdaError("consistency: shape mismatch")
+    B, C = z1.shape[:2]
+    HW = z1.numel() // (B * C)
+    g1, g2 = torch.empty_like(z1), torch.empty_like(z2)
+    out = torch.empty(1, dtype=torch.float32, device=z1.device)
+    ws = workspace(8, z1.device)
+    call("consistency_fwd_bwd", ptr(z1), ptr(z2), ci(dt(z1)), ptr(g1), ptr(g2), ptr(out), ptr(ws), ci(B), ci(C),
+         ll(HW), float(temperature), float(out_scale), _stream())
+    _count(3)
+    return out, g1, g2
+
+
+def entropy(z, out_scale=1.0):
+    _chk(z, "entropy.z")
+    B, C = z.shape[:2]
+    HW = z.numel() // (B * C)
+    g = torch.empty_like(z)
+    out = torch.empty(1, dtype=torch.float32, device=z.device)
+    ws = workspace(8, z.device)
+    call("entropy_fwd_bwd", ptr(z), ci(dt(z)), ptr(g), ptr(out), ptr(ws), ci(B), ci(C), ll(HW), float(out_scale),
+         _stream())
+    _count(3)
+    return out, g
+
+
+def bce_logits(x, label, scale=1.0, out=None, accumulate=False, want_grad=True):
+    _chk(x, "bce.x", torch.float32)
+    grad = torch.empty_like(x) if want_grad else None
+    if out is None:
+        out = torch.empty(1, dtype=torch.float32, device=x.device)
+    call("bce_logits_fwd_bwd", ptr(x), ptr(grad), ptr(out), ll(x.numel()), float(label), float(scale),
+         ci(1 if accumulate else 0), _stream())
+    _count()
+    return out, grad
+
+
+def argmax_confmat(logits, target=None, num_classes=None, ignore_index=None, want_mask=True, mask_dtype=torch.int64,
+                   hist=None):
+    """argmax over dim 1 (+ confusion matrix against ``target``).  Returns (mask | None, hist | None)."""
+    _chk(logits, "argmax_confmat.logits")
+    B, C = logits.shape[:2]
+    HW = logits.numel() // (B * C)
+    spatial = tuple(logits.shape[2:])
+    mask64 = mask8 = None
+    if want_mask:
+        if mask_dtype == torch.int64:
+            mask64 = torch.empty((B,) + spatial, dtype=torch.int64, device=logits.device)
+        elif mask_dtype == torch.uint8:
+            mask8 = torch.empty((B,) + spatial, dtype=torch.uint8, device=logits.device)
+        else:
+            raise TypeError("mask dtype must be int64 or uint8")
+    zero = 0
+    if target is not None:
+        _chk(target, "argmax_confmat.target", torch.int64)
+        if num_classes is not None and num_classes != C:
+            raise _lib.UdaError("argmax_confmat: num_classes must equal the logits' channel count")
+        if hist is None:
+            hist = torch.empty((C, C), dtype=torch.int64, device=logits.device)
+            zero = 1
+    call("argmax_confmat", ptr(logits), ci(dt(logits)), ptr(target), ptr(mask64), ptr(mask8),
+         ptr(hist) if target is not None else ptr(None), ci(B), ci(C), ll(HW),
+         ll(ignore_index if ignore_index is not None else 0), ci(0 if ignore_index is None else 1), ci(zero), _stream())
+    _count()
+    return (mask64 if mask64 is not None else mask8), (hist if target is not None else None)
+
+
+def confmat(pred, target, num_classes, ignore_index=None, hist=None):
+    _chk(pred, "confmat.pred"); _chk(target, "confmat.target", torch.int64)
+    if pred.numel() != target.numel():
+        raise _lib.UdaError("confmat: pred/target size mismatch")
+    if pred.dtype == torch.int64:
+        pd = I64
+    elif pred.dtype == torch.uint8:
+        pd = U8
+    else:
+        raise TypeError("confmat: pred must be int64 or uint8")
+    zero = 0
+    if hist is None:
+        hist = torch.empty((num_classes, num_classes), dtype=torch.int64, device=pred.device)
+        zero = 1
+    bad = torch.empty(1, dtype=torch.int64, device=pred.device)
+    call("confmat", ptr(pred), ci(pd), ptr(target), ptr(hist), ptr(bad), ll(pred.numel()), ci(num_classes),
+         ll(ignore_index if ignore_index is not None else 0), ci(0 if ignore_index is None else 1), ci(zero), _stream())
+    _count()
+    return hist, bad
