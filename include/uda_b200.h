@@ -131,7 +131,10 @@ int uda_conv2d_tc_supported(int op, int B, int H, int W, int Cin, int Cout, int 
 int uda_conv2d_tc_fwd(const void* x, const void* w, const float* bias, void* y_nhwc, float* y_nchw_f32,
                       double* bn_sums, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
                       void* stream);
-int uda_conv2d_tc_dgrad(const void* dy, const void* w, const void* addend, void* dx, int B, int H, int W, int Cin,
+/* dgrad takes w_ft = uda_conv2d_weight_flip_transpose(w): [Cin][KH][KW][Cout] bf16 (the weights of the
+ * equivalent forward convolution of dy); addend as in uda_conv2d_direct_dgrad. */
+int uda_conv2d_weight_flip_transpose(const void* w, void* w_ft, int Cout, int Cin, int KH, int KW, void* stream);
+int uda_conv2d_tc_dgrad(const void* dy, const void* w_ft, const void* addend, void* dx, int B, int H, int W, int Cin,
                         int Cout, int KH, int KW, int stride, int pad, void* stream);
 int uda_conv2d_tc_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, int KH,
                         int KW, int stride, int pad, void* stream);

@@ -13,6 +13,7 @@ import torch
 import torch.nn.functional as F
 
 LAUNCHES = 0
+USE_TC = False
 #: arithmetic dtype of the restatements; tests switch it to float64 to check the engine's backward
 #: *logic* free of the ReLU-mask-flip noise that fp32 round-off causes in deep randomly-initialised nets
 _F = torch.float32
@@ -61,7 +62,7 @@ def conv_fwd(x, w, bias=None, stride=1, pad=1, nchw_out=False, bn_sums=None, for
     return _nhwc(y).to(x.dtype)
 
 
-def conv_dgrad(dy, w, x_shape, stride=1, pad=1, addend=None, force_direct=False):
+def conv_dgrad(dy, w, x_shape, stride=1, pad=1, addend=None, force_direct=False, w_ft=None):
     B, H, W, Cin = x_shape
     dx = torch.nn.grad.conv2d_input((B, Cin, H, W), _w_oihw(w), _nchw(dy.to(_F)), stride, pad)
     dx = _nhwc(dx)

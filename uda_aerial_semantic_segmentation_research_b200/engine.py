@@ -135,7 +135,9 @@ class ParamStore:
                 p.data = v
         self.flat = flat
         self.shadow = torch.empty(self.total, dtype=torch.bfloat16, device=device)
+        self.shadow_ft = torch.empty(self.total, dtype=torch.bfloat16, device=device)
         self.shadow_version = None
+        self.shadow_ft_version = None
 
     def refresh_shadow(self, force=False):
         ver = self.flat._version
@@ -145,6 +147,22 @@ class ParamStore:
 
     def mark_shadow_fresh(self):
         self.shadow_version = self.flat._version
+        self.shadow_ft_version = None
+
+    def w_ft(self, p):
+        """[Cin][KH][KW][Cout] flipped/transposed bf16 copy of conv weight ``p`` (dgrad on the tensor cores);
+        all copies are refreshed together, lazily, the first time a backward needs them after an update."""
+        if self.shadow_ft_version != self.flat._version or self.shadow_ft_version is None:
+            for q in self.params:
+                if q.dim() == 4:
+                    O, I, KH, KW = q.shape
+                    off = self.offsets[id(q)]
+                    ops.weight_flip_transpose(self.shadow[off:off + q.numel()].view(O, KH, KW, I),
+                                              self.shadow_ft[off:off + q.numel()].view(I, KH, KW, O))
+            self.shadow_ft_version = self.flat._version
+        off = self.offsets[id(p)]
+        O, I, KH, KW = p.shape
+        return self.shadow_ft[off:off + p.numel()].view(I, KH, KW, O)
 
     def w(self, p, dtype):
         """OHWI kernel view of conv weight ``p`` in ``dtype`` (bf16 -> shadow copy)."""
@@ -176,7 +194,14 @@ class Ctx:
 
     def __init__(self, store, dtype, training, tape):
         self.store, self.dtype, self.training, self.tape = store, dtype, training, tape
-        self.grad_ready = None  # optional callback(offset) fired when grads >= offset are final (DDP overlap)
+        self.sync = None  # optional gradient-sync object (ddp.GradSync): param_done(store, param)
+
+    def done(self, *params):
+        """Tell the data-parallel layer that the gradients of ``params`` are final for this backward."""
+        if self.sync is not None:
+            for p in params:
+                if p is not None:
+                    self.sync.param_done(self.store, p)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -198,9 +223,9 @@ def conv(ctx, xin, cp, nchw_out=False):
                 ops.colsum(dy, st.g(cp.bias))
             ops.conv_wgrad(dy, xin.t, st.g(cp.weight), cp.stride, cp.padding)
             if xin.g is not False:  # False marks "no gradient needed" (network input)
-                xin.g = ops.conv_dgrad(dy, w, xin.t.shape, cp.stride, cp.padding, addend=xin.g)
-            if ctx.grad_ready is not None:
-                ctx.grad_ready(st.offsets[id(cp.weight)])
+                wft = st.w_ft(cp.weight) if (ctx.dtype == torch.bfloat16 and ops.USE_TC) else None
+                xin.g = ops.conv_dgrad(dy, w, xin.t.shape, cp.stride, cp.padding, addend=xin.g, w_ft=wft)
+            ctx.done(cp.weight, cp.bias)
         ctx.tape.push(bwd)
     return out
 
@@ -238,6 +263,7 @@ def bn_act(ctx, zin, bn, slope=0.0, residual=None):
                                st.g(bn.weight), st.g(bn.bias), dres=dres, dres_accumulate=acc)
             if residual is not None:
                 residual.g = dres
+            ctx.done(bn.weight, bn.bias)
         ctx.tape.push(bwd)
     return out
 

@@ -132,8 +132,21 @@ def conv_fwd(x, w, bias=None, stride=1, pad=1, nchw_out=False, bn_sums=None, for
     return y_nchw if nchw_out else y_nhwc
 
 
-def conv_dgrad(dy, w, x_shape, stride=1, pad=1, addend=None, force_direct=False):
-    """dx = conv_transpose(dy, w) (+ addend, accumulated in place into ``addend``'s buffer when given)."""
+def weight_flip_transpose(w, out=None):
+    """OHWI bf16 weights -> [Cin][KH][KW][Cout] flipped copy (the forward-conv weights of dgrad)."""
+    _chk(w, "weight_flip_transpose.w", torch.bfloat16)
+    O, KH, KW, I = w.shape
+    if out is None:
+        out = torch.empty((I, KH, KW, O), dtype=torch.bfloat16, device=w.device)
+    call("conv2d_weight_flip_transpose", ptr(w), ptr(out), ci(O), ci(I), ci(KH), ci(KW), _stream())
+    _count()
+    return out
+
+
+def conv_dgrad(dy, w, x_shape, stride=1, pad=1, addend=None, force_direct=False, w_ft=None):
+    """dx = conv_transpose(dy, w) (+ addend, accumulated in place into ``addend``'s buffer when given).
+
+    ``w_ft`` (optional): cached ``weight_flip_transpose(w)`` for the tensor-core path."""
     _chk(dy, "conv_dgrad.dy"); _chk(w, "conv_dgrad.w")
     B, H, W, Cin, Cout, KH, KW, Ho, Wo = _geom(x_shape, w.shape, stride, pad)
     if tuple(dy.shape) != (B, Ho, Wo, Cout):
@@ -148,7 +161,9 @@ def conv_dgrad(dy, w, x_shape, stride=1, pad=1, addend=None, force_direct=False)
     use_tc = (not force_direct and dy.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
               and tc_supported(1, B, H, W, Cin, Cout, KH, KW, stride, pad))
     if use_tc:
-        call("conv2d_tc_dgrad", ptr(dy), ptr(w), ptr(addend), ptr(dx), ci(B), ci(H), ci(W), ci(Cin), ci(Cout), ci(KH), ci(KW),
+        if w_ft is None:
+            w_ft = weight_flip_transpose(w)
+        call("conv2d_tc_dgrad", ptr(dy), ptr(w_ft), ptr(addend), ptr(dx), ci(B), ci(H), ci(W), ci(Cin), ci(Cout), ci(KH), ci(KW),
              ci(stride), ci(pad), _stream())
     else:
         call("conv2d_direct_dgrad", ptr(dy), ci(dt(dy)), ptr(w), ci(dt(w)), ptr(addend), ptr(dx), ci(B), ci(H), ci(W), ci(Cin),

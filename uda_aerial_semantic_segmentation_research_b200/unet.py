@@ -181,11 +181,11 @@ class _UnetFn(torch.autograd.Function):
         for v, need in zip(ctx.in_vars, in_need):
             if v is not None and not need:
                 v.g = False
-        if net._grad_ready_cb is not None:
-            net._grad_ready_cb(None, st)  # backward begins
+        if net._grad_sync is not None:
+            net._grad_sync.begin(st)
         tape.backward()
-        if net._grad_ready_cb is not None:
-            net._grad_ready_cb(0, st)  # every gradient is final
+        if net._grad_sync is not None:
+            net._grad_sync.end(st)  # waits for the bucketed all-reduces issued during the tape replay
         gin = []
         for v, need in zip(ctx.in_vars, in_need):
             if need and v is not None and isinstance(v.g, torch.Tensor):
@@ -234,7 +234,7 @@ class Unet(nn.Module):
         self.classes = classes
         self.name = f"u-{encoder_name}"
         self._store = ParamStore(self)
-        self._grad_ready_cb = None
+        self._grad_sync = None
         import weakref
         ref = weakref.ref(self)
         for m in (self.encoder, self.decoder, self.segmentation_head):
@@ -254,6 +254,7 @@ class Unet(nn.Module):
         dtype = self.compute_dtype
         tape = Tape() if record else None
         ctx = Ctx(self._store, dtype, self.training, tape)
+        ctx.sync = self._grad_sync
         if part in ("full", "encoder"):
             x = inputs[0]
             B, C, H, W = x.shape
