@@ -188,16 +188,16 @@ def upcat_bwd(dout, C1, C2):
 
 def gap_linear_sigmoid_fwd(x, w, b):
     pooled = x.to(_F).mean((1, 2))
-    y = torch.sigmoid(pooled @ w.detach().t() + b.detach())
+    y = torch.sigmoid(pooled @ w.detach().to(_F).t() + b.detach().to(_F))
     return y, pooled
 
 
 def gap_linear_sigmoid_bwd(dout, y, pooled, w, dw, db, x_shape, dtype, accumulate=True):
     B, H, W, C = x_shape
-    dz = dout * y * (1 - y)
-    dw.copy_((dw if accumulate else 0) + dz.t() @ pooled)
-    db.copy_((db if accumulate else 0) + dz.sum(0))
-    dx = (dz @ w.detach()).reshape(B, 1, 1, C).expand(B, H, W, C) / (H * W)
+    dz = dout.to(_F) * y * (1 - y)
+    dw.copy_((dw if accumulate else 0) + (dz.t() @ pooled).to(dw.dtype))
+    db.copy_((db if accumulate else 0) + dz.sum(0).to(db.dtype))
+    dx = (dz @ w.detach().to(_F)).reshape(B, 1, 1, C).expand(B, H, W, C) / (H * W)
     return dx.to(dtype).contiguous()
 
 

@@ -1,0 +1,89 @@
+"""GPU parity of the tcgen05/TMEM/TMA convolution against (a) the oracle's torch conv on the same bf16
+inputs and (b) the FP32-pipe direct kernel.  bf16 output: 2^-8 relative per element; the fp32 NCHW edge
+output is held to 2e-3 of the tensor's max (bf16 products, fp32 accumulation order)."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import ref_ops as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+SHAPES = [
+    # B, H, W, Cin, Cout, k, stride, pad            every U-Net r34 family at reduced spatial size
+    (2, 32, 32, 64, 64, 3, 1, 1),       # layer1
+    (2, 32, 32, 64, 128, 3, 2, 1),      # layer2.0 conv1 (stride 2)
+    (2, 32, 32, 64, 128, 1, 2, 0),      # downsample 1x1 stride 2
+    (2, 16, 16, 128, 128, 3, 1, 1),     # layer2
+    (2, 8, 8, 256, 256, 3, 1, 1),       # layer3 (two images per tile)
+    (4, 8, 8, 512, 512, 3, 1, 1),       # layer4: 4 N tiles
+    (2, 8, 8, 768, 256, 3, 1, 1),       # decoder block 0 conv1 (concat input)
+    (2, 16, 16, 192, 64, 3, 1, 1),      # decoder block 2 conv1
+    (1, 64, 64, 128, 32, 3, 1, 1),      # decoder block 3 conv1 (N=32)
+    (1, 64, 64, 32, 32, 3, 1, 1),       # KC=32 (64-byte swizzle)
+    (1, 128, 128, 32, 16, 3, 1, 1),     # decoder block 4 conv1: N=16 padded to 32, TW=128
+    (1, 128, 128, 16, 16, 3, 1, 1),     # KC=16 (32-byte swizzle)
+    (1, 128, 128, 16, 24, 3, 1, 1),     # head: N=24, bias, NCHW fp32 edge
+    (2, 64, 64, 64, 128, 4, 2, 1),      # discriminator layer 2 (4x4 stride 2)
+    (1, 256, 256, 64, 64, 3, 1, 1),     # wide rows: TW=128, 2 tiles per row
+]
+
+
+def _ops():
+    from uda_aerial_semantic_segmentation_research_b200 import ops
+    return ops
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).bfloat16()
+
+
+@pytest.mark.parametrize("cfg", SHAPES, ids=[f"B{c[0]}_{c[1]}x{c[2]}_{c[3]}to{c[4]}_k{c[5]}s{c[6]}" for c in SHAPES])
+def test_tc_forward_and_dgrad(cfg):
+    ops = _ops()
+    B, H, W, Cin, Cout, k, s, p = cfg
+    assert ops.tc_supported(0, B, H, W, Cin, Cout, k, k, s, p), "shape expected on the tensor-core path"
+    x = _rand((B, H, W, Cin), 1)
+    w = _rand((Cout, k, k, Cin), 2, (k * k * Cin) ** -0.5)
+    bias = torch.randn(Cout)
+    xg, wg, bg = x.to(DEV), w.to(DEV), bias.to(DEV)
+    yr = R.conv_fwd(x.float(), w.float(), bias, s, p)                    # fp32 reference on bf16-valued inputs
+    y = ops.conv_fwd(xg, wg, bg, s, p)
+    yd = ops.conv_fwd(xg, wg, bg, s, p, force_direct=True)
+    e_tc, e_direct = rel_err(y.float().cpu(), yr), rel_err(yd.float().cpu(), yr)
+    assert e_tc < 1e-2, (e_tc, e_direct)
+    yn = ops.conv_fwd(xg, wg, bg, s, p, nchw_out=True)
+    assert rel_err(yn.cpu(), yr.permute(0, 3, 1, 2)) < 2e-3
+    y0 = ops.conv_fwd(xg, wg, None, s, p)
+    assert rel_err(y0.float().cpu(), R.conv_fwd(x.float(), w.float(), None, s, p)) < 1e-2
+    if s == 1:
+        assert ops.tc_supported(1, B, H, W, Cin, Cout, k, k, s, p)
+        dy = _rand(tuple(yr.shape), 3)
+        dxr = R.conv_dgrad(dy.float(), w.float(), x.shape, s, p)
+        dx = ops.conv_dgrad(dy.to(DEV), wg, x.shape, s, p)
+        assert rel_err(dx.float().cpu(), dxr) < 1e-2
+        add = _rand(tuple(x.shape), 4)
+        acc = add.clone().to(DEV)
+        out = ops.conv_dgrad(dy.to(DEV), wg, x.shape, s, p, addend=acc)
+        assert out.data_ptr() == acc.data_ptr()
+        assert rel_err(out.float().cpu(), dxr + add.float()) < 1e-2
+
+
+def test_weight_flip_transpose():
+    ops = _ops()
+    w = _rand((6, 3, 3, 4), 5)
+    wt = ops.weight_flip_transpose(w.to(DEV)).cpu()
+    ref = w.flip(1, 2).permute(3, 1, 2, 0).contiguous()
+    assert torch.equal(wt, ref)
+
+
+def test_unsupported_shapes_fall_back_loudly():
+    ops = _ops()
+    from uda_aerial_semantic_segmentation_research_b200 import _lib
+    assert not ops.tc_supported(0, 2, 16, 16, 3, 64, 7, 7, 2, 3)      # stem: Cin=3
+    with pytest.raises(_lib.UdaError, match="not covered"):
+        _lib.call("conv2d_tc_fwd", _lib.ptr(torch.zeros(8, device=DEV)), _lib.ptr(torch.zeros(8, device=DEV)), None,
+                  _lib.ptr(torch.zeros(8, device=DEV)), None, None, _lib.ci(2), _lib.ci(16), _lib.ci(16), _lib.ci(3),
+                  _lib.ci(64), _lib.ci(7), _lib.ci(7), _lib.ci(2), _lib.ci(3), None)

@@ -1,0 +1,183 @@
+"""GPU parity of every layer kernel (through the C ABI) against the oracle's torch restatement of the
+same op on the same inputs: fp32 kernels to 1e-5, bf16 kernels against the oracle evaluated on the
+bf16-rounded inputs to bf16 output precision (2^-8)."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import ref_ops as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _ops():
+    from uda_aerial_semantic_segmentation_research_b200 import ops
+    return ops
+
+
+def _tol(dtype):
+    return 2e-5 if dtype == torch.float32 else 1.2e-2
+
+
+def _rand(shape, dtype, seed, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype)
+
+
+DT = [torch.float32, torch.bfloat16]
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_layout_roundtrip(dtype):
+    ops = _ops()
+    x = _rand((2, 3, 20, 24), torch.float32, 1)
+    y = ops.nchw_to_nhwc(x.to(DEV), dtype, cpad=8)
+    assert y.shape == (2, 20, 24, 8) and (y[..., 3:] == 0).all()
+    assert rel_err(y[..., :3].float().cpu(), x.permute(0, 2, 3, 1).to(dtype).float()) == 0
+    back = ops.nhwc_to_nchw(y, C=3)
+    assert rel_err(back.cpu(), x.to(dtype).float()) == 0
+    z = _rand((3, 24, 16, 16), torch.float32, 2)
+    assert rel_err(ops.nhwc_to_nchw(ops.nchw_to_nhwc(z.to(DEV), dtype)).cpu(), z.to(dtype).float()) == 0
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("cfg", [
+    # B, H, W, Cin, Cout, k, stride, pad
+    (2, 16, 16, 3, 64, 7, 2, 3),      # stem
+    (2, 12, 20, 16, 24, 3, 1, 1),     # head-like, ragged spatial
+    (1, 8, 8, 32, 48, 1, 2, 0),       # 1x1 stride-2 downsample
+    (2, 16, 16, 3, 64, 4, 2, 1),      # discriminator layer 1
+    (1, 9, 7, 5, 6, 3, 2, 1),         # odd everything
+])
+def test_conv_direct(dtype, cfg):
+    ops = _ops()
+    B, H, W, Cin, Cout, k, s, p = cfg
+    x = _rand((B, H, W, Cin), dtype, 3)
+    w = _rand((Cout, k, k, Cin), dtype, 4, 0.2)
+    bias = _rand((Cout,), torch.float32, 5)
+    tol = _tol(dtype)
+    y = ops.conv_fwd(x.to(DEV), w.to(DEV), bias.to(DEV), s, p, force_direct=True)
+    yr = R.conv_fwd(x, w, bias, s, p)
+    assert rel_err(y.float().cpu(), yr.float()) < tol
+    yn = ops.conv_fwd(x.to(DEV), w.to(DEV), bias.to(DEV), s, p, nchw_out=True, force_direct=True)
+    assert yn.dtype == torch.float32 and rel_err(yn.cpu(), R.conv_fwd(x, w, bias, s, p, nchw_out=True)) < (2e-5 if dtype == torch.float32 else 1e-5 + 0)
+    dy = _rand(tuple(yr.shape), dtype, 6)
+    dx = ops.conv_dgrad(dy.to(DEV), w.to(DEV), x.shape, s, p, force_direct=True)
+    assert rel_err(dx.float().cpu(), R.conv_dgrad(dy, w, x.shape, s, p).float()) < tol
+    add = _rand(tuple(x.shape), dtype, 7)
+    acc = add.clone().to(DEV)
+    dx2 = ops.conv_dgrad(dy.to(DEV), w.to(DEV), x.shape, s, p, addend=acc, force_direct=True)
+    assert dx2.data_ptr() == acc.data_ptr()
+    assert rel_err(dx2.float().cpu(), R.conv_dgrad(dy, w, x.shape, s, p, addend=add.clone()).float()) < tol
+    dw = torch.zeros((Cout, k, k, Cin), device=DEV)
+    ops.conv_wgrad(dy.to(DEV), x.to(DEV), dw, s, p, force_direct=True)
+    dwr = R.conv_wgrad(dy, x, torch.zeros(Cout, k, k, Cin), s, p)
+    assert rel_err(dw.cpu(), dwr) < 1e-4
+    ops.conv_wgrad(dy.to(DEV), x.to(DEV), dw, s, p, force_direct=True)   # accumulates
+    assert rel_err(dw.cpu(), 2 * dwr) < 1e-4
+
+
+@pytest.mark.parametrize("dtype", DT)
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (3, 5, 7, 16), (1, 8, 8, 512), (2, 4, 4, 24)])
+@pytest.mark.parametrize("slope", [0.0, 0.2, 1.0])
+def test_batchnorm(dtype, shape, slope):
+    ops = _ops()
+    C = shape[-1]
+    x = _rand(shape, dtype, 8, 2.0) + 0.5
+    res = _rand(shape, dtype, 9)
+    gamma, beta = torch.rand(C) + 0.5, torch.randn(C)
+    rm, rv = torch.randn(C) * 0.1, torch.rand(C) + 0.5
+    rm_g, rv_g = rm.clone().to(DEV), rv.clone().to(DEV)
+    mean, rstd, scale, shift = ops.bn_stats(x.to(DEV), gamma.to(DEV), beta.to(DEV), rm_g, rv_g, 1e-5, 0.1)
+    rm_r, rv_r = rm.clone(), rv.clone()
+    mr, rr, sr, fr = R.bn_stats(x, gamma, beta, rm_r, rv_r, 1e-5, 0.1)
+    for a, b in ((mean, mr), (rstd, rr), (scale, sr), (shift, fr), (rm_g, rm_r), (rv_g, rv_r)):
+        assert rel_err(a.cpu(), b) < 1e-5
+    tol = _tol(dtype)
+    for use_res in (False, True):
+        y = ops.bn_apply(x.to(DEV), scale, shift, res.to(DEV) if use_res else None, slope)
+        yr = R.bn_apply(x, sr, fr, res if use_res else None, slope)
+        assert rel_err(y.float().cpu(), yr.float()) < tol
+        dy = _rand(shape, dtype, 10)
+        a = yr if slope != 1.0 else None
+        dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        dres = torch.empty(shape, dtype=dtype, device=DEV) if use_res else None
+        dx = ops.bn_bwd(dy.to(DEV), x.to(DEV), a.to(DEV) if a is not None else None, gamma.to(DEV), mean, rstd, slope,
+                        dg, db, dres=dres)
+        dgr, dbr = torch.zeros(C), torch.zeros(C)
+        dresr = torch.empty(shape, dtype=dtype) if use_res else None
+        dxr = R.bn_bwd(dy, x, a, gamma, mr, rr, slope, dgr, dbr, dres=dresr)
+        assert rel_err(dx.float().cpu(), dxr.float()) < tol
+        assert rel_err(dg.cpu(), dgr) < 1e-4 and rel_err(db.cpu(), dbr) < 1e-4
+        if use_res:
+            assert rel_err(dres.float().cpu(), dresr.float()) < tol
+    sc, sf = ops.bn_eval_coeffs(gamma.to(DEV), beta.to(DEV), rm_g, rv_g)
+    scr, sfr = R.bn_eval_coeffs(gamma, beta, rm_r, rv_r)
+    assert rel_err(sc.cpu(), scr) < 1e-5 and rel_err(sf.cpu(), sfr) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_pool_upcat_bias_colsum(dtype):
+    ops = _ops()
+    tol = _tol(dtype)
+    x = torch.relu(_rand((2, 14, 10, 16), dtype, 11))   # ReLU output: many exact-zero ties
+    y, idx = ops.maxpool_fwd(x.to(DEV))
+    yr, idxr = R.maxpool_fwd(x)
+    assert rel_err(y.float().cpu(), yr.float()) == 0
+    dy = _rand(tuple(yr.shape), dtype, 12)
+    dx = ops.maxpool_bwd(dy.to(DEV), idx, x.shape)
+    assert rel_err(dx.float().cpu(), R.maxpool_bwd(dy, idxr, x.shape).float()) < tol
+    add = _rand(tuple(x.shape), dtype, 13)
+    acc = add.clone().to(DEV)
+    ops.maxpool_bwd(dy.to(DEV), idx, x.shape, addend=acc)
+    assert rel_err(acc.float().cpu(), R.maxpool_bwd(dy, idxr, x.shape, addend=add.clone()).float()) < tol
+    lo, skip = _rand((2, 6, 5, 32), dtype, 14), _rand((2, 12, 10, 16), dtype, 15)
+    for sk in (skip, None):
+        u = ops.upcat_fwd(lo.to(DEV), sk.to(DEV) if sk is not None else None)
+        assert rel_err(u.float().cpu(), R.upcat_fwd(lo, sk).float()) == 0
+        du = _rand(tuple(u.shape), dtype, 16)
+        d1, d2 = ops.upcat_bwd(du.to(DEV), 32, 16 if sk is not None else 0)
+        r1, r2 = R.upcat_bwd(du, 32, 16 if sk is not None else 0)
+        assert rel_err(d1.float().cpu(), r1.float()) < tol
+        assert (d2 is None) == (r2 is None) and (d2 is None or rel_err(d2.float().cpu(), r2.float()) == 0)
+    b = _rand((16,), torch.float32, 17)
+    assert rel_err(ops.bias_act(x.to(DEV), b.to(DEV), 0.2).float().cpu(), R.bias_act(x, b, 0.2).float()) < tol
+    a = R.bias_act(x, b, 0.2)
+    assert rel_err(ops.act_bwd(x.to(DEV), a.to(DEV), 0.2).float().cpu(), R.act_bwd(x, a, 0.2).float()) < tol
+    out = torch.ones(16, device=DEV)
+    ops.colsum(x.to(DEV), out, 0.5, True)
+    assert rel_err(out.cpu(), R.colsum(x, torch.ones(16), 0.5, True)) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", DT)
+def test_gap_linear_sigmoid(dtype):
+    ops = _ops()
+    x = _rand((3, 4, 4, 512), dtype, 18)
+    w, b = _rand((1, 512), torch.float32, 19, 0.05), torch.tensor([0.1])
+    y, pooled = ops.gap_linear_sigmoid_fwd(x.to(DEV), w.to(DEV), b.to(DEV))
+    yr, pr = R.gap_linear_sigmoid_fwd(x, w, b)
+    assert y.shape == (3, 1) and rel_err(y.cpu(), yr) < 1e-5 and rel_err(pooled.cpu(), pr) < 1e-5
+    dout = torch.tensor([[1.0], [-0.5], [2.0]])
+    dw, db = torch.zeros(1, 512, device=DEV), torch.zeros(1, device=DEV)
+    dx = ops.gap_linear_sigmoid_bwd(dout.to(DEV), y, pooled, w.to(DEV), dw, db, x.shape, dtype)
+    dwr, dbr = torch.zeros(1, 512), torch.zeros(1)
+    dxr = R.gap_linear_sigmoid_bwd(dout, yr, pr, w, dwr, dbr, x.shape, dtype)
+    assert rel_err(dx.float().cpu(), dxr.float()) < _tol(dtype)
+    assert rel_err(dw.cpu(), dwr) < 1e-5 and rel_err(db.cpu(), dbr) < 1e-5
+
+
+def test_adam_and_clip():
+    ops = _ops()
+    n = 100_003
+    p, g = _rand((n,), torch.float32, 20), _rand((n,), torch.float32, 21, 1e-3)
+    m, v = _rand((n,), torch.float32, 22, 1e-3), torch.rand(n) * 1e-6
+    pg, mg, vg = p.clone().to(DEV), m.clone().to(DEV), v.clone().to(DEV)
+    sh = torch.empty(n, dtype=torch.bfloat16, device=DEV)
+    coef, norm = ops.grad_clip_coef(g.to(DEV), 0.01, 1.0)
+    cr, nr = R.grad_clip_coef(g, 0.01, 1.0)
+    assert rel_err(coef.cpu(), cr) < 1e-5 and rel_err(norm.cpu(), nr) < 1e-5
+    ops.adam_step(pg, g.to(DEV), mg, vg, sh, 1e-3, 0.9, 0.999, 1e-8, 0.01, 3, 1.0, coef)
+    R.adam_step(p, g, m, v, None, 1e-3, 0.9, 0.999, 1e-8, 0.01, 3, 1.0, cr)
+    assert rel_err(pg.cpu(), p) < 1e-6 and rel_err(mg.cpu(), m) < 1e-6 and rel_err(vg.cpu(), v) < 1e-6
+    assert torch.equal(sh.cpu(), p.bfloat16()) or rel_err(sh.float().cpu(), p) < 4e-3

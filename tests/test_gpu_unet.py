@@ -1,0 +1,206 @@
+"""GPU parity of the whole hot path behind the reference's entry points (model creation, losses,
+optimizer step, prediction) against the fp32 oracle on identical synthetic inputs and weights.
+
+Tolerances (north-star): logits 1e-4 relative in fp32 mode / 2e-2 in bf16; losses 1e-3.  Gradients: the
+logit-gradient and every per-kernel gradient are held to 1e-3 in tests/test_gpu_layers.py and
+tests/test_gpu_losses.py; for whole-network WEIGHT gradients at random initialisation the max-norm is
+dominated by ReLU-mask flips caused by 1e-6-level forward differences (the fp32 oracle disagrees with
+its own fp64 run by up to 5e-2 there — see DESIGN.md "Gradient parity"), so they are compared in the
+L2 norm with the tolerance stated next to each assertion."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN, rel_err, l2_err
+from oracle.ref_unet import RefUnet
+from oracle.ref_discriminator import RefDomainDiscriminator
+from oracle import ref_losses as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _pkg():
+    import uda_aerial_semantic_segmentation_research_b200 as U
+    return U
+
+
+def _pair(enc, classes, dtype, seed=0):
+    U = _pkg()
+    torch.manual_seed(seed)
+    ref = RefUnet(enc, classes=classes)
+    m = U.Unet(encoder_name=enc, encoder_weights=None, in_channels=3, classes=classes, compute_dtype=dtype)
+    m.load_state_dict(ref.state_dict())
+    return m.to(DEV), ref
+
+
+@pytest.mark.parametrize("enc", ["resnet34", "resnet50"])
+def test_fp32_mode_logits_and_gradients(enc):
+    m, ref = _pair(enc, 24, torch.float32)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(2, 3, 64, 64, generator=g)
+    t = torch.randint(0, 24, (2, 64, 64), generator=g)
+    y = m(x.to(DEV))
+    yr = ref(x)
+    assert y.shape == (2, 24, 64, 64) and y.dtype == torch.float32
+    assert rel_err(y.detach().cpu(), yr.detach()) < 1e-4            # north-star: 1e-4 in fp32 mode
+    from uda_aerial_semantic_segmentation_research_b200.losses import CombinedCEDiceLoss
+    loss = CombinedCEDiceLoss()(y, t.to(DEV))
+    lr = R.cross_entropy(yr, t) + R.dice_loss(yr, t)
+    assert abs(loss.item() - lr.item()) < 1e-3 * lr.item()          # north-star: 1e-3
+    loss.backward(); lr.backward()
+    worst = 0.0
+    for (n, p), (_, p2) in zip(m.named_parameters(), ref.named_parameters()):
+        worst = max(worst, l2_err(p.grad.cpu(), p2.grad))
+    assert worst < 8e-2, worst     # mask-flip dominated (see module docstring); logic is exact in fp64 on CPU
+    # head and last decoder BN are upstream of any flip amplification: tight
+    pg = dict(m.named_parameters()); rg = dict(ref.named_parameters())
+    for n in ("segmentation_head.0.weight", "segmentation_head.0.bias", "decoder.blocks.4.conv2.1.weight"):
+        assert rel_err(pg[n].grad.cpu(), rg[n].grad) < 1e-3, n
+    for (n, b), (_, b2) in zip(m.named_buffers(), ref.named_buffers()):
+        assert rel_err(b.cpu(), b2) < 1e-3, n
+
+
+def test_bf16_mode_logits_cfg1():
+    """BASELINE config 1: U-Net r34, batch 2 @256x256, 24 classes, fwd/bwd + CE/Dice."""
+    m, ref = _pair("resnet34", 24, torch.bfloat16)
+    g = torch.Generator().manual_seed(1234)
+    x = torch.randn(2, 3, 256, 256, generator=g)
+    t = torch.randint(0, 24, (2, 16, 16), generator=g).repeat_interleave(16, 1).repeat_interleave(16, 2)
+    y = m(x.to(DEV))
+    with torch.no_grad():
+        yr = ref(x)
+    err = rel_err(y.detach().cpu(), yr)
+    assert err < 2e-2, err                                           # north-star: 2e-2 in bf16
+    from uda_aerial_semantic_segmentation_research_b200.losses import CombinedCEDiceLoss
+    loss = CombinedCEDiceLoss()(y, t.to(DEV))
+    lr = R.cross_entropy(yr, t) + R.dice_loss(yr, t)
+    assert abs(loss.item() - lr.item()) < 2e-2 * lr.item()          # loss of bf16 logits vs fp32 logits
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    # bf16 tensor-core path and FP32-pipe direct path agree on the same weights
+    from uda_aerial_semantic_segmentation_research_b200 import ops
+    ops.USE_TC = False
+    try:
+        y_direct = m(x.to(DEV))
+    finally:
+        ops.USE_TC = True
+    assert rel_err(y.detach(), y_direct.detach()) < 2e-2
+
+
+def test_training_reduces_loss_and_matches_oracle_trend():
+    """Reference step semantics (src/models/train.py:336-346): zero_grad, forward, CE, backward, Adam step."""
+    U = _pkg()
+    from uda_aerial_semantic_segmentation_research_b200.losses import CrossEntropyLoss
+    from uda_aerial_semantic_segmentation_research_b200.optim import FusedAdam
+    for dtype in (torch.float32, torch.bfloat16):
+        m, ref = _pair("resnet34", 6, dtype, seed=3)
+        g = torch.Generator().manual_seed(5)
+        x = torch.randn(4, 3, 64, 64, generator=g)
+        t = torch.randint(0, 6, (4, 4, 4), generator=g).repeat_interleave(16, 1).repeat_interleave(16, 2)
+        opt, opt_r = FusedAdam(m, lr=1e-3), torch.optim.Adam(ref.parameters(), lr=1e-3)
+        crit = CrossEntropyLoss()
+        ls, lrs = [], []
+        for _ in range(8):
+            opt.zero_grad(); opt_r.zero_grad()
+            l = crit(m(x.to(DEV)), t.to(DEV)); l.backward(); opt.step(); ls.append(l.item())
+            lr = F.cross_entropy(ref(x), t); lr.backward(); opt_r.step(); lrs.append(lr.item())
+        assert ls[-1] < 0.7 * ls[0], ls
+        assert abs(ls[0] - lrs[0]) < 2e-2 * lrs[0]
+        assert abs(ls[-1] - lrs[-1]) < 0.25 * lrs[0], (ls, lrs)     # same trajectory, chaotic in the details
+    # the stock torch optimizer also works on the same parameters (drop-in: train.py:461)
+    m, _ = _pair("resnet34", 6, torch.bfloat16, seed=4)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    l0 = None
+    for _ in range(4):
+        opt.zero_grad()
+        l = crit(m(x.to(DEV)), t.to(DEV)); l.backward(); opt.step()
+        l0 = l0 or l.item()
+    assert l.item() < l0
+
+
+def test_discriminator_golden_and_adversarial_step():
+    """DomainDiscriminator against the golden vectors of the reference's own module (fp32 mode), then one
+    reference adversarial iteration (src/models/adversarial_trainer.py:76-114) end to end in bf16."""
+    from uda_aerial_semantic_segmentation_research_b200.discriminator import DomainDiscriminator
+    from uda_aerial_semantic_segmentation_research_b200.losses import AdversarialLoss, CrossEntropyLoss
+    from uda_aerial_semantic_segmentation_research_b200.optim import FusedAdam
+    d = np.load(os.path.join(GOLDEN, "discriminator_small.npz"))
+    torch.manual_seed(11)
+    ref = RefDomainDiscriminator(3)        # same construction order as the reference module -> same init
+    ok = all(abs(float(v.double().abs().sum()) - float(d["sd_abs_sum/" + k])) <= 1e-6 * max(1.0, float(d["sd_abs_sum/" + k]))
+             for k, v in ref.state_dict().items() if "running" not in k and "num_batches" not in k)
+    if not ok:
+        pytest.skip("torch RNG stream differs from the fixture's; weights cannot be regenerated")
+    D = DomainDiscriminator(3, compute_dtype=torch.float32)
+    D.load_state_dict(ref.state_dict())
+    D = D.to(DEV).train()
+    x = torch.from_numpy(d["x"]).to(DEV).requires_grad_()
+    y = D(x)
+    assert y.shape == (2, 1) and rel_err(y.detach().cpu(), d["y_train"]) < 1e-4
+    loss = AdversarialLoss().discriminator_loss(y[:1], y[1:])
+    assert abs(loss.item() - float(d["loss"])) < 1e-4 * float(d["loss"])
+    loss.backward()
+    assert rel_err(x.grad.cpu(), d["grad_x"]) < 1e-3
+    for n, p in D.named_parameters():
+        if "grad/" + n in d.files:
+            gref = d["grad/" + n]
+            if np.abs(gref).max() < 1e-9:
+                assert p.grad.abs().max().item() < 1e-6, n
+            else:
+                assert rel_err(p.grad.cpu(), gref) < 1e-3, n
+    for k in d.files:
+        if k.startswith("sd_after/") and "running" in k:
+            assert rel_err(D.state_dict()[k[len("sd_after/"):]].cpu(), d[k]) < 1e-4, k
+    D.eval()
+    with torch.no_grad():
+        assert rel_err(D(x.detach()).cpu(), d["y_eval"]) < 1e-4
+    # --- one adversarial iteration, bf16, reference semantics ---
+    U = _pkg()
+    torch.manual_seed(0)
+    model = U.Unet("resnet34", classes=24).to(DEV)
+    disc = DomainDiscriminator(3).to(DEV)
+    opt, dopt = FusedAdam(model, lr=1e-4), FusedAdam(disc, lr=1e-4)
+    adv, crit = AdversarialLoss(0.001), CrossEntropyLoss()
+    src, tgt = torch.randn(2, 3, 64, 64, device=DEV), torch.randn(2, 3, 64, 64, device=DEV)
+    masks = torch.randint(0, 24, (2, 64, 64), device=DEV)
+    model.train(); disc.train()
+    dopt.zero_grad()
+    sp, tp = disc(src), disc(tgt)
+    assert sp.shape == (2, 1) and bool(((sp >= 0) & (sp <= 1)).all())
+    d_loss = adv.discriminator_loss(sp, tp)
+    d_loss.backward(); dopt.step()
+    opt.zero_grad()
+    seg_loss = crit(model(src), masks)
+    adv_loss = adv.generator_loss(disc(tgt))
+    total = seg_loss + adv_loss
+    total.backward(); opt.step()
+    assert torch.isfinite(total).item() and d_loss.item() > 0
+
+
+def test_predict_batch_and_sliding_window():
+    U = _pkg()
+    from uda_aerial_semantic_segmentation_research_b200.predict import predict_batch, sliding_window_evaluate, tile_windows
+    m, ref = _pair("resnet34", 24, torch.float32, seed=9)
+    ref.eval()
+    x = torch.randn(2, 3, 64, 64)
+    pm = predict_batch(m, x, DEV)
+    assert pm.dtype == np.int64 and pm.shape == (2, 64, 64)
+    with torch.no_grad():
+        logits = m(x.to(DEV))                     # eval mode (predict_batch switched it)
+        assert rel_err(logits.cpu(), ref(x)) < 1e-4
+    assert np.array_equal(pm, logits.argmax(1).cpu().numpy())   # bit-exact given identical logits
+    tile = torch.randn(3, 128, 192, device=DEV)
+    target = torch.randint(0, 24, (128, 192), device=DEV)
+    out = sliding_window_evaluate(m, tile, target, 24, window=64, batch=4, return_mask=True)
+    wins = tile_windows(tile, 64)
+    with torch.no_grad():
+        full = torch.cat([m(wins[i:i + 4]) for i in range(0, wins.shape[0], 4)]).argmax(1)
+    full = full.reshape(2, 3, 64, 64).permute(0, 2, 1, 3).reshape(128, 192)
+    assert torch.equal(out["mask"], full)
+    from oracle import ref_metrics as M
+    assert np.array_equal(out["hist"].cpu().numpy(), M.fast_hist(full.cpu().numpy(), target.cpu().numpy(), 24))
+    assert out["hist"].sum().item() == 128 * 192

@@ -1,0 +1,138 @@
+"""CPU: the oracle restatements against the golden vectors generated from the reference's own modules
+(oracle/gen_golden.py), against the reference imported live when /root/reference is present, and
+against the survey's closed-form known-answer values."""
+import glob
+import math
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN, REFERENCE, rel_err
+from oracle import ref_losses as R
+from oracle import ref_metrics as M
+
+CASES = sorted(glob.glob(os.path.join(GOLDEN, "losses_*.npz")))
+
+
+def _load(path):
+    d = np.load(path)
+    return d, torch.from_numpy(d["z1"]), torch.from_numpy(d["z2"]), torch.from_numpy(d["target"]), \
+        torch.from_numpy(d["class_weights"])
+
+
+@pytest.mark.parametrize("path", CASES, ids=[os.path.basename(c) for c in CASES])
+def test_losses_match_golden(path):
+    d, z1, z2, t, w = _load(path)
+    C = z1.shape[1]
+
+    def check(key, fn, wrt):
+        leaves = [x.clone().requires_grad_() for x in wrt]
+        loss = fn(*leaves)
+        grads = torch.autograd.grad(loss, leaves)
+        assert abs(loss.item() - float(d[key])) <= 2e-6 * max(1.0, abs(float(d[key]))), key
+        for i, g in enumerate(grads):
+            assert rel_err(g, d[f"{key}_grad{i}"]) < 1e-5, (key, i)
+
+    check("ce", lambda z: R.cross_entropy(z, t), [z1])
+    check("dice", lambda z: R.dice_loss(z, t), [z1])
+    check("ce_plus_dice", lambda z: R.cross_entropy(z, t) + R.dice_loss(z, t), [z1])
+    check("weighted", lambda z: R.weighted_segmentation_loss(z, t, w, domain_weight=0.7), [z1])
+    check("weighted_noweights_sum", lambda z: R.weighted_segmentation_loss(z, t, None, reduction="sum"), [z1])
+    check("consistency", lambda a, b: R.consistency_loss(a, b, 0.5), [z1, z2])
+    check("consistency_T1", lambda a, b: R.consistency_loss(a, b, 1.0), [z1, z2])
+    s, dd = torch.from_numpy(d["d_src"]), torch.from_numpy(d["d_tgt"])
+    check("disc_loss", lambda a, b: R.discriminator_loss(a, b), [s, dd])
+    check("gen_loss", lambda a: R.generator_loss(a), [dd])
+    for ep in (0, 20, 60):
+        r = R.fine_tuning_loss(z1, z2, dd, ep, supervised_pred=z1, supervised_target=t)
+        assert abs(r["total"].item() - float(d[f"ft_total_ep{ep}"])) <= 2e-6 * max(1, abs(float(d[f"ft_total_ep{ep}"])))
+        assert r["rampup_weight"].item() == float(d[f"ft_ramp_ep{ep}"])
+    # evaluation path: integer results are bit-exact
+    pred = M.argmax_mask(d["z1"])
+    assert np.array_equal(pred, d["argmax"])
+    assert np.array_equal(M.fast_hist(pred, d["target"], C), d["hist"])
+    assert np.array_equal(M.fast_hist(pred, d["target"], C, ignore_index=0), d["hist_ignore0"])
+    iou = M.batch_iou(pred, d["target"], C)
+    assert abs(iou["mean_iou"] - float(d["mean_iou"])) < 1e-12
+    assert np.allclose([iou["class_iou"][i] for i in range(C)], d["class_iou"], atol=1e-12)
+    assert abs(M.pixel_accuracy(pred, d["target"]) - float(d["pixel_acc"])) < 1e-12
+    assert np.allclose(M.f1_scores(pred, d["target"], C), d["f1"], atol=1e-12)
+
+
+def test_closed_form_kats():
+    # SURVEY.md 8c known answers
+    assert abs(R.dice_loss(torch.zeros(1, 24, 8, 8), torch.zeros(1, 8, 8, dtype=torch.long)).item() - 0.734736) < 1e-6
+    z = torch.zeros(4, 1)
+    assert abs(R.discriminator_loss(z, z).item() - math.log(2)) < 1e-6
+    assert abs(R.generator_loss(z).item() - 1e-3 * math.log(2)) < 1e-9
+    x = torch.randn(2, 5, 4, 4)
+    assert abs(R.consistency_loss(x, x).item()) < 1e-7
+    assert R.rampup(0) == 0 and R.rampup(20) == 0.5 and R.rampup(40) == 1 and R.rampup(99) == 1
+    g = torch.ones(3, requires_grad=True)
+    R.gradient_reverse_layer(g, 0.3).sum().backward()
+    assert torch.allclose(g.grad, torch.full((3,), -0.3))
+
+
+def test_reference_range_assertions():
+    """The reference's own (range / shape) assertions: src/test_system.py:110-124,141-148,313-319,527-580."""
+    torch.manual_seed(0)
+    C = 24
+    pred = torch.rand(4, C, 32, 32)
+    t = torch.randint(0, C, (4, 32, 32))
+    onehot = torch.nn.functional.one_hot(t, C).permute(0, 3, 1, 2).float()
+    l = R.dice_loss(pred, onehot)
+    assert l.shape == torch.Size([]) and 0 <= l <= 1
+    assert R.weighted_segmentation_loss(torch.randn(4, C, 32, 32), t) >= 0
+    r0 = R.fine_tuning_loss(pred, pred.flip(0), torch.rand(4, 1), 0)
+    r40 = R.fine_tuning_loss(pred, pred.flip(0), torch.rand(4, 1), 40, pred, t)
+    assert r0["rampup_weight"] == 0 and r40["rampup_weight"] == 1 and r40["supervised"] > 0 and r40["total"] >= 0
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "src")), reason="reference tree not present")
+def test_oracle_matches_reference_live():
+    sys.path.insert(0, REFERENCE)
+    try:
+        from src.models import losses as L
+        from src.models.discriminator import DomainDiscriminator
+        from src.analysis.metrics import SegmentationMetrics
+    finally:
+        sys.path.remove(REFERENCE)
+    from oracle.ref_discriminator import RefDomainDiscriminator
+    torch.manual_seed(3)
+    z1, z2 = torch.randn(2, 7, 12, 20) * 4, torch.randn(2, 7, 12, 20) * 4
+    t = torch.randint(0, 7, (2, 12, 20))
+    w = torch.rand(7) + 0.5
+    assert abs(R.dice_loss(z1, t) - L.DiceLoss()(z1, t)) < 1e-6
+    assert abs(R.weighted_segmentation_loss(z1, t, w) - L.WeightedSegmentationLoss(7, w)(z1, t)) < 1e-6
+    assert abs(R.consistency_loss(z1, z2) - L.ConsistencyLoss()(z1, z2)) < 1e-3  # value ~1e3, fp32
+    d = torch.rand(2, 1)
+    f, g = L.FineTuningLoss()(z1, z2, d, 13, z1, t), R.fine_tuning_loss(z1, z2, d, 13, z1, t)
+    assert abs(f["total"] - g["total"]) < 1e-3
+    D, Dr = DomainDiscriminator(), RefDomainDiscriminator()
+    Dr.load_state_dict(D.state_dict())
+    x = torch.randn(2, 3, 32, 32)
+    assert torch.allclose(D(x), Dr(x), atol=1e-6)
+    p = z1.argmax(1)
+    assert np.array_equal(SegmentationMetrics(7)._fast_hist(p.flatten(), t.flatten()), M.fast_hist(p.numpy(), t.numpy(), 7))
+
+
+def test_unet_oracle_structure():
+    """Structure pinned by the reference's logged graph: op counts, params, keys."""
+    from collections import Counter
+    from oracle.ref_unet import RefUnet
+    m34, m50 = RefUnet("resnet34", classes=24), RefUnet("resnet50", classes=23)
+    assert sum(p.numel() for p in m34.parameters()) == 24_439_704
+    c = Counter(type(x).__name__ for x in m50.modules())
+    assert c["Conv2d"] == 64 and c["BatchNorm2d"] == 63
+    c = Counter(type(x).__name__ for x in m34.modules())
+    assert c["Conv2d"] == 47 and c["BatchNorm2d"] == 46
+    keys = list(m34.state_dict().keys())
+    assert keys[0] == "encoder.conv1.weight" and keys[-1] == "segmentation_head.0.bias"
+    assert "decoder.blocks.0.conv1.0.weight" in keys and "decoder.blocks.4.conv2.1.running_var" in keys
+    assert "decoder.blocks.0.conv1.0.bias" not in keys  # decoder convs have no bias, the head has one
+    m50.eval()
+    with torch.no_grad():
+        assert m50(torch.zeros(1, 3, 64, 64)).shape == (1, 23, 64, 64)

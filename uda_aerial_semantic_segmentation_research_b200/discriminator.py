@@ -91,12 +91,15 @@ class DomainDiscriminator(nn.Module):
         out, pooled = ops.gap_linear_sigmoid_fwd(y.t, self._store.w2d(lin.weight), lin.bias)
         return out, tape, xin, (y, out, pooled)
 
-    def forward(self, x):
-        if x.device.type != "cuda":
+    def _prepare(self, device):
+        if device.type != "cuda":
             raise RuntimeError("uda_b200.DomainDiscriminator runs on CUDA (sm_100a) only — no CPU fallback")
-        self._store.ensure_flat(x.device)
+        self._store.ensure_flat(device)
         if self.compute_dtype == torch.bfloat16:
             self._store.refresh_shadow()
+
+    def forward(self, x):
+        self._prepare(x.device)
         record = torch.is_grad_enabled() and (any(p.requires_grad for p in self._store.params) or x.requires_grad)
         return _DiscFn.apply(self, record, x, *self._store.params)
 
