@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""Benchmark of the segmentation-training hot path (BASELINE.json metric: UDA train images/s @512x512).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload supervised|adversarial]
+
+One step = one pass of the hot path over one batch of synthetic input:
+  supervised  (BASELINE configs[1], default): U-Net r34, batch 16 @512x512 bf16, 24 classes —
+              zero_grad, forward, cross-entropy, backward, Adam step   (reference src/models/train.py:336-346)
+  adversarial (configs[2]): the reference's discriminator step + generator step on a source and a target
+              batch (src/models/adversarial_trainer.py:76-114), 8+8 images per GPU
+For N>1 the script is launched by torchrun (one rank per GPU, NCCL); each rank processes its own batch
+(weak scaling) and gradients are all-reduced in buckets overlapped with backward.  Rank 0 prints ONE JSON line.
+`--impl reference` times the reference's own CPU path (oracle port: fp32 PyTorch on all host cores).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CLASSES = 24
+# algorithmic conv FLOPs of U-Net r34 / 24 classes per 512x512 image (counted on the oracle)
+FWD_GFLOP_PER_IMG_512 = 64.248
+TRAIN_GFLOP_PER_IMG_512 = 191.51
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "which": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "which": "fallback"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons of one GPU during the timed region (NVML)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def synthetic_batch(B, size, seed, device=None, pinned=False):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, 3, size, size, generator=g)
+    # blocky label map (nearest-upsampled 16x16 grid): aerial-like regions, skewed histogram bins
+    t = torch.randint(0, CLASSES, (B, 16, 16), generator=g).repeat_interleave(size // 16, 1).repeat_interleave(size // 16, 2)
+    t = t.contiguous()
+    if pinned:
+        return x.pin_memory(), t.pin_memory()
+    if device is not None:
+        return x.to(device), t.to(device)
+    return x, t
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation of the path (oracle port)
+# ------------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle.ref_unet import RefUnet
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    size, B = args.size, args.ref_batch
+    model = RefUnet("resnet34", classes=CLASSES).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    crit = torch.nn.CrossEntropyLoss()
+    x, t = synthetic_batch(B, size, 1234)
+
+    def step():
+        opt.zero_grad()
+        loss = crit(model(x), t)
+        loss.backward()
+        opt.step()
+        return loss.item()
+
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    val = B * args.steps / dt
+    sample = f"{args.steps} steps of batch {B} @{size}x{size} (bounded sample of the batch-{args.batch} workload), fp32, oneDNN"
+    print(json.dumps({
+        "impl": "reference", "metric": "train_images_per_s", "value": val, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"supervised U-Net resnet34 @{size}x{size}, {CLASSES} classes, CE + Adam (reference CPU path)",
+                   "sample_batch": B},
+        "cpu_baseline": {"value": val, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline(size, budget_s=20.0):
+    """Oracle port on the box's host cores, bounded sample (rank 0, N=1 only)."""
+    import torch
+    from oracle.ref_unet import RefUnet
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    B = 2
+    model = RefUnet("resnet34", classes=CLASSES).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3)
+    x, t = synthetic_batch(B, size, 1234)
+
+    def step():
+        opt.zero_grad()
+        torch.nn.functional.cross_entropy(model(x), t).backward()
+        opt.step()
+
+    step()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        step(); n += 1
+        if time.perf_counter() - t0 > budget_s or n >= 10:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": B * n / dt, "unit": "images/s", "cores": cores, "kind": "port",
+            "sample": f"{n} steps of batch {B} @{size}x{size} after 1 warm-up (fp32 oracle U-Net r34 + CE + Adam)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import uda_aerial_semantic_segmentation_research_b200 as U
+    from uda_aerial_semantic_segmentation_research_b200 import ops, _lib
+    from uda_aerial_semantic_segmentation_research_b200.losses import CrossEntropyLoss, AdversarialLoss
+    from uda_aerial_semantic_segmentation_research_b200.optim import FusedAdam
+    from uda_aerial_semantic_segmentation_research_b200.discriminator import DomainDiscriminator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)
+    size, B = args.size, args.batch
+    model = U.Unet("resnet34", encoder_weights=None, in_channels=3, classes=CLASSES).to(dev).train()
+    nets = [model]
+    adversarial = args.workload == "adversarial"
+    if adversarial:
+        disc = DomainDiscriminator(3).to(dev).train()
+        nets.append(disc)
+        dopt = FusedAdam(disc, lr=1e-4)
+        adv = AdversarialLoss(0.001)
+    opt = FusedAdam(model, lr=1e-3)
+    crit = CrossEntropyLoss()
+    if world > 1:
+        from uda_aerial_semantic_segmentation_research_b200.ddp import GradSync
+        GradSync(nets)
+    Bs = B // 2 if adversarial else B
+    x, t = synthetic_batch(Bs, size, 1234 + rank, dev)
+    xt = synthetic_batch(Bs, size, 4321 + rank, dev)[0] if adversarial else None
+    hx, ht = synthetic_batch(Bs, size, 1234 + rank, pinned=True)
+    hxt = synthetic_batch(Bs, size, 4321 + rank, pinned=True)[0] if adversarial else None
+
+    def step(xs, ts, xtg):
+        if adversarial:   # src/models/adversarial_trainer.py:84-114
+            dopt.zero_grad()
+            d_loss = adv.discriminator_loss(disc(xs), disc(xtg))
+            d_loss.backward()
+            dopt.step()
+            opt.zero_grad()
+            total = crit(model(xs), ts) + adv.generator_loss(disc(xtg))
+            total.backward()
+            opt.step()
+            return total
+        opt.zero_grad()
+        loss = crit(model(xs), ts)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident arm -----------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step(x, t, xt)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = ops.LAUNCHES
+    ms = timed(lambda: step(x, t, xt), args.steps)
+    launches = ops.LAUNCHES - l0
+    sampler.stop_flag = True
+    sampler.join(1.0)
+    imgs = B * world * args.steps
+    value = imgs / (ms * 1e-3)
+
+    # ---- end-to-end arm: pinned host inputs, H2D inside the timed region, loss read back ------
+    def e2e_step():
+        xs = hx.to(dev, non_blocking=True)
+        ts = ht.to(dev, non_blocking=True)
+        xtg = hxt.to(dev, non_blocking=True) if adversarial else None
+        return step(xs, ts, xtg).item()
+
+    for _ in range(2):
+        e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+    h2d = hx.numel() * 4 + ht.numel() * 8 + (hxt.numel() * 4 if adversarial else 0)
+    e2e = {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
+
+    # ---- per-kernel CUDA-event profile of a few steps (rank 0): roofline of the dominant kernel ----
+    roof = None
+    breakdown = {}
+    if rank == 0:
+        _lib.PROFILE = {}
+        prof_steps = 3
+        sync()
+        f0 = ops.TC_FLOPS
+        for _ in range(prof_steps):
+            step(x, t, xt)
+        torch.cuda.synchronize()
+        prof, _lib.PROFILE = _lib.PROFILE, None
+        for name, evs in prof.items():
+            tot = sum(a.elapsed_time(b) for a, b in evs)
+            breakdown[name] = {"ms_per_step": tot / prof_steps, "launches_per_step": len(evs) / prof_steps}
+        pk = peaks()
+        # tensor-core convolution family: algorithmic FLOPs routed through the tcgen05 kernels
+        tc_ms = sum(breakdown.get(k, {}).get("ms_per_step", 0.0) for k in ("conv2d_tc_fwd", "conv2d_tc_dgrad", "conv2d_tc_wgrad"))
+        tc_n = sum(breakdown.get(k, {}).get("launches_per_step", 0.0) for k in ("conv2d_tc_fwd", "conv2d_tc_dgrad", "conv2d_tc_wgrad"))
+        tc_gflop = (ops.TC_FLOPS - f0) / prof_steps / 1e9
+        top = max(breakdown.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if breakdown else None
+        if tc_ms > 0:
+            ach = tc_gflop / tc_ms  # GFLOP / ms == TFLOP/s
+            roof = {"bound": "tensor", "kernel": "conv_tc_fwd_kernel (tcgen05 implicit-GEMM conv: fwd + dgrad launches)",
+                    "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                    "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+                    "peak_source": pk["which"] + " (sustained: kernel timed inside a long step)",
+                    "ms_per_step": tc_ms, "launches_per_step": tc_n, "top_entry_point_by_time": top}
+
+    out = None
+    if rank == 0:
+        wl = (f"supervised source-domain training, U-Net resnet34, batch {B}/GPU @{size}x{size}, {CLASSES} classes, "
+              "CE loss + Adam (BASELINE configs[1])") if not adversarial else \
+             (f"adversarial UDA step (D step + G step), U-Net resnet34 + image discriminator, {Bs}+{Bs} images/GPU "
+              f"@{size}x{size} (BASELINE configs[2])")
+        out = {
+            "metric": "train_images_per_s", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": wl, "global_batch": B * world, "image_size": size, "classes": CLASSES,
+                       "parallelism": f"dp{world}", "l2": "inputs+activations per step (>3 GB) exceed the 126 MB L2"},
+            "e2e": e2e, "gpu_launches": launches, "clocks": sampler.result(),
+            "roofline": roof, "kernel_breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in
+                                                               sorted(breakdown.items(), key=lambda kv: -kv[1]["ms_per_step"])},
+            "fraction_of_flop_roofline": value / world / (peaks()["bf16_tflops"] * 1e3 / TRAIN_GFLOP_PER_IMG_512 * (512 / size) ** 2),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline(size)
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="supervised", choices=["supervised", "adversarial"])
+    ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--ref-batch", type=int, default=2, help="bounded sample batch of the reference arm")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

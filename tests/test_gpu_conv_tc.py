@@ -59,7 +59,8 @@ def test_tc_forward_and_dgrad(cfg):
     y0 = ops.conv_fwd(xg, wg, None, s, p)
     assert rel_err(y0.float().cpu(), R.conv_fwd(x.float(), w.float(), None, s, p)) < 1e-2
     if s == 1:
-        assert ops.tc_supported(1, B, H, W, Cin, Cout, k, k, s, p)
+        # dgrad contracts over Cout: covered when Cout is a multiple of 16 (the 24-class head falls back)
+        assert ops.tc_supported(1, B, H, W, Cin, Cout, k, k, s, p) == (Cout % 16 == 0)
         dy = _rand(tuple(yr.shape), 3)
         dxr = R.conv_dgrad(dy.float(), w.float(), x.shape, s, p)
         dx = ops.conv_dgrad(dy.to(DEV), wg, x.shape, s, p)

