@@ -58,18 +58,28 @@ def test_tc_forward_and_dgrad(cfg):
     assert rel_err(yn.cpu(), yr.permute(0, 3, 1, 2)) < 2e-3
     y0 = ops.conv_fwd(xg, wg, None, s, p)
     assert rel_err(y0.float().cpu(), R.conv_fwd(x.float(), w.float(), None, s, p)) < 1e-2
-    if s == 1:
-        # dgrad contracts over Cout: covered when Cout is a multiple of 16 (the 24-class head falls back)
-        assert ops.tc_supported(1, B, H, W, Cin, Cout, k, k, s, p) == (Cout % 16 == 0)
-        dy = _rand(tuple(yr.shape), 3)
-        dxr = R.conv_dgrad(dy.float(), w.float(), x.shape, s, p)
-        dx = ops.conv_dgrad(dy.to(DEV), wg, x.shape, s, p)
-        assert rel_err(dx.float().cpu(), dxr) < 1e-2
-        add = _rand(tuple(x.shape), 4)
-        acc = add.clone().to(DEV)
-        out = ops.conv_dgrad(dy.to(DEV), wg, x.shape, s, p, addend=acc)
-        assert out.data_ptr() == acc.data_ptr()
-        assert rel_err(out.float().cpu(), dxr + add.float()) < 1e-2
+    # dgrad (stride 1: one launch on flipped weights; stride 2: one launch per output parity)
+    assert ops.tc_supported(1, B, H, W, Cin, Cout, k, k, s, p)
+    dy = _rand(tuple(yr.shape), 3)
+    dxr = R.conv_dgrad(dy.float(), w.float(), x.shape, s, p)
+    dx = ops.conv_dgrad(dy.to(DEV), wg, x.shape, s, p)
+    assert rel_err(dx.float().cpu(), dxr) < 1e-2
+    add = _rand(tuple(x.shape), 4)
+    acc = add.clone().to(DEV)
+    out = ops.conv_dgrad(dy.to(DEV), wg, x.shape, s, p, addend=acc)
+    assert out.data_ptr() == acc.data_ptr()
+    assert rel_err(out.float().cpu(), dxr + add.float()) < 1e-2
+    # wgrad (MN-major operands straight from the NHWC tensors), accumulating into fp32
+    assert ops.tc_supported(2, B, H, W, Cin, Cout, k, k, s, p)
+    dwr = R.conv_wgrad(dy.float(), x.float(), torch.zeros(Cout, k, k, Cin), s, p)
+    dw = torch.zeros((Cout, k, k, Cin), device=DEV)
+    ops.conv_wgrad(dy.to(DEV), xg, dw, s, p)
+    e_w = rel_err(dw.cpu(), dwr)
+    dwd = torch.zeros((Cout, k, k, Cin), device=DEV)
+    ops.conv_wgrad(dy.to(DEV), xg, dwd, s, p, force_direct=True)
+    assert e_w < 2e-3, (e_w, rel_err(dwd.cpu(), dwr))        # fp32 accumulation of exact bf16 products
+    ops.conv_wgrad(dy.to(DEV), xg, dw, s, p)                 # accumulates
+    assert rel_err(dw.cpu(), 2 * dwr) < 2e-3
 
 
 def test_weight_flip_transpose():

@@ -30,12 +30,14 @@ constexpr int kMaxTaps = 16;
 struct FwdParams {
   int TW, TH, NB;              // tile = NB images x TH rows x TW cols = 128 output pixels
   int tiles_w, tiles_h;        // tiles per image row / column
-  int MH, MW;                  // output spatial size
+  int MH, MW;                  // spatial size of the GEMM-M pixel grid the tiles cover
+  int OH, OW, os, oh, ow;      // output tensor spatial size; M-grid pixel (i,j) -> output (i*os+oh, j*os+ow)
   int Cout, Cred;              // GEMM N, reduction channels per tap
-  int ntaps, kchunks;          // taps, Cred / KC
+  int ntaps, kchunks;          // taps, ceil(Cred / KC)
   int rank5;                   // 0: stride-1 4-D map {C,W,H,B}; 1: stride-2 5-D map {2C,W/2,2,H/2,B}
   signed char dh[kMaxTaps], dw[kMaxTaps];   // per-tap source offset (rows / cols; pair units for rank5)
   signed char ph[kMaxTaps], pw[kMaxTaps];   // rank5 only: row / column parity
+  unsigned char wtap[kMaxTaps];             // per-tap index into the weight matrix' tap dimension
   bf16* out;                   // NHWC bf16 [B,MH,MW,Cout] or null
   float* out_nchw;             // fp32 [B,Cout,MH,MW] or null
   const float* bias;           // [Cout] or null
@@ -118,7 +120,7 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                       h0 + p.dh[tap], b0);
         else
           tma_load_4d(a_dst, &map_a, full_bar(s), c0, w0 + p.dw[tap], h0 + p.dh[tap], b0);
-        tma_load_2d(b_dst, &map_b, full_bar(s), tap * p.Cred + c0, n0);
+        tma_load_2d(b_dst, &map_b, full_bar(s), p.wtap[tap] * p.Cred + c0, n0);
       }
     }
   } else if (warp == 1) {
@@ -149,8 +151,8 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int r = q * 32 + lane;  // row of the tile = output pixel
     const int nb = r / (p.TH * p.TW);
     const int th = (r / p.TW) % p.TH, tw = r % p.TW;
-    const int b = b0 + nb, h = h0 + th, w = w0 + tw;
-    const long long pix = ((long long)b * p.MH + h) * p.MW + w;
+    const int b = b0 + nb, h = (h0 + th) * p.os + p.oh, w = (w0 + tw) * p.os + p.ow;
+    const long long pix = ((long long)b * p.OH + h) * p.OW + w;
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -188,8 +190,8 @@ conv_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         }
       }
       if (p.out_nchw) {
-        const long long hw = (long long)p.MH * p.MW;
-        float* dst = p.out_nchw + ((long long)b * p.Cout + nbase) * hw + (long long)h * p.MW + w;
+        const long long hw = (long long)p.OH * p.OW;
+        float* dst = p.out_nchw + ((long long)b * p.Cout + nbase) * hw + (long long)h * p.OW + w;
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (nbase + j < p.Cout) dst[(long long)j * hw] = f[j];
@@ -237,20 +239,19 @@ TilePlan plan_tiles(int B, int MH, int MW) {
   return t;
 }
 
-int pick_kc(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : (c % 16 == 0 ? 16 : 0)); }
+// channels per K chunk (= swizzle span / 2).  Channel counts that are not a multiple of 16 (the 24-class
+// head) use one 32-wide chunk: the missing channels are zero-filled by TMA on the activation side, so
+// whatever the weight box picks up there is multiplied by zero.
+int pick_kc(int c) {
+  if (c % 64 == 0) return 64;
+  if (c % 32 == 0) return 32;
+  if (c % 16 == 0) return 16;
+  if (c % 8 == 0 && c < 32) return c <= 16 ? 16 : 32;
+  return 0;
+}
 int pick_bn(int cout) { return cout > 64 ? 128 : (cout > 32 ? 64 : 32); }
 
-bool fwd_shape_ok(int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad) {
-  if (pick_kc(Cin) == 0 || Cout % 8 || Cout < 8) return false;
-  if (KH * KW > kMaxTaps || KH != KW) return false;
-  if (stride != 1 && stride != 2) return false;
-  if (stride == 2 && (H % 2 || W % 2)) return false;
-  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
-  if (Ho <= 0 || Wo <= 0) return false;
-  if (stride == 1 && (Ho != H || Wo != W)) return false;  // "same" convolutions only
-  if (stride == 2 && (Ho != H / 2 || Wo != W / 2)) return false;
-  return plan_tiles(B, Ho, Wo).ok;
-}
+int floor_div2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
 template <int KC, int BN>
 int launch_fwd(const CUtensorMap& ma, const CUtensorMap& mb, const FwdParams& p, int n_tiles, cudaStream_t st) {
@@ -267,58 +268,62 @@ int launch_fwd(const CUtensorMap& ma, const CUtensorMap& mb, const FwdParams& p,
   return UDA_OK;
 }
 
-// x: [B,H,W,Cin] bf16; w: [Cout][KH*KW][Cin] bf16; generic "same"/stride-2 forward convolution
-int run_fwd(const void* x, const void* w, const float* bias, const void* addend, void* y, float* y_nchw, int B,
-            int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, cudaStream_t st) {
-  UDA_REQUIRE(fwd_shape_ok(B, H, W, Cin, Cout, KH, KW, stride, pad), UDA_ERR_UNSUPPORTED,
-              "conv_tc: shape not covered by the tensor-core kernel (B=%d H=%d W=%d Cin=%d Cout=%d k=%d s=%d p=%d)",
-              B, H, W, Cin, Cout, KH, stride, pad);
-  UDA_REQUIRE(aligned<bf16>(x, 16) && aligned<bf16>(w, 16) && (!y || aligned<bf16>(y, 16)) &&
-                  (!addend || aligned<bf16>(addend, 16)),
+// One implicit-GEMM launch:  out[b, i*os+oh, j*os+ow, :] = sum_taps src[b, (i,j)+tap, :] * wmat[:, wtap, :]
+//   src  : [B,SH,SW,Cred] bf16, read through a stride-1 4-D map (src_s2 = 0; M-grid = SHxSW) or the
+//          stride-2 space-to-depth 5-D map (src_s2 = 1; M-grid = SH/2 x SW/2)
+//   wmat : [Cout][wtaps][Cred] bf16
+struct GemmConv {
+  const void* src; int B, SH, SW, Cred;
+  int src_s2;
+  const void* wmat; int Cout, wtaps;
+  int ntaps; int dh[kMaxTaps], dw[kMaxTaps], ph[kMaxTaps], pw[kMaxTaps], wtap[kMaxTaps];
+  int OH, OW, os, oh, ow;
+  const float* bias; const void* addend; void* out; float* out_nchw;
+};
+
+int run_gemm_conv(const GemmConv& g, cudaStream_t st) {
+  const int MH = g.src_s2 ? g.SH / 2 : g.SH, MW = g.src_s2 ? g.SW / 2 : g.SW;
+  const TilePlan tp = plan_tiles(g.B, MH, MW);
+  const int KC = pick_kc(g.Cred), BN = pick_bn(g.Cout);
+  UDA_REQUIRE(tp.ok && KC > 0 && g.ntaps >= 1 && g.ntaps <= kMaxTaps && g.Cout % 8 == 0, UDA_ERR_UNSUPPORTED,
+              "conv_tc: shape not covered by the tensor-core kernel (B=%d grid=%dx%d Cred=%d Cout=%d taps=%d)", g.B,
+              MH, MW, g.Cred, g.Cout, g.ntaps);
+  UDA_REQUIRE(aligned<bf16>(g.src, 16) && aligned<bf16>(g.wmat, 16) && (!g.out || aligned<bf16>(g.out, 16)) &&
+                  (!g.addend || aligned<bf16>(g.addend, 16)),
               UDA_ERR_BAD_ARG, "conv_tc: pointers must be 16-byte aligned");
-  const int Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? W : W / 2;
-  const TilePlan tp = plan_tiles(B, Ho, Wo);
-  const int KC = pick_kc(Cin), BN = pick_bn(Cout);
   FwdParams p{};
   p.TW = tp.TW; p.TH = tp.TH; p.NB = tp.NB;
-  p.tiles_w = Wo / tp.TW; p.tiles_h = Ho / tp.TH;
-  p.MH = Ho; p.MW = Wo; p.Cout = Cout; p.Cred = Cin;
-  p.ntaps = KH * KW; p.kchunks = Cin / KC; p.rank5 = stride == 2;
-  for (int kh = 0; kh < KH; ++kh)
-    for (int kw = 0; kw < KW; ++kw) {
-      const int t = kh * KW + kw;
-      const int oh = kh - pad, ow = kw - pad;
-      if (stride == 1) {
-        p.dh[t] = (signed char)oh; p.dw[t] = (signed char)ow; p.ph[t] = 0; p.pw[t] = 0;
-      } else {
-        const int ah = oh >= 0 ? oh / 2 : -((-oh + 1) / 2), aw = ow >= 0 ? ow / 2 : -((-ow + 1) / 2);  // floor
-        p.dh[t] = (signed char)ah; p.dw[t] = (signed char)aw;
-        p.ph[t] = (signed char)(oh - 2 * ah); p.pw[t] = (signed char)(ow - 2 * aw);
-      }
-    }
-  p.out = (bf16*)y; p.out_nchw = y_nchw; p.bias = bias; p.addend = (const bf16*)addend;
+  p.tiles_w = MW / tp.TW; p.tiles_h = MH / tp.TH;
+  p.MH = MH; p.MW = MW; p.OH = g.OH; p.OW = g.OW; p.os = g.os; p.oh = g.oh; p.ow = g.ow;
+  p.Cout = g.Cout; p.Cred = g.Cred; p.ntaps = g.ntaps; p.kchunks = (g.Cred + KC - 1) / KC; p.rank5 = g.src_s2;
+  for (int t = 0; t < g.ntaps; ++t) {
+    p.dh[t] = (signed char)g.dh[t]; p.dw[t] = (signed char)g.dw[t];
+    p.ph[t] = (signed char)g.ph[t]; p.pw[t] = (signed char)g.pw[t];
+    p.wtap[t] = (unsigned char)g.wtap[t];
+  }
+  p.out = (bf16*)g.out; p.out_nchw = g.out_nchw; p.bias = g.bias; p.addend = (const bf16*)g.addend;
 
   CUtensorMap ma, mb;
-  const uint64_t C = (uint64_t)Cin;
-  if (stride == 1) {
-    uint64_t dims[4] = {C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
-    uint64_t str[3] = {C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+  const uint64_t C = (uint64_t)g.Cred, H = (uint64_t)g.SH, W = (uint64_t)g.SW;
+  if (!g.src_s2) {
+    uint64_t dims[4] = {C, W, H, (uint64_t)g.B};
+    uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
     uint32_t box[4] = {(uint32_t)KC, (uint32_t)tp.TW, (uint32_t)tp.TH, (uint32_t)tp.NB};
-    if (int rc = make_tmap_bf16(&ma, x, 4, dims, str, box, KC * 2)) return rc;
+    if (int rc = make_tmap_bf16(&ma, g.src, 4, dims, str, box, KC * 2)) return rc;
   } else {
-    uint64_t dims[5] = {2 * C, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)B};
-    uint64_t str[4] = {2 * C * 2, (uint64_t)W * C * 2, 2 * (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint64_t dims[5] = {2 * C, W / 2, 2, H / 2, (uint64_t)g.B};
+    uint64_t str[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
     uint32_t box[5] = {(uint32_t)KC, (uint32_t)tp.TW, 1, (uint32_t)tp.TH, (uint32_t)tp.NB};
-    if (int rc = make_tmap_bf16(&ma, x, 5, dims, str, box, KC * 2)) return rc;
+    if (int rc = make_tmap_bf16(&ma, g.src, 5, dims, str, box, KC * 2)) return rc;
   }
   {
-    const uint64_t Kt = (uint64_t)KH * KW * Cin;
-    uint64_t dims[2] = {Kt, (uint64_t)Cout};
+    const uint64_t Kt = (uint64_t)g.wtaps * g.Cred;
+    uint64_t dims[2] = {Kt, (uint64_t)g.Cout};
     uint64_t str[1] = {Kt * 2};
     uint32_t box[2] = {(uint32_t)KC, (uint32_t)BN};
-    if (int rc = make_tmap_bf16(&mb, w, 2, dims, str, box, KC * 2)) return rc;
+    if (int rc = make_tmap_bf16(&mb, g.wmat, 2, dims, str, box, KC * 2)) return rc;
   }
-  const int n_tiles = (B / tp.NB) * p.tiles_w * p.tiles_h;
+  const int n_tiles = (g.B / tp.NB) * p.tiles_w * p.tiles_h;
 #define UDA_TC(KCv, BNv) \
   if (KC == KCv && BN == BNv) return launch_fwd<KCv, BNv>(ma, mb, p, n_tiles, st);
   UDA_TC(64, 128) UDA_TC(64, 64) UDA_TC(64, 32)
@@ -326,6 +331,370 @@ int run_fwd(const void* x, const void* w, const float* bias, const void* addend,
   UDA_TC(16, 128) UDA_TC(16, 64) UDA_TC(16, 32)
 #undef UDA_TC
   return set_error(UDA_ERR_UNSUPPORTED, "conv_tc: no kernel instance for KC=%d BN=%d", KC, BN);
+}
+
+bool fwd_shape_ok(int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad) {
+  if (pick_kc(Cin) == 0 || Cout % 8 || Cout < 8) return false;
+  if (KH * KW > kMaxTaps || KH != KW) return false;
+  if (stride != 1 && stride != 2) return false;
+  if (stride == 2 && (H % 2 || W % 2)) return false;
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  if (Ho <= 0 || Wo <= 0) return false;
+  if (stride == 1 && (Ho != H || Wo != W)) return false;  // "same" convolutions only
+  if (stride == 2 && (Ho != H / 2 || Wo != W / 2)) return false;
+  return plan_tiles(B, Ho, Wo).ok;
+}
+
+// x: [B,H,W,Cin] bf16; w: [Cout][KH*KW][Cin] bf16; "same" (stride 1) or halving (stride 2) forward convolution
+int run_fwd(const void* x, const void* w, const float* bias, const void* addend, void* y, float* y_nchw, int B,
+            int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, cudaStream_t st) {
+  UDA_REQUIRE(fwd_shape_ok(B, H, W, Cin, Cout, KH, KW, stride, pad), UDA_ERR_UNSUPPORTED,
+              "conv_tc: shape not covered by the tensor-core kernel (B=%d H=%d W=%d Cin=%d Cout=%d k=%d s=%d p=%d)",
+              B, H, W, Cin, Cout, KH, stride, pad);
+  GemmConv g{};
+  g.src = x; g.B = B; g.SH = H; g.SW = W; g.Cred = Cin; g.src_s2 = stride == 2;
+  g.wmat = w; g.Cout = Cout; g.wtaps = KH * KW; g.ntaps = KH * KW;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) {
+      const int t = kh * KW + kw, oh = kh - pad, ow = kw - pad;
+      g.wtap[t] = t;
+      if (stride == 1) {
+        g.dh[t] = oh; g.dw[t] = ow; g.ph[t] = 0; g.pw[t] = 0;
+      } else {
+        g.dh[t] = floor_div2(oh); g.dw[t] = floor_div2(ow);
+        g.ph[t] = oh - 2 * g.dh[t]; g.pw[t] = ow - 2 * g.dw[t];
+      }
+    }
+  g.OH = stride == 1 ? H : H / 2; g.OW = stride == 1 ? W : W / 2; g.os = 1; g.oh = 0; g.ow = 0;
+  g.bias = bias; g.addend = addend; g.out = y; g.out_nchw = y_nchw;
+  return run_gemm_conv(g, st);
+}
+
+bool dgrad_shape_ok(int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad) {
+  if (KH != KW || KH * KW > kMaxTaps) return false;
+  if (pick_kc(Cout) == 0 || Cin % 8 || Cin < 8) return false;
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  if (stride == 1) return Ho == H && Wo == W && plan_tiles(B, H, W).ok;
+  if (stride == 2) return H % 2 == 0 && W % 2 == 0 && Ho == H / 2 && Wo == W / 2 && plan_tiles(B, Ho, Wo).ok;
+  return false;
+}
+
+// dX[B,H,W,Cin] (+= addend) from dY[B,Ho,Wo,Cout] with w_ft = [Cin][KH][KW][Cout] (flipped + transposed).
+// stride 1: one "same" forward convolution of dY.  stride 2: one launch per output parity (ph,pw): the taps
+// with kh = ph+pad (mod 2) read dY[i + (ph+pad-kh)/2, ...] and write dX[2i+ph, 2j+pw] (every dX pixel is
+// produced by exactly one launch; parities without any tap are zero).
+int run_dgrad(const void* dy, const void* w_ft, const void* addend, void* dx, int B, int H, int W, int Cin, int Cout,
+              int KH, int KW, int stride, int pad, cudaStream_t st) {
+  UDA_REQUIRE(dgrad_shape_ok(B, H, W, Cin, Cout, KH, KW, stride, pad), UDA_ERR_UNSUPPORTED,
+              "conv_tc_dgrad: shape not covered (B=%d H=%d W=%d Cin=%d Cout=%d k=%d s=%d p=%d)", B, H, W, Cin, Cout,
+              KH, stride, pad);
+  GemmConv g{};
+  g.src = dy; g.B = B; g.Cred = Cout; g.src_s2 = 0;
+  g.wmat = w_ft; g.Cout = Cin; g.wtaps = KH * KW;
+  g.OH = H; g.OW = W; g.bias = nullptr; g.addend = addend; g.out = dx; g.out_nchw = nullptr;
+  if (stride == 1) {
+    g.SH = H; g.SW = W; g.os = 1; g.oh = 0; g.ow = 0; g.ntaps = KH * KW;
+    const int padp = KH - 1 - pad;
+    for (int kh = 0; kh < KH; ++kh)
+      for (int kw = 0; kw < KW; ++kw) {
+        const int t = kh * KW + kw;
+        g.dh[t] = kh - padp; g.dw[t] = kw - padp; g.ph[t] = g.pw[t] = 0; g.wtap[t] = t;  // w_ft is already flipped
+      }
+    return run_gemm_conv(g, st);
+  }
+  g.SH = H / 2; g.SW = W / 2; g.os = 2;
+  if (KH < 2 && !addend)  // some output parities receive no tap at all: they are zero
+    UDA_CUDA_OK(cudaMemsetAsync(dx, 0, (size_t)B * H * W * Cin * 2, st));
+  for (int ph = 0; ph < 2; ++ph)
+    for (int pw = 0; pw < 2; ++pw) {
+      int n = 0;
+      for (int kh = 0; kh < KH; ++kh) {
+        if (((ph + pad - kh) % 2 + 2) % 2) continue;
+        for (int kw = 0; kw < KW; ++kw) {
+          if (((pw + pad - kw) % 2 + 2) % 2) continue;
+          g.dh[n] = floor_div2(ph + pad - kh); g.dw[n] = floor_div2(pw + pad - kw);
+          g.ph[n] = g.pw[n] = 0;
+          g.wtap[n] = (KH - 1 - kh) * KW + (KW - 1 - kw);  // position of tap (kh,kw) inside the flipped w_ft
+          ++n;
+        }
+      }
+      g.oh = ph; g.ow = pw; g.ntaps = n;
+      if (n == 0) continue;  // no tap reaches this parity (1x1 stride 2): zero gradient, see the memset above
+      if (int rc = run_gemm_conv(g, st)) return rc;
+    }
+  return UDA_OK;
+}
+
+// ================================================================================================
+// wgrad:  dW[co][tap][ci] += sum_pixels dY[pix][co] * X[pix + tap][ci]
+//
+// GEMM with the pixel index as the reduction dimension.  Both operands are read straight from the NHWC
+// tensors with the SAME TMA boxes as the forward kernel (128 pixels x channel atom), i.e. they sit in
+// shared memory as [pixel rows][channels contiguous] — MN-major operands for tcgen05.mma (a_major =
+// b_major = 1).  The 128 rows of D are (tap, ci) pairs: 128/ATOM_A channel atoms, each loaded with its own
+// tap shift; the columns are output channels (BN/ATOM_B atoms).  A CTA accumulates a range of pixel tiles
+// in TMEM and adds its partial result to the fp32 gradient with one atomic per element.
+// ================================================================================================
+struct WgradParams {
+  int TW, TH, NB, tiles_w, tiles_h;     // pixel tiles over the OUTPUT grid (Ho x Wo)
+  int Cin, Cout, ntaps, cchunks;        // cchunks = Cin / ATOM_A
+  int rank5;                            // input read through the stride-2 space-to-depth view
+  signed char dh[kMaxTaps], dw[kMaxTaps], ph[kMaxTaps], pw[kMaxTaps];
+  int n_pixel_tiles, tiles_per_split;
+  float* dw_out;                        // [Cout][ntaps][Cin] fp32
+};
+
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t row_bytes, uint32_t atom_bytes) {
+  // MN-major canonical layout (units of 16 B): ((8,n),(8,k)) : ((1,LBO),(8,SBO)) for 128-byte rows —
+  // rows (k = pixels) are row_bytes apart, 8-row groups SBO = 8*row_bytes apart, channel atoms LBO apart.
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((atom_bytes >> 4) & 0x3FFFu) << 16;   // LBO
+  d |= (uint64_t)((8u * row_bytes) >> 4) << 32;          // SBO
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+
+template <int ATOM_A, int ATOM_B, int BN>
+struct WgradSmem {
+  static constexpr int kAAtoms = 128 / ATOM_A;
+  static constexpr int kBAtoms = BN / ATOM_B;
+  static constexpr int kAAtomBytes = 128 * ATOM_A * 2;
+  static constexpr int kBAtomBytes = 128 * ATOM_B * 2;
+  static constexpr int kABytes = kAAtoms * kAAtomBytes;   // 32 KB
+  static constexpr int kBBytes = kBAtoms * kBAtomBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int stages() {
+    int s = (196 * 1024) / kStageBytes;
+    return s > 6 ? 6 : s;
+  }
+  static constexpr int bytes() { return stages() * kStageBytes + 1024 + 256; }
+};
+
+template <int ATOM_A, int ATOM_B, int BN>
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_wgrad_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+                     const WgradParams p) {
+  using L = WgradSmem<ATOM_A, ATOM_B, BN>;
+  constexpr int S = L::stages();
+  constexpr uint32_t kTmemCols = BN < 32 ? 32 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * L::kStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S + 1);
+  const uint32_t smem_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (S + s); };
+  const uint32_t tmem_full_bar = bar_base + 8u * (2 * S);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int mtile = blockIdx.x;
+  const int n0 = blockIdx.y * BN;
+  const int total_atoms = p.ntaps * p.cchunks;
+  int valid_atoms = total_atoms - mtile * L::kAAtoms;
+  if (valid_atoms > L::kAAtoms) valid_atoms = L::kAAtoms;
+  const int pt_begin = blockIdx.z * p.tiles_per_split;
+  int pt_end = pt_begin + p.tiles_per_split;
+  if (pt_end > p.n_pixel_tiles) pt_end = p.n_pixel_tiles;
+  const int n_iters = pt_end - pt_begin;   // >= 1 by construction of the grid
+  const int tiles_per_group = p.tiles_w * p.tiles_h;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_dy); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      mbar_init(tmem_full_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % S;
+        const uint32_t phs = (it / S) & 1;
+        mbar_wait(empty_bar(s), phs ^ 1);
+        const int tile = pt_begin + it;
+        const int grp = tile / tiles_per_group, tin = tile % tiles_per_group;
+        const int b0 = grp * p.NB, h0 = (tin / p.tiles_w) * p.TH, w0 = (tin % p.tiles_w) * p.TW;
+        const uint32_t a_dst = smem_base + s * L::kStageBytes;
+        const uint32_t b_dst = a_dst + L::kABytes;
+        mbar_expect_tx(full_bar(s), valid_atoms * L::kAAtomBytes + L::kBBytes);
+        for (int a = 0; a < valid_atoms; ++a) {
+          const int gidx = mtile * L::kAAtoms + a;
+          const int tap = gidx / p.cchunks, c0 = (gidx % p.cchunks) * ATOM_A;
+          if (p.rank5)
+            tma_load_5d(a_dst + a * L::kAAtomBytes, &map_x, full_bar(s), p.pw[tap] * p.Cin + c0, w0 + p.dw[tap],
+                        p.ph[tap], h0 + p.dh[tap], b0);
+          else
+            tma_load_4d(a_dst + a * L::kAAtomBytes, &map_x, full_bar(s), c0, w0 + p.dw[tap], h0 + p.dh[tap], b0);
+        }
+#pragma unroll
+        for (int j = 0; j < L::kBAtoms; ++j)
+          tma_load_4d(b_dst + j * L::kBAtomBytes, &map_dy, full_bar(s), n0 + j * ATOM_B, w0, h0, b0);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      // M = 128 rows (tap,ci), N = BN output channels, both operands MN-major (bits 15 and 16)
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN) | (1u << 15) | (1u << 16);
+      for (int it = 0; it < n_iters; ++it) {
+        const int s = it % S;
+        const uint32_t phs = (it / S) & 1;
+        mbar_wait(full_bar(s), phs);
+        tc_fence_after();
+        const uint32_t a_addr = smem_base + s * L::kStageBytes;
+        const uint32_t b_addr = a_addr + L::kABytes;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {  // 16 pixels per MMA
+          const uint64_t adesc = make_mnmajor_desc(a_addr + k * 16 * (ATOM_A * 2), ATOM_A * 2, L::kAAtomBytes);
+          const uint64_t bdesc = make_mnmajor_desc(b_addr + k * 16 * (ATOM_B * 2), ATOM_B * 2, L::kBAtomBytes);
+          umma_bf16(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int a = r / ATOM_A, j = r % ATOM_A;
+    const int gidx = mtile * L::kAAtoms + a;
+    const bool row_ok = a < valid_atoms;
+    const int tap = row_ok ? gidx / p.cchunks : 0;
+    const int ci = row_ok ? (gidx % p.cchunks) * ATOM_A + j : 0;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t v[32];
+      if (BN >= 32) {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      } else {
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16), v);  // 32 columns are allocated; first BN are valid
+      }
+      tmem_ld_wait();
+      if (row_ok) {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const int co = n0 + c + k;
+          if (c + k < BN && co < p.Cout)
+            atomicAdd(p.dw_out + ((long long)co * p.ntaps + tap) * p.Cin + ci, __uint_as_float(v[k]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+int pick_atom(int c) { return c % 64 == 0 ? 64 : (c % 32 == 0 ? 32 : (c % 16 == 0 ? 16 : 0)); }
+
+bool wgrad_shape_ok(int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad) {
+  if (KH != KW || KH * KW > kMaxTaps) return false;
+  if (pick_atom(Cin) == 0 || Cout % 8 || Cout < 8) return false;
+  if (stride != 1 && stride != 2) return false;
+  if (stride == 2 && (H % 2 || W % 2)) return false;
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  if (stride == 1 && (Ho != H || Wo != W)) return false;
+  if (stride == 2 && (Ho != H / 2 || Wo != W / 2)) return false;
+  return plan_tiles(B, Ho, Wo).ok;
+}
+
+template <int ATOM_A, int ATOM_B, int BN>
+int launch_wgrad(const CUtensorMap& mx, const CUtensorMap& mdy, WgradParams& p, cudaStream_t st) {
+  using L = WgradSmem<ATOM_A, ATOM_B, BN>;
+  static bool configured = false;
+  if (!configured) {
+    UDA_CUDA_OK(cudaFuncSetAttribute(conv_tc_wgrad_kernel<ATOM_A, ATOM_B, BN>,
+                                     cudaFuncAttributeMaxDynamicSharedMemorySize, L::bytes()));
+    configured = true;
+  }
+  const int m_tiles = (p.ntaps * p.cchunks + L::kAAtoms - 1) / L::kAAtoms;
+  const int n_tiles = (p.Cout + BN - 1) / BN;
+  int splits = (num_sms() + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
+  if (splits > p.n_pixel_tiles) splits = p.n_pixel_tiles;
+  if (splits < 1) splits = 1;
+  p.tiles_per_split = (p.n_pixel_tiles + splits - 1) / splits;
+  splits = (p.n_pixel_tiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  dim3 grid((unsigned)m_tiles, (unsigned)n_tiles, (unsigned)splits);
+  conv_tc_wgrad_kernel<ATOM_A, ATOM_B, BN><<<grid, kTcThreads, L::bytes(), st>>>(mx, mdy, p);
+  UDA_LAUNCH_OK("conv_tc_wgrad_kernel");
+  return UDA_OK;
+}
+
+int run_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, int KH, int KW,
+              int stride, int pad, cudaStream_t st) {
+  UDA_REQUIRE(wgrad_shape_ok(B, H, W, Cin, Cout, KH, KW, stride, pad), UDA_ERR_UNSUPPORTED,
+              "conv_tc_wgrad: shape not covered (B=%d H=%d W=%d Cin=%d Cout=%d k=%d s=%d p=%d)", B, H, W, Cin, Cout,
+              KH, stride, pad);
+  UDA_REQUIRE(aligned<bf16>(dy, 16) && aligned<bf16>(x, 16) && aligned<float>(dw, 4), UDA_ERR_BAD_ARG,
+              "conv_tc_wgrad: pointers must be 16-byte aligned");
+  const int Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? W : W / 2;
+  const TilePlan tp = plan_tiles(B, Ho, Wo);
+  const int atomA = pick_atom(Cin);
+  // output-channel atoms: 64-wide when possible, else 32 / 16 (the 24-class head: two 16-wide atoms, the
+  // upper half of the second one is zero-filled by TMA)
+  const int atomB = Cout % 64 == 0 ? 64 : (Cout % 32 == 0 ? 32 : 16);
+  int BN = Cout >= 128 ? 128 : (Cout + atomB - 1) / atomB * atomB;
+  if (BN > 128) BN = 128;
+  WgradParams p{};
+  p.TW = tp.TW; p.TH = tp.TH; p.NB = tp.NB; p.tiles_w = Wo / tp.TW; p.tiles_h = Ho / tp.TH;
+  p.Cin = Cin; p.Cout = Cout; p.ntaps = KH * KW; p.cchunks = Cin / atomA; p.rank5 = stride == 2;
+  for (int kh = 0; kh < KH; ++kh)
+    for (int kw = 0; kw < KW; ++kw) {
+      const int t = kh * KW + kw, oh = kh - pad, ow = kw - pad;
+      if (stride == 1) {
+        p.dh[t] = (signed char)oh; p.dw[t] = (signed char)ow; p.ph[t] = p.pw[t] = 0;
+      } else {
+        const int ah = floor_div2(oh), aw = floor_div2(ow);
+        p.dh[t] = (signed char)ah; p.dw[t] = (signed char)aw;
+        p.ph[t] = (signed char)(oh - 2 * ah); p.pw[t] = (signed char)(ow - 2 * aw);
+      }
+    }
+  p.n_pixel_tiles = (B / tp.NB) * p.tiles_w * p.tiles_h;
+  p.dw_out = dw;
+  CUtensorMap mx, mdy;
+  const uint64_t C = (uint64_t)Cin;
+  if (stride == 1) {
+    uint64_t dims[4] = {C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    uint64_t str[3] = {C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {(uint32_t)atomA, (uint32_t)tp.TW, (uint32_t)tp.TH, (uint32_t)tp.NB};
+    if (int rc = make_tmap_bf16(&mx, x, 4, dims, str, box, atomA * 2)) return rc;
+  } else {
+    uint64_t dims[5] = {2 * C, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)B};
+    uint64_t str[4] = {2 * C * 2, (uint64_t)W * C * 2, 2 * (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[5] = {(uint32_t)atomA, (uint32_t)tp.TW, 1, (uint32_t)tp.TH, (uint32_t)tp.NB};
+    if (int rc = make_tmap_bf16(&mx, x, 5, dims, str, box, atomA * 2)) return rc;
+  }
+  {
+    const uint64_t Co = (uint64_t)Cout;
+    uint64_t dims[4] = {Co, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+    uint64_t str[3] = {Co * 2, (uint64_t)Wo * Co * 2, (uint64_t)Ho * Wo * Co * 2};
+    uint32_t box[4] = {(uint32_t)atomB, (uint32_t)tp.TW, (uint32_t)tp.TH, (uint32_t)tp.NB};
+    if (int rc = make_tmap_bf16(&mdy, dy, 4, dims, str, box, atomB * 2)) return rc;
+  }
+#define UDA_WG(A, Bv, N) \
+  if (atomA == A && atomB == Bv && BN == N) return launch_wgrad<A, Bv, N>(mx, mdy, p, st);
+  UDA_WG(64, 64, 128) UDA_WG(64, 64, 64) UDA_WG(64, 32, 32) UDA_WG(64, 16, 16) UDA_WG(64, 16, 32)
+  UDA_WG(32, 64, 128) UDA_WG(32, 64, 64) UDA_WG(32, 32, 32) UDA_WG(32, 16, 16) UDA_WG(32, 16, 32)
+  UDA_WG(16, 64, 128) UDA_WG(16, 64, 64) UDA_WG(16, 32, 32) UDA_WG(16, 16, 16) UDA_WG(16, 16, 32)
+#undef UDA_WG
+  return set_error(UDA_ERR_UNSUPPORTED, "conv_tc_wgrad: no kernel instance for atoms %d/%d BN=%d", atomA, atomB, BN);
 }
 
 }  // namespace
@@ -337,14 +706,9 @@ extern "C" int uda_conv2d_tc_supported(int op, int B, int H, int W, int Cin, int
                                        int pad) {
   if (!uda_device_supported()) return 0;
   if (op == 0) return fwd_shape_ok(B, H, W, Cin, Cout, KH, KW, stride, pad) ? 1 : 0;
-  if (op == 1) {
-    // dgrad of a stride-1 "same" convolution == forward "same" convolution of dy with flipped/transposed weights
-    if (stride != 1) return 0;
-    const int Ho = (H + 2 * pad - KH) + 1, Wo = (W + 2 * pad - KW) + 1;
-    if (Ho != H || Wo != W) return 0;
-    return fwd_shape_ok(B, H, W, Cout, Cin, KH, KW, 1, KH - 1 - pad) ? 1 : 0;
-  }
-  return 0;  // wgrad: see conv_tc_wgrad.cu
+  if (op == 1) return dgrad_shape_ok(B, H, W, Cin, Cout, KH, KW, stride, pad) ? 1 : 0;
+  if (op == 2) return wgrad_shape_ok(B, H, W, Cin, Cout, KH, KW, stride, pad) ? 1 : 0;
+  return 0;
 }
 
 extern "C" int uda_conv2d_tc_fwd(const void* x, const void* w, const float* bias, void* y_nhwc, float* y_nchw_f32,
@@ -360,9 +724,7 @@ extern "C" int uda_conv2d_tc_fwd(const void* x, const void* w, const float* bias
 extern "C" int uda_conv2d_tc_dgrad(const void* dy, const void* w_ft, const void* addend, void* dx, int B, int H, int W,
                                    int Cin, int Cout, int KH, int KW, int stride, int pad, void* stream) {
   UDA_REQUIRE(dy && w_ft && dx, UDA_ERR_BAD_ARG, "conv_tc_dgrad: null pointer");
-  UDA_REQUIRE(stride == 1, UDA_ERR_UNSUPPORTED, "conv_tc_dgrad: stride %d not covered", stride);
-  return run_fwd(dy, w_ft, nullptr, addend, dx, nullptr, B, H, W, Cout, Cin, KH, KW, 1, KH - 1 - pad,
-                 (cudaStream_t)stream);
+  return run_dgrad(dy, w_ft, addend, dx, B, H, W, Cin, Cout, KH, KW, stride, pad, (cudaStream_t)stream);
 }
 
 extern "C" int uda_conv2d_weight_flip_transpose(const void* w, void* w_ft, int Cout, int Cin, int KH, int KW,
@@ -378,5 +740,6 @@ extern "C" int uda_conv2d_weight_flip_transpose(const void* w, void* w_ft, int C
 
 extern "C" int uda_conv2d_tc_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout,
                                    int KH, int KW, int stride, int pad, void* stream) {
-  return set_error(UDA_ERR_UNSUPPORTED, "conv_tc_wgrad: not implemented yet (use the direct kernel)");
+  UDA_REQUIRE(dy && x && dw, UDA_ERR_BAD_ARG, "conv_tc_wgrad: null pointer");
+  return run_wgrad(dy, x, dw, B, H, W, Cin, Cout, KH, KW, stride, pad, (cudaStream_t)stream);
 }
