@@ -17,15 +17,16 @@
 // Replaces aten::_convolution (cuDNN) for the U-Net / discriminator convolutions the reference reaches
 // through smp.Unet and DomainDiscriminator.  dgrad of stride-1 convolutions runs
 // through the same kernel on flipped/transposed weights (uda_conv2d_weight_flip_transpose).
-#include "tc_common.cuh"
+#include "conv_tc_internal.cuh"
+#include <stdlib.h>
 
 namespace uda {
 namespace {
 
 using namespace tc;
+using namespace tcconv;
 
 constexpr int kTcThreads = 192;  // 6 warps
-constexpr int kMaxTaps = 16;
 
 struct FwdParams {
   int TW, TH, NB;              // tile = NB images x TH rows x TW cols = 128 output pixels
@@ -222,35 +223,6 @@ __global__ void weight_flip_transpose_kernel(const bf16* __restrict__ w, bf16* _
   }
 }
 
-struct TilePlan { int TW, TH, NB; bool ok; };
-
-TilePlan plan_tiles(int B, int MH, int MW) {
-  TilePlan t{0, 0, 0, false};
-  if (MW <= 0 || MH <= 0) return t;
-  t.TW = MW < 128 ? MW : 128;
-  if (128 % t.TW || MW % t.TW) return t;
-  int rows = 128 / t.TW;
-  t.TH = rows < MH ? rows : MH;
-  if (rows % t.TH || MH % t.TH) return t;
-  t.NB = rows / t.TH;
-  if (B % t.NB) return t;
-  if (t.TW > 256 || t.TH > 256 || t.NB > 256) return t;
-  t.ok = true;
-  return t;
-}
-
-// channels per K chunk (= swizzle span / 2).  Channel counts that are not a multiple of 16 (the 24-class
-// head) use one 32-wide chunk: the missing channels are zero-filled by TMA on the activation side, so
-// whatever the weight box picks up there is multiplied by zero.
-int pick_kc(int c) {
-  if (c % 64 == 0) return 64;
-  if (c % 32 == 0) return 32;
-  if (c % 16 == 0) return 16;
-  if (c % 8 == 0 && c < 32) return c <= 16 ? 16 : 32;
-  return 0;
-}
-int pick_bn(int cout) { return cout > 64 ? 128 : (cout > 32 ? 64 : 32); }
-
 int floor_div2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
 template <int KC, int BN>
@@ -268,38 +240,36 @@ int launch_fwd(const CUtensorMap& ma, const CUtensorMap& mb, const FwdParams& p,
   return UDA_OK;
 }
 
-// One implicit-GEMM launch:  out[b, i*os+oh, j*os+ow, :] = sum_taps src[b, (i,j)+tap, :] * wmat[:, wtap, :]
-//   src  : [B,SH,SW,Cred] bf16, read through a stride-1 4-D map (src_s2 = 0; M-grid = SHxSW) or the
-//          stride-2 space-to-depth 5-D map (src_s2 = 1; M-grid = SH/2 x SW/2)
-//   wmat : [Cout][wtaps][Cred] bf16
-struct GemmConv {
-  const void* src; int B, SH, SW, Cred;
-  int src_s2;
-  const void* wmat; int Cout, wtaps;
-  int ntaps; int dh[kMaxTaps], dw[kMaxTaps], ph[kMaxTaps], pw[kMaxTaps], wtap[kMaxTaps];
-  int OH, OW, os, oh, ow;
-  const float* bias; const void* addend; void* out; float* out_nchw;
-};
+bool use_persistent() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UDA_B200_TC_PERSIST");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
-int run_gemm_conv(const GemmConv& g, cudaStream_t st) {
+// Non-persistent path: one launch per tap class (conv_tc_fwd_kernel, one CTA per 128-pixel tile).
+int run_gemm_conv_class(const GemmConv& g, int ci, cudaStream_t st) {
+  const TapClass& c = g.cls[ci];
   const int MH = g.src_s2 ? g.SH / 2 : g.SH, MW = g.src_s2 ? g.SW / 2 : g.SW;
   const TilePlan tp = plan_tiles(g.B, MH, MW);
   const int KC = pick_kc(g.Cred), BN = pick_bn(g.Cout);
-  UDA_REQUIRE(tp.ok && KC > 0 && g.ntaps >= 1 && g.ntaps <= kMaxTaps && g.Cout % 8 == 0, UDA_ERR_UNSUPPORTED,
+  UDA_REQUIRE(tp.ok && KC > 0 && c.ntaps >= 1 && c.ntaps <= kMaxTaps && g.Cout % 8 == 0, UDA_ERR_UNSUPPORTED,
               "conv_tc: shape not covered by the tensor-core kernel (B=%d grid=%dx%d Cred=%d Cout=%d taps=%d)", g.B,
-              MH, MW, g.Cred, g.Cout, g.ntaps);
+              MH, MW, g.Cred, g.Cout, c.ntaps);
   UDA_REQUIRE(aligned<bf16>(g.src, 16) && aligned<bf16>(g.wmat, 16) && (!g.out || aligned<bf16>(g.out, 16)) &&
                   (!g.addend || aligned<bf16>(g.addend, 16)),
               UDA_ERR_BAD_ARG, "conv_tc: pointers must be 16-byte aligned");
   FwdParams p{};
   p.TW = tp.TW; p.TH = tp.TH; p.NB = tp.NB;
   p.tiles_w = MW / tp.TW; p.tiles_h = MH / tp.TH;
-  p.MH = MH; p.MW = MW; p.OH = g.OH; p.OW = g.OW; p.os = g.os; p.oh = g.oh; p.ow = g.ow;
-  p.Cout = g.Cout; p.Cred = g.Cred; p.ntaps = g.ntaps; p.kchunks = (g.Cred + KC - 1) / KC; p.rank5 = g.src_s2;
-  for (int t = 0; t < g.ntaps; ++t) {
-    p.dh[t] = (signed char)g.dh[t]; p.dw[t] = (signed char)g.dw[t];
-    p.ph[t] = (signed char)g.ph[t]; p.pw[t] = (signed char)g.pw[t];
-    p.wtap[t] = (unsigned char)g.wtap[t];
+  p.MH = MH; p.MW = MW; p.OH = g.OH; p.OW = g.OW; p.os = g.os; p.oh = c.oh; p.ow = c.ow;
+  p.Cout = g.Cout; p.Cred = g.Cred; p.ntaps = c.ntaps; p.kchunks = (g.Cred + KC - 1) / KC; p.rank5 = g.src_s2;
+  for (int t = 0; t < c.ntaps; ++t) {
+    p.dh[t] = (signed char)c.dh[t]; p.dw[t] = (signed char)c.dw[t];
+    p.ph[t] = (signed char)c.ph[t]; p.pw[t] = (signed char)c.pw[t];
+    p.wtap[t] = (unsigned char)c.wtap[t];
   }
   p.out = (bf16*)g.out; p.out_nchw = g.out_nchw; p.bias = g.bias; p.addend = (const bf16*)g.addend;
 
@@ -333,6 +303,13 @@ int run_gemm_conv(const GemmConv& g, cudaStream_t st) {
   return set_error(UDA_ERR_UNSUPPORTED, "conv_tc: no kernel instance for KC=%d BN=%d", KC, BN);
 }
 
+int run_gemm_conv(const GemmConv& g, cudaStream_t st) {
+  if (use_persistent()) return run_gemm_conv_persistent(g, st);
+  for (int ci = 0; ci < g.ncls; ++ci)
+    if (int rc = run_gemm_conv_class(g, ci, st)) return rc;
+  return UDA_OK;
+}
+
 bool fwd_shape_ok(int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad) {
   if (pick_kc(Cin) == 0 || Cout % 8 || Cout < 8) return false;
   if (KH * KW > kMaxTaps || KH != KW) return false;
@@ -353,19 +330,21 @@ int run_fwd(const void* x, const void* w, const float* bias, const void* addend,
               B, H, W, Cin, Cout, KH, stride, pad);
   GemmConv g{};
   g.src = x; g.B = B; g.SH = H; g.SW = W; g.Cred = Cin; g.src_s2 = stride == 2;
-  g.wmat = w; g.Cout = Cout; g.wtaps = KH * KW; g.ntaps = KH * KW;
+  g.wmat = w; g.Cout = Cout; g.wtaps = KH * KW; g.ncls = 1;
+  TapClass& c = g.cls[0];
+  c.ntaps = KH * KW; c.oh = 0; c.ow = 0;
   for (int kh = 0; kh < KH; ++kh)
     for (int kw = 0; kw < KW; ++kw) {
       const int t = kh * KW + kw, oh = kh - pad, ow = kw - pad;
-      g.wtap[t] = t;
+      c.wtap[t] = t;
       if (stride == 1) {
-        g.dh[t] = oh; g.dw[t] = ow; g.ph[t] = 0; g.pw[t] = 0;
+        c.dh[t] = oh; c.dw[t] = ow; c.ph[t] = 0; c.pw[t] = 0;
       } else {
-        g.dh[t] = floor_div2(oh); g.dw[t] = floor_div2(ow);
-        g.ph[t] = oh - 2 * g.dh[t]; g.pw[t] = ow - 2 * g.dw[t];
+        c.dh[t] = floor_div2(oh); c.dw[t] = floor_div2(ow);
+        c.ph[t] = oh - 2 * c.dh[t]; c.pw[t] = ow - 2 * c.dw[t];
       }
     }
-  g.OH = stride == 1 ? H : H / 2; g.OW = stride == 1 ? W : W / 2; g.os = 1; g.oh = 0; g.ow = 0;
+  g.OH = stride == 1 ? H : H / 2; g.OW = stride == 1 ? W : W / 2; g.os = 1;
   g.bias = bias; g.addend = addend; g.out = y; g.out_nchw = y_nchw;
   return run_gemm_conv(g, st);
 }
@@ -393,36 +372,40 @@ int run_dgrad(const void* dy, const void* w_ft, const void* addend, void* dx, in
   g.wmat = w_ft; g.Cout = Cin; g.wtaps = KH * KW;
   g.OH = H; g.OW = W; g.bias = nullptr; g.addend = addend; g.out = dx; g.out_nchw = nullptr;
   if (stride == 1) {
-    g.SH = H; g.SW = W; g.os = 1; g.oh = 0; g.ow = 0; g.ntaps = KH * KW;
+    g.SH = H; g.SW = W; g.os = 1; g.ncls = 1;
+    TapClass& c = g.cls[0];
+    c.ntaps = KH * KW; c.oh = 0; c.ow = 0;
     const int padp = KH - 1 - pad;
     for (int kh = 0; kh < KH; ++kh)
       for (int kw = 0; kw < KW; ++kw) {
         const int t = kh * KW + kw;
-        g.dh[t] = kh - padp; g.dw[t] = kw - padp; g.ph[t] = g.pw[t] = 0; g.wtap[t] = t;  // w_ft is already flipped
+        c.dh[t] = kh - padp; c.dw[t] = kw - padp; c.ph[t] = c.pw[t] = 0; c.wtap[t] = t;  // w_ft is already flipped
       }
     return run_gemm_conv(g, st);
   }
-  g.SH = H / 2; g.SW = W / 2; g.os = 2;
+  g.SH = H / 2; g.SW = W / 2; g.os = 2; g.ncls = 0;
   if (KH < 2 && !addend)  // some output parities receive no tap at all: they are zero
     UDA_CUDA_OK(cudaMemsetAsync(dx, 0, (size_t)B * H * W * Cin * 2, st));
-  for (int ph = 0; ph < 2; ++ph)
-    for (int pw = 0; pw < 2; ++pw) {
-      int n = 0;
-      for (int kh = 0; kh < KH; ++kh) {
-        if (((ph + pad - kh) % 2 + 2) % 2) continue;
-        for (int kw = 0; kw < KW; ++kw) {
-          if (((pw + pad - kw) % 2 + 2) % 2) continue;
-          g.dh[n] = floor_div2(ph + pad - kh); g.dw[n] = floor_div2(pw + pad - kw);
-          g.ph[n] = g.pw[n] = 0;
-          g.wtap[n] = (KH - 1 - kh) * KW + (KW - 1 - kw);  // position of tap (kh,kw) inside the flipped w_ft
-          ++n;
+  // classes with the most taps first (static round-robin of the persistent kernel balances better)
+  for (int ph = 1; ph >= 0; --ph)
+    for (int pw = 1; pw >= 0; --pw) {
+        TapClass c{};
+        int n = 0;
+        for (int kh = 0; kh < KH; ++kh) {
+          if (((ph + pad - kh) % 2 + 2) % 2) continue;
+          for (int kw = 0; kw < KW; ++kw) {
+            if (((pw + pad - kw) % 2 + 2) % 2) continue;
+            c.dh[n] = floor_div2(ph + pad - kh); c.dw[n] = floor_div2(pw + pad - kw);
+            c.ph[n] = c.pw[n] = 0;
+            c.wtap[n] = (KH - 1 - kh) * KW + (KW - 1 - kw);  // position of tap (kh,kw) inside the flipped w_ft
+            ++n;
+          }
         }
-      }
-      g.oh = ph; g.ow = pw; g.ntaps = n;
-      if (n == 0) continue;  // no tap reaches this parity (1x1 stride 2): zero gradient, see the memset above
-      if (int rc = run_gemm_conv(g, st)) return rc;
+        if (n == 0) continue;   // parities without any tap: zero gradient (memset above)
+        c.ntaps = n; c.oh = ph; c.ow = pw;
+        g.cls[g.ncls++] = c;
     }
-  return UDA_OK;
+  return run_gemm_conv(g, st);
 }
 
 // ================================================================================================

@@ -1,0 +1,62 @@
+// Internal interface between the tensor-core convolution translation units.
+#pragma once
+#include "tc_common.cuh"
+
+namespace uda {
+namespace tcconv {
+
+constexpr int kMaxTaps = 16;
+constexpr int kMaxClasses = 4;
+
+struct TilePlan { int TW, TH, NB; bool ok; };
+
+// Tile of `target` (128 or 256) pixels = NB images x TH rows x TW columns of a [B, MH, MW] pixel grid.
+inline TilePlan plan_tiles(int B, int MH, int MW, int target = 128) {
+  TilePlan t{0, 0, 0, false};
+  if (MW <= 0 || MH <= 0) return t;
+  t.TW = MW < target ? MW : target;
+  if (target % t.TW || MW % t.TW) return t;
+  int rows = target / t.TW;
+  t.TH = rows < MH ? rows : MH;
+  if (rows % t.TH || MH % t.TH) return t;
+  t.NB = rows / t.TH;
+  if (B % t.NB) return t;
+  if (t.TW > 256 || t.TH > 256 || t.NB > 256) return t;
+  t.ok = true;
+  return t;
+}
+
+// One tap class: a set of taps that all write the same output sub-grid (oh, ow).  A forward convolution or
+// a stride-1 dgrad has one class; a stride-2 dgrad has one class per output parity.
+struct TapClass {
+  int ntaps;
+  int dh[kMaxTaps], dw[kMaxTaps], ph[kMaxTaps], pw[kMaxTaps], wtap[kMaxTaps];
+  int oh, ow;
+};
+
+// out[b, i*os+oh, j*os+ow, :] = sum_taps src[b, (i,j)+tap, :] * wmat[:, wtap, :]   (+bias, +addend)
+//   src  : [B,SH,SW,Cred] bf16 read through a stride-1 4-D map (src_s2 = 0; M-grid = SHxSW) or the stride-2
+//          space-to-depth 5-D map (src_s2 = 1; M-grid = SH/2 x SW/2);   wmat : [Cout][wtaps][Cred] bf16
+struct GemmConv {
+  const void* src; int B, SH, SW, Cred;
+  int src_s2;
+  const void* wmat; int Cout, wtaps;
+  int ncls; TapClass cls[kMaxClasses];
+  int OH, OW, os;
+  const float* bias; const void* addend; void* out; float* out_nchw;
+};
+
+inline int pick_kc(int c) {
+  if (c % 64 == 0) return 64;
+  if (c % 32 == 0) return 32;
+  if (c % 16 == 0) return 16;
+  if (c % 8 == 0 && c < 32) return c <= 16 ? 16 : 32;
+  return 0;
+}
+inline int pick_bn(int cout) { return cout > 64 ? 128 : (cout > 32 ? 64 : 32); }
+
+// conv_tc_persist.cu: persistent, TMEM-double-buffered kernel (all classes in one launch)
+int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st);
+
+}  // namespace tcconv
+}  // namespace uda

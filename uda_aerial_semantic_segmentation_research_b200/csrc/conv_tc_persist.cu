@@ -1,0 +1,333 @@
+// Persistent tcgen05 implicit-GEMM convolution (forward / dgrad), sm_100a.
+//
+// Same operand scheme as conv_tc.cu (TMA boxes of the NHWC tensor as the A operand, OHWI weights as the
+// K-major B operand, accumulators in TMEM) with the per-CTA costs amortised:
+//   * grid = number of SMs; every CTA walks a static round-robin list of output tiles
+//     (tap class x pixel tile x channel tile), so barrier init, TMEM allocation and descriptor prefetch
+//     happen once per SM instead of once per 128 pixels;
+//   * the TMA producer streams across tile boundaries (the smem ring never drains);
+//   * TMEM holds TWO accumulator sets: the epilogue warps drain tile j (tcgen05.ld -> bf16 NHWC /
+//     fp32 NCHW stores) while the MMA thread already accumulates tile j+1;
+//   * MT = 2: a tile is 256 pixels = two 128-row MMAs that share every weight tile (halves the weight
+//     traffic per FLOP, one TMA instruction per 256 pixels);
+//   * weight-stationary mode: when the layer's whole weight matrix fits (<= 96 KB, Cout <= 128) it is loaded
+//     into shared memory once per CTA and the main loop streams activations only — the 16/32/64-channel
+//     high-resolution layers (decoder blocks 2-4, head, layer1) are HBM/issue bound, not FLOP bound;
+//   * stride-2 dgrad: the four output-parity classes are tiles of ONE launch.
+#include "conv_tc_internal.cuh"
+
+namespace uda {
+namespace tcconv {
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 12;
+
+struct PClass {
+  int ntaps;
+  signed char dh[kMaxTaps], dw[kMaxTaps], ph[kMaxTaps], pw[kMaxTaps];
+  unsigned char wtap[kMaxTaps];
+  short oh, ow;
+};
+
+struct PParams {
+  int TW, TH, NB, tiles_w, tiles_h;   // pixel tile (128*MT pixels) and tiles per image group
+  int m_tiles, n_tiles, ncls;
+  int MH, MW, OH, OW, os;
+  int Cout, Cred, kchunks, rank5, wtaps;
+  int stages, ws;
+  PClass cls[kMaxClasses];
+  bf16* out; float* out_nchw; const float* bias; const bf16* addend;
+};
+
+template <int KC, int BN, int MT>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                       const PParams p) {
+  constexpr int kABytes = MT * 128 * KC * 2;
+  constexpr int kBBytes = BN * KC * 2;
+  constexpr uint32_t kAccCols = MT * BN;                      // one accumulator set
+  constexpr uint32_t kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // power of two for every (MT,BN)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.stages;
+  const int ws_bytes = p.ws ? p.wtaps * p.kchunks * kBBytes : 0;
+  const int stage_bytes = kABytes + (p.ws ? 0 : kBBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ws_bytes + S * stage_bytes);
+  // bars: full[kMaxStages], empty[kMaxStages], tmem_full[2], tmem_empty[2], ws_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
+  const uint32_t ws_base = smem_u32(smem);
+  const uint32_t ring_base = ws_base + ws_bytes;
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (kMaxStages + s); };
+  auto tfull_bar = [&](int q) { return bar_base + 8u * (2 * kMaxStages + q); };
+  auto tempty_bar = [&](int q) { return bar_base + 8u * (2 * kMaxStages + 2 + q); };
+  const uint32_t ws_bar = bar_base + 8u * (2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_cls = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.ncls * tiles_per_cls;
+  const int tiles_per_group = p.tiles_w * p.tiles_h;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      for (int q = 0; q < 2; ++q) { mbar_init(tfull_bar(q), 1); mbar_init(tempty_bar(q), 4); }
+      mbar_init(ws_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      if (p.ws) {
+        mbar_expect_tx(ws_bar, ws_bytes);
+        for (int wt = 0; wt < p.wtaps; ++wt)
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            tma_load_2d(ws_base + (wt * p.kchunks + kc) * kBBytes, &map_b, ws_bar, wt * p.Cred + kc * KC, 0);
+      }
+      int it = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int ci = t / tiles_per_cls, rem = t % tiles_per_cls;
+        const int mt = rem / p.n_tiles, n0 = (rem % p.n_tiles) * BN;
+        const int grp = mt / tiles_per_group, tin = mt % tiles_per_group;
+        const int b0 = grp * p.NB, h0 = (tin / p.tiles_w) * p.TH, w0 = (tin % p.tiles_w) * p.TW;
+        const PClass& c = p.cls[ci];
+        for (int tap = 0; tap < c.ntaps; ++tap) {
+          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+            const int s = it % S;
+            const uint32_t phs = (it / S) & 1;
+            mbar_wait(empty_bar(s), phs ^ 1);
+            const uint32_t a_dst = ring_base + s * stage_bytes;
+            mbar_expect_tx(full_bar(s), stage_bytes);
+            if (p.rank5)
+              tma_load_5d(a_dst, &map_a, full_bar(s), c.pw[tap] * p.Cred + kc * KC, w0 + c.dw[tap], c.ph[tap],
+                          h0 + c.dh[tap], b0);
+            else
+              tma_load_4d(a_dst, &map_a, full_bar(s), kc * KC, w0 + c.dw[tap], h0 + c.dh[tap], b0);
+            if (!p.ws) tma_load_2d(a_dst + kABytes, &map_b, full_bar(s), c.wtap[tap] * p.Cred + kc * KC, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN);
+      if (p.ws) { mbar_wait(ws_bar, 0); tc_fence_after(); }
+      int it = 0, j = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+        const int ci = t / tiles_per_cls;
+        const PClass& c = p.cls[ci];
+        const int q = j & 1;
+        mbar_wait(tempty_bar(q), ((j >> 1) & 1) ^ 1);   // epilogue has drained this accumulator set
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)q * kAccCols;
+        for (int tap = 0; tap < c.ntaps; ++tap) {
+          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+            const int s = it % S;
+            const uint32_t phs = (it / S) & 1;
+            mbar_wait(full_bar(s), phs);
+            tc_fence_after();
+            const uint32_t a_addr = ring_base + s * stage_bytes;
+            const uint32_t b_addr = p.ws ? ws_base + (c.wtap[tap] * p.kchunks + kc) * kBBytes : a_addr + kABytes;
+            const uint64_t bdesc = make_kmajor_desc(b_addr, KC * 2);
+#pragma unroll
+            for (int sub = 0; sub < MT; ++sub) {
+              const uint64_t adesc = make_kmajor_desc(a_addr + sub * (128 * KC * 2), KC * 2);
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k)
+                umma_bf16(acc + (uint32_t)sub * BN, adesc + 2ull * k, bdesc + 2ull * k, idesc,
+                          (tap > 0 || kc > 0 || k > 0) ? 1u : 0u);
+            }
+            umma_commit(empty_bar(s));
+          }
+        }
+        umma_commit(tfull_bar(q));
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps) =====================
+    const int qw = warp & 3;
+    int j = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+      const int ci = t / tiles_per_cls, rem = t % tiles_per_cls;
+      const int mt = rem / p.n_tiles, n0 = (rem % p.n_tiles) * BN;
+      const int grp = mt / tiles_per_group, tin = mt % tiles_per_group;
+      const int b0 = grp * p.NB, h0 = (tin / p.tiles_w) * p.TH, w0 = (tin % p.tiles_w) * p.TW;
+      const int oh = p.cls[ci].oh, ow = p.cls[ci].ow;
+      const int q = j & 1;
+      mbar_wait(tfull_bar(q), (j >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int sub = 0; sub < MT; ++sub) {
+        const int r = sub * 128 + qw * 32 + lane;
+        const int nb = r / (p.TH * p.TW);
+        const int th = (r / p.TW) % p.TH, tw = r % p.TW;
+        const int b = b0 + nb, h = (h0 + th) * p.os + oh, w = (w0 + tw) * p.os + ow;
+        const long long pix = ((long long)b * p.OH + h) * p.OW + w;
+        const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)q * kAccCols + (uint32_t)sub * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          const int nbase = n0 + c0;
+          if (nbase >= p.Cout) break;   // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32(tbase + (uint32_t)c0, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
+          if (p.bias) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (nbase + k < p.Cout) f[k] += __ldg(p.bias + nbase + k);
+          }
+          if (p.out) {
+            bf16* dst = p.out + pix * p.Cout + nbase;
+            const bf16* add = p.addend ? p.addend + pix * p.Cout + nbase : nullptr;
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              if (nbase + k < p.Cout) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = f[k + e];
+                if (add) {
+                  float a8[8];
+                  ld_vec<8>(add + k, a8);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) o[e] += a8[e];
+                }
+                st_vec<8>(dst + k, o);
+              }
+            }
+          }
+          if (p.out_nchw) {
+            const long long hw = (long long)p.OH * p.OW;
+            float* dst = p.out_nchw + ((long long)b * p.Cout + nbase) * hw + (long long)h * p.OW + w;
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (nbase + k < p.Cout) dst[(long long)k * hw] = f[k];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(q));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int KC, int BN, int MT>
+int launch_persist(const CUtensorMap& ma, const CUtensorMap& mb, PParams& p, int total_tiles, cudaStream_t st) {
+  constexpr int kABytes = MT * 128 * KC * 2, kBBytes = BN * KC * 2;
+  const int budget = 200 * 1024;
+  const int ws_bytes = p.wtaps * p.kchunks * kBBytes;
+  p.ws = (p.n_tiles == 1 && ws_bytes <= 96 * 1024) ? 1 : 0;
+  const int stage_bytes = kABytes + (p.ws ? 0 : kBBytes);
+  int S = (budget - (p.ws ? ws_bytes : 0)) / stage_bytes;
+  if (S > kMaxStages) S = kMaxStages;
+  UDA_REQUIRE(S >= 2, UDA_ERR_UNSUPPORTED, "conv_tc_persist: not enough shared memory for a 2-stage ring");
+  p.stages = S;
+  const int smem = (p.ws ? ws_bytes : 0) + S * stage_bytes + 1024 + 512;
+  static int configured = 0;
+  if (configured < smem) {
+    UDA_CUDA_OK(cudaFuncSetAttribute(conv_tc_persist_kernel<KC, BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024));
+    configured = 227 * 1024;
+  }
+  int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  conv_tc_persist_kernel<KC, BN, MT><<<grid, kThreads, smem, st>>>(ma, mb, p);
+  UDA_LAUNCH_OK("conv_tc_persist_kernel");
+  return UDA_OK;
+}
+
+}  // namespace
+
+int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
+  const int MH = g.src_s2 ? g.SH / 2 : g.SH, MW = g.src_s2 ? g.SW / 2 : g.SW;
+  const int KC = pick_kc(g.Cred), BN = pick_bn(g.Cout);
+  UDA_REQUIRE(KC > 0 && g.ncls >= 1 && g.ncls <= kMaxClasses && g.Cout % 8 == 0, UDA_ERR_UNSUPPORTED,
+              "conv_tc_persist: shape not covered (Cred=%d Cout=%d)", g.Cred, g.Cout);
+  const int n_tiles = (g.Cout + BN - 1) / BN;
+  // 256-pixel tiles when that still leaves at least two tiles per SM, else 128-pixel tiles
+  TilePlan tp = plan_tiles(g.B, MH, MW, 256);
+  int MT = 2;
+  if (tp.ok) {
+    const long long t2 = (long long)g.ncls * n_tiles * ((long long)g.B * MH * MW / 256);
+    if (t2 < 2LL * num_sms()) tp.ok = false;
+  }
+  if (!tp.ok) { tp = plan_tiles(g.B, MH, MW, 128); MT = 1; }
+  UDA_REQUIRE(tp.ok, UDA_ERR_UNSUPPORTED, "conv_tc_persist: pixel grid %dx%dx%d cannot be tiled", g.B, MH, MW);
+  UDA_REQUIRE(aligned<bf16>(g.src, 16) && aligned<bf16>(g.wmat, 16) && (!g.out || aligned<bf16>(g.out, 16)) &&
+                  (!g.addend || aligned<bf16>(g.addend, 16)),
+              UDA_ERR_BAD_ARG, "conv_tc_persist: pointers must be 16-byte aligned");
+  PParams p{};
+  p.TW = tp.TW; p.TH = tp.TH; p.NB = tp.NB; p.tiles_w = MW / tp.TW; p.tiles_h = MH / tp.TH;
+  p.m_tiles = (g.B / tp.NB) * p.tiles_w * p.tiles_h; p.n_tiles = n_tiles; p.ncls = g.ncls;
+  p.MH = MH; p.MW = MW; p.OH = g.OH; p.OW = g.OW; p.os = g.os;
+  p.Cout = g.Cout; p.Cred = g.Cred; p.kchunks = (g.Cred + KC - 1) / KC; p.rank5 = g.src_s2; p.wtaps = g.wtaps;
+  for (int c = 0; c < g.ncls; ++c) {
+    const TapClass& s = g.cls[c];
+    UDA_REQUIRE(s.ntaps >= 1 && s.ntaps <= kMaxTaps, UDA_ERR_BAD_ARG, "conv_tc_persist: bad tap class");
+    PClass& d = p.cls[c];
+    d.ntaps = s.ntaps; d.oh = (short)s.oh; d.ow = (short)s.ow;
+    for (int t = 0; t < s.ntaps; ++t) {
+      d.dh[t] = (signed char)s.dh[t]; d.dw[t] = (signed char)s.dw[t];
+      d.ph[t] = (signed char)s.ph[t]; d.pw[t] = (signed char)s.pw[t];
+      d.wtap[t] = (unsigned char)s.wtap[t];
+    }
+  }
+  p.out = (bf16*)g.out; p.out_nchw = g.out_nchw; p.bias = g.bias; p.addend = (const bf16*)g.addend;
+
+  CUtensorMap ma, mb;
+  const uint64_t C = (uint64_t)g.Cred, H = (uint64_t)g.SH, W = (uint64_t)g.SW;
+  if (!g.src_s2) {
+    uint64_t dims[4] = {C, W, H, (uint64_t)g.B};
+    uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
+    uint32_t box[4] = {(uint32_t)KC, (uint32_t)tp.TW, (uint32_t)tp.TH, (uint32_t)tp.NB};
+    if (int rc = make_tmap_bf16(&ma, g.src, 4, dims, str, box, KC * 2)) return rc;
+  } else {
+    uint64_t dims[5] = {2 * C, W / 2, 2, H / 2, (uint64_t)g.B};
+    uint64_t str[4] = {2 * C * 2, W * C * 2, 2 * W * C * 2, H * W * C * 2};
+    uint32_t box[5] = {(uint32_t)KC, (uint32_t)tp.TW, 1, (uint32_t)tp.TH, (uint32_t)tp.NB};
+    if (int rc = make_tmap_bf16(&ma, g.src, 5, dims, str, box, KC * 2)) return rc;
+  }
+  {
+    const uint64_t Kt = (uint64_t)g.wtaps * g.Cred;
+    uint64_t dims[2] = {Kt, (uint64_t)g.Cout};
+    uint64_t str[1] = {Kt * 2};
+    uint32_t box[2] = {(uint32_t)KC, (uint32_t)BN};
+    if (int rc = make_tmap_bf16(&mb, g.wmat, 2, dims, str, box, KC * 2)) return rc;
+  }
+  const int total_tiles = p.ncls * p.m_tiles * p.n_tiles;
+#define UDA_P(KCv, BNv)                                                                            \
+  if (KC == KCv && BN == BNv)                                                                      \
+    return MT == 2 ? launch_persist<KCv, BNv, 2>(ma, mb, p, total_tiles, st)                       \
+                   : launch_persist<KCv, BNv, 1>(ma, mb, p, total_tiles, st);
+  UDA_P(64, 128) UDA_P(64, 64) UDA_P(64, 32)
+  UDA_P(32, 128) UDA_P(32, 64) UDA_P(32, 32)
+  UDA_P(16, 128) UDA_P(16, 64) UDA_P(16, 32)
+#undef UDA_P
+  return set_error(UDA_ERR_UNSUPPORTED, "conv_tc_persist: no kernel instance for KC=%d BN=%d", KC, BN);
+}
+
+}  // namespace tcconv
+}  // namespace uda
