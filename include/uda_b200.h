@@ -134,15 +134,34 @@ int uda_conv2d_tc_fwd(const void* x, const void* w, const float* bias, void* y_n
 /* dgrad takes w_ft = uda_conv2d_weight_flip_transpose(w): [Cin][KH][KW][Cout] bf16 (the weights of the
  * equivalent forward convolution of dy); addend as in uda_conv2d_direct_dgrad. */
 int uda_conv2d_weight_flip_transpose(const void* w, void* w_ft, int Cout, int Cin, int KH, int KW, void* stream);
+/* the same for every conv weight of a network in one launch: both bases are bf16 buffers with identical offsets;
+ * table_dev = device int[n_weights][5] = {element offset, Cout, Cin, KH, KW} */
+int uda_conv2d_weight_flip_transpose_batch(const void* w_base, void* w_ft_base, const int* table_dev, int n_weights,
+                                           void* stream);
 int uda_conv2d_tc_dgrad(const void* dy, const void* w_ft, const void* addend, void* dx, int B, int H, int W, int Cin,
                         int Cout, int KH, int KW, int stride, int pad, void* stream);
 int uda_conv2d_tc_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, int KH,
                         int KW, int stride, int pad, void* stream);
 
+/* Cin = 3 stems (U-Net 7x7 s2 p3, discriminator 4x4 s2 p1) on the tensor cores: the fp32 NCHW image is repacked
+ * into a zero-padded 4-channel bf16 buffer (uda_stem_packed_input_elems elements) whose kernel rows are K chunks of
+ * an overlapping-stride TMA view; weights are repacked to [Cout][K][8*4 or 4*4].  uda_stem_tc_wgrad accumulates
+ * into dw ([Cout][K][K][3] fp32) using dws_scratch (fp32 [Cout][K][32 or 16]). */
+int uda_stem_tc_supported(int B, int H, int W, int Cin, int Cout, int K, int stride, int pad);
+size_t uda_stem_packed_input_elems(int B, int H, int W);
+int uda_stem_pack_input(const float* x_nchw, void* xs, int B, int H, int W, int pad, void* stream);
+int uda_stem_pack_weight(const void* w, void* ws, int Cout, int K, void* stream);
+int uda_stem_tc_fwd(const void* xs, const void* ws, const float* bias, void* y, int B, int H, int W, int Cout, int K,
+                    int pad, void* stream);
+int uda_stem_tc_wgrad(const void* dy, const void* xs, float* dw, float* dws_scratch, int B, int H, int W, int Cout,
+                      int K, int pad, void* stream);
+
 /* BatchNorm2d (train: batch statistics; eps 1e-5, momentum 0.1 in the reference's graph).
- * x [M,C] NHWC rows.  uda_bn_stats: workspace 2*C doubles; writes mean/rstd/scale/shift (float[C])
- * and updates running statistics when non-NULL.  uda_bn_apply: y = act(x*scale+shift (+residual)),
- * slope 1 = identity, 0 = ReLU, 0.2 = LeakyReLU.  uda_bn_bwd: workspace 2*C doubles + 3*C floats;
+ * x [M,C] NHWC rows.  uda_bn_stats: writes mean/rstd/scale/shift (float[C]) and updates running statistics
+ * when non-NULL; the per-channel finalize runs in the last CTA of the same launch.  Its workspace (2*C+1
+ * doubles) and uda_bn_bwd's (2*C+1 doubles + 3*C floats) must be ZERO on entry and are left zero on exit
+ * (a dedicated, once-zeroed buffer: no per-call memset).  uda_bn_apply: y = act(x*scale+shift (+residual)),
+ * slope 1 = identity, 0 = ReLU, 0.2 = LeakyReLU.  uda_bn_bwd:
  * `a` = saved post-activation output (NULL for identity activation); dres (nullable) receives the
  * activation-masked gradient of the residual branch. */
 int uda_bn_stats(const void* x, int dtype, long long M, int C, const float* gamma, const float* beta,

@@ -14,6 +14,10 @@ import torch.nn.functional as F
 
 LAUNCHES = 0
 USE_TC = False
+
+
+def stem_supported(*a):
+    return False
 #: arithmetic dtype of the restatements; tests switch it to float64 to check the engine's backward
 #: *logic* free of the ReLU-mask-flip noise that fp32 round-off causes in deep randomly-initialised nets
 _F = torch.float32
@@ -296,3 +300,11 @@ def confmat(pred, target, num_classes, ignore_index=None, hist=None):
         hist += h
         h = hist
     return h, torch.zeros(1, dtype=torch.int64)
+
+
+def weight_flip_transpose_batch(base, out, table):
+    for off, O, I, KH, KW in table.tolist():
+        n = O * I * KH * KW
+        w = base[off:off + n].view(O, KH, KW, I)
+        out[off:off + n].copy_(w.flip(1, 2).permute(3, 1, 2, 0).reshape(-1))
+    return out

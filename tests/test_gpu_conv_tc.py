@@ -98,3 +98,32 @@ def test_unsupported_shapes_fall_back_loudly():
         _lib.call("conv2d_tc_fwd", _lib.ptr(torch.zeros(8, device=DEV)), _lib.ptr(torch.zeros(8, device=DEV)), None,
                   _lib.ptr(torch.zeros(8, device=DEV)), None, None, _lib.ci(2), _lib.ci(16), _lib.ci(16), _lib.ci(3),
                   _lib.ci(64), _lib.ci(7), _lib.ci(7), _lib.ci(2), _lib.ci(3), None)
+
+
+@pytest.mark.parametrize("cfg", [(2, 64, 64, 64, 7, 3), (2, 128, 256, 64, 7, 3), (2, 64, 64, 64, 4, 1), (16, 32, 32, 64, 7, 3)],
+                         ids=["unet_stem_64", "unet_stem_128x256", "disc_stem_64", "unet_stem_b16"])
+def test_stem_on_tensor_cores(cfg):
+    """Cin=3 stems (U-Net 7x7 s2 p3, discriminator 4x4 s2 p1) through the padded 4-channel row view."""
+    ops = _ops()
+    B, H, W, Cout, K, pad = cfg
+    assert ops.stem_supported(B, H, W, 3, Cout, K, 2, pad)
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, 3, H, W, generator=g).bfloat16().float()          # bf16-valued image
+    w = _rand((Cout, K, K, 3), 12, 0.1)
+    bias = torch.randn(Cout, generator=g)
+    xs = ops.stem_pack_input(x.to(DEV), pad)
+    assert xs.shape == (B, H + 8, W + 8, 4)
+    assert torch.equal(xs[:, pad:pad + H, pad:pad + W, :3].float().cpu(), x.permute(0, 2, 3, 1))
+    assert float(xs[..., 3].abs().max()) == 0 and float(xs[:, :pad].abs().max()) == 0
+    ws = ops.stem_pack_weight(w.to(DEV))
+    y = ops.stem_fwd(xs, ws, bias.to(DEV), H, W, K, pad)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    yr = R.conv_fwd(x_nhwc, w.float(), bias, 2, pad)
+    assert rel_err(y.float().cpu(), yr) < 1e-2
+    dy = _rand(tuple(yr.shape), 13)
+    dw = torch.zeros((Cout, K, K, 3), device=DEV)
+    ops.stem_wgrad(dy.to(DEV), xs, dw, H, W, K, pad)
+    dwr = R.conv_wgrad(dy.float(), x_nhwc, torch.zeros(Cout, K, K, 3), 2, pad)
+    assert rel_err(dw.cpu(), dwr) < 2e-3
+    ops.stem_wgrad(dy.to(DEV), xs, dw, H, W, K, pad)
+    assert rel_err(dw.cpu(), 2 * dwr) < 2e-3

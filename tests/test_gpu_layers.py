@@ -37,6 +37,11 @@ def test_layout_roundtrip(dtype):
     assert rel_err(y[..., :3].float().cpu(), x.permute(0, 2, 3, 1).to(dtype).float()) == 0
     back = ops.nhwc_to_nchw(y, C=3)
     assert rel_err(back.cpu(), x.to(dtype).float()) == 0
+    # small-channel fast path (logit gradients): C=24 -> NHWC, and a ragged spatial size
+    for shp in ((2, 24, 12, 20), (1, 5, 7, 9), (2, 32, 8, 8)):
+        zz = _rand(shp, torch.float32, 22)
+        yy = ops.nchw_to_nhwc(zz.to(DEV), dtype)
+        assert rel_err(yy.float().cpu(), zz.permute(0, 2, 3, 1).to(dtype).float()) == 0
     z = _rand((3, 24, 16, 16), torch.float32, 2)
     assert rel_err(ops.nhwc_to_nchw(ops.nchw_to_nhwc(z.to(DEV), dtype)).cpu(), z.to(dtype).float()) == 0
 

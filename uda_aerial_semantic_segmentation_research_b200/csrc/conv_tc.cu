@@ -223,6 +223,26 @@ __global__ void weight_flip_transpose_kernel(const bf16* __restrict__ w, bf16* _
   }
 }
 
+// all conv weights of a network in one launch: table[i] = {element offset, O, I, KH, KW}
+__global__ void weight_flip_transpose_batch_kernel(const bf16* __restrict__ base, bf16* __restrict__ out,
+                                                   const int* __restrict__ table) {
+  const int* e = table + 5 * blockIdx.y;
+  const long long off = e[0];
+  const int O = e[1], I = e[2], KH = e[3], KW = e[4];
+  const bf16* w = base + off;
+  bf16* wt = out + off;
+  const long long n = (long long)O * I * KH * KW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int co = (int)(i % O);
+    long long t = i / O;
+    const int kw = (int)(t % KW); t /= KW;
+    const int kh = (int)(t % KH);
+    const int ci = (int)(t / KH);
+    wt[i] = w[(((long long)co * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)) * I + ci];
+  }
+}
+
 int floor_div2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
 template <int KC, int BN>
@@ -680,10 +700,169 @@ int run_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int
   return set_error(UDA_ERR_UNSUPPORTED, "conv_tc_wgrad: no kernel instance for atoms %d/%d BN=%d", atomA, atomB, BN);
 }
 
+// ================================================================================================
+// Cin = 3 stems (U-Net 7x7 s2 p3, discriminator 4x4 s2 p1) on the tensor cores.
+//
+// The image is repacked once per forward into a zero-padded 4-channel bf16 buffer Xs[B][H+8][W+8][4]
+// (top/left border = pad).  For output pixel (ho,wo) and kernel row kh, the KS = 8 (k=7) or 4 (k=4)
+// consecutive padded pixels starting at column 2*wo of padded row 2*ho+kh are KS*4 contiguous elements:
+// a K chunk of 32 / 16 channels.  Consecutive output pixels start 2 pixels = 16 bytes apart, so the A
+// operand is an OVERLAPPING-stride TMA view {KS*4, Wo (16 B), 2 (row parity), (H+8)/2 (row pairs), B}: each
+// kernel row is one tap of a K=KS*4 implicit GEMM against weights repacked to [Cout][k][KS*4] (zero in the
+// padded slots).  Same kernels as every other convolution; only the tensor map differs.
+// ================================================================================================
+constexpr int kStemPad = 8;   // Xs rows = H + 8, cols = W + 8
+
+bool stem_shape_ok(int B, int H, int W, int Cin, int Cout, int K, int stride, int pad) {
+  if (Cin != 3 || stride != 2 || H % 2 || W % 2 || Cout % 8 || Cout < 8) return false;
+  if (!((K == 7 && pad == 3) || (K == 4 && pad == 1))) return false;
+  if ((H + 2 * pad - K) / 2 + 1 != H / 2 || (W + 2 * pad - K) / 2 + 1 != W / 2) return false;
+  return plan_tiles(B, H / 2, W / 2).ok;
+}
+inline int stem_slots(int K) { return K == 7 ? 8 : 4; }
+
+__global__ void stem_pack_input_kernel(const float* __restrict__ x, bf16* __restrict__ xs, int B, int H, int W,
+                                       int pad) {
+  const int Hp = H + kStemPad, Wp = W + kStemPad;
+  const long long total = (long long)B * Hp * Wp;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int wp = (int)(i % Wp);
+    long long t = i / Wp;
+    const int hp = (int)(t % Hp);
+    const int b = (int)(t / Hp);
+    const int h = hp - pad, w = wp - pad;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (h >= 0 && h < H && w >= 0 && w < W) {
+      const float* s = x + ((long long)b * 3 * H + h) * W + w;
+      v[0] = __ldg(s); v[1] = __ldg(s + (long long)H * W); v[2] = __ldg(s + 2LL * H * W);
+    }
+    st_vec<4>(xs + i * 4, v);
+  }
+}
+// w [Cout][K][K][3] bf16 -> ws [Cout][K][KS*4] bf16 (slot kw*4+c; zero elsewhere)
+__global__ void stem_pack_weight_kernel(const bf16* __restrict__ w, bf16* __restrict__ ws, int Cout, int K, int KS) {
+  const int n = Cout * K * KS * 4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = i % 4, kw = (i / 4) % KS, kh = (i / (4 * KS)) % K, co = i / (4 * KS * K);
+    ws[i] = (c < 3 && kw < K) ? w[((co * K + kh) * K + kw) * 3 + c] : __float2bfloat16_rn(0.f);
+  }
+}
+// dw [Cout][K][K][3] fp32 += dws [Cout][K][KS*4]
+__global__ void stem_unpack_wgrad_kernel(const float* __restrict__ dws, float* __restrict__ dw, int Cout, int K,
+                                         int KS) {
+  const int n = Cout * K * K * 3;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int c = i % 3, kw = (i / 3) % K, kh = (i / (3 * K)) % K, co = i / (3 * K * K);
+    dw[i] += dws[((co * K + kh) * KS + kw) * 4 + c];
+  }
+}
+
+int make_stem_map(CUtensorMap* m, const void* xs, int B, int H, int W, int K, const TilePlan& tp) {
+  const int KS = stem_slots(K);
+  const uint64_t Hp = H + kStemPad, Wp = W + kStemPad;
+  uint64_t dims[5] = {(uint64_t)KS * 4, (uint64_t)W / 2, 2, Hp / 2, (uint64_t)B};
+  uint64_t str[4] = {16, Wp * 8, 2 * Wp * 8, Hp * Wp * 8};
+  uint32_t box[5] = {(uint32_t)KS * 4, (uint32_t)tp.TW, 1, (uint32_t)tp.TH, (uint32_t)tp.NB};
+  return make_tmap_bf16(m, xs, 5, dims, str, box, KS * 8);
+}
+
+int run_stem_fwd(const void* xs, const void* ws, const float* bias, void* y, int B, int H, int W, int Cout, int K,
+                 cudaStream_t st) {
+  const TilePlan tp = plan_tiles(B, H / 2, W / 2);
+  CUtensorMap ma;
+  if (int rc = make_stem_map(&ma, xs, B, H, W, K, tp)) return rc;
+  GemmConv g{};
+  g.src = xs; g.B = B; g.SH = H; g.SW = W; g.Cred = stem_slots(K) * 4; g.src_s2 = 1;
+  g.wmat = ws; g.Cout = Cout; g.wtaps = K; g.ncls = 1;
+  TapClass& c = g.cls[0];
+  c.ntaps = K; c.oh = 0; c.ow = 0;
+  for (int kh = 0; kh < K; ++kh) { c.dh[kh] = kh >> 1; c.ph[kh] = kh & 1; c.dw[kh] = 0; c.pw[kh] = 0; c.wtap[kh] = kh; }
+  g.OH = H / 2; g.OW = W / 2; g.os = 1;
+  g.bias = bias; g.addend = nullptr; g.out = y; g.out_nchw = nullptr;
+  g.a_map = &ma; g.a_MH = H / 2; g.a_MW = W / 2; g.a_kc = stem_slots(K) * 4;
+  return run_gemm_conv_persistent(g, st);
+}
+
+int run_stem_wgrad(const void* dy, const void* xs, float* dws, int B, int H, int W, int Cout, int K,
+                   cudaStream_t st) {
+  const int Ho = H / 2, Wo = W / 2, KS = stem_slots(K);
+  const TilePlan tp = plan_tiles(B, Ho, Wo);
+  const int atomA = KS * 4;   // 32 or 16 "channels" per kernel row
+  const int atomB = Cout % 64 == 0 ? 64 : (Cout % 32 == 0 ? 32 : 16);
+  int BN = Cout >= 128 ? 128 : (Cout + atomB - 1) / atomB * atomB;
+  WgradParams p{};
+  p.TW = tp.TW; p.TH = tp.TH; p.NB = tp.NB; p.tiles_w = Wo / tp.TW; p.tiles_h = Ho / tp.TH;
+  p.Cin = atomA; p.Cout = Cout; p.ntaps = K; p.cchunks = 1; p.rank5 = 1;
+  for (int kh = 0; kh < K; ++kh) { p.dh[kh] = (signed char)(kh >> 1); p.ph[kh] = (signed char)(kh & 1); p.dw[kh] = 0; p.pw[kh] = 0; }
+  p.n_pixel_tiles = (B / tp.NB) * p.tiles_w * p.tiles_h;
+  p.dw_out = dws;
+  CUtensorMap mx, mdy;
+  if (int rc = make_stem_map(&mx, xs, B, H, W, K, tp)) return rc;
+  {
+    const uint64_t Co = (uint64_t)Cout;
+    uint64_t dims[4] = {Co, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)B};
+    uint64_t str[3] = {Co * 2, (uint64_t)Wo * Co * 2, (uint64_t)Ho * Wo * Co * 2};
+    uint32_t box[4] = {(uint32_t)atomB, (uint32_t)tp.TW, (uint32_t)tp.TH, (uint32_t)tp.NB};
+    if (int rc = make_tmap_bf16(&mdy, dy, 4, dims, str, box, atomB * 2)) return rc;
+  }
+#define UDA_WG(A, Bv, N) \
+  if (atomA == A && atomB == Bv && BN == N) return launch_wgrad<A, Bv, N>(mx, mdy, p, st);
+  UDA_WG(32, 64, 128) UDA_WG(32, 64, 64) UDA_WG(32, 32, 32) UDA_WG(32, 16, 16) UDA_WG(32, 16, 32)
+  UDA_WG(16, 64, 128) UDA_WG(16, 64, 64) UDA_WG(16, 32, 32) UDA_WG(16, 16, 16) UDA_WG(16, 16, 32)
+#undef UDA_WG
+  return set_error(UDA_ERR_UNSUPPORTED, "stem_wgrad: no kernel instance for atoms %d/%d BN=%d", atomA, atomB, BN);
+}
+
 }  // namespace
 }  // namespace uda
 
 using namespace uda;
+
+// ---- Cin = 3 stem entry points (xs: packed input of uda_stem_pack_input; ws: uda_stem_pack_weight) ----
+extern "C" int uda_stem_tc_supported(int B, int H, int W, int Cin, int Cout, int K, int stride, int pad) {
+  if (!uda_device_supported() || !use_persistent()) return 0;
+  return stem_shape_ok(B, H, W, Cin, Cout, K, stride, pad) ? 1 : 0;
+}
+extern "C" size_t uda_stem_packed_input_elems(int B, int H, int W) {
+  return (size_t)B * (H + kStemPad) * (W + kStemPad) * 4;
+}
+extern "C" int uda_stem_pack_input(const float* x_nchw, void* xs, int B, int H, int W, int pad, void* stream) {
+  UDA_REQUIRE(x_nchw && xs && B > 0 && H > 0 && W > 0 && pad >= 0 && pad <= 3, UDA_ERR_BAD_ARG, "stem_pack_input: bad argument");
+  const long long total = (long long)B * (H + kStemPad) * (W + kStemPad);
+  long long blocks = (total + 255) / 256;
+  if (blocks > 8LL * num_sms()) blocks = 8LL * num_sms();
+  stem_pack_input_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_nchw, (bf16*)xs, B, H, W, pad);
+  UDA_LAUNCH_OK("stem_pack_input_kernel");
+  return UDA_OK;
+}
+extern "C" int uda_stem_pack_weight(const void* w, void* ws, int Cout, int K, void* stream) {
+  UDA_REQUIRE(w && ws && Cout > 0 && (K == 7 || K == 4), UDA_ERR_BAD_ARG, "stem_pack_weight: bad argument");
+  const int KS = stem_slots(K), n = Cout * K * KS * 4;
+  stem_pack_weight_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>((const bf16*)w, (bf16*)ws, Cout, K, KS);
+  UDA_LAUNCH_OK("stem_pack_weight_kernel");
+  return UDA_OK;
+}
+extern "C" int uda_stem_tc_fwd(const void* xs, const void* ws, const float* bias, void* y, int B, int H, int W,
+                               int Cout, int K, int pad, void* stream) {
+  UDA_REQUIRE(xs && ws && y, UDA_ERR_BAD_ARG, "stem_tc_fwd: null pointer");
+  UDA_REQUIRE(stem_shape_ok(B, H, W, 3, Cout, K, 2, pad), UDA_ERR_UNSUPPORTED, "stem_tc_fwd: shape not covered");
+  return run_stem_fwd(xs, ws, bias, y, B, H, W, Cout, K, (cudaStream_t)stream);
+}
+// dw [Cout][K][K][3] fp32 += wgrad; dws_scratch: fp32 [Cout][K][KS*4] scratch (KS = 8 for K = 7, 4 for K = 4)
+extern "C" int uda_stem_tc_wgrad(const void* dy, const void* xs, float* dw, float* dws_scratch, int B, int H, int W,
+                                 int Cout, int K, int pad, void* stream) {
+  UDA_REQUIRE(dy && xs && dw && dws_scratch, UDA_ERR_BAD_ARG, "stem_tc_wgrad: null pointer");
+  UDA_REQUIRE(stem_shape_ok(B, H, W, 3, Cout, K, 2, pad), UDA_ERR_UNSUPPORTED, "stem_tc_wgrad: shape not covered");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int KS = stem_slots(K);
+  UDA_CUDA_OK(cudaMemsetAsync(dws_scratch, 0, (size_t)Cout * K * KS * 4 * sizeof(float), st));
+  if (int rc = run_stem_wgrad(dy, xs, dws_scratch, B, H, W, Cout, K, st)) return rc;
+  const int n = Cout * K * K * 3;
+  stem_unpack_wgrad_kernel<<<(n + 255) / 256, 256, 0, st>>>(dws_scratch, dw, Cout, K, KS);
+  UDA_LAUNCH_OK("stem_unpack_wgrad_kernel");
+  return UDA_OK;
+}
 
 extern "C" int uda_conv2d_tc_supported(int op, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride,
                                        int pad) {
@@ -718,6 +897,16 @@ extern "C" int uda_conv2d_weight_flip_transpose(const void* w, void* w_ft, int C
   if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
   weight_flip_transpose_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const bf16*)w, (bf16*)w_ft, Cout, Cin, KH, KW);
   UDA_LAUNCH_OK("weight_flip_transpose_kernel");
+  return UDA_OK;
+}
+
+extern "C" int uda_conv2d_weight_flip_transpose_batch(const void* w_base, void* w_ft_base, const int* table_dev,
+                                                      int n_weights, void* stream) {
+  UDA_REQUIRE(w_base && w_ft_base && table_dev && n_weights > 0 && n_weights <= 65535, UDA_ERR_BAD_ARG,
+              "weight_flip_transpose_batch: bad argument");
+  weight_flip_transpose_batch_kernel<<<dim3(48, (unsigned)n_weights), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)w_base, (bf16*)w_ft_base, table_dev);
+  UDA_LAUNCH_OK("weight_flip_transpose_batch_kernel");
   return UDA_OK;
 }
 

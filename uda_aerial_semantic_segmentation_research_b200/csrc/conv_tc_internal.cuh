@@ -44,6 +44,9 @@ struct GemmConv {
   int ncls; TapClass cls[kMaxClasses];
   int OH, OW, os;
   const float* bias; const void* addend; void* out; float* out_nchw;
+  // optional: caller-built A-operand tensor map (rank-5 coordinate form {c, w, ph, h, b}) over an M-grid of
+  // MH x MW pixels — used by the Cin=3 stem, whose A operand is a padded 4-channel row view of the image
+  const CUtensorMap* a_map; int a_MH, a_MW, a_kc;
 };
 
 inline int pick_kc(int c) {

@@ -262,14 +262,15 @@ int launch_persist(const CUtensorMap& ma, const CUtensorMap& mb, PParams& p, int
 }  // namespace
 
 int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
-  const int MH = g.src_s2 ? g.SH / 2 : g.SH, MW = g.src_s2 ? g.SW / 2 : g.SW;
-  const int KC = pick_kc(g.Cred), BN = pick_bn(g.Cout);
+  const int MH = g.a_map ? g.a_MH : (g.src_s2 ? g.SH / 2 : g.SH), MW = g.a_map ? g.a_MW : (g.src_s2 ? g.SW / 2 : g.SW);
+  const int KC = g.a_map ? g.a_kc : pick_kc(g.Cred), BN = pick_bn(g.Cout);
   UDA_REQUIRE(KC > 0 && g.ncls >= 1 && g.ncls <= kMaxClasses && g.Cout % 8 == 0, UDA_ERR_UNSUPPORTED,
               "conv_tc_persist: shape not covered (Cred=%d Cout=%d)", g.Cred, g.Cout);
   const int n_tiles = (g.Cout + BN - 1) / BN;
   // 256-pixel tiles when that still leaves at least two tiles per SM, else 128-pixel tiles
   TilePlan tp = plan_tiles(g.B, MH, MW, 256);
   int MT = 2;
+  if (g.a_map) tp.ok = false;   // caller-built maps use 128-pixel boxes
   if (tp.ok) {
     const long long t2 = (long long)g.ncls * n_tiles * ((long long)g.B * MH * MW / 256);
     if (t2 < 2LL * num_sms()) tp.ok = false;
@@ -283,7 +284,8 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
   p.TW = tp.TW; p.TH = tp.TH; p.NB = tp.NB; p.tiles_w = MW / tp.TW; p.tiles_h = MH / tp.TH;
   p.m_tiles = (g.B / tp.NB) * p.tiles_w * p.tiles_h; p.n_tiles = n_tiles; p.ncls = g.ncls;
   p.MH = MH; p.MW = MW; p.OH = g.OH; p.OW = g.OW; p.os = g.os;
-  p.Cout = g.Cout; p.Cred = g.Cred; p.kchunks = (g.Cred + KC - 1) / KC; p.rank5 = g.src_s2; p.wtaps = g.wtaps;
+  p.Cout = g.Cout; p.Cred = g.Cred; p.kchunks = (g.Cred + KC - 1) / KC; p.rank5 = (g.src_s2 || g.a_map) ? 1 : 0;
+  p.wtaps = g.wtaps;
   for (int c = 0; c < g.ncls; ++c) {
     const TapClass& s = g.cls[c];
     UDA_REQUIRE(s.ntaps >= 1 && s.ntaps <= kMaxTaps, UDA_ERR_BAD_ARG, "conv_tc_persist: bad tap class");
@@ -299,7 +301,9 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
 
   CUtensorMap ma, mb;
   const uint64_t C = (uint64_t)g.Cred, H = (uint64_t)g.SH, W = (uint64_t)g.SW;
-  if (!g.src_s2) {
+  if (g.a_map) {
+    ma = *g.a_map;
+  } else if (!g.src_s2) {
     uint64_t dims[4] = {C, W, H, (uint64_t)g.B};
     uint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};
     uint32_t box[4] = {(uint32_t)KC, (uint32_t)tp.TW, (uint32_t)tp.TH, (uint32_t)tp.NB};

@@ -21,6 +21,20 @@ inline unsigned grid_for(long long work_items, int per_sm = 8) {
   return (unsigned)blocks;
 }
 
+// grid whose total thread count is a multiple of `period` (= C/VEC channel vectors), so that a
+// grid-stride loop keeps every thread on the same channel vector
+inline unsigned grid_for_channels(long long work_items, int period, int per_sm = 8) {
+  long long blocks = (work_items + kThreads - 1) / kThreads;
+  long long cap = (long long)num_sms() * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  // kThreads * blocks must be a multiple of period
+  long long need = 1;
+  while ((need * kThreads) % period) ++need;   // period <= 512 in practice: tiny loop
+  blocks = (blocks + need - 1) / need * need;
+  return (unsigned)blocks;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Layout: per image, transpose a [C][HW] fp32 matrix <-> [HW][Cpad] T matrix through a 32x33 tile.
 // ---------------------------------------------------------------------------------------------
@@ -43,6 +57,38 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, T* __restrict
     long long p = p0 + i;
     int c = c0 + threadIdx.x;
     if (p < HW && c < Cpad) d[p * Cpad + c] = from_f<T>(tile[threadIdx.x][i]);
+  }
+}
+
+// Small channel counts (images: C=3, logit gradients: C<=32): one thread per pixel reads C planes
+// (coalesced across the warp) and writes its Cpad contiguous channels with 16-byte stores.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+nchw_to_nhwc_smallc_kernel(const float* __restrict__ src, T* __restrict__ dst, int B, int C, int Cpad, long long HW) {
+  const long long total = (long long)B * HW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / HW, p = i - b * HW;
+    const float* s = src + b * C * HW + p;
+    float v[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) v[c] = (c < C) ? __ldg(s + (long long)c * HW) : 0.f;
+    T* d = dst + i * Cpad;
+    if (Cpad % 8 == 0) {
+#pragma unroll
+      for (int c = 0; c < 32; c += 8) {
+        if (c < Cpad) {
+          float o[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) o[k] = v[c + k];
+          st_vec<8>(d + c, o);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 32; ++c)
+        if (c < Cpad) d[c] = from_f<T>(v[c]);
+    }
   }
 }
 
@@ -78,11 +124,69 @@ __global__ void cast_f32_kernel(const float* __restrict__ src, T* __restrict__ d
 // ---------------------------------------------------------------------------------------------
 // BatchNorm.  x is [M][C] (M = B*H*W rows, C innermost).  VEC channels per thread.
 // ---------------------------------------------------------------------------------------------
+// mean/var -> scale/shift (+ running statistics update, momentum, unbiased running var)
+struct BnFwdFinal {
+  const float* gamma; const float* beta; float* running_mean; float* running_var;
+  float* mean_out; float* rstd_out; float* scale_out; float* shift_out;
+  long long M; float eps, momentum;
+  unsigned int* counter;   // zero on entry, zero again on exit
+};
+__device__ __forceinline__ void bn_fwd_finalize_channel(const BnFwdFinal& f, double s1, double s2, int c) {
+  double mean = s1 / (double)f.M;
+  double var = s2 / (double)f.M - mean * mean;
+  if (var < 0.0) var = 0.0;
+  double rstd = 1.0 / sqrt(var + (double)f.eps);
+  float g = f.gamma ? f.gamma[c] : 1.f, b = f.beta ? f.beta[c] : 0.f;
+  f.mean_out[c] = (float)mean;
+  f.rstd_out[c] = (float)rstd;
+  f.scale_out[c] = (float)((double)g * rstd);
+  f.shift_out[c] = (float)((double)b - mean * (double)g * rstd);
+  if (f.running_mean) {
+    double unb = (f.M > 1) ? var * (double)f.M / (double)(f.M - 1) : var;
+    f.running_mean[c] = (float)((1.0 - f.momentum) * (double)f.running_mean[c] + f.momentum * mean);
+    f.running_var[c] = (float)((1.0 - f.momentum) * (double)f.running_var[c] + f.momentum * unb);
+  }
+}
+
+// "last block done": returns true in every thread of the block that finished last (all partial sums of
+// all blocks are then visible).  Classic threadfence reduction pattern.
+__device__ __forceinline__ bool last_block_done(unsigned int* counter) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == total - 1);
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// dgamma = sums[C+c], dbeta = sums[c] (accumulated into fp32 grads), and the per-channel
+// coefficients of the apply pass:  dx = k0*g - k1 - k2*xhat
+struct BnBwdFinal {
+  const float* gamma; const float* rstd; float* dgamma; float* dbeta; float* coef;
+  long long M; int accumulate;
+  unsigned int* counter;
+};
+__device__ __forceinline__ void bn_bwd_finalize_channel(const BnBwdFinal& f, double s1, double s2, int c, int C) {
+  float g = f.gamma ? f.gamma[c] : 1.f;
+  double k0 = (double)g * (double)f.rstd[c];
+  if (f.dgamma) f.dgamma[c] = (f.accumulate ? f.dgamma[c] : 0.f) + (float)s2;
+  if (f.dbeta) f.dbeta[c] = (f.accumulate ? f.dbeta[c] : 0.f) + (float)s1;
+  f.coef[c] = (float)k0;
+  f.coef[C + c] = (float)(k0 * s1 / (double)f.M);
+  f.coef[2 * C + c] = (float)(k0 * s2 / (double)f.M);
+}
+
 // sums[c] += sum_rows x, sums[C+c] += sum_rows x^2   (double accumulators, zeroed by the host)
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
-bn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, long long M, int Ctot, int C) {
-  // blockIdx.y selects a slab of C channels out of Ctot (C <= blockDim.x * VEC)
+bn_stats_kernel(const T* __restrict__ x, double* sums, long long M, int Ctot, int C, const BnFwdFinal fin) {
+  // blockIdx.y selects a slab of C channels out of Ctot (C <= blockDim.x * VEC).  Each thread owns one
+  // channel vector and walks rows with 4 independent 16-byte loads in flight.
   extern __shared__ float sh[];  // [groups][C][2]
   const int c_off = blockIdx.y * C;
   x += c_off;
@@ -93,11 +197,24 @@ bn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, long long M,
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   if (g < groups) {
-    for (long long r = (long long)blockIdx.x * groups + g; r < M; r += (long long)gridDim.x * groups) {
-      float xv[VEC];
-      ld_vec<VEC>(x + r * Ctot + v * VEC, xv);
+    const long long stride = (long long)gridDim.x * groups;
+    const T* px = x + v * VEC;
+    for (long long r = (long long)blockIdx.x * groups + g; r < M; r += 4 * stride) {
+      float xv[4][VEC];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) { s1[j] += xv[j]; s2[j] += xv[j] * xv[j]; }
+      for (int u = 0; u < 4; ++u) {
+        const long long rr = r + u * stride;
+        if (rr < M) {
+          ld_vec<VEC>(px + rr * Ctot, xv[u]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) xv[u][j] = 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) { s1[j] += xv[u][j]; s2[j] += xv[u][j] * xv[u][j]; }
     }
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -112,29 +229,13 @@ bn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, long long M,
     for (int gg = 0; gg < groups; ++gg) a += (double)sh[(gg * C + c) * 2 + k];
     atomicAdd(sums + k * Ctot + c_off + c, a);
   }
-}
-
-// mean/var -> scale/shift (+ running statistics update, momentum, unbiased running var)
-__global__ void bn_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
-                                   const float* __restrict__ beta, float* __restrict__ running_mean,
-                                   float* __restrict__ running_var, float* __restrict__ mean_out,
-                                   float* __restrict__ rstd_out, float* __restrict__ scale_out,
-                                   float* __restrict__ shift_out, long long M, int C, float eps, float momentum) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double mean = sums[c] / (double)M;
-  double var = sums[C + c] / (double)M - mean * mean;
-  if (var < 0.0) var = 0.0;
-  double rstd = 1.0 / sqrt(var + (double)eps);
-  float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
-  mean_out[c] = (float)mean;
-  rstd_out[c] = (float)rstd;
-  scale_out[c] = (float)((double)g * rstd);
-  shift_out[c] = (float)((double)b - mean * (double)g * rstd);
-  if (running_mean) {
-    double unb = (M > 1) ? var * (double)M / (double)(M - 1) : var;
-    running_mean[c] = (float)((1.0 - momentum) * (double)running_mean[c] + momentum * mean);
-    running_var[c] = (float)((1.0 - momentum) * (double)running_var[c] + momentum * unb);
+  if (last_block_done(fin.counter)) {   // fused finalize; leaves the workspace zeroed for the next call
+    for (int c = threadIdx.x; c < Ctot; c += blockDim.x) {
+      const double s1 = __ldcg(sums + c), s2 = __ldcg(sums + Ctot + c);
+      bn_fwd_finalize_channel(fin, s1, s2, c);
+      sums[c] = 0.0; sums[Ctot + c] = 0.0;
+    }
+    if (threadIdx.x == 0) *fin.counter = 0u;
   }
 }
 
@@ -157,22 +258,38 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
                 const float* __restrict__ scale, const float* __restrict__ shift, long long n, int C, float slope) {
+  // The host sizes the grid so that (gridDim.x*blockDim.x) % (C/VEC) == 0: a thread then always sees the
+  // same channel vector and keeps its scale/shift in registers; 4 vectors in flight per thread.
   const long long nv = n / VEC;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)((i * VEC) % C);
-    float xv[VEC], rv[VEC], sc[VEC], sf[VEC];
-    ld_vec<VEC>(x + i * VEC, xv);
-    if (residual) ld_vec<VEC>(residual + i * VEC, rv);
-    ld_vec<VEC>(scale + c, sc);
-    ld_vec<VEC>(shift + c, sf);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)((i0 * VEC) % C);
+  float sc[VEC], sf[VEC];
+  ld_vec<VEC>(scale + c, sc);
+  ld_vec<VEC>(shift + c, sf);
+  for (long long i = i0; i < nv; i += 4 * stride) {
+    float xv[4][VEC], rv[4][VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      float v = xv[j] * sc[j] + sf[j];
-      if (residual) v += rv[j];
-      xv[j] = act_fwd(v, slope);
+    for (int u = 0; u < 4; ++u) {
+      const long long ii = i + u * stride;
+      if (ii < nv) {
+        ld_vec<VEC>(x + ii * VEC, xv[u]);
+        if (residual) ld_vec<VEC>(residual + ii * VEC, rv[u]);
+      }
     }
-    st_vec<VEC>(y + i * VEC, xv);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long ii = i + u * stride;
+      if (ii < nv) {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float v = xv[u][j] * sc[j] + sf[j];
+          if (residual) v += rv[u][j];
+          xv[u][j] = act_fwd(v, slope);
+        }
+        st_vec<VEC>(y + ii * VEC, xv[u]);
+      }
+    }
   }
 }
 
@@ -182,7 +299,7 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ a,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
-                     double* __restrict__ sums, long long M, int Ctot, int C, float slope) {
+                     double* sums, long long M, int Ctot, int C, float slope, const BnBwdFinal fin) {
   extern __shared__ float sh[];
   const int c_off = blockIdx.y * C;
   dy += c_off; x += c_off; if (a) a += c_off;
@@ -197,18 +314,31 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
     float mu[VEC], rs[VEC];
     ld_vec<VEC>(mean + v * VEC, mu);
     ld_vec<VEC>(rstd + v * VEC, rs);
-    for (long long r = (long long)blockIdx.x * groups + g; r < M; r += (long long)gridDim.x * groups) {
-      float dv[VEC], xv[VEC], av[VEC];
-      ld_vec<VEC>(dy + r * Ctot + v * VEC, dv);
-      ld_vec<VEC>(x + r * Ctot + v * VEC, xv);
-      if (a) ld_vec<VEC>(a + r * Ctot + v * VEC, av);
+    const long long stride = (long long)gridDim.x * groups;
+    const long long co = v * VEC;
+    for (long long r = (long long)blockIdx.x * groups + g; r < M; r += 2 * stride) {
+      float dv[2][VEC], xv[2][VEC], av[2][VEC];
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        float gg = dv[j];
-        if (a) gg *= (av[j] > 0.f) ? 1.f : slope;
-        s1[j] += gg;
-        s2[j] += gg * (xv[j] - mu[j]) * rs[j];
+      for (int u = 0; u < 2; ++u) {
+        const long long rr = r + u * stride;
+        if (rr < M) {
+          ld_vec<VEC>(dy + rr * Ctot + co, dv[u]);
+          ld_vec<VEC>(x + rr * Ctot + co, xv[u]);
+          if (a) ld_vec<VEC>(a + rr * Ctot + co, av[u]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) { dv[u][j] = 0.f; xv[u][j] = 0.f; av[u][j] = 1.f; }
+        }
       }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float gg = dv[u][j];
+          if (a) gg *= (av[u][j] > 0.f) ? 1.f : slope;
+          s1[j] += gg;
+          s2[j] += gg * (xv[u][j] - mu[j]) * rs[j];
+        }
     }
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
@@ -223,24 +353,14 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
     for (int gg = 0; gg < groups; ++gg) acc += (double)sh[(gg * C + c) * 2 + k];
     atomicAdd(sums + k * Ctot + c_off + c, acc);
   }
-}
-
-// dgamma = sums[C+c], dbeta = sums[c] (accumulated into fp32 grads), and the per-channel
-// coefficients of the apply pass:  dx = k0*g - k1 - k2*xhat
-__global__ void bn_bwd_finalize_kernel(const double* __restrict__ sums, const float* __restrict__ gamma,
-                                       const float* __restrict__ rstd, float* __restrict__ dgamma,
-                                       float* __restrict__ dbeta, float* __restrict__ coef, long long M, int C,
-                                       int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = sums[c], s2 = sums[C + c];
-  float g = gamma ? gamma[c] : 1.f;
-  double k0 = (double)g * (double)rstd[c];
-  if (dgamma) dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s2;
-  if (dbeta) dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s1;
-  coef[c] = (float)k0;
-  coef[C + c] = (float)(k0 * s1 / (double)M);
-  coef[2 * C + c] = (float)(k0 * s2 / (double)M);
+  if (last_block_done(fin.counter)) {
+    for (int c = threadIdx.x; c < Ctot; c += blockDim.x) {
+      const double s1 = __ldcg(sums + c), s2 = __ldcg(sums + Ctot + c);
+      bn_bwd_finalize_channel(fin, s1, s2, c, Ctot);
+      sums[c] = 0.0; sums[Ctot + c] = 0.0;
+    }
+    if (threadIdx.x == 0) *fin.counter = 0u;
+  }
 }
 
 // dx = k0*g - k1 - k2*xhat ;  optionally d_residual (+)= g  (identity branch of a residual block)
@@ -248,31 +368,48 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ a,
                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const float* __restrict__ coef, T* __restrict__ dx, T* __restrict__ dres, int dres_accumulate,
+                    const float* __restrict__ coef, T* __restrict__ dx, T* dres, int dres_accumulate,
                     long long n, int C, float slope) {
+  // grid sized so that a thread always sees the same channel vector (see bn_apply_kernel)
   const long long nv = n / VEC;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nv;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)((i * VEC) % C);
-    float dv[VEC], xv[VEC], av[VEC], mu[VEC], rs[VEC], k0[VEC], k1[VEC], k2[VEC], ov[VEC], rv[VEC];
-    ld_vec<VEC>(dy + i * VEC, dv);
-    ld_vec<VEC>(x + i * VEC, xv);
-    if (a) ld_vec<VEC>(a + i * VEC, av);
-    ld_vec<VEC>(mean + c, mu);
-    ld_vec<VEC>(rstd + c, rs);
-    ld_vec<VEC>(coef + c, k0);
-    ld_vec<VEC>(coef + C + c, k1);
-    ld_vec<VEC>(coef + 2 * C + c, k2);
-    if (dres && dres_accumulate) ld_vec<VEC>(dres + i * VEC, rv);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = (int)((i0 * VEC) % C);
+  float mu[VEC], rs[VEC], k0[VEC], k1[VEC], k2[VEC];
+  ld_vec<VEC>(mean + c, mu);
+  ld_vec<VEC>(rstd + c, rs);
+  ld_vec<VEC>(coef + c, k0);
+  ld_vec<VEC>(coef + C + c, k1);
+  ld_vec<VEC>(coef + 2 * C + c, k2);
+  const bool racc = dres && dres_accumulate;
+  for (long long i = i0; i < nv; i += 2 * stride) {
+    float dv[2][VEC], xv[2][VEC], av[2][VEC], rv[2][VEC];
 #pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      float g = dv[j];
-      if (a) g *= (av[j] > 0.f) ? 1.f : slope;
-      ov[j] = k0[j] * g - k1[j] - k2[j] * (xv[j] - mu[j]) * rs[j];
-      dv[j] = (dres && dres_accumulate) ? rv[j] + g : g;
+    for (int u = 0; u < 2; ++u) {
+      const long long ii = i + u * stride;
+      if (ii < nv) {
+        ld_vec<VEC>(dy + ii * VEC, dv[u]);
+        ld_vec<VEC>(x + ii * VEC, xv[u]);
+        if (a) ld_vec<VEC>(a + ii * VEC, av[u]);
+        if (racc) ld_vec<VEC>(dres + ii * VEC, rv[u]);
+      }
     }
-    st_vec<VEC>(dx + i * VEC, ov);
-    if (dres) st_vec<VEC>(dres + i * VEC, dv);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long ii = i + u * stride;
+      if (ii < nv) {
+        float ov[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) {
+          float g = dv[u][j];
+          if (a) g *= (av[u][j] > 0.f) ? 1.f : slope;
+          ov[j] = k0[j] * g - k1[j] - k2[j] * (xv[u][j] - mu[j]) * rs[j];
+          dv[u][j] = racc ? rv[u][j] + g : g;
+        }
+        st_vec<VEC>(dx + ii * VEC, ov);
+        if (dres) st_vec<VEC>(dres + ii * VEC, dv[u]);
+      }
+    }
   }
 }
 
@@ -627,6 +764,15 @@ extern "C" int uda_nchw_f32_to_nhwc(const float* src, void* dst, int dtype, int 
                                     long long HW, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   UDA_REQUIRE(src && dst && B > 0 && C > 0 && Cpad >= C && HW > 0, UDA_ERR_BAD_ARG, "nchw_to_nhwc: bad argument");
+  if (Cpad <= 32) {
+    const bool v8 = reinterpret_cast<uintptr_t>(dst) % 16 == 0;
+    UDA_REQUIRE(v8 || Cpad % 8, UDA_ERR_BAD_ARG, "nchw_to_nhwc: destination must be 16-byte aligned");
+#define K(T, ...) nchw_to_nhwc_smallc_kernel<T><<<grid_for((long long)B * HW), kThreads, 0, st>>>(src, (T*)dst, B, C, Cpad, HW)
+    UDA_DT(dtype, K, 0);
+#undef K
+    UDA_LAUNCH_OK("nchw_to_nhwc_smallc_kernel");
+    return UDA_OK;
+  }
   dim3 grid((unsigned)((HW + 31) / 32), (unsigned)((Cpad + 31) / 32), (unsigned)B), block(32, 8);
   UDA_REQUIRE(B <= 65535 && grid.y <= 65535, UDA_ERR_UNSUPPORTED, "nchw_to_nhwc: shape too large");
 #define K(T, ...) nchw_to_nhwc_kernel<T><<<grid, block, 0, st>>>(src, (T*)dst, C, Cpad, HW)
@@ -667,8 +813,9 @@ extern "C" int uda_bn_stats(const void* x, int dtype, long long M, int C, const 
   cudaStream_t st = (cudaStream_t)stream;
   UDA_REQUIRE(x && mean && rstd && scale && shift && workspace, UDA_ERR_BAD_ARG, "bn_stats: null pointer");
   UDA_REQUIRE(M > 0 && C > 0 && C <= 4096, UDA_ERR_BAD_ARG, "bn_stats: bad shape M=%lld C=%d", M, C);
-  double* sums = (double*)workspace;
-  UDA_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st));
+  double* sums = (double*)workspace;                      // zero on entry (contract), zero again on exit
+  BnFwdFinal fin{gamma, beta, running_mean, running_var, mean, rstd, scale, shift, M, eps, momentum,
+                 reinterpret_cast<unsigned int*>(sums + 2 * C)};
   const int vec = vec_for(dtype, C, x);
   int slabs = 1;
   while ((C / slabs) / vec > kThreads || (C % slabs)) ++slabs;  // channel slabs of <= 256*vec channels
@@ -676,19 +823,16 @@ extern "C" int uda_bn_stats(const void* x, int dtype, long long M, int C, const 
   UDA_REQUIRE(Cs % vec == 0, UDA_ERR_UNSUPPORTED, "bn_stats: C=%d not supported", C);
   const int groups = kThreads / (Cs / vec);
   long long blocks = (M + groups - 1) / groups;
-  long long cap = ((long long)num_sms() * 4 + slabs - 1) / slabs;
+  long long cap = ((long long)num_sms() * 8 + slabs - 1) / slabs;
   if (blocks > cap) blocks = cap;
   size_t smem = (size_t)groups * Cs * 2 * sizeof(float);
   UDA_REQUIRE(smem <= 48 * 1024, UDA_ERR_UNSUPPORTED, "bn_stats: C=%d needs too much shared memory", C);
-#define K(T, V) bn_stats_kernel<T, V><<<dim3((unsigned)blocks, slabs), kThreads, smem, st>>>((const T*)x, sums, M, C, Cs)
+#define K(T, V) bn_stats_kernel<T, V><<<dim3((unsigned)blocks, slabs), kThreads, smem, st>>>((const T*)x, sums, M, C, Cs, fin)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV
 #undef K
   UDA_LAUNCH_OK("bn_stats_kernel");
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, gamma, beta, running_mean, running_var, mean, rstd,
-                                                      scale, shift, M, C, eps, momentum);
-  UDA_LAUNCH_OK("bn_finalize_kernel");
   return UDA_OK;
 }
 
@@ -709,7 +853,7 @@ extern "C" int uda_bn_apply(const void* x, const void* residual, void* y, int dt
   int vec = vec_for(dtype, C, x, residual, y);
   if (reinterpret_cast<uintptr_t>(scale) % 16 || reinterpret_cast<uintptr_t>(shift) % 16) vec = 1;
   const long long n = M * C;
-#define K(T, V) bn_apply_kernel<T, V><<<grid_for(n / V), kThreads, 0, st>>>((const T*)x, (const T*)residual, (T*)y, scale, shift, n, C, slope)
+#define K(T, V) bn_apply_kernel<T, V><<<grid_for_channels(n / V / 4, C / V), kThreads, 0, st>>>((const T*)x, (const T*)residual, (T*)y, scale, shift, n, C, slope)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV
@@ -726,9 +870,10 @@ extern "C" int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtyp
   cudaStream_t st = (cudaStream_t)stream;
   UDA_REQUIRE(dy && x && mean && rstd && dx && workspace, UDA_ERR_BAD_ARG, "bn_bwd: null pointer");
   UDA_REQUIRE(M > 0 && C > 0 && C <= 4096, UDA_ERR_BAD_ARG, "bn_bwd: bad shape");
-  double* sums = (double*)workspace;
-  float* coef = (float*)(sums + 2 * C);
-  UDA_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * C * sizeof(double), st));
+  double* sums = (double*)workspace;                      // zero on entry (contract), zero again on exit
+  unsigned int* counter = reinterpret_cast<unsigned int*>(sums + 2 * C);
+  float* coef = (float*)(sums + 2 * C + 2);   // keep 16-byte alignment
+  BnBwdFinal fin{gamma, rstd, dgamma, dbeta, coef, M, param_accumulate, counter};
   int vec = vec_for(dtype, C, dy, x, a, dx);
   if (dres) vec = vec < vec_for(dtype, C, dres) ? vec : vec_for(dtype, C, dres);
   if (vec > 1 && (reinterpret_cast<uintptr_t>(mean) % 16 || reinterpret_cast<uintptr_t>(rstd) % 16 ||
@@ -740,20 +885,18 @@ extern "C" int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtyp
   UDA_REQUIRE(Cs % rvec == 0, UDA_ERR_UNSUPPORTED, "bn_bwd: C=%d not supported", C);
   const int groups = kThreads / (Cs / rvec);
   long long blocks = (M + groups - 1) / groups;
-  long long cap = ((long long)num_sms() * 4 + slabs - 1) / slabs;
+  long long cap = ((long long)num_sms() * 8 + slabs - 1) / slabs;
   if (blocks > cap) blocks = cap;
   size_t smem = (size_t)groups * Cs * 2 * sizeof(float);
   UDA_REQUIRE(smem <= 48 * 1024, UDA_ERR_UNSUPPORTED, "bn_bwd: C=%d needs too much shared memory", C);
-#define K(T, V) bn_bwd_reduce_kernel<T, V><<<dim3((unsigned)blocks, slabs), kThreads, smem, st>>>((const T*)dy, (const T*)x, (const T*)a, mean, rstd, sums, M, C, Cs, slope)
+#define K(T, V) bn_bwd_reduce_kernel<T, V><<<dim3((unsigned)blocks, slabs), kThreads, smem, st>>>((const T*)dy, (const T*)x, (const T*)a, mean, rstd, sums, M, C, Cs, slope, fin)
 #define KV(T, ...) do { if (rvec == 8) K(T, 8); else if (rvec == 4) K(T, 4); else if (rvec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV
 #undef K
   UDA_LAUNCH_OK("bn_bwd_reduce_kernel");
-  bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, gamma, rstd, dgamma, dbeta, coef, M, C, param_accumulate);
-  UDA_LAUNCH_OK("bn_bwd_finalize_kernel");
   const long long n = M * C;
-#define K(T, V) bn_bwd_apply_kernel<T, V><<<grid_for(n / V), kThreads, 0, st>>>((const T*)dy, (const T*)x, (const T*)a, mean, rstd, coef, (T*)dx, (T*)dres, dres_accumulate, n, C, slope)
+#define K(T, V) bn_bwd_apply_kernel<T, V><<<grid_for_channels(n / V / 2, C / V), kThreads, 0, st>>>((const T*)dy, (const T*)x, (const T*)a, mean, rstd, coef, (T*)dx, (T*)dres, dres_accumulate, n, C, slope)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV
@@ -805,7 +948,7 @@ extern "C" int uda_colsum(const void* x, int dtype, float* out, long long M, int
   UDA_REQUIRE(Cs % vec == 0, UDA_ERR_UNSUPPORTED, "colsum: C=%d not supported", C);
   const int groups = kThreads / (Cs / vec);
   long long blocks = (M + groups - 1) / groups;
-  long long cap = ((long long)num_sms() * 4 + slabs - 1) / slabs;
+  long long cap = ((long long)num_sms() * 8 + slabs - 1) / slabs;
   if (blocks > cap) blocks = cap;
   size_t smem = (size_t)groups * Cs * sizeof(float);
 #define K(T, V) colsum_kernel<T, V><<<dim3((unsigned)blocks, slabs), kThreads, smem, st>>>((const T*)x, sums, M, C, Cs)

@@ -82,7 +82,7 @@ class DomainDiscriminator(nn.Module):
         tape = Tape() if record else None
         ctx = Ctx(self._store, dtype, self.training, tape)
         ctx.sync = self._grad_sync
-        xin = Var(ops.nchw_to_nhwc(x.contiguous().float(), dtype))
+        xin = E.input_var(x, dtype, self.features[0], record and x.requires_grad)
         f = self.features
         y = E.bias_act(ctx, E.conv(ctx, xin, f[0]), 0.2)
         for ci, bi in ((2, 3), (5, 6), (8, 9)):

@@ -16,12 +16,24 @@ from . import ops
 
 
 class Var:
-    """An activation (NHWC tensor) plus its gradient slot on the tape."""
-    __slots__ = ("t", "g")
+    """An activation (NHWC tensor) plus its gradient slot on the tape.  A network input that feeds a
+    tensor-core stem keeps the raw fp32 NCHW image in ``nchw`` instead (``t`` is None)."""
+    __slots__ = ("t", "g", "nchw")
 
-    def __init__(self, t):
+    def __init__(self, t, nchw=None):
         self.t = t
         self.g = None
+        self.nchw = nchw
+
+
+def input_var(x, dtype, cp, need_grad):
+    """Network input: NHWC copy, or (Cin=3 stem on the tensor cores, no input gradient needed) the raw image."""
+    x = x.contiguous().float()
+    B, C, H, W = x.shape
+    if (dtype == torch.bfloat16 and not need_grad and x.is_cuda
+            and ops.stem_supported(B, H, W, C, cp.out_channels, cp.kernel_size, cp.stride, cp.padding)):
+        return Var(None, nchw=x)
+    return Var(ops.nchw_to_nhwc(x, dtype))
 
 
 class Tape:
@@ -138,6 +150,7 @@ class ParamStore:
         self.shadow_ft = torch.empty(self.total, dtype=torch.bfloat16, device=device)
         self.shadow_version = None
         self.shadow_ft_version = None
+        self._ft_table = None
 
     def refresh_shadow(self, force=False):
         ver = self.flat._version
@@ -153,12 +166,11 @@ class ParamStore:
         """[Cin][KH][KW][Cout] flipped/transposed bf16 copy of conv weight ``p`` (dgrad on the tensor cores);
         all copies are refreshed together, lazily, the first time a backward needs them after an update."""
         if self.shadow_ft_version != self.flat._version or self.shadow_ft_version is None:
-            for q in self.params:
-                if q.dim() == 4:
-                    O, I, KH, KW = q.shape
-                    off = self.offsets[id(q)]
-                    ops.weight_flip_transpose(self.shadow[off:off + q.numel()].view(O, KH, KW, I),
-                                              self.shadow_ft[off:off + q.numel()].view(I, KH, KW, O))
+            if self._ft_table is None:
+                rows = [[self.offsets[id(q)]] + [q.shape[0], q.shape[1], q.shape[2], q.shape[3]]
+                        for q in self.params if q.dim() == 4]
+                self._ft_table = torch.tensor(rows, dtype=torch.int32, device=self.flat.device).contiguous()
+            ops.weight_flip_transpose_batch(self.shadow, self.shadow_ft, self._ft_table)
             self.shadow_ft_version = self.flat._version
         off = self.offsets[id(p)]
         O, I, KH, KW = p.shape
@@ -211,6 +223,23 @@ def conv(ctx, xin, cp, nchw_out=False):
     """y = conv(x) (+bias).  Returns Var (NHWC) or, with nchw_out, a raw fp32 NCHW tensor + grad hook."""
     st = ctx.store
     w = st.w(cp.weight, ctx.dtype)
+    if xin.t is None:   # Cin = 3 stem on the tensor cores (see ops.stem_*)
+        H, W = xin.nchw.shape[2:]
+        K, pad = cp.kernel_size, cp.padding
+        xs = ops.stem_pack_input(xin.nchw, pad)
+        out = Var(ops.stem_fwd(xs, ops.stem_pack_weight(w), cp.bias, H, W, K, pad))
+        if ctx.tape is not None:
+            def bwd_stem():
+                dy = out.g
+                out.g = None
+                if dy is None:
+                    return
+                if cp.bias is not None:
+                    ops.colsum(dy, st.g(cp.bias))
+                ops.stem_wgrad(dy, xs, st.g(cp.weight), H, W, K, pad)
+                ctx.done(cp.weight, cp.bias)
+            ctx.tape.push(bwd_stem)
+        return out
     y = ops.conv_fwd(xin.t, w, cp.bias, cp.stride, cp.padding, nchw_out=nchw_out)
     out = Var(y)
     if ctx.tape is not None:

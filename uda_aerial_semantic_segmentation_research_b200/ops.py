@@ -67,6 +67,20 @@ def workspace(nbytes, device):
     return ws
 
 
+_BN_WS = {}
+
+
+def bn_workspace(device, C):
+    """Once-zeroed scratch of the BatchNorm reductions (the kernels leave it zeroed: no per-call memset)."""
+    key = (device.index if device.index is not None else torch.cuda.current_device())
+    ws = _BN_WS.get(key)
+    need = (2 * C + 2) * 8 + 3 * C * 4 + 64
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros(max(need, 1 << 17), dtype=torch.uint8, device=device)
+        _BN_WS[key] = ws
+    return ws
+
+
 # ------------------------------------------------------------------------------------------------
 # layout
 # ------------------------------------------------------------------------------------------------
@@ -153,6 +167,65 @@ def weight_flip_transpose(w, out=None):
     return out
 
 
+# ---- Cin = 3 stems on the tensor cores ----------------------------------------------------------
+def stem_supported(B, H, W, Cin, Cout, K, stride, pad):
+    if not USE_TC:
+        return False
+    return bool(_lib.lib().uda_stem_tc_supported(ci(B), ci(H), ci(W), ci(Cin), ci(Cout), ci(K), ci(stride), ci(pad)))
+
+
+def stem_pack_input(x, pad):
+    """fp32 NCHW image -> zero-padded 4-channel bf16 buffer [B, H+8, W+8, 4]."""
+    _chk(x, "stem_pack_input.x", torch.float32)
+    B, C, H, W = x.shape
+    if C != 3:
+        raise _lib.UdaError("stem_pack_input: expected 3 input channels")
+    xs = torch.empty((B, H + 8, W + 8, 4), dtype=torch.bfloat16, device=x.device)
+    call("stem_pack_input", ptr(x), ptr(xs), ci(B), ci(H), ci(W), ci(pad), _stream())
+    _count()
+    return xs
+
+
+def stem_pack_weight(w):
+    """OHWI bf16 [Cout,K,K,3] -> [Cout, K, KS*4] with KS = 8 (K=7) or 4 (K=4)."""
+    _chk(w, "stem_pack_weight.w", torch.bfloat16)
+    O, K, _, I = w.shape
+    KS = 8 if K == 7 else 4
+    ws = torch.empty((O, K, KS * 4), dtype=torch.bfloat16, device=w.device)
+    call("stem_pack_weight", ptr(w), ptr(ws), ci(O), ci(K), _stream())
+    _count()
+    return ws
+
+
+def stem_fwd(xs, ws, bias, H, W, K, pad):
+    B = xs.shape[0]
+    O = ws.shape[0]
+    y = torch.empty((B, H // 2, W // 2, O), dtype=torch.bfloat16, device=xs.device)
+    call("stem_tc_fwd", ptr(xs), ptr(ws), ptr(bias), ptr(y), ci(B), ci(H), ci(W), ci(O), ci(K), ci(pad), _stream())
+    _tc_account(B, H // 2, W // 2, O, 3, K, K)
+    _count()
+    return y
+
+
+def stem_wgrad(dy, xs, dw, H, W, K, pad):
+    """dw (fp32 OHWI [Cout,K,K,3]) += wgrad."""
+    _chk(dy, "stem_wgrad.dy", torch.bfloat16); _chk(dw, "stem_wgrad.dw", torch.float32)
+    B, O = xs.shape[0], dw.shape[0]
+    KS = 8 if K == 7 else 4
+    scratch = workspace(O * K * KS * 4 * 4, dy.device)
+    call("stem_tc_wgrad", ptr(dy), ptr(xs), ptr(dw), ptr(scratch), ci(B), ci(H), ci(W), ci(O), ci(K), ci(pad), _stream())
+    _tc_account(B, H // 2, W // 2, O, 3, K, K)
+    _count(3)
+    return dw
+
+
+def weight_flip_transpose_batch(base, out, table):
+    """Flip/transpose every conv weight of a flat bf16 buffer in one launch (table: int32 [n,5] on device)."""
+    call("conv2d_weight_flip_transpose_batch", ptr(base), ptr(out), ptr(table), ci(table.shape[0]), _stream())
+    _count()
+    return out
+
+
 def conv_dgrad(dy, w, x_shape, stride=1, pad=1, addend=None, force_direct=False, w_ft=None):
     """dx = conv_transpose(dy, w) (+ addend, accumulated in place into ``addend``'s buffer when given).
 
@@ -211,10 +284,10 @@ def bn_stats(x, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1):
     C = x.shape[-1]
     M = x.numel() // C
     st = torch.empty((4, C), dtype=torch.float32, device=x.device)
-    ws = workspace(2 * C * 8, x.device)
+    ws = bn_workspace(x.device, C)
     call("bn_stats", ptr(x), ci(dt(x)), ll(M), ci(C), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
          ptr(st[0]), ptr(st[1]), ptr(st[2]), ptr(st[3]), float(eps), float(momentum), ptr(ws), _stream())
-    _count(2)
+    _count(1)
     return st[0], st[1], st[2], st[3]
 
 
@@ -246,11 +319,11 @@ def bn_bwd(dy, x, a, gamma, mean, rstd, slope, dgamma, dbeta, dres=None, dres_ac
     C = x.shape[-1]
     M = x.numel() // C
     dx = torch.empty_like(x)
-    ws = workspace(2 * C * 8 + 3 * C * 4, x.device)
+    ws = bn_workspace(x.device, C)
     call("bn_bwd", ptr(dy), ptr(x), ptr(a), ci(dt(x)), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx), ptr(dres),
          ci(1 if dres_accumulate else 0), ptr(dgamma), ptr(dbeta), ci(1 if param_accumulate else 0), ll(M), ci(C),
          float(slope), ptr(ws), _stream())
-    _count(3)
+    _count(2)
     return dx
 
 

@@ -260,7 +260,7 @@ class Unet(nn.Module):
             B, C, H, W = x.shape
             if H % 32 or W % 32:
                 raise RuntimeError(f"Unet: input height and width must be divisible by 32, got {H}x{W}")
-            xin = Var(ops.nchw_to_nhwc(x.contiguous().float(), dtype))
+            xin = E.input_var(x, dtype, self.encoder.conv1, record and x.requires_grad)
             in_vars = [xin]
             feats = self.encoder.run(ctx, xin)
             if part == "encoder":
