@@ -158,9 +158,9 @@ int uda_stem_tc_wgrad(const void* dy, const void* xs, float* dw, float* dws_scra
 
 /* BatchNorm2d (train: batch statistics; eps 1e-5, momentum 0.1 in the reference's graph).
  * x [M,C] NHWC rows.  uda_bn_stats: writes mean/rstd/scale/shift (float[C]) and updates running statistics
- * when non-NULL; the per-channel finalize runs in the last CTA of the same launch.  Its workspace (2*C+1
- * doubles) and uda_bn_bwd's (2*C+1 doubles + 3*C floats) must be ZERO on entry and are left zero on exit
- * (a dedicated, once-zeroed buffer: no per-call memset).  uda_bn_apply: y = act(x*scale+shift (+residual)),
+ * when non-NULL; the per-channel finalize runs in the last CTA of the same launch.  uda_bn_stats and uda_bn_bwd
+ * share one dedicated 128 KB workspace (C <= 4096) whose first 16 + 2*4096*8 bytes must be ZERO on entry and are
+ * left zero on exit (allocate it zeroed once: no per-call memset).  uda_bn_apply: y = act(x*scale+shift (+residual)),
  * slope 1 = identity, 0 = ReLU, 0.2 = LeakyReLU.  uda_bn_bwd:
  * `a` = saved post-activation output (NULL for identity activation); dres (nullable) receives the
  * activation-masked gradient of the residual branch. */

@@ -258,20 +258,18 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
                 const float* __restrict__ scale, const float* __restrict__ shift, long long n, int C, float slope) {
-  // The host sizes the grid so that (gridDim.x*blockDim.x) % (C/VEC) == 0: a thread then always sees the
-  // same channel vector and keeps its scale/shift in registers; 4 vectors in flight per thread.
+  // per-channel coefficients live in shared memory; a CTA streams 4 x 256 consecutive 16-byte vectors per
+  // iteration (4 independent loads in flight per thread, DRAM-page friendly)
+  extern __shared__ float sp[];   // [2][C]
+  for (int c = threadIdx.x; c < C; c += blockDim.x) { sp[c] = scale[c]; sp[C + c] = shift[c]; }
+  __syncthreads();
   const long long nv = n / VEC;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int c = (int)((i0 * VEC) % C);
-  float sc[VEC], sf[VEC];
-  ld_vec<VEC>(scale + c, sc);
-  ld_vec<VEC>(shift + c, sf);
-  for (long long i = i0; i < nv; i += 4 * stride) {
+  const long long chunk = 4LL * blockDim.x;
+  for (long long base = (long long)blockIdx.x * chunk; base < nv; base += (long long)gridDim.x * chunk) {
     float xv[4][VEC], rv[4][VEC];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const long long ii = i + u * stride;
+      const long long ii = base + u * blockDim.x + threadIdx.x;
       if (ii < nv) {
         ld_vec<VEC>(x + ii * VEC, xv[u]);
         if (residual) ld_vec<VEC>(residual + ii * VEC, rv[u]);
@@ -279,11 +277,12 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __re
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const long long ii = i + u * stride;
+      const long long ii = base + u * blockDim.x + threadIdx.x;
       if (ii < nv) {
+        const int c = (int)((ii * VEC) % C);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          float v = xv[u][j] * sc[j] + sf[j];
+          float v = xv[u][j] * sp[c + j] + sp[C + c + j];
           if (residual) v += rv[u][j];
           xv[u][j] = act_fwd(v, slope);
         }
@@ -370,23 +369,20 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
                     const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ coef, T* __restrict__ dx, T* dres, int dres_accumulate,
                     long long n, int C, float slope) {
-  // grid sized so that a thread always sees the same channel vector (see bn_apply_kernel)
+  extern __shared__ float sp[];   // [5][C]: mean, rstd, k0, k1, k2
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    sp[c] = mean[c]; sp[C + c] = rstd[c];
+    sp[2 * C + c] = coef[c]; sp[3 * C + c] = coef[C + c]; sp[4 * C + c] = coef[2 * C + c];
+  }
+  __syncthreads();
   const long long nv = n / VEC;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int c = (int)((i0 * VEC) % C);
-  float mu[VEC], rs[VEC], k0[VEC], k1[VEC], k2[VEC];
-  ld_vec<VEC>(mean + c, mu);
-  ld_vec<VEC>(rstd + c, rs);
-  ld_vec<VEC>(coef + c, k0);
-  ld_vec<VEC>(coef + C + c, k1);
-  ld_vec<VEC>(coef + 2 * C + c, k2);
   const bool racc = dres && dres_accumulate;
-  for (long long i = i0; i < nv; i += 2 * stride) {
+  const long long chunk = 2LL * blockDim.x;
+  for (long long base = (long long)blockIdx.x * chunk; base < nv; base += (long long)gridDim.x * chunk) {
     float dv[2][VEC], xv[2][VEC], av[2][VEC], rv[2][VEC];
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const long long ii = i + u * stride;
+      const long long ii = base + u * blockDim.x + threadIdx.x;
       if (ii < nv) {
         ld_vec<VEC>(dy + ii * VEC, dv[u]);
         ld_vec<VEC>(x + ii * VEC, xv[u]);
@@ -396,14 +392,15 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
-      const long long ii = i + u * stride;
+      const long long ii = base + u * blockDim.x + threadIdx.x;
       if (ii < nv) {
+        const int c = (int)((ii * VEC) % C);
         float ov[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           float g = dv[u][j];
           if (a) g *= (av[u][j] > 0.f) ? 1.f : slope;
-          ov[j] = k0[j] * g - k1[j] - k2[j] * (xv[u][j] - mu[j]) * rs[j];
+          ov[j] = sp[2 * C + c + j] * g - sp[3 * C + c + j] - sp[4 * C + c + j] * (xv[u][j] - sp[c + j]) * sp[C + c + j];
           dv[u][j] = racc ? rv[u][j] + g : g;
         }
         st_vec<VEC>(dx + ii * VEC, ov);
@@ -813,9 +810,11 @@ extern "C" int uda_bn_stats(const void* x, int dtype, long long M, int C, const 
   cudaStream_t st = (cudaStream_t)stream;
   UDA_REQUIRE(x && mean && rstd && scale && shift && workspace, UDA_ERR_BAD_ARG, "bn_stats: null pointer");
   UDA_REQUIRE(M > 0 && C > 0 && C <= 4096, UDA_ERR_BAD_ARG, "bn_stats: bad shape M=%lld C=%d", M, C);
-  double* sums = (double*)workspace;                      // zero on entry (contract), zero again on exit
+  // workspace layout (fixed offsets, C <= 4096): [counter: 16 B][sums: 2*4096 doubles][bwd coefficients]
+  // counter + sums are zero on entry (contract) and zero again on exit
+  double* sums = (double*)workspace + 2;
   BnFwdFinal fin{gamma, beta, running_mean, running_var, mean, rstd, scale, shift, M, eps, momentum,
-                 reinterpret_cast<unsigned int*>(sums + 2 * C)};
+                 reinterpret_cast<unsigned int*>(workspace)};
   const int vec = vec_for(dtype, C, x);
   int slabs = 1;
   while ((C / slabs) / vec > kThreads || (C % slabs)) ++slabs;  // channel slabs of <= 256*vec channels
@@ -823,7 +822,7 @@ extern "C" int uda_bn_stats(const void* x, int dtype, long long M, int C, const 
   UDA_REQUIRE(Cs % vec == 0, UDA_ERR_UNSUPPORTED, "bn_stats: C=%d not supported", C);
   const int groups = kThreads / (Cs / vec);
   long long blocks = (M + groups - 1) / groups;
-  long long cap = ((long long)num_sms() * 8 + slabs - 1) / slabs;
+  long long cap = ((long long)num_sms() * 2 + slabs - 1) / slabs;
   if (blocks > cap) blocks = cap;
   size_t smem = (size_t)groups * Cs * 2 * sizeof(float);
   UDA_REQUIRE(smem <= 48 * 1024, UDA_ERR_UNSUPPORTED, "bn_stats: C=%d needs too much shared memory", C);
@@ -853,7 +852,7 @@ extern "C" int uda_bn_apply(const void* x, const void* residual, void* y, int dt
   int vec = vec_for(dtype, C, x, residual, y);
   if (reinterpret_cast<uintptr_t>(scale) % 16 || reinterpret_cast<uintptr_t>(shift) % 16) vec = 1;
   const long long n = M * C;
-#define K(T, V) bn_apply_kernel<T, V><<<grid_for_channels(n / V / 4, C / V), kThreads, 0, st>>>((const T*)x, (const T*)residual, (T*)y, scale, shift, n, C, slope)
+#define K(T, V) bn_apply_kernel<T, V><<<grid_for(n / V / 4), kThreads, 2 * C * sizeof(float), st>>>((const T*)x, (const T*)residual, (T*)y, scale, shift, n, C, slope)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV
@@ -870,9 +869,9 @@ extern "C" int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtyp
   cudaStream_t st = (cudaStream_t)stream;
   UDA_REQUIRE(dy && x && mean && rstd && dx && workspace, UDA_ERR_BAD_ARG, "bn_bwd: null pointer");
   UDA_REQUIRE(M > 0 && C > 0 && C <= 4096, UDA_ERR_BAD_ARG, "bn_bwd: bad shape");
-  double* sums = (double*)workspace;                      // zero on entry (contract), zero again on exit
-  unsigned int* counter = reinterpret_cast<unsigned int*>(sums + 2 * C);
-  float* coef = (float*)(sums + 2 * C + 2);   // keep 16-byte alignment
+  double* sums = (double*)workspace + 2;                  // see uda_bn_stats for the layout
+  unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
+  float* coef = (float*)((double*)workspace + 2 + 2 * 4096);
   BnBwdFinal fin{gamma, rstd, dgamma, dbeta, coef, M, param_accumulate, counter};
   int vec = vec_for(dtype, C, dy, x, a, dx);
   if (dres) vec = vec < vec_for(dtype, C, dres) ? vec : vec_for(dtype, C, dres);
@@ -885,7 +884,7 @@ extern "C" int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtyp
   UDA_REQUIRE(Cs % rvec == 0, UDA_ERR_UNSUPPORTED, "bn_bwd: C=%d not supported", C);
   const int groups = kThreads / (Cs / rvec);
   long long blocks = (M + groups - 1) / groups;
-  long long cap = ((long long)num_sms() * 8 + slabs - 1) / slabs;
+  long long cap = ((long long)num_sms() * 2 + slabs - 1) / slabs;
   if (blocks > cap) blocks = cap;
   size_t smem = (size_t)groups * Cs * 2 * sizeof(float);
   UDA_REQUIRE(smem <= 48 * 1024, UDA_ERR_UNSUPPORTED, "bn_bwd: C=%d needs too much shared memory", C);
@@ -896,7 +895,7 @@ extern "C" int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtyp
 #undef K
   UDA_LAUNCH_OK("bn_bwd_reduce_kernel");
   const long long n = M * C;
-#define K(T, V) bn_bwd_apply_kernel<T, V><<<grid_for_channels(n / V / 2, C / V), kThreads, 0, st>>>((const T*)dy, (const T*)x, (const T*)a, mean, rstd, coef, (T*)dx, (T*)dres, dres_accumulate, n, C, slope)
+#define K(T, V) bn_bwd_apply_kernel<T, V><<<grid_for(n / V / 2), kThreads, 5 * C * sizeof(float), st>>>((const T*)dy, (const T*)x, (const T*)a, mean, rstd, coef, (T*)dx, (T*)dres, dres_accumulate, n, C, slope)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV
@@ -948,7 +947,7 @@ extern "C" int uda_colsum(const void* x, int dtype, float* out, long long M, int
   UDA_REQUIRE(Cs % vec == 0, UDA_ERR_UNSUPPORTED, "colsum: C=%d not supported", C);
   const int groups = kThreads / (Cs / vec);
   long long blocks = (M + groups - 1) / groups;
-  long long cap = ((long long)num_sms() * 8 + slabs - 1) / slabs;
+  long long cap = ((long long)num_sms() * 2 + slabs - 1) / slabs;
   if (blocks > cap) blocks = cap;
   size_t smem = (size_t)groups * Cs * sizeof(float);
 #define K(T, V) colsum_kernel<T, V><<<dim3((unsigned)blocks, slabs), kThreads, smem, st>>>((const T*)x, sums, M, C, Cs)

@@ -74,7 +74,7 @@ def bn_workspace(device, C):
     """Once-zeroed scratch of the BatchNorm reductions (the kernels leave it zeroed: no per-call memset)."""
     key = (device.index if device.index is not None else torch.cuda.current_device())
     ws = _BN_WS.get(key)
-    need = (2 * C + 2) * 8 + 3 * C * 4 + 64
+    need = 16 + 2 * 4096 * 8 + 3 * 4096 * 4   # fixed layout, see uda_bn_stats
     if ws is None or ws.numel() < need:
         ws = torch.zeros(max(need, 1 << 17), dtype=torch.uint8, device=device)
         _BN_WS[key] = ws
