@@ -323,8 +323,23 @@ int run_gemm_conv_class(const GemmConv& g, int ci, cudaStream_t st) {
   return set_error(UDA_ERR_UNSUPPORTED, "conv_tc: no kernel instance for KC=%d BN=%d", KC, BN);
 }
 
+bool use_halo() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UDA_B200_TC_HALO");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 int run_gemm_conv(const GemmConv& g, cudaStream_t st) {
-  if (use_persistent()) return run_gemm_conv_persistent(g, st);
+  if (use_persistent()) {
+    if (use_halo()) {
+      const int rc = run_gemm_conv_halo(g, st);
+      if (rc != UDA_ERR_UNSUPPORTED) return rc;
+    }
+    return run_gemm_conv_persistent(g, st);
+  }
   for (int ci = 0; ci < g.ncls; ++ci)
     if (int rc = run_gemm_conv_class(g, ci, st)) return rc;
   return UDA_OK;

@@ -60,6 +60,9 @@ inline int pick_bn(int cout) { return cout > 64 ? 128 : (cout > 32 ? 64 : 32); }
 
 // conv_tc_persist.cu: persistent, TMEM-double-buffered kernel (all classes in one launch)
 int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st);
+// conv_tc_halo.cu: halo-tile kernel for 3x3 stride-1 convolutions on wide images; returns UDA_ERR_UNSUPPORTED
+// (no message) when the shape does not qualify
+int run_gemm_conv_halo(const GemmConv& g, cudaStream_t st);
 
 }  // namespace tcconv
 }  // namespace uda
