@@ -662,6 +662,10 @@ int run_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int
               KH, stride, pad);
   UDA_REQUIRE(aligned<bf16>(dy, 16) && aligned<bf16>(x, 16) && aligned<float>(dw, 4), UDA_ERR_BAD_ARG,
               "conv_tc_wgrad: pointers must be 16-byte aligned");
+  if (KH == 3 && KW == 3 && stride == 1 && pad == 1 && use_persistent() && use_halo()) {
+    const int rc = run_wgrad_halo(dy, x, dw, B, H, W, Cin, Cout, st);
+    if (rc != UDA_ERR_UNSUPPORTED) return rc;
+  }
   const int Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? W : W / 2;
   const TilePlan tp = plan_tiles(B, Ho, Wo);
   const int atomA = pick_atom(Cin);

@@ -63,6 +63,8 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st);
 // conv_tc_halo.cu: halo-tile kernel for 3x3 stride-1 convolutions on wide images; returns UDA_ERR_UNSUPPORTED
 // (no message) when the shape does not qualify
 int run_gemm_conv_halo(const GemmConv& g, cudaStream_t st);
+// conv_tc_wgrad_halo.cu: halo-tile wgrad (3x3 stride 1 pad 1, W % 128 == 0); UDA_ERR_UNSUPPORTED otherwise
+int run_wgrad_halo(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, cudaStream_t st);
 
 }  // namespace tcconv
 }  // namespace uda
