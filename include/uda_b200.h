@@ -151,8 +151,8 @@ int uda_stem_tc_supported(int B, int H, int W, int Cin, int Cout, int K, int str
 size_t uda_stem_packed_input_elems(int B, int H, int W);
 int uda_stem_pack_input(const float* x_nchw, void* xs, int B, int H, int W, int pad, void* stream);
 int uda_stem_pack_weight(const void* w, void* ws, int Cout, int K, void* stream);
-int uda_stem_tc_fwd(const void* xs, const void* ws, const float* bias, void* y, int B, int H, int W, int Cout, int K,
-                    int pad, void* stream);
+int uda_stem_tc_fwd(const void* xs, const void* ws, const float* bias, void* y, double* bn_sums, int B, int H, int W,
+                    int Cout, int K, int pad, void* stream);
 int uda_stem_tc_wgrad(const void* dy, const void* xs, float* dw, float* dws_scratch, int B, int H, int W, int Cout,
                       int K, int pad, void* stream);
 
@@ -171,6 +171,12 @@ int uda_bn_eval_coeffs(const float* gamma, const float* beta, const float* runni
                        float* scale, float* shift, int C, float eps, void* stream);
 int uda_bn_apply(const void* x, const void* residual, void* y, int dtype, const float* scale, const float* shift,
                  long long M, int C, float slope, void* stream);
+/* bn_apply with the batch statistics produced by the convolution epilogue (uda_conv2d_tc_fwd's bn_sums):
+ * normalise + activation and, in CTA 0, mean/rstd/scale/shift outputs + running-statistics update. */
+int uda_bn_apply_fused(const void* x, const void* residual, void* y, int dtype, const double* sums, const float* gamma,
+                       const float* beta, float* running_mean, float* running_var, float* mean, float* rstd,
+                       float* scale, float* shift, long long M, int C, float eps, float momentum, float slope,
+                       void* stream);
 int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtype, const float* gamma, const float* mean,
                const float* rstd, void* dx, void* dres, int dres_accumulate, float* dgamma, float* dbeta,
                int param_accumulate, long long M, int C, float slope, void* workspace, void* stream);

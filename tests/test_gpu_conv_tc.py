@@ -62,6 +62,22 @@ def test_tc_forward_and_dgrad(cfg):
     assert rel_err(yn.cpu(), yr.permute(0, 3, 1, 2)) < 2e-3
     y0 = ops.conv_fwd(xg, wg, None, s, p)
     assert rel_err(y0.float().cpu(), R.conv_fwd(x.float(), w.float(), None, s, p)) < 1e-2
+    # BatchNorm batch statistics emitted by the epilogue == sums over the bf16 output it wrote
+    sums = torch.zeros(2 * Cout, dtype=torch.float64, device=DEV)
+    y1 = ops.conv_fwd(xg, wg, None, s, p, bn_sums=sums)
+    assert torch.equal(y1, y0)
+    yf = y0.double().reshape(-1, Cout)
+    assert rel_err(sums[:Cout].cpu(), yf.sum(0).cpu()) < 1e-5 + 1e-4 * float(yf.abs().sum(0).max() / (yf.sum(0).abs().max() + 1e-9)) * 1e-2
+    assert rel_err(sums[Cout:].cpu(), (yf * yf).sum(0).cpu()) < 1e-4
+    g, b = torch.rand(Cout, device=DEV) + 0.5, torch.randn(Cout, device=DEV)
+    rm1, rv1 = torch.zeros(Cout, device=DEV), torch.ones(Cout, device=DEV)
+    rm2, rv2 = rm1.clone(), rv1.clone()
+    a1, mean1, rstd1 = ops.bn_apply_fused(y0, sums, g, b, rm1, rv1, 1e-5, 0.1, None, 0.0)
+    mean2, rstd2, sc2, sh2 = ops.bn_stats(y0, g, b, rm2, rv2, 1e-5, 0.1)
+    a2 = ops.bn_apply(y0, sc2, sh2, None, 0.0)
+    assert rel_err(mean1, mean2) < 1e-4 and rel_err(rstd1, rstd2) < 1e-4
+    assert rel_err(rm1, rm2) < 1e-4 and rel_err(rv1, rv2) < 1e-4
+    assert rel_err(a1.float(), a2.float()) < 1e-2
     # dgrad (stride 1: one launch on flipped weights; stride 2: one launch per output parity)
     assert ops.tc_supported(1, B, H, W, Cin, Cout, k, k, s, p)
     dy = _rand(tuple(yr.shape), 3)

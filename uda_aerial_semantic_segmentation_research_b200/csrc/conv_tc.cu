@@ -358,8 +358,9 @@ bool fwd_shape_ok(int B, int H, int W, int Cin, int Cout, int KH, int KW, int st
 }
 
 // x: [B,H,W,Cin] bf16; w: [Cout][KH*KW][Cin] bf16; "same" (stride 1) or halving (stride 2) forward convolution
-int run_fwd(const void* x, const void* w, const float* bias, const void* addend, void* y, float* y_nchw, int B,
-            int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, cudaStream_t st) {
+int run_fwd(const void* x, const void* w, const float* bias, const void* addend, void* y, float* y_nchw,
+            double* bn_sums, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+            cudaStream_t st) {
   UDA_REQUIRE(fwd_shape_ok(B, H, W, Cin, Cout, KH, KW, stride, pad), UDA_ERR_UNSUPPORTED,
               "conv_tc: shape not covered by the tensor-core kernel (B=%d H=%d W=%d Cin=%d Cout=%d k=%d s=%d p=%d)",
               B, H, W, Cin, Cout, KH, stride, pad);
@@ -380,7 +381,7 @@ int run_fwd(const void* x, const void* w, const float* bias, const void* addend,
       }
     }
   g.OH = stride == 1 ? H : H / 2; g.OW = stride == 1 ? W : W / 2; g.os = 1;
-  g.bias = bias; g.addend = addend; g.out = y; g.out_nchw = y_nchw;
+  g.bias = bias; g.addend = addend; g.out = y; g.out_nchw = y_nchw; g.bn_sums = bn_sums;
   return run_gemm_conv(g, st);
 }
 
@@ -786,8 +787,8 @@ int make_stem_map(CUtensorMap* m, const void* xs, int B, int H, int W, int K, co
   return make_tmap_bf16(m, xs, 5, dims, str, box, KS * 8);
 }
 
-int run_stem_fwd(const void* xs, const void* ws, const float* bias, void* y, int B, int H, int W, int Cout, int K,
-                 cudaStream_t st) {
+int run_stem_fwd(const void* xs, const void* ws, const float* bias, void* y, double* bn_sums, int B, int H, int W,
+                 int Cout, int K, cudaStream_t st) {
   const TilePlan tp = plan_tiles(B, H / 2, W / 2);
   CUtensorMap ma;
   if (int rc = make_stem_map(&ma, xs, B, H, W, K, tp)) return rc;
@@ -798,7 +799,7 @@ int run_stem_fwd(const void* xs, const void* ws, const float* bias, void* y, int
   c.ntaps = K; c.oh = 0; c.ow = 0;
   for (int kh = 0; kh < K; ++kh) { c.dh[kh] = kh >> 1; c.ph[kh] = kh & 1; c.dw[kh] = 0; c.pw[kh] = 0; c.wtap[kh] = kh; }
   g.OH = H / 2; g.OW = W / 2; g.os = 1;
-  g.bias = bias; g.addend = nullptr; g.out = y; g.out_nchw = nullptr;
+  g.bias = bias; g.addend = nullptr; g.out = y; g.out_nchw = nullptr; g.bn_sums = bn_sums;
   g.a_map = &ma; g.a_MH = H / 2; g.a_MW = W / 2; g.a_kc = stem_slots(K) * 4;
   return run_gemm_conv_persistent(g, st);
 }
@@ -862,11 +863,11 @@ extern "C" int uda_stem_pack_weight(const void* w, void* ws, int Cout, int K, vo
   UDA_LAUNCH_OK("stem_pack_weight_kernel");
   return UDA_OK;
 }
-extern "C" int uda_stem_tc_fwd(const void* xs, const void* ws, const float* bias, void* y, int B, int H, int W,
-                               int Cout, int K, int pad, void* stream) {
+extern "C" int uda_stem_tc_fwd(const void* xs, const void* ws, const float* bias, void* y, double* bn_sums, int B,
+                               int H, int W, int Cout, int K, int pad, void* stream) {
   UDA_REQUIRE(xs && ws && y, UDA_ERR_BAD_ARG, "stem_tc_fwd: null pointer");
   UDA_REQUIRE(stem_shape_ok(B, H, W, 3, Cout, K, 2, pad), UDA_ERR_UNSUPPORTED, "stem_tc_fwd: shape not covered");
-  return run_stem_fwd(xs, ws, bias, y, B, H, W, Cout, K, (cudaStream_t)stream);
+  return run_stem_fwd(xs, ws, bias, y, bn_sums, B, H, W, Cout, K, (cudaStream_t)stream);
 }
 // dw [Cout][K][K][3] fp32 += wgrad; dws_scratch: fp32 [Cout][K][KS*4] scratch (KS = 8 for K = 7, 4 for K = 4)
 extern "C" int uda_stem_tc_wgrad(const void* dy, const void* xs, float* dw, float* dws_scratch, int B, int H, int W,
@@ -896,8 +897,9 @@ extern "C" int uda_conv2d_tc_fwd(const void* x, const void* w, const float* bias
                                  double* bn_sums, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride,
                                  int pad, void* stream) {
   UDA_REQUIRE(x && w && (y_nhwc || y_nchw_f32), UDA_ERR_BAD_ARG, "conv_tc_fwd: null pointer");
-  UDA_REQUIRE(bn_sums == nullptr, UDA_ERR_UNSUPPORTED, "conv_tc_fwd: fused BN statistics are not implemented yet");
-  return run_fwd(x, w, bias, nullptr, y_nhwc, y_nchw_f32, B, H, W, Cin, Cout, KH, KW, stride, pad,
+  UDA_REQUIRE(bn_sums == nullptr || use_persistent(), UDA_ERR_UNSUPPORTED,
+              "conv_tc_fwd: fused BN statistics need the persistent kernels");
+  return run_fwd(x, w, bias, nullptr, y_nhwc, y_nchw_f32, bn_sums, B, H, W, Cin, Cout, KH, KW, stride, pad,
                  (cudaStream_t)stream);
 }
 

@@ -27,6 +27,7 @@ struct HParams {
   int Cout, Cred, kchunks;
   int stages;
   bf16* out; float* out_nchw; const float* bias; const bf16* addend;
+  double* bn_sums;
 };
 
 template <int KC, int BN, int R>
@@ -133,6 +134,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   } else {
     // ===================== epilogue (4 warps): one image row of 128 pixels per sub-tile =====================
     const int qw = warp & 3;
+    constexpr int kChunks = (BN + 31) / 32;
+    float bn_s[kChunks], bn_q[kChunks];
+#pragma unroll
+    for (int cc = 0; cc < kChunks; ++cc) { bn_s[cc] = 0.f; bn_q[cc] = 0.f; }
     int j = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
       const int b = t / tiles_per_img, tin = t % tiles_per_img;
@@ -146,7 +151,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int h = h0 + sub;
         const long long pix = ((long long)b * p.H + h) * p.W + w;
         const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)q * kAccCols + (uint32_t)sub * BN;
-#pragma unroll 1
+#pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
           if (c0 >= p.Cout) break;
           uint32_t v[32];
@@ -160,6 +165,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int k = 0; k < 32; ++k)
               if (c0 + k < p.Cout) f[k] += __ldg(p.bias + c0 + k);
           }
+          if (p.bn_sums) bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);
           if (p.out) {
             bf16* dst = p.out + pix * p.Cout + c0;
             const bf16* add = p.addend ? p.addend + pix * p.Cout + c0 : nullptr;
@@ -191,6 +197,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(q));
+    }
+    if (p.bn_sums) {
+#pragma unroll
+      for (int cc = 0; cc < kChunks; ++cc) {
+        const int col = cc * 32 + lane;
+        if (col < p.Cout) { atomicAdd(p.bn_sums + col, (double)bn_s[cc]); atomicAdd(p.bn_sums + p.Cout + col, (double)bn_q[cc]); }
+      }
     }
   }
   tc_fence_before();
@@ -253,6 +266,7 @@ int run_gemm_conv_halo(const GemmConv& g, cudaStream_t st) {
   p.total_tiles = g.B * p.tiles_w * p.tiles_h;
   p.Cout = g.Cout; p.Cred = g.Cred; p.kchunks = kchunks;
   p.out = (bf16*)g.out; p.out_nchw = g.out_nchw; p.bias = g.bias; p.addend = (const bf16*)g.addend;
+  p.bn_sums = g.bn_sums;
   CUtensorMap ma, mb;
   {
     const uint64_t C = (uint64_t)g.Cred;

@@ -44,6 +44,7 @@ struct GemmConv {
   int ncls; TapClass cls[kMaxClasses];
   int OH, OW, os;
   const float* bias; const void* addend; void* out; float* out_nchw;
+  double* bn_sums;   // optional [2*Cout]: += per-channel sum / sum of squares of the bf16-rounded outputs
   // optional: caller-built A-operand tensor map (rank-5 coordinate form {c, w, ph, h, b}) over an M-grid of
   // MH x MW pixels — used by the Cin=3 stem, whose A operand is a padded 4-channel row view of the image
   const CUtensorMap* a_map; int a_MH, a_MW, a_kc;
@@ -57,6 +58,36 @@ inline int pick_kc(int c) {
   return 0;
 }
 inline int pick_bn(int cout) { return cout > 64 ? 128 : (cout > 32 ? 64 : 32); }
+
+#ifdef __CUDACC__
+// Column sums over the 32 rows a warp holds (one row per lane, 32 values per lane): recursive halving,
+// 31 shuffles; afterwards lane L holds the sum of column L in v[0].
+__device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+// BatchNorm batch statistics of one 32-column chunk held by an epilogue warp: the values are rounded to bf16
+// first (exactly what the separate bn_stats pass would read back), then summed over the warp's 32 rows.
+__device__ __forceinline__ void bn_chunk_stats(const float (&f)[32], int lane, float& s, float& q) {
+  float t[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) t[k] = __bfloat162float(__float2bfloat16_rn(f[k]));
+  float u[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) u[k] = t[k] * t[k];
+  s += warp_column_sums(t, lane);
+  q += warp_column_sums(u, lane);
+}
+#endif
 
 // conv_tc_persist.cu: persistent, TMEM-double-buffered kernel (all classes in one launch)
 int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st);

@@ -40,6 +40,7 @@ struct PParams {
   int stages, ws;
   PClass cls[kMaxClasses];
   bf16* out; float* out_nchw; const float* bias; const bf16* addend;
+  double* bn_sums;
 };
 
 template <int KC, int BN, int MT>
@@ -101,7 +102,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       int it = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int ci = t / tiles_per_cls, rem = t % tiles_per_cls;
-        const int mt = rem / p.n_tiles, n0 = (rem % p.n_tiles) * BN;
+        const int mt = rem % p.m_tiles, n0 = (rem / p.m_tiles) * BN;
         const int grp = mt / tiles_per_group, tin = mt % tiles_per_group;
         const int b0 = grp * p.NB, h0 = (tin / p.tiles_w) * p.TH, w0 = (tin % p.tiles_w) * p.TW;
         const PClass& c = p.cls[ci];
@@ -161,14 +162,30 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   } else {
     // ===================== epilogue (4 warps) =====================
     const int qw = warp & 3;
+    constexpr int kChunks = (BN + 31) / 32;
+    float bn_s[kChunks], bn_q[kChunks];
+#pragma unroll
+    for (int cc = 0; cc < kChunks; ++cc) { bn_s[cc] = 0.f; bn_q[cc] = 0.f; }
+    int bn_n0 = -1;
     int j = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
       const int ci = t / tiles_per_cls, rem = t % tiles_per_cls;
-      const int mt = rem / p.n_tiles, n0 = (rem % p.n_tiles) * BN;
+      const int mt = rem % p.m_tiles, n0 = (rem / p.m_tiles) * BN;
       const int grp = mt / tiles_per_group, tin = mt % tiles_per_group;
       const int b0 = grp * p.NB, h0 = (tin / p.tiles_w) * p.TH, w0 = (tin % p.tiles_w) * p.TW;
       const int oh = p.cls[ci].oh, ow = p.cls[ci].ow;
       const int q = j & 1;
+      if (p.bn_sums && n0 != bn_n0) {   // channel tile changed: flush the partial statistics
+        if (bn_n0 >= 0) {
+#pragma unroll
+          for (int cc = 0; cc < kChunks; ++cc) {
+            const int col = bn_n0 + cc * 32 + lane;
+            if (col < p.Cout) { atomicAdd(p.bn_sums + col, (double)bn_s[cc]); atomicAdd(p.bn_sums + p.Cout + col, (double)bn_q[cc]); }
+            bn_s[cc] = 0.f; bn_q[cc] = 0.f;
+          }
+        }
+        bn_n0 = n0;
+      }
       mbar_wait(tfull_bar(q), (j >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -179,7 +196,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const int b = b0 + nb, h = (h0 + th) * p.os + oh, w = (w0 + tw) * p.os + ow;
         const long long pix = ((long long)b * p.OH + h) * p.OW + w;
         const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)q * kAccCols + (uint32_t)sub * BN;
-#pragma unroll 1
+#pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
           const int nbase = n0 + c0;
           if (nbase >= p.Cout) break;   // warp-uniform
@@ -194,6 +211,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             for (int k = 0; k < 32; ++k)
               if (nbase + k < p.Cout) f[k] += __ldg(p.bias + nbase + k);
           }
+          if (p.bn_sums) bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);
           if (p.out) {
             bf16* dst = p.out + pix * p.Cout + nbase;
             const bf16* add = p.addend ? p.addend + pix * p.Cout + nbase : nullptr;
@@ -225,6 +243,13 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(q));
+    }
+    if (p.bn_sums && bn_n0 >= 0) {
+#pragma unroll
+      for (int cc = 0; cc < kChunks; ++cc) {
+        const int col = bn_n0 + cc * 32 + lane;
+        if (col < p.Cout) { atomicAdd(p.bn_sums + col, (double)bn_s[cc]); atomicAdd(p.bn_sums + p.Cout + col, (double)bn_q[cc]); }
+      }
     }
   }
   tc_fence_before();
@@ -298,6 +323,7 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
     }
   }
   p.out = (bf16*)g.out; p.out_nchw = g.out_nchw; p.bias = g.bias; p.addend = (const bf16*)g.addend;
+  p.bn_sums = g.bn_sums;
 
   CUtensorMap ma, mb;
   const uint64_t C = (uint64_t)g.Cred, H = (uint64_t)g.SH, W = (uint64_t)g.SW;

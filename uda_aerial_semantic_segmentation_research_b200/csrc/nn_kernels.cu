@@ -21,6 +21,16 @@ inline unsigned grid_for(long long work_items, int per_sm = 8) {
   return (unsigned)blocks;
 }
 
+// CTAs of a per-channel reduction: enough to fill the machine for big tensors, few for small ones (every CTA
+// ends with 2*C atomics onto the same addresses)
+inline long long reduce_grid_cap(long long bytes, int slabs) {
+  long long want = bytes / (96 * 1024);            // >= 96 KB of input per CTA
+  const long long hi = 4LL * num_sms();
+  if (want > hi) want = hi;
+  if (want < 1) want = 1;
+  return (want + slabs - 1) / slabs;
+}
+
 // grid whose total thread count is a multiple of `period` (= C/VEC channel vectors), so that a
 // grid-stride loop keeps every thread on the same channel vector
 inline unsigned grid_for_channels(long long work_items, int period, int per_sm = 8) {
@@ -199,10 +209,10 @@ bn_stats_kernel(const T* __restrict__ x, double* sums, long long M, int Ctot, in
   if (g < groups) {
     const long long stride = (long long)gridDim.x * groups;
     const T* px = x + v * VEC;
-    for (long long r = (long long)blockIdx.x * groups + g; r < M; r += 4 * stride) {
-      float xv[4][VEC];
+    for (long long r = (long long)blockIdx.x * groups + g; r < M; r += 8 * stride) {
+      float xv[8][VEC];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 8; ++u) {
         const long long rr = r + u * stride;
         if (rr < M) {
           ld_vec<VEC>(px + rr * Ctot, xv[u]);
@@ -212,7 +222,7 @@ bn_stats_kernel(const T* __restrict__ x, double* sums, long long M, int Ctot, in
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 8; ++u)
 #pragma unroll
         for (int j = 0; j < VEC; ++j) { s1[j] += xv[u][j]; s2[j] += xv[u][j] * xv[u][j]; }
     }
@@ -257,13 +267,31 @@ __device__ __forceinline__ float act_fwd(float v, float slope) { return v > 0.f 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
-                const float* __restrict__ scale, const float* __restrict__ shift, long long n, int C, float slope) {
+                const float* __restrict__ scale, const float* __restrict__ shift, long long n, int C, float slope,
+                const double* __restrict__ sums, const BnFwdFinal fin) {
   // per-channel coefficients live in shared memory; a CTA streams 4 x 256 consecutive 16-byte vectors per
-  // iteration (4 independent loads in flight per thread, DRAM-page friendly)
+  // iteration (4 independent loads in flight per thread, DRAM-page friendly).
+  // sums != null: the batch statistics come straight from the producing convolution's epilogue (sum and sum
+  // of squares per channel); every CTA derives scale/shift from them, CTA 0 also publishes mean / rstd for
+  // the backward pass and updates the running statistics (the separate finalize launch disappears).
   extern __shared__ float sp[];   // [2][C]
-  for (int c = threadIdx.x; c < C; c += blockDim.x) { sp[c] = scale[c]; sp[C + c] = shift[c]; }
+  if (sums) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      const double mean = sums[c] / (double)fin.M;
+      double var = sums[C + c] / (double)fin.M - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const double rstd = 1.0 / sqrt(var + (double)fin.eps);
+      const float g = fin.gamma ? fin.gamma[c] : 1.f, b = fin.beta ? fin.beta[c] : 0.f;
+      sp[c] = (float)((double)g * rstd);
+      sp[C + c] = (float)((double)b - mean * (double)g * rstd);
+      if (blockIdx.x == 0) bn_fwd_finalize_channel(fin, sums[c], sums[C + c], c);
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) { sp[c] = scale[c]; sp[C + c] = shift[c]; }
+  }
   __syncthreads();
   const long long nv = n / VEC;
+  const bool pow2 = (C & (C - 1)) == 0;
   const long long chunk = 4LL * blockDim.x;
   for (long long base = (long long)blockIdx.x * chunk; base < nv; base += (long long)gridDim.x * chunk) {
     float xv[4][VEC], rv[4][VEC];
@@ -279,7 +307,7 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __re
     for (int u = 0; u < 4; ++u) {
       const long long ii = base + u * blockDim.x + threadIdx.x;
       if (ii < nv) {
-        const int c = (int)((ii * VEC) % C);
+        const int c = pow2 ? ((int)ii * VEC) & (C - 1) : (int)((ii * VEC) % C);
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           float v = xv[u][j] * sp[c + j] + sp[C + c + j];
@@ -376,6 +404,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
   }
   __syncthreads();
   const long long nv = n / VEC;
+  const bool pow2 = (C & (C - 1)) == 0;
   const bool racc = dres && dres_accumulate;
   const long long chunk = 2LL * blockDim.x;
   for (long long base = (long long)blockIdx.x * chunk; base < nv; base += (long long)gridDim.x * chunk) {
@@ -394,7 +423,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
     for (int u = 0; u < 2; ++u) {
       const long long ii = base + u * blockDim.x + threadIdx.x;
       if (ii < nv) {
-        const int c = (int)((ii * VEC) % C);
+        const int c = pow2 ? ((int)ii * VEC) & (C - 1) : (int)((ii * VEC) % C);
         float ov[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
@@ -822,7 +851,7 @@ extern "C" int uda_bn_stats(const void* x, int dtype, long long M, int C, const 
   UDA_REQUIRE(Cs % vec == 0, UDA_ERR_UNSUPPORTED, "bn_stats: C=%d not supported", C);
   const int groups = kThreads / (Cs / vec);
   long long blocks = (M + groups - 1) / groups;
-  long long cap = ((long long)num_sms() * 2 + slabs - 1) / slabs;
+  long long cap = reduce_grid_cap(M * (long long)C * (dtype == UDA_BF16 ? 2 : 4), slabs);
   if (blocks > cap) blocks = cap;
   size_t smem = (size_t)groups * Cs * 2 * sizeof(float);
   UDA_REQUIRE(smem <= 48 * 1024, UDA_ERR_UNSUPPORTED, "bn_stats: C=%d needs too much shared memory", C);
@@ -852,12 +881,33 @@ extern "C" int uda_bn_apply(const void* x, const void* residual, void* y, int dt
   int vec = vec_for(dtype, C, x, residual, y);
   if (reinterpret_cast<uintptr_t>(scale) % 16 || reinterpret_cast<uintptr_t>(shift) % 16) vec = 1;
   const long long n = M * C;
-#define K(T, V) bn_apply_kernel<T, V><<<grid_for(n / V / 4), kThreads, 2 * C * sizeof(float), st>>>((const T*)x, (const T*)residual, (T*)y, scale, shift, n, C, slope)
+#define K(T, V) bn_apply_kernel<T, V><<<grid_for(n / V / 4), kThreads, 2 * C * sizeof(float), st>>>((const T*)x, (const T*)residual, (T*)y, scale, shift, n, C, slope, nullptr, BnFwdFinal{})
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV
 #undef K
   UDA_LAUNCH_OK("bn_apply_kernel");
+  return UDA_OK;
+}
+
+// BatchNorm apply with the statistics taken from the producing convolution's epilogue (sums = [sum | sum of squares],
+// double[2*C]); scale/shift (float[C], scratch outputs kept for API symmetry) may be NULL.
+extern "C" int uda_bn_apply_fused(const void* x, const void* residual, void* y, int dtype, const double* sums,
+                                  const float* gamma, const float* beta, float* running_mean, float* running_var,
+                                  float* mean, float* rstd, float* scale, float* shift, long long M, int C, float eps,
+                                  float momentum, float slope, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  UDA_REQUIRE(x && y && sums && mean && rstd && scale && shift && M > 0 && C > 0 && C <= 4096, UDA_ERR_BAD_ARG,
+              "bn_apply_fused: bad argument");
+  int vec = vec_for(dtype, C, x, residual, y);
+  const long long n = M * C;
+  BnFwdFinal fin{gamma, beta, running_mean, running_var, mean, rstd, scale, shift, M, eps, momentum, nullptr};
+#define K(T, V) bn_apply_kernel<T, V><<<grid_for(n / V / 4), kThreads, 2 * C * sizeof(float), st>>>((const T*)x, (const T*)residual, (T*)y, nullptr, nullptr, n, C, slope, sums, fin)
+#define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
+  UDA_DT(dtype, KV, 0);
+#undef KV
+#undef K
+  UDA_LAUNCH_OK("bn_apply_kernel<fused>");
   return UDA_OK;
 }
 
@@ -884,7 +934,7 @@ extern "C" int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtyp
   UDA_REQUIRE(Cs % rvec == 0, UDA_ERR_UNSUPPORTED, "bn_bwd: C=%d not supported", C);
   const int groups = kThreads / (Cs / rvec);
   long long blocks = (M + groups - 1) / groups;
-  long long cap = ((long long)num_sms() * 2 + slabs - 1) / slabs;
+  long long cap = reduce_grid_cap(M * (long long)C * (dtype == UDA_BF16 ? 2 : 4), slabs);
   if (blocks > cap) blocks = cap;
   size_t smem = (size_t)groups * Cs * 2 * sizeof(float);
   UDA_REQUIRE(smem <= 48 * 1024, UDA_ERR_UNSUPPORTED, "bn_bwd: C=%d needs too much shared memory", C);
@@ -947,7 +997,7 @@ extern "C" int uda_colsum(const void* x, int dtype, float* out, long long M, int
   UDA_REQUIRE(Cs % vec == 0, UDA_ERR_UNSUPPORTED, "colsum: C=%d not supported", C);
   const int groups = kThreads / (Cs / vec);
   long long blocks = (M + groups - 1) / groups;
-  long long cap = ((long long)num_sms() * 2 + slabs - 1) / slabs;
+  long long cap = reduce_grid_cap(M * (long long)C * (dtype == UDA_BF16 ? 2 : 4), slabs);
   if (blocks > cap) blocks = cap;
   size_t smem = (size_t)groups * Cs * sizeof(float);
 #define K(T, V) colsum_kernel<T, V><<<dim3((unsigned)blocks, slabs), kThreads, smem, st>>>((const T*)x, sums, M, C, Cs)

@@ -18,12 +18,13 @@ from . import ops
 class Var:
     """An activation (NHWC tensor) plus its gradient slot on the tape.  A network input that feeds a
     tensor-core stem keeps the raw fp32 NCHW image in ``nchw`` instead (``t`` is None)."""
-    __slots__ = ("t", "g", "nchw")
+    __slots__ = ("t", "g", "nchw", "sums")
 
     def __init__(self, t, nchw=None):
         self.t = t
         self.g = None
         self.nchw = nchw
+        self.sums = None   # BatchNorm batch statistics emitted by the producing conv epilogue (double[2C])
 
 
 def input_var(x, dtype, cp, need_grad):
@@ -219,15 +220,31 @@ class Ctx:
 # ------------------------------------------------------------------------------------------------
 # tape ops
 # ------------------------------------------------------------------------------------------------
-def conv(ctx, xin, cp, nchw_out=False):
-    """y = conv(x) (+bias).  Returns Var (NHWC) or, with nchw_out, a raw fp32 NCHW tensor + grad hook."""
+def _fused_stats_ok(ctx, xin, cp):
+    """Can the tensor-core conv of this layer emit the BatchNorm statistics from its epilogue?"""
+    if not (ctx.training and ctx.dtype == torch.bfloat16 and ops.USE_TC and ops.FUSE_BN_STATS):
+        return False
+    if xin.t is None:
+        return True
+    B, H, W, Cin = xin.t.shape
+    return ops.tc_supported(0, B, H, W, Cin, cp.out_channels, cp.kernel_size, cp.kernel_size, cp.stride, cp.padding)
+
+
+def conv(ctx, xin, cp, nchw_out=False, bn=None):
+    """y = conv(x) (+bias).  Returns Var (NHWC) or, with nchw_out, a raw fp32 NCHW tensor + grad hook.
+    ``bn``: the BatchNorm that consumes the output — its batch statistics are then accumulated by the conv
+    epilogue (``out.sums``) instead of a separate pass over the output."""
     st = ctx.store
     w = st.w(cp.weight, ctx.dtype)
+    sums = None
+    if bn is not None and _fused_stats_ok(ctx, xin, cp):
+        sums = torch.zeros(2 * cp.out_channels, dtype=torch.float64, device=w.device)
     if xin.t is None:   # Cin = 3 stem on the tensor cores (see ops.stem_*)
         H, W = xin.nchw.shape[2:]
         K, pad = cp.kernel_size, cp.padding
         xs = ops.stem_pack_input(xin.nchw, pad)
-        out = Var(ops.stem_fwd(xs, ops.stem_pack_weight(w), cp.bias, H, W, K, pad))
+        out = Var(ops.stem_fwd(xs, ops.stem_pack_weight(w), cp.bias, H, W, K, pad, bn_sums=sums))
+        out.sums = sums
         if ctx.tape is not None:
             def bwd_stem():
                 dy = out.g
@@ -240,8 +257,9 @@ def conv(ctx, xin, cp, nchw_out=False):
                 ctx.done(cp.weight, cp.bias)
             ctx.tape.push(bwd_stem)
         return out
-    y = ops.conv_fwd(xin.t, w, cp.bias, cp.stride, cp.padding, nchw_out=nchw_out)
+    y = ops.conv_fwd(xin.t, w, cp.bias, cp.stride, cp.padding, nchw_out=nchw_out, bn_sums=sums)
     out = Var(y)
+    out.sums = sums
     if ctx.tape is not None:
         def bwd():
             dy = out.g
@@ -262,14 +280,20 @@ def conv(ctx, xin, cp, nchw_out=False):
 def bn_act(ctx, zin, bn, slope=0.0, residual=None):
     """a = act(BN(z) (+ residual)); train mode uses batch statistics and updates the running ones."""
     st = ctx.store
-    if ctx.training:
-        mean, rstd, scale, shift = ops.bn_stats(zin.t, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                                bn.eps, bn.momentum)
+    res_t = residual.t if residual is not None else None
+    if ctx.training and zin.sums is not None:
+        a, mean, rstd = ops.bn_apply_fused(zin.t, zin.sums, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                           bn.eps, bn.momentum, res_t, slope)
         bn.num_batches_tracked += 1
     else:
-        scale, shift = ops.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
-        mean = rstd = None
-    a = ops.bn_apply(zin.t, scale, shift, residual.t if residual is not None else None, slope)
+        if ctx.training:
+            mean, rstd, scale, shift = ops.bn_stats(zin.t, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                                    bn.eps, bn.momentum)
+            bn.num_batches_tracked += 1
+        else:
+            scale, shift = ops.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
+            mean = rstd = None
+        a = ops.bn_apply(zin.t, scale, shift, res_t, slope)
     out = Var(a)
     if ctx.tape is not None:
         if not ctx.training:

@@ -16,6 +16,8 @@ from ._lib import call, ptr, ll, ci, F32, BF16, I64, U8
 _WS = {}
 #: set to "0" to force the FP32-pipe direct convolution everywhere (debug / A-B comparison)
 USE_TC = os.environ.get("UDA_B200_USE_TC", "1") != "0"
+#: BatchNorm batch statistics from the tensor-core conv epilogue (set "0" to use the separate bn_stats pass)
+FUSE_BN_STATS = os.environ.get("UDA_B200_FUSE_BN_STATS", "1") != "0"
 #: counts launches issued through this module (bench.py reports it as gpu_launches)
 LAUNCHES = 0
 #: algorithmic FLOPs (2*M*N*K) and call count of the convolutions routed to the tcgen05 kernels
@@ -197,11 +199,11 @@ def stem_pack_weight(w):
     return ws
 
 
-def stem_fwd(xs, ws, bias, H, W, K, pad):
+def stem_fwd(xs, ws, bias, H, W, K, pad, bn_sums=None):
     B = xs.shape[0]
     O = ws.shape[0]
     y = torch.empty((B, H // 2, W // 2, O), dtype=torch.bfloat16, device=xs.device)
-    call("stem_tc_fwd", ptr(xs), ptr(ws), ptr(bias), ptr(y), ci(B), ci(H), ci(W), ci(O), ci(K), ci(pad), _stream())
+    call("stem_tc_fwd", ptr(xs), ptr(ws), ptr(bias), ptr(y), ptr(bn_sums), ci(B), ci(H), ci(W), ci(O), ci(K), ci(pad), _stream())
     _tc_account(B, H // 2, W // 2, O, 3, K, K)
     _count()
     return y
@@ -310,6 +312,21 @@ def bn_apply(x, scale, shift, residual=None, slope=0.0, out=None):
          float(slope), _stream())
     _count()
     return y
+
+
+def bn_apply_fused(x, sums, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, residual=None, slope=0.0):
+    """Normalise + activation with batch statistics taken from the conv epilogue (``sums`` double[2C]).
+    Returns (y, mean, rstd); running statistics are updated in place."""
+    _chk(x, "bn_apply_fused.x")
+    C = x.shape[-1]
+    M = x.numel() // C
+    st = torch.empty((4, C), dtype=torch.float32, device=x.device)
+    y = torch.empty_like(x)
+    call("bn_apply_fused", ptr(x), ptr(residual), ptr(y), ci(dt(x)), ptr(sums), ptr(gamma), ptr(beta),
+         ptr(running_mean), ptr(running_var), ptr(st[0]), ptr(st[1]), ptr(st[2]), ptr(st[3]), ll(M), ci(C), float(eps),
+         float(momentum), float(slope), _stream())
+    _count()
+    return y, st[0], st[1]
 
 
 def bn_bwd(dy, x, a, gamma, mean, rstd, slope, dgamma, dbeta, dres=None, dres_accumulate=False,
