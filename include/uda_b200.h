@@ -177,9 +177,12 @@ int uda_bn_apply_fused(const void* x, const void* residual, void* y, int dtype, 
                        const float* beta, float* running_mean, float* running_var, float* mean, float* rstd,
                        float* scale, float* shift, long long M, int C, float eps, float momentum, float slope,
                        void* stream);
+/* a == NULL with scale/shift given: the activation mask is recomputed from x*scale+shift (non-residual layers),
+ * which saves reading the saved output in both backward passes. */
 int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtype, const float* gamma, const float* mean,
-               const float* rstd, void* dx, void* dres, int dres_accumulate, float* dgamma, float* dbeta,
-               int param_accumulate, long long M, int C, float slope, void* workspace, void* stream);
+               const float* rstd, const float* scale, const float* shift, void* dx, void* dres, int dres_accumulate,
+               float* dgamma, float* dbeta, int param_accumulate, long long M, int C, float slope, void* workspace,
+               void* stream);
 int uda_act_bwd(const void* dy, const void* a, void* dx, int dtype, long long n, float slope, void* stream);
 int uda_bias_act(const void* x, const float* bias, void* y, int dtype, long long M, int C, float slope, void* stream);
 int uda_colsum(const void* x, int dtype, float* out, long long M, int C, float scale, int accumulate,

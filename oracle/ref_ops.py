@@ -123,11 +123,14 @@ def bn_apply(x, scale, shift, residual=None, slope=0.0, out=None):
 
 
 def bn_bwd(dy, x, a, gamma, mean, rstd, slope, dgamma, dbeta, dres=None, dres_accumulate=False,
-           param_accumulate=True):
+           param_accumulate=True, scale=None, shift=None):
     C = x.shape[-1]
     g = dy.to(_F)
     if a is not None:
         g = g * torch.where(a.to(_F) > 0, torch.ones_like(g), torch.full_like(g, slope))
+    elif scale is not None:
+        pre = x.to(_F) * scale + shift
+        g = g * torch.where(pre > 0, torch.ones_like(g), torch.full_like(g, slope))
     xhat = (x.to(_F) - mean) * rstd
     M = x.numel() // C
     s1 = g.reshape(-1, C).sum(0)

@@ -117,6 +117,14 @@ def test_batchnorm(dtype, shape, slope):
         assert rel_err(dg.cpu(), dgr) < 1e-4 and rel_err(db.cpu(), dbr) < 1e-4
         if use_res:
             assert rel_err(dres.float().cpu(), dresr.float()) < tol
+        elif slope != 1.0:
+            # mask recomputed from z*scale+shift instead of reading the saved output
+            dg2, db2 = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+            dx2 = ops.bn_bwd(dy.to(DEV), x.to(DEV), None, gamma.to(DEV), mean, rstd, slope, dg2, db2, scale=scale, shift=shift)
+            dgr2, dbr2 = torch.zeros(C), torch.zeros(C)
+            dxr2 = R.bn_bwd(dy, x, None, gamma, mr, rr, slope, dgr2, dbr2, scale=sr, shift=fr)
+            assert rel_err(dx2.float().cpu(), dxr2.float()) < tol
+            assert rel_err(dg2.cpu(), dgr2) < 1e-4 and rel_err(db2.cpu(), dbr2) < 1e-4
     sc, sf = ops.bn_eval_coeffs(gamma.to(DEV), beta.to(DEV), rm_g, rv_g)
     scr, sfr = R.bn_eval_coeffs(gamma, beta, rm_r, rv_r)
     assert rel_err(sc.cpu(), scr) < 1e-5 and rel_err(sf.cpu(), sfr) < 1e-5

@@ -24,8 +24,8 @@ inline unsigned grid_for(long long work_items, int per_sm = 8) {
 // CTAs of a per-channel reduction: enough to fill the machine for big tensors, few for small ones (every CTA
 // ends with 2*C atomics onto the same addresses)
 inline long long reduce_grid_cap(long long bytes, int slabs) {
-  long long want = bytes / (96 * 1024);            // >= 96 KB of input per CTA
-  const long long hi = 4LL * num_sms();
+  long long want = bytes / (256 * 1024);           // >= 256 KB of input per CTA
+  const long long hi = 2LL * num_sms();
   if (want > hi) want = hi;
   if (want < 1) want = 1;
   return (want + slabs - 1) / slabs;
@@ -293,6 +293,14 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __re
   const long long nv = n / VEC;
   const bool pow2 = (C & (C - 1)) == 0;
   const long long chunk = 4LL * blockDim.x;
+  // (VEC * blockDim) % C == 0: a thread always meets the same channels -> coefficients live in registers
+  const bool fixed_c = ((VEC * (int)blockDim.x) % C) == 0;
+  float sc[VEC], sf[VEC];
+  if (fixed_c) {
+    const int c = (threadIdx.x * VEC) % C;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) { sc[j] = sp[c + j]; sf[j] = sp[C + c + j]; }
+  }
   for (long long base = (long long)blockIdx.x * chunk; base < nv; base += (long long)gridDim.x * chunk) {
     float xv[4][VEC], rv[4][VEC];
 #pragma unroll
@@ -307,10 +315,14 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __re
     for (int u = 0; u < 4; ++u) {
       const long long ii = base + u * blockDim.x + threadIdx.x;
       if (ii < nv) {
-        const int c = pow2 ? ((int)ii * VEC) & (C - 1) : (int)((ii * VEC) % C);
+        if (!fixed_c) {
+          const int c = pow2 ? ((int)ii * VEC) & (C - 1) : (int)((ii * VEC) % C);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) { sc[j] = sp[c + j]; sf[j] = sp[C + c + j]; }
+        }
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
-          float v = xv[u][j] * sp[c + j] + sp[C + c + j];
+          float v = xv[u][j] * sc[j] + sf[j];
           if (residual) v += rv[u][j];
           xv[u][j] = act_fwd(v, slope);
         }
@@ -326,11 +338,15 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ a,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const float* __restrict__ scale, const float* __restrict__ shift,
                      double* sums, long long M, int Ctot, int C, float slope, const BnBwdFinal fin) {
+  // activation mask: from the saved output `a` when given, else (scale/shift given) recomputed from the
+  // pre-activation z*scale+shift — saves reading `a` for every non-residual layer
   extern __shared__ float sh[];
   const int c_off = blockIdx.y * C;
   dy += c_off; x += c_off; if (a) a += c_off;
   mean += c_off; rstd += c_off;
+  const bool zmask = (a == nullptr) && (scale != nullptr);
   const int cv = C / VEC;
   const int groups = blockDim.x / cv;
   const int g = threadIdx.x / cv, v = threadIdx.x % cv;
@@ -338,15 +354,16 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
 #pragma unroll
   for (int j = 0; j < VEC; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   if (g < groups) {
-    float mu[VEC], rs[VEC];
+    float mu[VEC], rs[VEC], sc[VEC], sf[VEC];
     ld_vec<VEC>(mean + v * VEC, mu);
     ld_vec<VEC>(rstd + v * VEC, rs);
+    if (zmask) { ld_vec<VEC>(scale + c_off + v * VEC, sc); ld_vec<VEC>(shift + c_off + v * VEC, sf); }
     const long long stride = (long long)gridDim.x * groups;
     const long long co = v * VEC;
-    for (long long r = (long long)blockIdx.x * groups + g; r < M; r += 2 * stride) {
-      float dv[2][VEC], xv[2][VEC], av[2][VEC];
+    for (long long r = (long long)blockIdx.x * groups + g; r < M; r += 4 * stride) {
+      float dv[4][VEC], xv[4][VEC], av[4][VEC];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < 4; ++u) {
         const long long rr = r + u * stride;
         if (rr < M) {
           ld_vec<VEC>(dy + rr * Ctot + co, dv[u]);
@@ -358,11 +375,12 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
         }
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           float gg = dv[u][j];
           if (a) gg *= (av[u][j] > 0.f) ? 1.f : slope;
+          else if (zmask) gg *= (xv[u][j] * sc[j] + sf[j] > 0.f) ? 1.f : slope;
           s1[j] += gg;
           s2[j] += gg * (xv[u][j] - mu[j]) * rs[j];
         }
@@ -395,18 +413,31 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ a,
                     const float* __restrict__ mean, const float* __restrict__ rstd,
-                    const float* __restrict__ coef, T* __restrict__ dx, T* dres, int dres_accumulate,
+                    const float* __restrict__ coef, const float* __restrict__ scale,
+                    const float* __restrict__ shift, T* __restrict__ dx, T* dres, int dres_accumulate,
                     long long n, int C, float slope) {
-  extern __shared__ float sp[];   // [5][C]: mean, rstd, k0, k1, k2
+  extern __shared__ float sp[];   // [7][C]: mean, rstd, k0, k1, k2, scale, shift
+  const bool zmask = (a == nullptr) && (scale != nullptr);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     sp[c] = mean[c]; sp[C + c] = rstd[c];
     sp[2 * C + c] = coef[c]; sp[3 * C + c] = coef[C + c]; sp[4 * C + c] = coef[2 * C + c];
+    sp[5 * C + c] = zmask ? scale[c] : 0.f; sp[6 * C + c] = zmask ? shift[c] : 0.f;
   }
   __syncthreads();
   const long long nv = n / VEC;
   const bool pow2 = (C & (C - 1)) == 0;
   const bool racc = dres && dres_accumulate;
   const long long chunk = 2LL * blockDim.x;
+  const bool fixed_c = ((VEC * (int)blockDim.x) % C) == 0;
+  float mu[VEC], rs[VEC], k0[VEC], k1[VEC], k2[VEC], sc[VEC], sf[VEC];
+  if (fixed_c) {
+    const int c = (threadIdx.x * VEC) % C;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      mu[j] = sp[c + j]; rs[j] = sp[C + c + j]; k0[j] = sp[2 * C + c + j]; k1[j] = sp[3 * C + c + j]; k2[j] = sp[4 * C + c + j];
+      sc[j] = sp[5 * C + c + j]; sf[j] = sp[6 * C + c + j];
+    }
+  }
   for (long long base = (long long)blockIdx.x * chunk; base < nv; base += (long long)gridDim.x * chunk) {
     float dv[2][VEC], xv[2][VEC], av[2][VEC], rv[2][VEC];
 #pragma unroll
@@ -423,13 +454,21 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
     for (int u = 0; u < 2; ++u) {
       const long long ii = base + u * blockDim.x + threadIdx.x;
       if (ii < nv) {
-        const int c = pow2 ? ((int)ii * VEC) & (C - 1) : (int)((ii * VEC) % C);
+        if (!fixed_c) {
+          const int c = pow2 ? ((int)ii * VEC) & (C - 1) : (int)((ii * VEC) % C);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            mu[j] = sp[c + j]; rs[j] = sp[C + c + j]; k0[j] = sp[2 * C + c + j]; k1[j] = sp[3 * C + c + j]; k2[j] = sp[4 * C + c + j];
+            sc[j] = sp[5 * C + c + j]; sf[j] = sp[6 * C + c + j];
+          }
+        }
         float ov[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           float g = dv[u][j];
           if (a) g *= (av[u][j] > 0.f) ? 1.f : slope;
-          ov[j] = sp[2 * C + c + j] * g - sp[3 * C + c + j] - sp[4 * C + c + j] * (xv[u][j] - sp[c + j]) * sp[C + c + j];
+          else if (zmask) g *= (xv[u][j] * sc[j] + sf[j] > 0.f) ? 1.f : slope;
+          ov[j] = k0[j] * g - k1[j] - k2[j] * (xv[u][j] - mu[j]) * rs[j];
           dv[u][j] = racc ? rv[u][j] + g : g;
         }
         st_vec<VEC>(dx + ii * VEC, ov);
@@ -913,7 +952,8 @@ extern "C" int uda_bn_apply_fused(const void* x, const void* residual, void* y, 
 
 // workspace: 2*C doubles + 3*C floats
 extern "C" int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtype, const float* gamma,
-                          const float* mean, const float* rstd, void* dx, void* dres, int dres_accumulate,
+                          const float* mean, const float* rstd, const float* scale, const float* shift, void* dx,
+                          void* dres, int dres_accumulate,
                           float* dgamma, float* dbeta, int param_accumulate, long long M, int C, float slope,
                           void* workspace, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
@@ -926,7 +966,9 @@ extern "C" int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtyp
   int vec = vec_for(dtype, C, dy, x, a, dx);
   if (dres) vec = vec < vec_for(dtype, C, dres) ? vec : vec_for(dtype, C, dres);
   if (vec > 1 && (reinterpret_cast<uintptr_t>(mean) % 16 || reinterpret_cast<uintptr_t>(rstd) % 16 ||
-                  reinterpret_cast<uintptr_t>(coef) % 16 || C % 4)) vec = 1;
+                  reinterpret_cast<uintptr_t>(coef) % 16 || C % 4 ||
+                  (scale && (reinterpret_cast<uintptr_t>(scale) % 16 || reinterpret_cast<uintptr_t>(shift) % 16)))) vec = 1;
+  UDA_REQUIRE((scale == nullptr) == (shift == nullptr), UDA_ERR_BAD_ARG, "bn_bwd: scale and shift go together");
   const int rvec = vec;
   int slabs = 1;
   while ((C / slabs) / rvec > kThreads || (C % slabs)) ++slabs;
@@ -938,14 +980,14 @@ extern "C" int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtyp
   if (blocks > cap) blocks = cap;
   size_t smem = (size_t)groups * Cs * 2 * sizeof(float);
   UDA_REQUIRE(smem <= 48 * 1024, UDA_ERR_UNSUPPORTED, "bn_bwd: C=%d needs too much shared memory", C);
-#define K(T, V) bn_bwd_reduce_kernel<T, V><<<dim3((unsigned)blocks, slabs), kThreads, smem, st>>>((const T*)dy, (const T*)x, (const T*)a, mean, rstd, sums, M, C, Cs, slope, fin)
+#define K(T, V) bn_bwd_reduce_kernel<T, V><<<dim3((unsigned)blocks, slabs), kThreads, smem, st>>>((const T*)dy, (const T*)x, (const T*)a, mean, rstd, scale, shift, sums, M, C, Cs, slope, fin)
 #define KV(T, ...) do { if (rvec == 8) K(T, 8); else if (rvec == 4) K(T, 4); else if (rvec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV
 #undef K
   UDA_LAUNCH_OK("bn_bwd_reduce_kernel");
   const long long n = M * C;
-#define K(T, V) bn_bwd_apply_kernel<T, V><<<grid_for(n / V / 2), kThreads, 5 * C * sizeof(float), st>>>((const T*)dy, (const T*)x, (const T*)a, mean, rstd, coef, (T*)dx, (T*)dres, dres_accumulate, n, C, slope)
+#define K(T, V) bn_bwd_apply_kernel<T, V><<<grid_for(n / V / 2), kThreads, 7 * C * sizeof(float), st>>>((const T*)dy, (const T*)x, (const T*)a, mean, rstd, coef, scale, shift, (T*)dx, (T*)dres, dres_accumulate, n, C, slope)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV

@@ -282,8 +282,8 @@ def bn_act(ctx, zin, bn, slope=0.0, residual=None):
     st = ctx.store
     res_t = residual.t if residual is not None else None
     if ctx.training and zin.sums is not None:
-        a, mean, rstd = ops.bn_apply_fused(zin.t, zin.sums, bn.weight, bn.bias, bn.running_mean, bn.running_var,
-                                           bn.eps, bn.momentum, res_t, slope)
+        a, mean, rstd, scale, shift = ops.bn_apply_fused(zin.t, zin.sums, bn.weight, bn.bias, bn.running_mean,
+                                                         bn.running_var, bn.eps, bn.momentum, res_t, slope)
         bn.num_batches_tracked += 1
     else:
         if ctx.training:
@@ -312,8 +312,12 @@ def bn_act(ctx, zin, bn, slope=0.0, residual=None):
                     dres = torch.empty_like(residual.t)
                 else:
                     dres, acc = residual.g, True
-            zin.g = ops.bn_bwd(da, zin.t, a if slope != 1.0 else None, bn.weight, mean, rstd, slope,
-                               st.g(bn.weight), st.g(bn.bias), dres=dres, dres_accumulate=acc)
+            # activation mask: non-residual layers recompute it from z (no read of `a`); residual ones need `a`
+            use_a = slope != 1.0 and residual is not None
+            zm = slope != 1.0 and residual is None
+            zin.g = ops.bn_bwd(da, zin.t, a if use_a else None, bn.weight, mean, rstd, slope,
+                               st.g(bn.weight), st.g(bn.bias), dres=dres, dres_accumulate=acc,
+                               scale=scale if zm else None, shift=shift if zm else None)
             if residual is not None:
                 residual.g = dres
             ctx.done(bn.weight, bn.bias)

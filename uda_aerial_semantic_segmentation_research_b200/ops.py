@@ -326,18 +326,20 @@ def bn_apply_fused(x, sums, gamma, beta, running_mean, running_var, eps=1e-5, mo
          ptr(running_mean), ptr(running_var), ptr(st[0]), ptr(st[1]), ptr(st[2]), ptr(st[3]), ll(M), ci(C), float(eps),
          float(momentum), float(slope), _stream())
     _count()
-    return y, st[0], st[1]
+    return y, st[0], st[1], st[2], st[3]
 
 
 def bn_bwd(dy, x, a, gamma, mean, rstd, slope, dgamma, dbeta, dres=None, dres_accumulate=False,
-           param_accumulate=True):
-    """BatchNorm(+activation) backward.  Returns dx; accumulates dgamma/dbeta; fills/accumulates dres."""
+           param_accumulate=True, scale=None, shift=None):
+    """BatchNorm(+activation) backward.  Returns dx; accumulates dgamma/dbeta; fills/accumulates dres.
+    ``a=None`` with ``scale``/``shift``: the activation mask is recomputed from x*scale+shift."""
     _chk(dy, "bn_bwd.dy"); _chk(x, "bn_bwd.x", dy.dtype)
     C = x.shape[-1]
     M = x.numel() // C
     dx = torch.empty_like(x)
     ws = bn_workspace(x.device, C)
-    call("bn_bwd", ptr(dy), ptr(x), ptr(a), ci(dt(x)), ptr(gamma), ptr(mean), ptr(rstd), ptr(dx), ptr(dres),
+    call("bn_bwd", ptr(dy), ptr(x), ptr(a), ci(dt(x)), ptr(gamma), ptr(mean), ptr(rstd), ptr(scale), ptr(shift),
+         ptr(dx), ptr(dres),
          ci(1 if dres_accumulate else 0), ptr(dgamma), ptr(dbeta), ci(1 if param_accumulate else 0), ll(M), ci(C),
          float(slope), ptr(ws), _stream())
     _count(2)
