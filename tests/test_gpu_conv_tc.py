@@ -72,7 +72,7 @@ def test_tc_forward_and_dgrad(cfg):
     g, b = torch.rand(Cout, device=DEV) + 0.5, torch.randn(Cout, device=DEV)
     rm1, rv1 = torch.zeros(Cout, device=DEV), torch.ones(Cout, device=DEV)
     rm2, rv2 = rm1.clone(), rv1.clone()
-    a1, mean1, rstd1 = ops.bn_apply_fused(y0, sums, g, b, rm1, rv1, 1e-5, 0.1, None, 0.0)
+    a1, mean1, rstd1, _sc1, _sh1 = ops.bn_apply_fused(y0, sums, g, b, rm1, rv1, 1e-5, 0.1, None, 0.0)
     mean2, rstd2, sc2, sh2 = ops.bn_stats(y0, g, b, rm2, rv2, 1e-5, 0.1)
     a2 = ops.bn_apply(y0, sc2, sh2, None, 0.0)
     assert rel_err(mean1, mean2) < 1e-4 and rel_err(rstd1, rstd2) < 1e-4

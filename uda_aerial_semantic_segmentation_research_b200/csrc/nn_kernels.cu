@@ -177,7 +177,7 @@ __device__ __forceinline__ bool last_block_done(unsigned int* counter) {
 // dgamma = sums[C+c], dbeta = sums[c] (accumulated into fp32 grads), and the per-channel
 // coefficients of the apply pass:  dx = k0*g - k1 - k2*xhat
 struct BnBwdFinal {
-  const float* gamma; const float* rstd; float* dgamma; float* dbeta; float* coef;
+  const float* gamma; const float* mean; const float* rstd; float* dgamma; float* dbeta; float* coef;
   long long M; int accumulate;
   unsigned int* counter;
 };
@@ -186,9 +186,13 @@ __device__ __forceinline__ void bn_bwd_finalize_channel(const BnBwdFinal& f, dou
   double k0 = (double)g * (double)f.rstd[c];
   if (f.dgamma) f.dgamma[c] = (f.accumulate ? f.dgamma[c] : 0.f) + (float)s2;
   if (f.dbeta) f.dbeta[c] = (f.accumulate ? f.dbeta[c] : 0.f) + (float)s1;
+  // dx = k0*g - k1 - k2*xhat  with  k1 = k0*s1/M, k2 = k0*s2/M, xhat = (x-mean)*rstd
+  //    = A*g + Bc*x + Cc     (three per-channel coefficients for the apply pass)
+  const double k1 = k0 * s1 / (double)f.M, k2 = k0 * s2 / (double)f.M;
+  const double rs = (double)f.rstd[c], mu = (double)f.mean[c];
   f.coef[c] = (float)k0;
-  f.coef[C + c] = (float)(k0 * s1 / (double)f.M);
-  f.coef[2 * C + c] = (float)(k0 * s2 / (double)f.M);
+  f.coef[C + c] = (float)(-k2 * rs);
+  f.coef[2 * C + c] = (float)(-k1 + k2 * rs * mu);
 }
 
 // sums[c] += sum_rows x, sums[C+c] += sum_rows x^2   (double accumulators, zeroed by the host)
@@ -265,7 +269,7 @@ __device__ __forceinline__ float act_fwd(float v, float slope) { return v > 0.f 
 
 // y = act(x*scale[c] + shift[c] (+ residual)),  act: slope=1 -> identity, 0 -> ReLU, 0.2 -> LeakyReLU
 template <typename T, int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __restrict__ y,
                 const float* __restrict__ scale, const float* __restrict__ shift, long long n, int C, float slope,
                 const double* __restrict__ sums, const BnFwdFinal fin) {
@@ -335,7 +339,7 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __re
 // Backward reduce: g = dy * act'(a);  sums[c] += sum g,  sums[C+c] += sum g * xhat,
 // xhat = (x - mean) * rstd.  `a` is the saved post-activation output (sign decides act').
 template <typename T, int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ a,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const float* __restrict__ scale, const float* __restrict__ shift,
@@ -360,10 +364,10 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
     if (zmask) { ld_vec<VEC>(scale + c_off + v * VEC, sc); ld_vec<VEC>(shift + c_off + v * VEC, sf); }
     const long long stride = (long long)gridDim.x * groups;
     const long long co = v * VEC;
-    for (long long r = (long long)blockIdx.x * groups + g; r < M; r += 4 * stride) {
-      float dv[4][VEC], xv[4][VEC], av[4][VEC];
+    for (long long r = (long long)blockIdx.x * groups + g; r < M; r += 2 * stride) {
+      float dv[2][VEC], xv[2][VEC], av[2][VEC];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < 2; ++u) {
         const long long rr = r + u * stride;
         if (rr < M) {
           ld_vec<VEC>(dy + rr * Ctot + co, dv[u]);
@@ -375,7 +379,7 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
         }
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int j = 0; j < VEC; ++j) {
           float gg = dv[u][j];
@@ -410,18 +414,18 @@ bn_bwd_reduce_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
 
 // dx = k0*g - k1 - k2*xhat ;  optionally d_residual (+)= g  (identity branch of a residual block)
 template <typename T, int VEC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ a,
-                    const float* __restrict__ mean, const float* __restrict__ rstd,
                     const float* __restrict__ coef, const float* __restrict__ scale,
                     const float* __restrict__ shift, T* __restrict__ dx, T* dres, int dres_accumulate,
                     long long n, int C, float slope) {
-  extern __shared__ float sp[];   // [7][C]: mean, rstd, k0, k1, k2, scale, shift
+  // dx = A*g + Bc*x + Cc with g = dy * act'(.) ; per-channel A, Bc, Cc from the reduce pass' last CTA.
+  // A thread meets the same channels in every iteration ((VEC*blockDim) % C == 0): coefficients in registers.
+  extern __shared__ float sp[];   // [5][C]: A, Bc, Cc, scale, shift
   const bool zmask = (a == nullptr) && (scale != nullptr);
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    sp[c] = mean[c]; sp[C + c] = rstd[c];
-    sp[2 * C + c] = coef[c]; sp[3 * C + c] = coef[C + c]; sp[4 * C + c] = coef[2 * C + c];
-    sp[5 * C + c] = zmask ? scale[c] : 0.f; sp[6 * C + c] = zmask ? shift[c] : 0.f;
+    sp[c] = coef[c]; sp[C + c] = coef[C + c]; sp[2 * C + c] = coef[2 * C + c];
+    sp[3 * C + c] = zmask ? scale[c] : 0.f; sp[4 * C + c] = zmask ? shift[c] : 0.f;
   }
   __syncthreads();
   const long long nv = n / VEC;
@@ -429,13 +433,12 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
   const bool racc = dres && dres_accumulate;
   const long long chunk = 2LL * blockDim.x;
   const bool fixed_c = ((VEC * (int)blockDim.x) % C) == 0;
-  float mu[VEC], rs[VEC], k0[VEC], k1[VEC], k2[VEC], sc[VEC], sf[VEC];
+  float kA[VEC], kB[VEC], kC[VEC], sc[VEC], sf[VEC];
   if (fixed_c) {
     const int c = (threadIdx.x * VEC) % C;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) {
-      mu[j] = sp[c + j]; rs[j] = sp[C + c + j]; k0[j] = sp[2 * C + c + j]; k1[j] = sp[3 * C + c + j]; k2[j] = sp[4 * C + c + j];
-      sc[j] = sp[5 * C + c + j]; sf[j] = sp[6 * C + c + j];
+      kA[j] = sp[c + j]; kB[j] = sp[C + c + j]; kC[j] = sp[2 * C + c + j]; sc[j] = sp[3 * C + c + j]; sf[j] = sp[4 * C + c + j];
     }
   }
   for (long long base = (long long)blockIdx.x * chunk; base < nv; base += (long long)gridDim.x * chunk) {
@@ -458,8 +461,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
           const int c = pow2 ? ((int)ii * VEC) & (C - 1) : (int)((ii * VEC) % C);
 #pragma unroll
           for (int j = 0; j < VEC; ++j) {
-            mu[j] = sp[c + j]; rs[j] = sp[C + c + j]; k0[j] = sp[2 * C + c + j]; k1[j] = sp[3 * C + c + j]; k2[j] = sp[4 * C + c + j];
-            sc[j] = sp[5 * C + c + j]; sf[j] = sp[6 * C + c + j];
+            kA[j] = sp[c + j]; kB[j] = sp[C + c + j]; kC[j] = sp[2 * C + c + j]; sc[j] = sp[3 * C + c + j]; sf[j] = sp[4 * C + c + j];
           }
         }
         float ov[VEC];
@@ -468,7 +470,7 @@ bn_bwd_apply_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* 
           float g = dv[u][j];
           if (a) g *= (av[u][j] > 0.f) ? 1.f : slope;
           else if (zmask) g *= (xv[u][j] * sc[j] + sf[j] > 0.f) ? 1.f : slope;
-          ov[j] = k0[j] * g - k1[j] - k2[j] * (xv[u][j] - mu[j]) * rs[j];
+          ov[j] = kA[j] * g + kB[j] * xv[u][j] + kC[j];
           dv[u][j] = racc ? rv[u][j] + g : g;
         }
         st_vec<VEC>(dx + ii * VEC, ov);
@@ -962,7 +964,7 @@ extern "C" int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtyp
   double* sums = (double*)workspace + 2;                  // see uda_bn_stats for the layout
   unsigned int* counter = reinterpret_cast<unsigned int*>(workspace);
   float* coef = (float*)((double*)workspace + 2 + 2 * 4096);
-  BnBwdFinal fin{gamma, rstd, dgamma, dbeta, coef, M, param_accumulate, counter};
+  BnBwdFinal fin{gamma, mean, rstd, dgamma, dbeta, coef, M, param_accumulate, counter};
   int vec = vec_for(dtype, C, dy, x, a, dx);
   if (dres) vec = vec < vec_for(dtype, C, dres) ? vec : vec_for(dtype, C, dres);
   if (vec > 1 && (reinterpret_cast<uintptr_t>(mean) % 16 || reinterpret_cast<uintptr_t>(rstd) % 16 ||
@@ -987,7 +989,7 @@ extern "C" int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtyp
 #undef K
   UDA_LAUNCH_OK("bn_bwd_reduce_kernel");
   const long long n = M * C;
-#define K(T, V) bn_bwd_apply_kernel<T, V><<<grid_for(n / V / 2), kThreads, 7 * C * sizeof(float), st>>>((const T*)dy, (const T*)x, (const T*)a, mean, rstd, coef, scale, shift, (T*)dx, (T*)dres, dres_accumulate, n, C, slope)
+#define K(T, V) bn_bwd_apply_kernel<T, V><<<grid_for(n / V / 2), kThreads, 5 * C * sizeof(float), st>>>((const T*)dy, (const T*)x, (const T*)a, coef, scale, shift, (T*)dx, (T*)dres, dres_accumulate, n, C, slope)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV
