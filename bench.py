@@ -180,7 +180,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     torch.manual_seed(0)
     size, B = args.size, args.batch
     model = U.Unet("resnet34", encoder_weights=None, in_channels=3, classes=CLASSES).to(dev).train()

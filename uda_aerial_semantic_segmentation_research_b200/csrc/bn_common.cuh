@@ -1,0 +1,79 @@
+// BatchNorm per-channel finalize helpers shared by nn_kernels.cu and stream_kernels.cu.
+#pragma once
+#include "common.cuh"
+
+namespace uda {
+namespace bn {
+
+// mean/var -> scale/shift (+ running statistics update, momentum, unbiased running var)
+struct BnFwdFinal {
+  const float* gamma; const float* beta; float* running_mean; float* running_var;
+  float* mean_out; float* rstd_out; float* scale_out; float* shift_out;
+  long long M; float eps, momentum;
+  unsigned int* counter;   // zero on entry, zero again on exit
+};
+__device__ __forceinline__ void bn_fwd_finalize_channel(const BnFwdFinal& f, double s1, double s2, int c) {
+  double mean = s1 / (double)f.M;
+  double var = s2 / (double)f.M - mean * mean;
+  if (var < 0.0) var = 0.0;
+  double rstd = 1.0 / sqrt(var + (double)f.eps);
+  float g = f.gamma ? f.gamma[c] : 1.f, b = f.beta ? f.beta[c] : 0.f;
+  f.mean_out[c] = (float)mean;
+  f.rstd_out[c] = (float)rstd;
+  f.scale_out[c] = (float)((double)g * rstd);
+  f.shift_out[c] = (float)((double)b - mean * (double)g * rstd);
+  if (f.running_mean) {
+    double unb = (f.M > 1) ? var * (double)f.M / (double)(f.M - 1) : var;
+    f.running_mean[c] = (float)((1.0 - f.momentum) * (double)f.running_mean[c] + f.momentum * mean);
+    f.running_var[c] = (float)((1.0 - f.momentum) * (double)f.running_var[c] + f.momentum * unb);
+  }
+}
+
+// "last block done": returns true in every thread of the block that finished last (all partial sums of
+// all blocks are then visible).  Classic threadfence reduction pattern.
+__device__ __forceinline__ bool last_block_done(unsigned int* counter) {
+  __shared__ bool is_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    unsigned int t = atomicAdd(counter, 1u);
+    is_last = (t == total - 1);
+  }
+  __syncthreads();
+  if (is_last) __threadfence();
+  return is_last;
+}
+
+// dgamma = sums[C+c], dbeta = sums[c] (accumulated into fp32 grads), and the per-channel
+// coefficients of the apply pass:  dx = k0*g - k1 - k2*xhat
+struct BnBwdFinal {
+  const float* gamma; const float* mean; const float* rstd; float* dgamma; float* dbeta; float* coef;
+  long long M; int accumulate;
+  unsigned int* counter;
+};
+__device__ __forceinline__ void bn_bwd_finalize_channel(const BnBwdFinal& f, double s1, double s2, int c, int C) {
+  float g = f.gamma ? f.gamma[c] : 1.f;
+  double k0 = (double)g * (double)f.rstd[c];
+  if (f.dgamma) f.dgamma[c] = (f.accumulate ? f.dgamma[c] : 0.f) + (float)s2;
+  if (f.dbeta) f.dbeta[c] = (f.accumulate ? f.dbeta[c] : 0.f) + (float)s1;
+  // dx = k0*g - k1 - k2*xhat  with  k1 = k0*s1/M, k2 = k0*s2/M, xhat = (x-mean)*rstd
+  //    = A*g + Bc*x + Cc     (three per-channel coefficients for the apply pass)
+  const double k1 = k0 * s1 / (double)f.M, k2 = k0 * s2 / (double)f.M;
+  const double rs = (double)f.rstd[c], mu = (double)f.mean[c];
+  f.coef[c] = (float)k0;
+  f.coef[C + c] = (float)(-k2 * rs);
+  f.coef[2 * C + c] = (float)(-k1 + k2 * rs * mu);
+}
+
+
+}  // namespace bn
+
+// stream_kernels.cu: bulk-copy streaming fast paths (bf16, C a power of two <= 2048, >= 1 MB tensors)
+bool bn_stream_ok(int dtype, long long M, int C);
+int bn_apply_stream(const void* x, const void* residual, void* y, const float* scale, const float* shift,
+                    const double* sums, const bn::BnFwdFinal& fin, long long M, int C, float slope, cudaStream_t st);
+int bn_bwd_stream(const void* dy, const void* x, const void* a, const float* mean, const float* rstd,
+                  const float* scale, const float* shift, void* dx, void* dres, int dres_accumulate, double* sums,
+                  float* coef, const bn::BnBwdFinal& fin, long long M, int C, float slope, cudaStream_t st);
+}  // namespace uda

@@ -6,12 +6,24 @@
 // BatchNorm2d eps=1e-5, momentum=0.1, ReLU, MaxPool2d(3,2,1), nearest x2 upsample + channel concat
 //  — and the discriminator's BatchNorm + LeakyReLU(0.2) + AdaptiveAvgPool
 // (src/models/discriminator.py:15-42); torch.optim.Adam defaults (src/models/train.py:461).
-#include "common.cuh"
+#include "bn_common.cuh"
+#include <stdlib.h>
 
 namespace uda {
 namespace {
 
+using namespace bn;
+
 constexpr int kThreads = 256;
+
+inline bool use_stream() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UDA_B200_BN_STREAM");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
 
 inline unsigned grid_for(long long work_items, int per_sm = 8) {
   long long blocks = (work_items + kThreads - 1) / kThreads;
@@ -134,67 +146,6 @@ __global__ void cast_f32_kernel(const float* __restrict__ src, T* __restrict__ d
 // ---------------------------------------------------------------------------------------------
 // BatchNorm.  x is [M][C] (M = B*H*W rows, C innermost).  VEC channels per thread.
 // ---------------------------------------------------------------------------------------------
-// mean/var -> scale/shift (+ running statistics update, momentum, unbiased running var)
-struct BnFwdFinal {
-  const float* gamma; const float* beta; float* running_mean; float* running_var;
-  float* mean_out; float* rstd_out; float* scale_out; float* shift_out;
-  long long M; float eps, momentum;
-  unsigned int* counter;   // zero on entry, zero again on exit
-};
-__device__ __forceinline__ void bn_fwd_finalize_channel(const BnFwdFinal& f, double s1, double s2, int c) {
-  double mean = s1 / (double)f.M;
-  double var = s2 / (double)f.M - mean * mean;
-  if (var < 0.0) var = 0.0;
-  double rstd = 1.0 / sqrt(var + (double)f.eps);
-  float g = f.gamma ? f.gamma[c] : 1.f, b = f.beta ? f.beta[c] : 0.f;
-  f.mean_out[c] = (float)mean;
-  f.rstd_out[c] = (float)rstd;
-  f.scale_out[c] = (float)((double)g * rstd);
-  f.shift_out[c] = (float)((double)b - mean * (double)g * rstd);
-  if (f.running_mean) {
-    double unb = (f.M > 1) ? var * (double)f.M / (double)(f.M - 1) : var;
-    f.running_mean[c] = (float)((1.0 - f.momentum) * (double)f.running_mean[c] + f.momentum * mean);
-    f.running_var[c] = (float)((1.0 - f.momentum) * (double)f.running_var[c] + f.momentum * unb);
-  }
-}
-
-// "last block done": returns true in every thread of the block that finished last (all partial sums of
-// all blocks are then visible).  Classic threadfence reduction pattern.
-__device__ __forceinline__ bool last_block_done(unsigned int* counter) {
-  __shared__ bool is_last;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    unsigned int total = gridDim.x * gridDim.y * gridDim.z;
-    unsigned int t = atomicAdd(counter, 1u);
-    is_last = (t == total - 1);
-  }
-  __syncthreads();
-  if (is_last) __threadfence();
-  return is_last;
-}
-
-// dgamma = sums[C+c], dbeta = sums[c] (accumulated into fp32 grads), and the per-channel
-// coefficients of the apply pass:  dx = k0*g - k1 - k2*xhat
-struct BnBwdFinal {
-  const float* gamma; const float* mean; const float* rstd; float* dgamma; float* dbeta; float* coef;
-  long long M; int accumulate;
-  unsigned int* counter;
-};
-__device__ __forceinline__ void bn_bwd_finalize_channel(const BnBwdFinal& f, double s1, double s2, int c, int C) {
-  float g = f.gamma ? f.gamma[c] : 1.f;
-  double k0 = (double)g * (double)f.rstd[c];
-  if (f.dgamma) f.dgamma[c] = (f.accumulate ? f.dgamma[c] : 0.f) + (float)s2;
-  if (f.dbeta) f.dbeta[c] = (f.accumulate ? f.dbeta[c] : 0.f) + (float)s1;
-  // dx = k0*g - k1 - k2*xhat  with  k1 = k0*s1/M, k2 = k0*s2/M, xhat = (x-mean)*rstd
-  //    = A*g + Bc*x + Cc     (three per-channel coefficients for the apply pass)
-  const double k1 = k0 * s1 / (double)f.M, k2 = k0 * s2 / (double)f.M;
-  const double rs = (double)f.rstd[c], mu = (double)f.mean[c];
-  f.coef[c] = (float)k0;
-  f.coef[C + c] = (float)(-k2 * rs);
-  f.coef[2 * C + c] = (float)(-k1 + k2 * rs * mu);
-}
-
 // sums[c] += sum_rows x, sums[C+c] += sum_rows x^2   (double accumulators, zeroed by the host)
 template <typename T, int VEC>
 __global__ void __launch_bounds__(kThreads)
@@ -919,6 +870,8 @@ extern "C" int uda_bn_apply(const void* x, const void* residual, void* y, int dt
                             const float* shift, long long M, int C, float slope, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   UDA_REQUIRE(x && y && scale && shift && M > 0 && C > 0, UDA_ERR_BAD_ARG, "bn_apply: bad argument");
+  if (use_stream() && bn_stream_ok(dtype, M, C) && vec_for(dtype, C, x, residual, y) == 8)
+    return bn_apply_stream(x, residual, y, scale, shift, nullptr, BnFwdFinal{}, M, C, slope, st);
   int vec = vec_for(dtype, C, x, residual, y);
   if (reinterpret_cast<uintptr_t>(scale) % 16 || reinterpret_cast<uintptr_t>(shift) % 16) vec = 1;
   const long long n = M * C;
@@ -943,6 +896,8 @@ extern "C" int uda_bn_apply_fused(const void* x, const void* residual, void* y, 
   int vec = vec_for(dtype, C, x, residual, y);
   const long long n = M * C;
   BnFwdFinal fin{gamma, beta, running_mean, running_var, mean, rstd, scale, shift, M, eps, momentum, nullptr};
+  if (use_stream() && bn_stream_ok(dtype, M, C) && vec == 8)
+    return bn_apply_stream(x, residual, y, nullptr, nullptr, sums, fin, M, C, slope, st);
 #define K(T, V) bn_apply_kernel<T, V><<<grid_for(n / V / 4), kThreads, 2 * C * sizeof(float), st>>>((const T*)x, (const T*)residual, (T*)y, nullptr, nullptr, n, C, slope, sums, fin)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
@@ -967,6 +922,9 @@ extern "C" int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtyp
   BnBwdFinal fin{gamma, mean, rstd, dgamma, dbeta, coef, M, param_accumulate, counter};
   int vec = vec_for(dtype, C, dy, x, a, dx);
   if (dres) vec = vec < vec_for(dtype, C, dres) ? vec : vec_for(dtype, C, dres);
+  UDA_REQUIRE((scale == nullptr) == (shift == nullptr), UDA_ERR_BAD_ARG, "bn_bwd: scale and shift go together");
+  if (use_stream() && bn_stream_ok(dtype, M, C) && vec == 8)
+    return bn_bwd_stream(dy, x, a, mean, rstd, scale, shift, dx, dres, dres_accumulate, sums, coef, fin, M, C, slope, st);
   if (vec > 1 && (reinterpret_cast<uintptr_t>(mean) % 16 || reinterpret_cast<uintptr_t>(rstd) % 16 ||
                   reinterpret_cast<uintptr_t>(coef) % 16 || C % 4 ||
                   (scale && (reinterpret_cast<uintptr_t>(scale) % 16 || reinterpret_cast<uintptr_t>(shift) % 16)))) vec = 1;
