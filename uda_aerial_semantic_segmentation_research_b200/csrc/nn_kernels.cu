@@ -231,14 +231,14 @@ bn_apply_kernel(const T* __restrict__ x, const T* __restrict__ residual, T* __re
   // the backward pass and updates the running statistics (the separate finalize launch disappears).
   extern __shared__ float sp[];   // [2][C]
   if (sums) {
+    const double inv_m = 1.0 / (double)fin.M;
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      const double mean = sums[c] / (double)fin.M;
-      double var = sums[C + c] / (double)fin.M - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const double rstd = 1.0 / sqrt(var + (double)fin.eps);
+      const double mean = sums[c] * inv_m;
+      const float var = fmaxf((float)(sums[C + c] * inv_m - mean * mean), 0.f);
+      const float rstd = rsqrtf(var + fin.eps);
       const float g = fin.gamma ? fin.gamma[c] : 1.f, b = fin.beta ? fin.beta[c] : 0.f;
-      sp[c] = (float)((double)g * rstd);
-      sp[C + c] = (float)((double)b - mean * (double)g * rstd);
+      sp[c] = g * rstd;
+      sp[C + c] = b - (float)mean * g * rstd;
       if (blockIdx.x == 0) bn_fwd_finalize_channel(fin, sums[c], sums[C + c], c);
     }
   } else {

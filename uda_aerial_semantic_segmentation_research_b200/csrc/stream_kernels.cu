@@ -100,16 +100,18 @@ __global__ void __launch_bounds__(kThreads) bn_apply_stream_kernel(const ApplyPa
   const int c = (threadIdx.x * 8) % C;   // (kThreads*8) % C == 0: fixed channels per thread
   float sc[8], sf[8];
   if (p.sums) {
+    // FP64 only where the cancellation lives (var = E[x^2] - mean^2: three DP instructions per channel);
+    // everything else in fp32 — B200's FP64 rate makes a DP divide/sqrt per CTA per channel cost tens of us
+    const double inv_m = 1.0 / (double)p.fin.M;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const double s1 = p.sums[c + j], s2 = p.sums[C + c + j];
-      const double mean = s1 / (double)p.fin.M;
-      double var = s2 / (double)p.fin.M - mean * mean;
-      if (var < 0.0) var = 0.0;
-      const double rstd = 1.0 / sqrt(var + (double)p.fin.eps);
+      const double mean = s1 * inv_m;
+      const float var = fmaxf((float)(s2 * inv_m - mean * mean), 0.f);
+      const float rstd = rsqrtf(var + p.fin.eps);
       const float g = p.fin.gamma ? p.fin.gamma[c + j] : 1.f, b = p.fin.beta ? p.fin.beta[c + j] : 0.f;
-      sc[j] = (float)((double)g * rstd);
-      sf[j] = (float)((double)b - mean * (double)g * rstd);
+      sc[j] = g * rstd;
+      sf[j] = b - (float)mean * g * rstd;
       if (blockIdx.x == 0 && threadIdx.x < C / 8) bn_fwd_finalize_channel(p.fin, s1, s2, c + j);
     }
   } else {
@@ -164,10 +166,10 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_stream_kernel(const Re
   const int C = p.C;
   const int c = (threadIdx.x * 8) % C;
   const bool zmask = !p.has_a && p.scale != nullptr;
-  float mu[8], rs[8], sc[8], sf[8], s1[8], s2[8];
+  float nmr[8], rs[8], sc[8], sf[8], s1[8], s2[8];   // nmr = -mean*rstd:  xhat = fma(x, rstd, nmr)
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    mu[j] = p.mean[c + j]; rs[j] = p.rstd[c + j];
+    rs[j] = p.rstd[c + j]; nmr[j] = -p.mean[c + j] * rs[j];
     sc[j] = zmask ? p.scale[c + j] : 0.f; sf[j] = zmask ? p.shift[c + j] : 0.f;
     s1[j] = 0.f; s2[j] = 0.f;
   }
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(kThreads) bn_bwd_reduce_stream_kernel(const Re
           if (p.has_a) g *= (a[j] > 0.f) ? 1.f : p.slope;
           else if (zmask) g *= (x[j] * sc[j] + sf[j] > 0.f) ? 1.f : p.slope;
           s1[j] += g;
-          s2[j] += g * (x[j] - mu[j]) * rs[j];
+          s2[j] = fmaf(g, fmaf(x[j], rs[j], nmr[j]), s2[j]);
         }
       }
     }
