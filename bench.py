@@ -281,6 +281,10 @@ def run_ours(args):
         for name, evs in prof.items():
             tot = sum(a.elapsed_time(b) for a, b in evs)
             breakdown[name] = {"ms_per_step": tot / prof_steps, "launches_per_step": len(evs) / prof_steps}
+            if os.environ.get("UDA_B200_PROFILE_DUMP"):   # per-call durations (us) of the last profiled step
+                per = len(evs) // prof_steps
+                last = [round(a.elapsed_time(b) * 1e3, 1) for a, b in evs[-per:]]
+                print(f"[profile] {name}: {last}", file=sys.stderr)
         pk = peaks()
         # tensor-core convolution family: algorithmic FLOPs routed through the tcgen05 kernels
         tc_keys = ("conv2d_tc_fwd", "conv2d_tc_dgrad", "conv2d_tc_wgrad", "stem_tc_fwd", "stem_tc_wgrad")

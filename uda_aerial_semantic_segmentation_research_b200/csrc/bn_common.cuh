@@ -12,20 +12,25 @@ struct BnFwdFinal {
   long long M; float eps, momentum;
   unsigned int* counter;   // zero on entry, zero again on exit
 };
+// B200's FP64 pipe is ~1/64 of FP32 and a DP divide / sqrt is a long software sequence: a per-channel finalize
+// written in double costs ~20 us per launch.  Only the cancellation-prone part (var = E[x^2] - mean^2) stays
+// in double (three DP instructions); everything else is fp32.
 __device__ __forceinline__ void bn_fwd_finalize_channel(const BnFwdFinal& f, double s1, double s2, int c) {
-  double mean = s1 / (double)f.M;
-  double var = s2 / (double)f.M - mean * mean;
-  if (var < 0.0) var = 0.0;
-  double rstd = 1.0 / sqrt(var + (double)f.eps);
-  float g = f.gamma ? f.gamma[c] : 1.f, b = f.beta ? f.beta[c] : 0.f;
-  f.mean_out[c] = (float)mean;
-  f.rstd_out[c] = (float)rstd;
-  f.scale_out[c] = (float)((double)g * rstd);
-  f.shift_out[c] = (float)((double)b - mean * (double)g * rstd);
+  const float inv_mf = 1.f / (float)f.M;
+  const double inv_m = (double)inv_mf;   // exact enough: M is a pixel count (power-of-two multiples in practice)
+  const double mean_d = s1 * inv_m;
+  const float mean = (float)mean_d;
+  const float var = fmaxf((float)(s2 * inv_m - mean_d * mean_d), 0.f);
+  const float rstd = rsqrtf(var + f.eps);
+  const float g = f.gamma ? f.gamma[c] : 1.f, b = f.beta ? f.beta[c] : 0.f;
+  f.mean_out[c] = mean;
+  f.rstd_out[c] = rstd;
+  f.scale_out[c] = g * rstd;
+  f.shift_out[c] = b - mean * g * rstd;
   if (f.running_mean) {
-    double unb = (f.M > 1) ? var * (double)f.M / (double)(f.M - 1) : var;
-    f.running_mean[c] = (float)((1.0 - f.momentum) * (double)f.running_mean[c] + f.momentum * mean);
-    f.running_var[c] = (float)((1.0 - f.momentum) * (double)f.running_var[c] + f.momentum * unb);
+    const float unb = (f.M > 1) ? var * ((float)f.M / (float)(f.M - 1)) : var;
+    f.running_mean[c] = (1.f - f.momentum) * f.running_mean[c] + f.momentum * mean;
+    f.running_var[c] = (1.f - f.momentum) * f.running_var[c] + f.momentum * unb;
   }
 }
 
@@ -52,20 +57,21 @@ struct BnBwdFinal {
   long long M; int accumulate;
   unsigned int* counter;
 };
-__device__ __forceinline__ void bn_bwd_finalize_channel(const BnBwdFinal& f, double s1, double s2, int c, int C) {
-  float g = f.gamma ? f.gamma[c] : 1.f;
-  double k0 = (double)g * (double)f.rstd[c];
-  if (f.dgamma) f.dgamma[c] = (f.accumulate ? f.dgamma[c] : 0.f) + (float)s2;
-  if (f.dbeta) f.dbeta[c] = (f.accumulate ? f.dbeta[c] : 0.f) + (float)s1;
+__device__ __forceinline__ void bn_bwd_finalize_channel(const BnBwdFinal& f, double s1d, double s2d, int c, int C) {
   // dx = k0*g - k1 - k2*xhat  with  k1 = k0*s1/M, k2 = k0*s2/M, xhat = (x-mean)*rstd
-  //    = A*g + Bc*x + Cc     (three per-channel coefficients for the apply pass)
-  const double k1 = k0 * s1 / (double)f.M, k2 = k0 * s2 / (double)f.M;
-  const double rs = (double)f.rstd[c], mu = (double)f.mean[c];
-  f.coef[c] = (float)k0;
-  f.coef[C + c] = (float)(-k2 * rs);
-  f.coef[2 * C + c] = (float)(-k1 + k2 * rs * mu);
+  //    = A*g + Bc*x + Cc     (three per-channel coefficients for the apply pass); fp32 throughout (see above)
+  const float s1 = (float)s1d, s2 = (float)s2d;
+  const float inv_m = 1.f / (float)f.M;
+  const float g = f.gamma ? f.gamma[c] : 1.f;
+  const float rs = f.rstd[c], mu = f.mean[c];
+  const float k0 = g * rs;
+  const float k1 = k0 * s1 * inv_m, k2 = k0 * s2 * inv_m;
+  if (f.dgamma) f.dgamma[c] = (f.accumulate ? f.dgamma[c] : 0.f) + s2;
+  if (f.dbeta) f.dbeta[c] = (f.accumulate ? f.dbeta[c] : 0.f) + s1;
+  f.coef[c] = k0;
+  f.coef[C + c] = -k2 * rs;
+  f.coef[2 * C + c] = -k1 + k2 * rs * mu;
 }
-
 
 }  // namespace bn
 

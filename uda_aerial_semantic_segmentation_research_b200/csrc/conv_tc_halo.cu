@@ -138,6 +138,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     float bn_s[kChunks], bn_q[kChunks];
 #pragma unroll
     for (int cc = 0; cc < kChunks; ++cc) { bn_s[cc] = 0.f; bn_q[cc] = 0.f; }
+    // BN <= 32 (the HBM-bound few-channel layers): per-thread running sums over all rows this thread ever
+    // owns, ONE cross-lane reduction at the very end of the CTA instead of 62 shuffles per 32x32 chunk
+    constexpr bool kLate = (kChunks == 1);
+    float late_s[kLate ? 32 : 1], late_q[kLate ? 32 : 1];
+#pragma unroll
+    for (int k = 0; k < (kLate ? 32 : 1); ++k) { late_s[k] = 0.f; late_q[k] = 0.f; }
     int j = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
       const int b = t / tiles_per_img, tin = t % tiles_per_img;
@@ -165,7 +171,18 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int k = 0; k < 32; ++k)
               if (c0 + k < p.Cout) f[k] += __ldg(p.bias + c0 + k);
           }
-          if (p.bn_sums) bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);
+          if (p.bn_sums) {
+            if constexpr (kLate) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                const float r = __bfloat162float(__float2bfloat16_rn(f[k]));
+                late_s[k] += r;
+                late_q[k] = fmaf(r, r, late_q[k]);
+              }
+            } else {
+              bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);
+            }
+          }
           if (p.out) {
             bf16* dst = p.out + pix * p.Cout + c0;
             const bf16* add = p.addend ? p.addend + pix * p.Cout + c0 : nullptr;
@@ -199,6 +216,13 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       if (lane == 0) mbar_arrive(tempty_bar(q));
     }
     if (p.bn_sums) {
+      if constexpr (kLate) {
+        float ts[32], tq[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { ts[k] = late_s[k]; tq[k] = late_q[k]; }
+        bn_s[0] = warp_column_sums(ts, lane);
+        bn_q[0] = warp_column_sums(tq, lane);
+      }
 #pragma unroll
       for (int cc = 0; cc < kChunks; ++cc) {
         const int col = cc * 32 + lane;

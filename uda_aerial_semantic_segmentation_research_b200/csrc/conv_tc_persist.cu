@@ -166,6 +166,12 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     float bn_s[kChunks], bn_q[kChunks];
 #pragma unroll
     for (int cc = 0; cc < kChunks; ++cc) { bn_s[cc] = 0.f; bn_q[cc] = 0.f; }
+    // BN <= 32 (the HBM-bound few-channel layers): per-thread running sums over all rows this thread ever
+    // owns, ONE cross-lane reduction at the very end of the CTA instead of 62 shuffles per 32x32 chunk
+    constexpr bool kLate = (kChunks == 1);
+    float late_s[kLate ? 32 : 1], late_q[kLate ? 32 : 1];
+#pragma unroll
+    for (int k = 0; k < (kLate ? 32 : 1); ++k) { late_s[k] = 0.f; late_q[k] = 0.f; }
     int bn_n0 = -1;
     int j = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
@@ -211,7 +217,18 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             for (int k = 0; k < 32; ++k)
               if (nbase + k < p.Cout) f[k] += __ldg(p.bias + nbase + k);
           }
-          if (p.bn_sums) bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);
+          if (p.bn_sums) {
+            if constexpr (kLate) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) {
+                const float r = __bfloat162float(__float2bfloat16_rn(f[k]));
+                late_s[k] += r;
+                late_q[k] = fmaf(r, r, late_q[k]);
+              }
+            } else {
+              bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);
+            }
+          }
           if (p.out) {
             bf16* dst = p.out + pix * p.Cout + nbase;
             const bf16* add = p.addend ? p.addend + pix * p.Cout + nbase : nullptr;
@@ -245,6 +262,13 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       if (lane == 0) mbar_arrive(tempty_bar(q));
     }
     if (p.bn_sums && bn_n0 >= 0) {
+      if constexpr (kLate) {   // BN = 32: a single channel tile, nothing was flushed before
+        float ts[32], tq[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) { ts[k] = late_s[k]; tq[k] = late_q[k]; }
+        bn_s[0] = warp_column_sums(ts, lane);
+        bn_q[0] = warp_column_sums(tq, lane);
+      }
 #pragma unroll
       for (int cc = 0; cc < kChunks; ++cc) {
         const int col = bn_n0 + cc * 32 + lane;
