@@ -206,10 +206,12 @@ int uda_gap_linear_sigmoid_bwd(const float* dout, const float* y, const float* p
 
 /* Optimizer: torch.optim.Adam semantics over a flat fp32 buffer
  * (src/models/train.py:461), optional bf16 shadow refresh, optional device-side clip coefficient
- * from uda_grad_clip_coef (clip_grad_norm_, src/models/unsupervised_trainer.py:144; workspace 8 bytes). */
+ * from uda_grad_clip_coef (clip_grad_norm_, src/models/unsupervised_trainer.py:144; workspace 8 bytes).
+ * dev_step (optional, device int): graph-capturable mode - the call increments *dev_step and uses it as the
+ * step count for the bias corrections instead of `step`. */
 int uda_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, float lr,
                   float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                  const float* dev_clip_coef, void* stream);
+                  const float* dev_clip_coef, int* dev_step, void* stream);
 int uda_grad_clip_coef(const float* g, long long n, float max_norm, float pre_scale, float* coef, float* norm_out,
                        void* workspace, void* stream);
 

@@ -208,7 +208,11 @@ def gap_linear_sigmoid_bwd(dout, y, pooled, w, dw, db, x_shape, dtype, accumulat
     return dx.to(dtype).contiguous()
 
 
-def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, clip_coef=None):
+def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, clip_coef=None,
+              dev_step=None):
+    if dev_step is not None:
+        dev_step += 1
+        step = int(dev_step)
     gi = g * grad_scale * (clip_coef if clip_coef is not None else 1.0)
     if weight_decay:
         gi = gi + weight_decay * p

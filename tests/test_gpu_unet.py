@@ -249,3 +249,42 @@ def test_predict_batch_and_sliding_window():
     from oracle import ref_metrics as M
     assert np.array_equal(out["hist"].cpu().numpy(), M.fast_hist(full.cpu().numpy(), target.cpu().numpy(), 24))
     assert out["hist"].sum().item() == 128 * 192
+
+
+def test_graphed_step_matches_eager_steps():
+    """graph.GraphedStep (CUDA-graph replay of zero_grad+fwd+loss+bwd, then fused Adam) walks the same loss
+    trajectory as the eager step sequence from the same initial state (fp32 mode, 1e-3 on each loss)."""
+    U = _pkg()
+    from uda_aerial_semantic_segmentation_research_b200.graph import GraphedStep
+    from uda_aerial_semantic_segmentation_research_b200.optim import FusedAdam
+    from uda_aerial_semantic_segmentation_research_b200.losses import CrossEntropyLoss
+    g = torch.Generator().manual_seed(5)
+    xs = [torch.randn(2, 3, 64, 64, generator=g) for _ in range(4)]
+    ts = [torch.randint(0, 6, (2, 64, 64), generator=g) for _ in range(4)]
+    warm = 2
+
+    def make():
+        torch.manual_seed(3)
+        m = U.Unet("resnet18", encoder_weights=None, classes=6, compute_dtype=torch.float32).to(DEV).train()
+        return m, FusedAdam(m, lr=1e-3), CrossEntropyLoss()
+
+    m1, o1, c1 = make()
+    eager = []
+    for i in [0] * warm + [0, 1, 2, 3]:          # GraphedStep's warm-up steps run on the example batch
+        o1.zero_grad()
+        loss = c1(m1(xs[i].to(DEV)), ts[i].to(DEV))
+        loss.backward()
+        o1.step()
+        eager.append(float(loss))
+    m2, o2, c2 = make()
+    step = GraphedStep(m2, c2, o2, xs[0], ts[0], warmup=warm)
+    got = [float(step(xs[0].pin_memory(), ts[0].pin_memory()))]
+    for i in (1, 2, 3):
+        step.stage(xs[i].pin_memory(), ts[i].pin_memory())
+        got.append(float(step()))
+    assert step.launches_per_step > 50
+    for a, b in zip(eager[warm:], got):
+        assert abs(a - b) <= 1e-3 * abs(a), (eager, got)
+    # parameters after the trajectory agree too
+    assert rel_err(m2._store.flat, m1._store.flat) < 1e-3
+    assert int(m2.encoder.bn1.num_batches_tracked) == int(m1.encoder.bn1.num_batches_tracked)

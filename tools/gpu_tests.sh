@@ -9,7 +9,9 @@ for f in losses eval layers conv_tc unet; do
 done
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "== smoke exit $? =="; tail -n 3 gpurun_out/smoke.log
 if [ "$1" == "bench" ]; then
-  timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "== bench exit $? =="; tail -c 3000 gpurun_out/bench.log; tail -n 5 gpurun_out/bench.err
+  timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "== bench exit $? =="; tail -c 3000 gpurun_out/bench.log; tail -n 5 gpurun_out/bench.err
+  timeout 600 python bench.py --steps 10 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/bench_eager.log 2> gpurun_out/bench_eager.err; echo "== eager bench exit $? =="; tail -c 600 gpurun_out/bench_eager.log | cut -c1-400; tail -n 5 gpurun_out/bench_eager.err
+  timeout 600 python bench.py --steps 10 --warmup 3 --workload adversarial --no-cpu-baseline > gpurun_out/bench_adv.log 2> gpurun_out/bench_adv.err; echo "== adversarial bench exit $? =="; tail -c 600 gpurun_out/bench_adv.log | cut -c1-400; tail -n 5 gpurun_out/bench_adv.err
 fi
 if [ "$1" == "prof" ]; then
   timeout 600 python tools/conv_bench.py > gpurun_out/conv_bench.log 2>&1; echo "== conv_bench exit $? =="; cat gpurun_out/conv_bench.log

@@ -708,8 +708,14 @@ __global__ void gap_linear_sigmoid_bwd_kernel(const float* __restrict__ dout, co
 __global__ void __launch_bounds__(kThreads)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             bf16* __restrict__ shadow, long long n, float lr, float beta1, float beta2, float eps,
-            float weight_decay, float bc1, float bc2_sqrt, float grad_scale, const float* __restrict__ dev_clip) {
+            float weight_decay, float bc1, float bc2_sqrt, float grad_scale, const float* __restrict__ dev_clip,
+            const int* __restrict__ dev_step) {
   const float clip = dev_clip ? *dev_clip : 1.f;
+  if (dev_step) {   // graph-capturable mode: the step count lives on the device
+    const double t = (double)*dev_step;
+    bc1 = (float)(1.0 - pow((double)beta1, t));
+    bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, t));
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
        i += (long long)gridDim.x * blockDim.x) {
     float gi = g[i] * grad_scale * clip;
@@ -725,6 +731,8 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     if (shadow) shadow[i] = __float2bfloat16_rn(pi);
   }
 }
+
+__global__ void step_increment_kernel(int* step) { *step += 1; }
 
 // sum of squares of a flat fp32 buffer -> out[0] (double); clip coefficient kernel for clip_grad_norm_
 __global__ void __launch_bounds__(kThreads) sumsq_kernel(const float* __restrict__ x, double* __restrict__ out, long long n) {
@@ -1106,14 +1114,20 @@ extern "C" int uda_gap_linear_sigmoid_bwd(const float* dout, const float* y, con
 
 extern "C" int uda_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shadow, long long n, float lr,
                              float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-                             const float* dev_clip_coef, void* stream) {
+                             const float* dev_clip_coef, int* dev_step, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  UDA_REQUIRE(p && g && m && v && n >= 0 && step >= 1, UDA_ERR_BAD_ARG, "adam: bad argument");
+  UDA_REQUIRE(p && g && m && v && n >= 0 && (dev_step || step >= 1), UDA_ERR_BAD_ARG, "adam: bad argument");
   if (n == 0) return UDA_OK;
+  if (dev_step) {
+    step_increment_kernel<<<1, 1, 0, st>>>(dev_step);
+    UDA_LAUNCH_OK("step_increment_kernel");
+    step = 1;
+  }
   const double bc1 = 1.0 - pow((double)beta1, (double)step);
   const double bc2 = 1.0 - pow((double)beta2, (double)step);
   adam_kernel<<<grid_for(n), kThreads, 0, st>>>(p, g, m, v, (bf16*)bf16_shadow, n, lr, beta1, beta2, eps,
-                                                weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale, dev_clip_coef);
+                                                weight_decay, (float)bc1, (float)sqrt(bc2), grad_scale, dev_clip_coef,
+                                                dev_step);
   UDA_LAUNCH_OK("adam_kernel");
   return UDA_OK;
 }

@@ -1,0 +1,140 @@
+"""CUDA-graph capture of the training step.
+
+One training step of the hot path is ~900 kernel launches; issued one by one from Python the host needs
+~13 ms per step — as long as the B200 needs to execute them.  ``GraphedStep`` captures
+``zero_grad -> forward -> loss -> backward`` once into a CUDA graph (all kernels, memsets and TMA
+descriptors of the step are baked in; shapes and buffer addresses are static) and replays it with a single
+launch; the gradient all-reduce (``ddp.GradSync``, when given) and the fused optimizer step run right
+after the replay.
+
+    step = GraphedStep(model, criterion, optimizer, example_images, example_masks)
+    loss = step(images, masks)          # images/masks: host (pinned) or device tensors of the captured shape
+
+The step function has exactly the reference's semantics (``src/models/train.py:336-346``).
+"""
+import torch
+import torch.distributed as dist
+
+
+class GraphedStep:
+    def __init__(self, model, criterion, optimizer, example_images, example_masks, warmup=3, extra_models=()):
+        dev = next(model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedStep needs the model on a CUDA device")
+        self.model, self.criterion, self.optimizer = model, criterion, optimizer
+        self.models = [model] + list(extra_models)
+        self.x = example_images.to(dev, non_blocking=True).clone()
+        self.t = example_masks.to(dev, non_blocking=True).clone()
+        self.sync = getattr(model, "_grad_sync", None)
+        # the bucketed all-reduce hooks are host-side logic; under capture the all-reduce runs once on the flat
+        # gradient buffer after the replay instead
+        saved = [(m, m._grad_sync) for m in self.models]
+        for m in self.models:
+            m._grad_sync = None
+        try:
+            s = torch.cuda.Stream(device=dev)
+            s.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(s):
+                for _ in range(warmup):           # allocator / workspace / attribute warm-up outside the capture
+                    self._fwd_bwd()
+                    self._finish()
+            torch.cuda.current_stream().wait_stream(s)
+            torch.cuda.synchronize()
+            for m in self.models:                 # make the captured step refresh the bf16 shadow weights itself
+                m._store.shadow_version = None
+                m._store.shadow_ft_version = None
+            self.graph = torch.cuda.CUDAGraph()
+            self.optimizer.zero_grad(set_to_none=True)
+            from . import ops
+            l0 = ops.LAUNCHES
+            with torch.cuda.graph(self.graph):
+                self.loss = self._fwd_bwd()
+            self.launches_per_step = ops.LAUNCHES - l0 + 1      # captured launches + the fused Adam launch
+        finally:
+            for m, gs in saved:
+                m._grad_sync = gs
+        # staging buffers: the next batch is copied host->device on a side stream while this step runs
+        self.xs, self.ts = torch.empty_like(self.x), torch.empty_like(self.t)
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.staged_ready, self.staged_free = torch.cuda.Event(), torch.cuda.Event()
+        self.staged_free.record()
+        self._staged = False
+
+    def _fwd_bwd(self):
+        self.optimizer.zero_grad(set_to_none=True)
+        loss = self.criterion(self.model(self.x), self.t)
+        loss.backward()
+        return loss.detach()
+
+    def _finish(self):
+        if self.sync is not None:
+            for m in self.models:
+                if m._store.grad is not None:
+                    dist.all_reduce(m._store.grad, op=dist.ReduceOp.AVG, group=self.sync.group)
+        self.optimizer.step()
+
+    def stage(self, images, masks):
+        """Start the asynchronous copy of the NEXT batch (pinned host or device tensors) into the staging buffers."""
+        self.copy_stream.wait_event(self.staged_free)
+        with torch.cuda.stream(self.copy_stream):
+            self.xs.copy_(images, non_blocking=True)
+            self.ts.copy_(masks, non_blocking=True)
+            self.staged_ready.record()
+        self._staged = True
+
+    def __call__(self, images=None, masks=None):
+        if images is None:
+            if not self._staged:
+                raise RuntimeError("GraphedStep(): no batch given and none staged")
+            torch.cuda.current_stream().wait_event(self.staged_ready)
+            images, masks = self.xs, self.ts
+        self.x.copy_(images, non_blocking=True)
+        self.t.copy_(masks, non_blocking=True)
+        if images is self.xs:
+            self.staged_free.record()
+            self._staged = False
+        self.graph.replay()
+        self._finish()
+        return self.loss
+
+
+class GraphedFn:
+    """Capture an arbitrary training-step function (e.g. the adversarial D/G step of
+    ``src/models/adversarial_trainer.py:84-114``) into one CUDA graph.
+
+    ``fn(*inputs)`` must do everything of the step on the device - zero_grad, forward, losses, backward and
+    ``FusedAdam(..., capturable=True).step()`` - and return a tensor (or tuple of tensors); single-process only
+    (no collective is captured).  ``networks`` are the uda_b200 networks used, so that the captured step refreshes
+    their bf16 shadow weights itself.
+    """
+
+    def __init__(self, fn, example_inputs, networks, warmup=3):
+        dev = example_inputs[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedFn needs CUDA example inputs")
+        for m in networks:
+            if getattr(m, "_grad_sync", None) is not None:
+                raise RuntimeError("GraphedFn does not capture the gradient all-reduce; use GraphedStep")
+        self.inputs = [t.clone() for t in example_inputs]
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                fn(*self.inputs)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        for m in networks:
+            m._store.shadow_version = None
+            m._store.shadow_ft_version = None
+        from . import ops
+        l0 = ops.LAUNCHES
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = fn(*self.inputs)
+        self.launches_per_step = ops.LAUNCHES - l0
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.inputs, inputs):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.out

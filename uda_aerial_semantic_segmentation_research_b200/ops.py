@@ -431,12 +431,17 @@ def gap_linear_sigmoid_bwd(dout, y, pooled, w, dw, db, x_shape, dtype, accumulat
 # ------------------------------------------------------------------------------------------------
 # optimizer
 # ------------------------------------------------------------------------------------------------
-def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, clip_coef=None):
+def adam_step(p, g, m, v, shadow, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, clip_coef=None,
+              dev_step=None):
+    """``dev_step`` (int32[1] device tensor): graph-capturable mode, incremented by the call and used instead of ``step``."""
     for t, n in ((p, "p"), (g, "g"), (m, "m"), (v, "v")):
         _chk(t, "adam." + n, torch.float32)
+    if dev_step is not None:
+        _chk(dev_step, "adam.dev_step", torch.int32)
     call("adam_step", ptr(p), ptr(g), ptr(m), ptr(v), ptr(shadow), ll(p.numel()), float(lr), float(beta1),
-         float(beta2), float(eps), float(weight_decay), ci(step), float(grad_scale), ptr(clip_coef), _stream())
-    _count()
+         float(beta2), float(eps), float(weight_decay), ci(step), float(grad_scale), ptr(clip_coef), ptr(dev_step),
+         _stream())
+    _count(2 if dev_step is not None else 1)
 
 
 def grad_clip_coef(g, max_norm, pre_scale=1.0):

@@ -15,7 +15,8 @@ class FusedAdam:
     engine filled; ``p.grad`` tensors are views of it).  ``zero_grad()`` drops them (set-to-none).
     """
 
-    def __init__(self, networks, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=None):
+    def __init__(self, networks, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, max_grad_norm=None,
+                 capturable=False):
         if not isinstance(networks, (list, tuple)):
             networks = [networks]
         self.networks = list(networks)
@@ -24,6 +25,9 @@ class FusedAdam:
         self.state = {}
         self.step_count = 0
         self.last_grad_norm = None
+        # capturable: the step count lives in a device int so that step() can be recorded into a CUDA graph
+        self.capturable = capturable
+        self._dev_step = {}
 
     def zero_grad(self, set_to_none=True):
         for net in self.networks:
@@ -59,7 +63,12 @@ class FusedAdam:
             if self.max_grad_norm is not None:
                 coef, self.last_grad_norm = ops.grad_clip_coef(g, self.max_grad_norm, grad_scale)
             shadow = st.shadow if getattr(net, "compute_dtype", None) == torch.bfloat16 else None
+            dev_step = None
+            if self.capturable:
+                if id(st) not in self._dev_step:
+                    self._dev_step[id(st)] = torch.full((1,), self.step_count - 1, dtype=torch.int32, device=st.flat.device)
+                dev_step = self._dev_step[id(st)]
             ops.adam_step(st.flat, g, m, v, shadow, self.lr, b1, b2, self.eps, self.weight_decay, self.step_count,
-                          grad_scale, coef)
+                          grad_scale, coef, dev_step)
             if shadow is not None:
                 st.mark_shadow_fresh()
