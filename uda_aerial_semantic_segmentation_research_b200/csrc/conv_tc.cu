@@ -667,6 +667,10 @@ int run_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int
     const int rc = run_wgrad_halo(dy, x, dw, B, H, W, Cin, Cout, st);
     if (rc != UDA_ERR_UNSUPPORTED) return rc;
   }
+  if (use_persistent()) {
+    const int rc = run_wgrad_big(dy, x, dw, B, H, W, Cin, Cout, KH, KW, stride, pad, st);
+    if (rc != UDA_ERR_UNSUPPORTED) return rc;
+  }
   const int Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? W : W / 2;
   const TilePlan tp = plan_tiles(B, Ho, Wo);
   const int atomA = pick_atom(Cin);

@@ -96,6 +96,9 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st);
 int run_gemm_conv_halo(const GemmConv& g, cudaStream_t st);
 // conv_tc_wgrad_halo.cu: halo-tile wgrad (3x3 stride 1 pad 1, W % 128 == 0); UDA_ERR_UNSUPPORTED otherwise
 int run_wgrad_halo(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, cudaStream_t st);
+// conv_tc_wgrad_big.cu: multi-accumulator wgrad sharing one dY tile (Cin, Cout multiples of 64); UDA_ERR_UNSUPPORTED otherwise
+int run_wgrad_big(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, int KH, int KW,
+                  int stride, int pad, cudaStream_t st);
 
 }  // namespace tcconv
 }  // namespace uda

@@ -13,6 +13,7 @@
 // all C classes of them (C <= CPAD kept in registers), so every global access is a 16-byte
 // (fp32) / 8-byte (bf16) coalesced vector per class plane and each logit is read once per pass.
 #include "common.cuh"
+#include "loss_stream.cuh"
 
 namespace uda {
 namespace {
@@ -332,9 +333,246 @@ int launch_seg(const SegLossParams& p, cudaStream_t st) {
   return UDA_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Streaming (cp.async.bulk) version of seg_loss_kernel: same passes, same arithmetic, hard targets only.
+// A CTA owns a contiguous range of tiles, so it crosses an image boundary at most a few times; the per-image
+// state (Dice coefficients in, Dice sums out) is reloaded / flushed at those crossings.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CPAD, int PPT, int PASS>
+__global__ void __launch_bounds__(pxstream::px_threads<PPT>(), 1)
+seg_loss_stream_kernel(const SegLossParams p, const pxstream::PxIO io) {
+  using namespace pxstream;
+  constexpr int NT = px_compute_threads<PPT>();
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* tail = smem + (size_t)io.stages * io.stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  float* coefA = reinterpret_cast<float*>(tail + 64);   // [CPAD]
+  float* coefB = coefA + CPAD;                           // [CPAD]
+  float* wsm = coefB + CPAD;                             // [CPAD]
+  float* red = wsm + CPAD;                               // reduction scratch
+  const int C = p.C;
+  if (threadIdx.x < CPAD) wsm[threadIdx.x] = (threadIdx.x < C && p.class_w) ? p.class_w[threadIdx.x] : 1.f;
+  PixelPipe<PPT, NT> pipe(io, smem, bars);    // (its constructor synchronises the CTA)
+  const float ce_scale = (PASS == 2) ? (p.has_ce ? *p.dev_scale : 0.f) : p.ce_grad_scale;
+  const bool dice = (PASS == 2) && p.has_dice;
+
+  float loss_sum = 0.f, denom_sum = 0.f, invalid = 0.f;
+  float psum[CPAD], inter[CPAD], tsum[CPAD];
+  if constexpr (PASS == 1) {
+#pragma unroll
+    for (int c = 0; c < CPAD; ++c) { psum[c] = 0.f; inter[c] = 0.f; tsum[c] = 0.f; }
+  }
+  auto flush_dice = [&](int b) {
+    if constexpr (PASS == 1) {
+      const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = NT >> 5;
+#pragma unroll
+      for (int c = 0; c < CPAD; ++c) {
+        float a = warp_sum(inter[c]), bsum = warp_sum(psum[c]), t = warp_sum(tsum[c]);
+        if (lane == 0) {
+          red[(0 * CPAD + c) * nw + wid] = a;
+          red[(1 * CPAD + c) * nw + wid] = bsum;
+          red[(2 * CPAD + c) * nw + wid] = t;
+        }
+        psum[c] = 0.f; inter[c] = 0.f; tsum[c] = 0.f;
+      }
+      named_sync(1, NT);
+      for (int i = threadIdx.x; i < 3 * CPAD; i += NT) {
+        int k = i / CPAD, c = i % CPAD;
+        if (c < C) {
+          float s = 0.f;
+          for (int w = 0; w < nw; ++w) s += red[i * nw + w];
+          atomicAdd(p.dice_sums + ((long long)b * C + c) * 3 + k, (double)s);
+        }
+      }
+      named_sync(1, NT);
+    }
+  };
+
+  int cur_b = -1;
+  if (pipe.is_io()) {
+    pipe.io_loop();
+  } else {
+  for (int k = 0; k < pipe.n_my; ++k) {
+    const int b = pipe.image_of(k);
+    if (b != cur_b) {
+      if (PASS == 1 && p.has_dice && cur_b >= 0) flush_dice(cur_b);
+      if (dice) {
+        named_sync(1, NT);
+        if (threadIdx.x < CPAD) {
+          const int c = threadIdx.x;
+          coefA[c] = c < C ? p.dice_coef[((long long)b * C + c) * 2 + 0] : 0.f;
+          coefB[c] = c < C ? p.dice_coef[((long long)b * C + c) * 2 + 1] : 0.f;
+        }
+        named_sync(1, NT);
+      }
+      cur_b = b;
+    }
+    pipe.wait(k);
+    const int px = threadIdx.x * PPT;
+    if (px < pipe.npix_of(k)) {
+      float z[CPAD][PPT];
+#pragma unroll
+      for (int c = 0; c < CPAD; ++c) {
+        if (c < C) {
+          ld_px<T, PPT>(pipe.row(k, 0, c), px, z[c]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) z[c][j] = -INFINITY;
+        }
+      }
+      int y[PPT];
+      bool valid[PPT];
+      const long long* trow = pipe.target_row(k);
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        const long long t = trow[px + j];
+        const bool ign = (t == p.ignore_index);
+        const bool ok = (t >= 0 && t < C);
+        valid[j] = ok && !ign;
+        y[j] = valid[j] ? (int)t : -1;
+        if (!ok && !ign) invalid += 1.f;
+      }
+      float coef[PPT];
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        float m = z[0][j];
+#pragma unroll
+        for (int c = 1; c < CPAD; ++c) m = fmaxf(m, z[c][j]);
+        float s = 0.f, zy = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) {
+          zy = (c == y[j]) ? z[c][j] : zy;
+          float e = exp2f((z[c][j] - m) * kLog2e);
+          z[c][j] = e;
+          s += e;
+        }
+        float inv = 1.f / s;
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) z[c][j] *= inv;
+        coef[j] = 0.f;
+        if (p.has_ce && valid[j]) {
+          float wy = wsm[y[j]];
+          float nll = -(zy - m - logf(s));
+          float ce = wy * nll;
+          if (p.focal) {
+            float pt = expf(-ce);
+            float omp = 1.f - pt;
+            float pw = powf(omp, p.gamma);
+            float dpw = p.gamma * powf(omp, p.gamma - 1.f);
+            if (PASS != 2) { loss_sum += p.alpha * pw * ce; }
+            coef[j] = p.alpha * (pw + dpw * pt * ce) * wy * ce_scale;
+          } else {
+            if (PASS != 2) { loss_sum += ce; denom_sum += wy; }
+            coef[j] = wy * ce_scale;
+          }
+        }
+      }
+      if constexpr (PASS == 1) {
+        if (p.has_dice) {
+#pragma unroll
+          for (int c = 0; c < CPAD; ++c) {
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+              const float tv = (y[j] == c) ? 1.f : 0.f;
+              psum[c] += z[c][j];
+              inter[c] += z[c][j] * tv;
+              tsum[c] += tv;
+            }
+          }
+        }
+      } else {
+        float dot[PPT];
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) dot[j] = 0.f;
+        if (dice) {
+#pragma unroll
+          for (int c = 0; c < CPAD; ++c)
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) dot[j] += (coefA[c] * ((y[j] == c) ? 1.f : 0.f) - coefB[c]) * z[c][j];
+        }
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) {
+          if (c < C) {
+            float g[PPT];
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+              const float onehot = (y[j] == c) ? 1.f : 0.f;
+              float v = coef[j] * (z[c][j] - onehot);
+              if (dice) v += z[c][j] * ((coefA[c] * onehot - coefB[c]) - dot[j]);
+              g[j] = v;
+            }
+            st_px<T, PPT>(pipe.row(k, 0, c), px, g);
+          }
+        }
+      }
+    }
+    pipe.release(k);
+  }
+  if (PASS == 1 && p.has_dice && cur_b >= 0) flush_dice(cur_b);
+  }
+  if constexpr (PASS != 2) {
+    float v[3] = {loss_sum, denom_sum, invalid}, o[3];
+    block_sum<3>(v, red, o);
+    if (threadIdx.x == 0) {
+      if (o[0] != 0.f) atomicAdd(p.acc + 0, (double)o[0]);
+      if (o[1] != 0.f) atomicAdd(p.acc + 1, (double)o[1]);
+      if (o[2] != 0.f) atomicAdd(p.acc + 2, (double)o[2]);
+    }
+  }
+}
+
+inline bool loss_stream_enabled() {
+  static const bool on = [] { const char* e = getenv("UDA_B200_LOSS_STREAM"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
+template <typename T, int CPAD, int PPT, int PASS>
+int launch_seg_stream_t(const SegLossParams& p, const pxstream::PxIO& io, cudaStream_t st) {
+  const size_t smem = 128 + (size_t)io.stages * io.stage_bytes + 64 + 3 * CPAD * 4 +
+                      (3 * CPAD * 17 + 32) * 4;
+  auto kfn = seg_loss_stream_kernel<T, CPAD, PPT, PASS>;
+  static bool attr = false;
+  if (!attr) {
+    UDA_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  kfn<<<pxstream::px_grid(io), pxstream::px_threads<PPT>(), smem, st>>>(p, io);
+  UDA_LAUNCH_OK("seg_loss_stream_kernel");
+  return UDA_OK;
+}
+
+// returns 1 when the streaming kernel was launched, 0 when the register kernel must be used, <0 on error
+template <typename T, int PASS>
+int try_seg_stream(const SegLossParams& p, cudaStream_t st) {
+  if (!loss_stream_enabled() || !p.target || p.soft_target) return 0;
+  pxstream::PxIO io{};
+  io.in[0] = (const uint8_t*)p.logits;
+  io.out[0] = (uint8_t*)p.grad;
+  io.target = p.target;
+  io.nten = 1; io.nout = (PASS == 1) ? 0 : 1;
+  io.B = p.B; io.C = p.C; io.HW = p.HW; io.esize = (int)sizeof(T);
+  int ppt = 0;
+  if (!pxstream::plan_px(io, ppt, 0)) return 0;
+  int rc;
+#define UDA_SEG_STREAM(CP)                                                                         \
+  rc = (ppt == 2) ? launch_seg_stream_t<T, CP, 2, PASS>(p, io, st) : launch_seg_stream_t<T, CP, 1, PASS>(p, io, st)
+  if (p.C <= 8) UDA_SEG_STREAM(8);
+  else if (p.C <= 16) UDA_SEG_STREAM(16);
+  else if (p.C <= 24) UDA_SEG_STREAM(24);
+  else UDA_SEG_STREAM(32);
+#undef UDA_SEG_STREAM
+  return rc == UDA_OK ? 1 : rc;
+}
+
 template <typename T, int PASS>
 int dispatch_seg(const SegLossParams& p, bool vec4, cudaStream_t st) {
   const int C = p.C;
+  {
+    const int rs = try_seg_stream<T, PASS>(p, st);
+    if (rs != 0) return rs == 1 ? UDA_OK : rs;
+  }
   if (vec4) {
     if (C <= 8) return launch_seg<T, 8, 4, PASS>(p, st);
     if (C <= 16) return launch_seg<T, 16, 4, PASS>(p, st);
@@ -511,6 +749,173 @@ __global__ void bce_logits_kernel(const float* __restrict__ x, float* __restrict
   }
 }
 
+
+// ---- streaming versions (see loss_stream.cuh): same arithmetic, tiles through shared memory ----
+template <typename T, int CPAD, int PPT>
+__global__ void __launch_bounds__(pxstream::px_threads<PPT>(), 1)
+consistency_stream_kernel(const pxstream::PxIO io, double* __restrict__ acc, float inv_T, float scale) {
+  using namespace pxstream;
+  constexpr int NT = px_compute_threads<PPT>();
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* tail = smem + (size_t)io.stages * io.stage_bytes;
+  PixelPipe<PPT, NT> pipe(io, smem, reinterpret_cast<uint64_t*>(tail));
+  float* red = reinterpret_cast<float*>(tail + 64);
+  const int C = io.C;
+  float lsum = 0.f;
+  if (pipe.is_io()) pipe.io_loop();
+  else
+  for (int k = 0; k < pipe.n_my; ++k) {
+    pipe.wait(k);
+    const int px = threadIdx.x * PPT;
+    if (px < pipe.npix_of(k)) {
+      float e1[CPAD][PPT], e2[CPAD][PPT], d[CPAD][PPT];
+#pragma unroll
+      for (int c = 0; c < CPAD; ++c) {
+        if (c < C) {
+          ld_px<T, PPT>(pipe.row(k, 0, c), px, e1[c]);
+          ld_px<T, PPT>(pipe.row(k, 1, c), px, e2[c]);
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) {
+            e1[c][j] *= inv_T; e2[c][j] *= inv_T;
+            d[c][j] = e2[c][j] - e1[c][j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) { e1[c][j] = -INFINITY; e2[c][j] = -INFINITY; d[c][j] = 0.f; }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        float m1 = e1[0][j], m2 = e2[0][j];
+#pragma unroll
+        for (int c = 1; c < CPAD; ++c) { m1 = fmaxf(m1, e1[c][j]); m2 = fmaxf(m2, e2[c][j]); }
+        float s1 = 0.f, s2 = 0.f, w1 = 0.f, w2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) {
+          float x1 = exp2f((e1[c][j] - m1) * kLog2e), x2 = exp2f((e2[c][j] - m2) * kLog2e);
+          e1[c][j] = x1; e2[c][j] = x2;
+          s1 += x1; s2 += x2;
+          w1 += x1 * d[c][j]; w2 += x2 * d[c][j];
+        }
+        const float r1 = 1.f / s1, r2 = 1.f / s2;
+        const float delta = (m2 + logf(s2)) - (m1 + logf(s1));
+        const float kl12 = delta - w1 * r1, kl21 = w2 * r2 - delta;
+        lsum += kl12 + kl21;
+        const float gs = inv_T * scale;
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) {
+          float p1 = e1[c][j] * r1, p2 = e2[c][j] * r2;
+          float D = d[c][j] - delta, q = p2 - p1;
+          e1[c][j] = (-q - p1 * (D + kl12)) * gs;
+          e2[c][j] = (q + p2 * (D - kl21)) * gs;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CPAD; ++c) {
+        if (c < C) {
+          st_px<T, PPT>(pipe.row(k, 0, c), px, e1[c]);
+          st_px<T, PPT>(pipe.row(k, 1, c), px, e2[c]);
+        }
+      }
+    }
+    pipe.release(k);
+  }
+  float v[1] = {lsum}, o[1];
+  block_sum<1>(v, red, o);
+  if (threadIdx.x == 0 && o[0] != 0.f) atomicAdd(acc, (double)o[0] * (double)scale);
+}
+
+template <typename T, int CPAD, int PPT>
+__global__ void __launch_bounds__(pxstream::px_threads<PPT>(), 1)
+entropy_stream_kernel(const pxstream::PxIO io, double* __restrict__ acc, float scale) {
+  using namespace pxstream;
+  constexpr int NT = px_compute_threads<PPT>();
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint8_t* tail = smem + (size_t)io.stages * io.stage_bytes;
+  PixelPipe<PPT, NT> pipe(io, smem, reinterpret_cast<uint64_t*>(tail));
+  float* red = reinterpret_cast<float*>(tail + 64);
+  const int C = io.C;
+  float lsum = 0.f;
+  if (pipe.is_io()) pipe.io_loop();
+  else
+  for (int k = 0; k < pipe.n_my; ++k) {
+    pipe.wait(k);
+    const int px = threadIdx.x * PPT;
+    if (px < pipe.npix_of(k)) {
+      float e[CPAD][PPT], x[CPAD][PPT];
+#pragma unroll
+      for (int c = 0; c < CPAD; ++c) {
+        if (c < C) {
+          ld_px<T, PPT>(pipe.row(k, 0, c), px, x[c]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < PPT; ++j) x[c][j] = -INFINITY;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < PPT; ++j) {
+        float m = x[0][j];
+#pragma unroll
+        for (int c = 1; c < CPAD; ++c) m = fmaxf(m, x[c][j]);
+        float s = 0.f, w = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) {
+          float xm = (c < C) ? x[c][j] - m : 0.f;
+          float ex = (c < C) ? exp2f(xm * kLog2e) : 0.f;
+          x[c][j] = xm; e[c][j] = ex;
+          s += ex; w += ex * xm;
+        }
+        const float r = 1.f / s, ls = logf(s);
+        const float H = ls - w * r;
+        lsum += H;
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) e[c][j] = -scale * (e[c][j] * r) * ((x[c][j] - ls) + H);
+      }
+#pragma unroll
+      for (int c = 0; c < CPAD; ++c)
+        if (c < C) st_px<T, PPT>(pipe.row(k, 0, c), px, e[c]);
+    }
+    pipe.release(k);
+  }
+  float v[1] = {lsum}, o[1];
+  block_sum<1>(v, red, o);
+  if (threadIdx.x == 0 && o[0] != 0.f) atomicAdd(acc, (double)o[0] * (double)scale);
+}
+
+template <int PPT, typename K, typename... Args>
+int launch_px_stream(K kfn, const pxstream::PxIO& io, cudaStream_t st, const char* what, Args... args) {
+  const size_t smem = 128 + (size_t)io.stages * io.stage_bytes + 64 + 64 * 4;
+  UDA_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  kfn<<<pxstream::px_grid(io), pxstream::px_threads<PPT>(), smem, st>>>(io, args...);
+  UDA_LAUNCH_OK(what);
+  return UDA_OK;
+}
+
+#define UDA_PX_DISPATCH(KERN, T, ...)                                                               \
+  do {                                                                                              \
+    if (ppt == 2) {                                                                                 \
+      if (io.C <= 8) return launch_px_stream<2>(KERN<T, 8, 2>, io, st, #KERN, __VA_ARGS__);            \
+      if (io.C <= 16) return launch_px_stream<2>(KERN<T, 16, 2>, io, st, #KERN, __VA_ARGS__);          \
+      if (io.C <= 24) return launch_px_stream<2>(KERN<T, 24, 2>, io, st, #KERN, __VA_ARGS__);          \
+      return launch_px_stream<2>(KERN<T, 32, 2>, io, st, #KERN, __VA_ARGS__);                          \
+    }                                                                                               \
+    if (io.C <= 8) return launch_px_stream<1>(KERN<T, 8, 1>, io, st, #KERN, __VA_ARGS__);              \
+    if (io.C <= 16) return launch_px_stream<1>(KERN<T, 16, 1>, io, st, #KERN, __VA_ARGS__);            \
+    if (io.C <= 24) return launch_px_stream<1>(KERN<T, 24, 1>, io, st, #KERN, __VA_ARGS__);            \
+    return launch_px_stream<1>(KERN<T, 32, 1>, io, st, #KERN, __VA_ARGS__);                            \
+  } while (0)
+
+template <typename T>
+int consistency_stream(const pxstream::PxIO& io, int ppt, double* acc, float inv_T, float scale, cudaStream_t st) {
+  UDA_PX_DISPATCH(consistency_stream_kernel, T, acc, inv_T, scale);
+}
+template <typename T>
+int entropy_stream(const pxstream::PxIO& io, int ppt, double* acc, float scale, cudaStream_t st) {
+  UDA_PX_DISPATCH(entropy_stream_kernel, T, acc, scale);
+}
+
 template <typename T, int CPAD, int VEC>
 int launch_consistency(const void* z1, const void* z2, void* g1, void* g2, double* acc, int B, int C,
                        long long HW, float inv_T, float scale, cudaStream_t st) {
@@ -558,6 +963,14 @@ int launch_entropy(const void* z, void* g, double* acc, int B, int C, long long 
 template <typename T>
 int consistency_dispatch(const void* z1, const void* z2, void* g1, void* g2, double* acc, int B, int C,
                          long long HW, float inv_T, float scale, cudaStream_t st) {
+  if (loss_stream_enabled()) {
+    pxstream::PxIO io{};
+    io.in[0] = (const uint8_t*)z1; io.in[1] = (const uint8_t*)z2;
+    io.out[0] = (uint8_t*)g1; io.out[1] = (uint8_t*)g2;
+    io.nten = 2; io.nout = 2; io.B = B; io.C = C; io.HW = HW; io.esize = (int)sizeof(T);
+    int ppt = 0;
+    if (pxstream::plan_px(io, ppt, 0)) return consistency_stream<T>(io, ppt, acc, inv_T, scale, st);
+  }
   bool v2 = (HW % 2 == 0) && aligned<T>(z1, 2 * sizeof(T)) && aligned<T>(z2, 2 * sizeof(T)) &&
             aligned<T>(g1, 2 * sizeof(T)) && aligned<T>(g2, 2 * sizeof(T));
   UDA_DISPATCH_CV(launch_consistency, T, C, v2, z1, z2, g1, g2, acc, B, C, HW, inv_T, scale, st);
@@ -565,6 +978,13 @@ int consistency_dispatch(const void* z1, const void* z2, void* g1, void* g2, dou
 template <typename T>
 int entropy_dispatch(const void* z, void* g, double* acc, int B, int C, long long HW, float scale,
                      cudaStream_t st) {
+  if (loss_stream_enabled()) {
+    pxstream::PxIO io{};
+    io.in[0] = (const uint8_t*)z; io.out[0] = (uint8_t*)g;
+    io.nten = 1; io.nout = 1; io.B = B; io.C = C; io.HW = HW; io.esize = (int)sizeof(T);
+    int ppt = 0;
+    if (pxstream::plan_px(io, ppt, 0)) return entropy_stream<T>(io, ppt, acc, scale, st);
+  }
   bool v2 = (HW % 2 == 0) && aligned<T>(z, 2 * sizeof(T)) && aligned<T>(g, 2 * sizeof(T));
   UDA_DISPATCH_CV(launch_entropy, T, C, v2, z, g, acc, B, C, HW, scale, st);
 }

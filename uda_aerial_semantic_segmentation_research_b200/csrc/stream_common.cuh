@@ -14,6 +14,7 @@ namespace stream {
 using tc::smem_u32;
 using tc::mbar_init;
 using tc::mbar_wait;
+using tc::mbar_arrive;
 using tc::mbar_expect_tx;
 using tc::fence_barrier_init;
 
