@@ -339,7 +339,29 @@ int launch_seg(const SegLossParams& p, cudaStream_t st) {
 // A CTA owns a contiguous range of tiles, so it crosses an image boundary at most a few times; the per-image
 // state (Dice coefficients in, Dice sums out) is reloaded / flushed at those crossings.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int CPAD, int PPT, int PASS>
+// ex2.approx on a non-positive argument: one MUFU, no denormal scaling (tiny results flush to zero)
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+template <typename T> __device__ __forceinline__ float ld_one(const uint8_t* row, int px);
+template <> __device__ __forceinline__ float ld_one<float>(const uint8_t* r, int px) { return reinterpret_cast<const float*>(r)[px]; }
+template <> __device__ __forceinline__ float ld_one<__nv_bfloat16>(const uint8_t* r, int px) {
+  return __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(r)[px]);
+}
+template <typename T> __device__ __forceinline__ void st_one(uint8_t* row, int px, float v);
+template <> __device__ __forceinline__ void st_one<float>(uint8_t* r, int px, float v) { reinterpret_cast<float*>(r)[px] = v; }
+template <> __device__ __forceinline__ void st_one<__nv_bfloat16>(uint8_t* r, int px, float v) {
+  reinterpret_cast<__nv_bfloat16*>(r)[px] = __float2bfloat16_rn(v);
+}
+
+// The arithmetic is arranged for the instruction budget of an HBM-bound kernel (ncu on the first version: 29
+// instructions per logit, issue-bound with 8 compute warps): per logit one FMNMX, one FFMA + MUFU.EX2, one FADD and
+// one FMUL (+ one FFMA for the Dice sums / two for the Dice gradient); everything that depends on the target class
+// (picked logit, one-hot terms of the gradient, Dice intersection / target counts) is done once per PIXEL through a
+// shared-memory access at the target's row instead of a compare-select per class.
+template <typename T, int CPAD, int PPT, int PASS, bool FULL>
 __global__ void __launch_bounds__(pxstream::px_threads<PPT>(), 1)
 seg_loss_stream_kernel(const SegLossParams p, const pxstream::PxIO io) {
   using namespace pxstream;
@@ -351,40 +373,43 @@ seg_loss_stream_kernel(const SegLossParams p, const pxstream::PxIO io) {
   float* coefA = reinterpret_cast<float*>(tail + 64);   // [CPAD]
   float* coefB = coefA + CPAD;                           // [CPAD]
   float* wsm = coefB + CPAD;                             // [CPAD]
-  float* red = wsm + CPAD;                               // reduction scratch
+  float* inter_s = wsm + CPAD;                           // [CPAD] Dice intersection of the current image
+  float* tsum_s = inter_s + CPAD;                        // [CPAD] target pixel counts of the current image
+  float* red = tsum_s + CPAD;                            // reduction scratch
   const int C = p.C;
-  if (threadIdx.x < CPAD) wsm[threadIdx.x] = (threadIdx.x < C && p.class_w) ? p.class_w[threadIdx.x] : 1.f;
+  if (threadIdx.x < CPAD) {
+    wsm[threadIdx.x] = (threadIdx.x < C && p.class_w) ? p.class_w[threadIdx.x] : 1.f;
+    inter_s[threadIdx.x] = 0.f; tsum_s[threadIdx.x] = 0.f;
+  }
   PixelPipe<PPT, NT> pipe(io, smem, bars);    // (its constructor synchronises the CTA)
   const float ce_scale = (PASS == 2) ? (p.has_ce ? *p.dev_scale : 0.f) : p.ce_grad_scale;
   const bool dice = (PASS == 2) && p.has_dice;
+  const bool sums = (PASS == 1) && p.has_dice;
 
   float loss_sum = 0.f, denom_sum = 0.f, invalid = 0.f;
-  float psum[CPAD], inter[CPAD], tsum[CPAD];
+  float psum[CPAD];
   if constexpr (PASS == 1) {
 #pragma unroll
-    for (int c = 0; c < CPAD; ++c) { psum[c] = 0.f; inter[c] = 0.f; tsum[c] = 0.f; }
+    for (int c = 0; c < CPAD; ++c) psum[c] = 0.f;
   }
   auto flush_dice = [&](int b) {
     if constexpr (PASS == 1) {
       const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = NT >> 5;
 #pragma unroll
       for (int c = 0; c < CPAD; ++c) {
-        float a = warp_sum(inter[c]), bsum = warp_sum(psum[c]), t = warp_sum(tsum[c]);
-        if (lane == 0) {
-          red[(0 * CPAD + c) * nw + wid] = a;
-          red[(1 * CPAD + c) * nw + wid] = bsum;
-          red[(2 * CPAD + c) * nw + wid] = t;
-        }
-        psum[c] = 0.f; inter[c] = 0.f; tsum[c] = 0.f;
+        const float bsum = warp_sum(psum[c]);
+        if (lane == 0) red[c * nw + wid] = bsum;
+        psum[c] = 0.f;
       }
-      named_sync(1, NT);
-      for (int i = threadIdx.x; i < 3 * CPAD; i += NT) {
-        int k = i / CPAD, c = i % CPAD;
-        if (c < C) {
-          float s = 0.f;
-          for (int w = 0; w < nw; ++w) s += red[i * nw + w];
-          atomicAdd(p.dice_sums + ((long long)b * C + c) * 3 + k, (double)s);
-        }
+      named_sync(1, NT);   // also orders every thread's shared-memory atomics of this image
+      for (int c = threadIdx.x; c < C; c += NT) {
+        float sp = 0.f;
+        for (int w = 0; w < nw; ++w) sp += red[c * nw + w];
+        double* dst = p.dice_sums + ((long long)b * C + c) * 3;
+        atomicAdd(dst + 0, (double)inter_s[c]);
+        atomicAdd(dst + 1, (double)sp);
+        atomicAdd(dst + 2, (double)tsum_s[c]);
+        inter_s[c] = 0.f; tsum_s[c] = 0.f;
       }
       named_sync(1, NT);
     }
@@ -394,127 +419,170 @@ seg_loss_stream_kernel(const SegLossParams p, const pxstream::PxIO io) {
   if (pipe.is_io()) {
     pipe.io_loop();
   } else {
-  for (int k = 0; k < pipe.n_my; ++k) {
-    const int b = pipe.image_of(k);
-    if (b != cur_b) {
-      if (PASS == 1 && p.has_dice && cur_b >= 0) flush_dice(cur_b);
-      if (dice) {
-        named_sync(1, NT);
-        if (threadIdx.x < CPAD) {
-          const int c = threadIdx.x;
-          coefA[c] = c < C ? p.dice_coef[((long long)b * C + c) * 2 + 0] : 0.f;
-          coefB[c] = c < C ? p.dice_coef[((long long)b * C + c) * 2 + 1] : 0.f;
-        }
-        named_sync(1, NT);
-      }
-      cur_b = b;
-    }
-    pipe.wait(k);
-    const int px = threadIdx.x * PPT;
-    if (px < pipe.npix_of(k)) {
-      float z[CPAD][PPT];
-#pragma unroll
-      for (int c = 0; c < CPAD; ++c) {
-        if (c < C) {
-          ld_px<T, PPT>(pipe.row(k, 0, c), px, z[c]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < PPT; ++j) z[c][j] = -INFINITY;
-        }
-      }
-      int y[PPT];
-      bool valid[PPT];
-      const long long* trow = pipe.target_row(k);
-#pragma unroll
-      for (int j = 0; j < PPT; ++j) {
-        const long long t = trow[px + j];
-        const bool ign = (t == p.ignore_index);
-        const bool ok = (t >= 0 && t < C);
-        valid[j] = ok && !ign;
-        y[j] = valid[j] ? (int)t : -1;
-        if (!ok && !ign) invalid += 1.f;
-      }
-      float coef[PPT];
-#pragma unroll
-      for (int j = 0; j < PPT; ++j) {
-        float m = z[0][j];
-#pragma unroll
-        for (int c = 1; c < CPAD; ++c) m = fmaxf(m, z[c][j]);
-        float s = 0.f, zy = 0.f;
-#pragma unroll
-        for (int c = 0; c < CPAD; ++c) {
-          zy = (c == y[j]) ? z[c][j] : zy;
-          float e = exp2f((z[c][j] - m) * kLog2e);
-          z[c][j] = e;
-          s += e;
-        }
-        float inv = 1.f / s;
-#pragma unroll
-        for (int c = 0; c < CPAD; ++c) z[c][j] *= inv;
-        coef[j] = 0.f;
-        if (p.has_ce && valid[j]) {
-          float wy = wsm[y[j]];
-          float nll = -(zy - m - logf(s));
-          float ce = wy * nll;
-          if (p.focal) {
-            float pt = expf(-ce);
-            float omp = 1.f - pt;
-            float pw = powf(omp, p.gamma);
-            float dpw = p.gamma * powf(omp, p.gamma - 1.f);
-            if (PASS != 2) { loss_sum += p.alpha * pw * ce; }
-            coef[j] = p.alpha * (pw + dpw * pt * ce) * wy * ce_scale;
-          } else {
-            if (PASS != 2) { loss_sum += ce; denom_sum += wy; }
-            coef[j] = wy * ce_scale;
-          }
-        }
-      }
-      if constexpr (PASS == 1) {
-        if (p.has_dice) {
-#pragma unroll
-          for (int c = 0; c < CPAD; ++c) {
-#pragma unroll
-            for (int j = 0; j < PPT; ++j) {
-              const float tv = (y[j] == c) ? 1.f : 0.f;
-              psum[c] += z[c][j];
-              inter[c] += z[c][j] * tv;
-              tsum[c] += tv;
-            }
-          }
-        }
-      } else {
-        float dot[PPT];
-#pragma unroll
-        for (int j = 0; j < PPT; ++j) dot[j] = 0.f;
+    for (int k = 0; k < pipe.n_my; ++k) {
+      const int b = pipe.image_of(k);
+      if (b != cur_b) {
+        if (sums && cur_b >= 0) flush_dice(cur_b);
         if (dice) {
-#pragma unroll
-          for (int c = 0; c < CPAD; ++c)
-#pragma unroll
-            for (int j = 0; j < PPT; ++j) dot[j] += (coefA[c] * ((y[j] == c) ? 1.f : 0.f) - coefB[c]) * z[c][j];
+          named_sync(1, NT);
+          if (threadIdx.x < CPAD) {
+            const int c = threadIdx.x;
+            coefA[c] = c < C ? p.dice_coef[((long long)b * C + c) * 2 + 0] : 0.f;
+            coefB[c] = c < C ? p.dice_coef[((long long)b * C + c) * 2 + 1] : 0.f;
+          }
+          named_sync(1, NT);
         }
+        cur_b = b;
+      }
+      pipe.wait(k);
+      const int px = threadIdx.x * PPT;
+      if (px < pipe.npix_of(k)) {
+        // row c of the tile, at this thread's pixels: compile-time offsets from one base address
+        constexpr int RS = kPxTile * (int)sizeof(T);
+        uint8_t* const rows = pipe.stage(k);
+        uint8_t* const col = rows + (size_t)px * sizeof(T);
+        float z[CPAD][PPT], m[PPT];
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) m[j] = -INFINITY;
 #pragma unroll
         for (int c = 0; c < CPAD; ++c) {
-          if (c < C) {
-            float g[PPT];
+          if (FULL || c < C) {
+            ld_px<T, PPT>(col + c * RS, 0, z[c]);
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) m[j] = fmaxf(m[j], z[c][j]);
+          }
+        }
+        // per-pixel target work: validity, picked logit (read from the target's row before it is overwritten)
+        int y[PPT];
+        float zy[PPT];
+        const long long* trow = pipe.target_row(k);
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+          const long long t = trow[px + j];
+          const bool ign = (t == p.ignore_index);
+          const bool ok = (t >= 0 && t < C);
+          y[j] = (ok && !ign) ? (int)t : -1;
+          if (!ok && !ign) invalid += 1.f;
+          zy[j] = y[j] >= 0 ? ld_one<T>(col + y[j] * RS, j) : 0.f;
+        }
+        float s[PPT], nm2[PPT];
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) { s[j] = 0.f; nm2[j] = -m[j] * kLog2e; }
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) {
+          if (FULL || c < C) {
 #pragma unroll
             for (int j = 0; j < PPT; ++j) {
-              const float onehot = (y[j] == c) ? 1.f : 0.f;
-              float v = coef[j] * (z[c][j] - onehot);
-              if (dice) v += z[c][j] * ((coefA[c] * onehot - coefB[c]) - dot[j]);
-              g[j] = v;
+              z[c][j] = ex2_fast(fmaf(z[c][j], kLog2e, nm2[j]));
+              s[j] += z[c][j];
             }
-            st_px<T, PPT>(pipe.row(k, 0, c), px, g);
+          }
+        }
+        float inv[PPT], coef[PPT], ey[PPT];
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+          inv[j] = 1.f / s[j];
+          ey[j] = ex2_fast(fmaf(zy[j], kLog2e, nm2[j]));   // bit-identical to the loop's value for class y
+          coef[j] = 0.f;
+          if (p.has_ce && y[j] >= 0) {
+            const float wy = wsm[y[j]];
+            const float nll = (m[j] - zy[j]) + logf(s[j]);
+            const float ce = wy * nll;
+            if (p.focal) {
+              const float pt = expf(-ce);
+              const float omp = 1.f - pt;
+              const float pw = powf(omp, p.gamma);
+              const float dpw = p.gamma * powf(omp, p.gamma - 1.f);
+              if (PASS != 2) { loss_sum += p.alpha * pw * ce; }
+              coef[j] = p.alpha * (pw + dpw * pt * ce) * wy * ce_scale;
+            } else {
+              if (PASS != 2) { loss_sum += ce; denom_sum += wy; }
+              coef[j] = wy * ce_scale;
+            }
+          }
+        }
+        if constexpr (PASS == 1) {
+          if (sums) {
+#pragma unroll
+            for (int c = 0; c < CPAD; ++c) {
+              if (FULL || c < C) {
+#pragma unroll
+                for (int j = 0; j < PPT; ++j) psum[c] = fmaf(z[c][j], inv[j], psum[c]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+              if (y[j] >= 0) {
+                atomicAdd(inter_s + y[j], ey[j] * inv[j]);
+                atomicAdd(tsum_s + y[j], 1.f);
+              }
+            }
+          }
+        } else {
+          if (dice) {
+            // dL/dz_c = p_c * (coef + u_c - sum_k u_k p_k) - coef*onehot_c,   u_c = coefA_c*onehot_c - coefB_c
+            float dotB[PPT];
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) dotB[j] = 0.f;
+#pragma unroll
+            for (int c = 0; c < CPAD; ++c) {
+              if (FULL || c < C) {
+                const float cb = coefB[c];
+#pragma unroll
+                for (int j = 0; j < PPT; ++j) dotB[j] = fmaf(cb, z[c][j], dotB[j]);
+              }
+            }
+            float k1[PPT], cay[PPT];
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+              cay[j] = y[j] >= 0 ? coefA[y[j]] : 0.f;
+              const float dot = (cay[j] * ey[j] - dotB[j]) * inv[j];
+              k1[j] = inv[j] * (coef[j] - dot);
+            }
+#pragma unroll
+            for (int c = 0; c < CPAD; ++c) {
+              if (FULL || c < C) {
+                const float cb = coefB[c];
+                float g[PPT];
+#pragma unroll
+                for (int j = 0; j < PPT; ++j) g[j] = z[c][j] * fmaf(-cb, inv[j], k1[j]);
+                st_px<T, PPT>(col + c * RS, 0, g);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+              if (y[j] >= 0) {
+                const float gy = ey[j] * (fmaf(-coefB[y[j]], inv[j], k1[j]) + cay[j] * inv[j]) - coef[j];
+                st_one<T>(col + y[j] * RS, j, gy);
+              }
+            }
+          } else {
+            float kk[PPT];
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) kk[j] = inv[j] * coef[j];
+#pragma unroll
+            for (int c = 0; c < CPAD; ++c) {
+              if (FULL || c < C) {
+                float g[PPT];
+#pragma unroll
+                for (int j = 0; j < PPT; ++j) g[j] = z[c][j] * kk[j];
+                st_px<T, PPT>(col + c * RS, 0, g);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < PPT; ++j)
+              if (y[j] >= 0) st_one<T>(col + y[j] * RS, j, fmaf(ey[j], kk[j], -coef[j]));
           }
         }
       }
+      pipe.release(k);
     }
-    pipe.release(k);
-  }
-  if (PASS == 1 && p.has_dice && cur_b >= 0) flush_dice(cur_b);
+    if (sums && cur_b >= 0) flush_dice(cur_b);
   }
   if constexpr (PASS != 2) {
     float v[3] = {loss_sum, denom_sum, invalid}, o[3];
-    block_sum<3>(v, red, o);
+    // separate scratch: the IO warp gets here while the compute warps may still be inside flush_dice (red)
+    block_sum<3>(v, red + CPAD * 17, o);
     if (threadIdx.x == 0) {
       if (o[0] != 0.f) atomicAdd(p.acc + 0, (double)o[0]);
       if (o[1] != 0.f) atomicAdd(p.acc + 1, (double)o[1]);
@@ -528,11 +596,11 @@ inline bool loss_stream_enabled() {
   return on;
 }
 
-template <typename T, int CPAD, int PPT, int PASS>
+template <typename T, int CPAD, int PPT, int PASS, bool FULL>
 int launch_seg_stream_t(const SegLossParams& p, const pxstream::PxIO& io, cudaStream_t st) {
-  const size_t smem = 128 + (size_t)io.stages * io.stage_bytes + 64 + 3 * CPAD * 4 +
-                      (3 * CPAD * 17 + 32) * 4;
-  auto kfn = seg_loss_stream_kernel<T, CPAD, PPT, PASS>;
+  const size_t smem = 128 + (size_t)io.stages * io.stage_bytes + 64 + 5 * CPAD * 4 +
+                      (CPAD * 17 + 64) * 4;
+  auto kfn = seg_loss_stream_kernel<T, CPAD, PPT, PASS, FULL>;
   static bool attr = false;
   if (!attr) {
     UDA_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -557,7 +625,8 @@ int try_seg_stream(const SegLossParams& p, cudaStream_t st) {
   if (!pxstream::plan_px(io, ppt, 0)) return 0;
   int rc;
 #define UDA_SEG_STREAM(CP)                                                                         \
-  rc = (ppt == 2) ? launch_seg_stream_t<T, CP, 2, PASS>(p, io, st) : launch_seg_stream_t<T, CP, 1, PASS>(p, io, st)
+  rc = (p.C == CP) ? launch_seg_stream_t<T, CP, 2, PASS, true>(p, io, st)                          \
+                   : launch_seg_stream_t<T, CP, 2, PASS, false>(p, io, st)
   if (p.C <= 8) UDA_SEG_STREAM(8);
   else if (p.C <= 16) UDA_SEG_STREAM(16);
   else if (p.C <= 24) UDA_SEG_STREAM(24);
@@ -750,76 +819,96 @@ __global__ void bce_logits_kernel(const float* __restrict__ x, float* __restrict
 }
 
 
-// ---- streaming versions (see loss_stream.cuh): same arithmetic, tiles through shared memory ----
+// ---- streaming versions (see loss_stream.cuh): tiles through shared memory, arithmetic arranged like
+// seg_loss_stream_kernel's (one FMNMX, one FFMA + MUFU.EX2 and a handful of FADD/FFMA per logit) ----
+constexpr float kLn2 = 0.6931471805599453f;
+
 template <typename T, int CPAD, int PPT>
 __global__ void __launch_bounds__(pxstream::px_threads<PPT>(), 1)
 consistency_stream_kernel(const pxstream::PxIO io, double* __restrict__ acc, float inv_T, float scale) {
   using namespace pxstream;
   constexpr int NT = px_compute_threads<PPT>();
+  constexpr int RS = kPxTile * (int)sizeof(T);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* tail = smem + (size_t)io.stages * io.stage_bytes;
   PixelPipe<PPT, NT> pipe(io, smem, reinterpret_cast<uint64_t*>(tail));
   float* red = reinterpret_cast<float*>(tail + 64);
   const int C = io.C;
+  const float k2 = inv_T * kLog2e;        // logits -> log2 units of the tempered softmax
+  const float gs = inv_T * scale;
   float lsum = 0.f;
-  if (pipe.is_io()) pipe.io_loop();
-  else
-  for (int k = 0; k < pipe.n_my; ++k) {
-    pipe.wait(k);
-    const int px = threadIdx.x * PPT;
-    if (px < pipe.npix_of(k)) {
-      float e1[CPAD][PPT], e2[CPAD][PPT], d[CPAD][PPT];
+  if (pipe.is_io()) {
+    pipe.io_loop();
+  } else {
+    for (int k = 0; k < pipe.n_my; ++k) {
+      pipe.wait(k);
+      const int px = threadIdx.x * PPT;
+      if (px < pipe.npix_of(k)) {
+        uint8_t* const col1 = pipe.stage(k) + (size_t)px * sizeof(T);
+        uint8_t* const col2 = col1 + (size_t)C * RS;
+        float e1[CPAD][PPT], e2[CPAD][PPT], dz[CPAD][PPT], m1[PPT], m2[PPT];
 #pragma unroll
-      for (int c = 0; c < CPAD; ++c) {
-        if (c < C) {
-          ld_px<T, PPT>(pipe.row(k, 0, c), px, e1[c]);
-          ld_px<T, PPT>(pipe.row(k, 1, c), px, e2[c]);
+        for (int j = 0; j < PPT; ++j) { m1[j] = -INFINITY; m2[j] = -INFINITY; }
 #pragma unroll
-          for (int j = 0; j < PPT; ++j) {
-            e1[c][j] *= inv_T; e2[c][j] *= inv_T;
-            d[c][j] = e2[c][j] - e1[c][j];
+        for (int c = 0; c < CPAD; ++c) {
+          if (c < C) {
+            ld_px<T, PPT>(col1 + c * RS, 0, e1[c]);
+            ld_px<T, PPT>(col2 + c * RS, 0, e2[c]);
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+              m1[j] = fmaxf(m1[j], e1[c][j]); m2[j] = fmaxf(m2[j], e2[c][j]);
+              dz[c][j] = e2[c][j] - e1[c][j];
+            }
           }
-        } else {
-#pragma unroll
-          for (int j = 0; j < PPT; ++j) { e1[c][j] = -INFINITY; e2[c][j] = -INFINITY; d[c][j] = 0.f; }
         }
-      }
+        float s1[PPT], s2[PPT], w1[PPT], w2[PPT], n1[PPT], n2[PPT];
 #pragma unroll
-      for (int j = 0; j < PPT; ++j) {
-        float m1 = e1[0][j], m2 = e2[0][j];
-#pragma unroll
-        for (int c = 1; c < CPAD; ++c) { m1 = fmaxf(m1, e1[c][j]); m2 = fmaxf(m2, e2[c][j]); }
-        float s1 = 0.f, s2 = 0.f, w1 = 0.f, w2 = 0.f;
+        for (int j = 0; j < PPT; ++j) {
+          s1[j] = 0.f; s2[j] = 0.f; w1[j] = 0.f; w2[j] = 0.f;
+          n1[j] = -m1[j] * k2; n2[j] = -m2[j] * k2;
+        }
 #pragma unroll
         for (int c = 0; c < CPAD; ++c) {
-          float x1 = exp2f((e1[c][j] - m1) * kLog2e), x2 = exp2f((e2[c][j] - m2) * kLog2e);
-          e1[c][j] = x1; e2[c][j] = x2;
-          s1 += x1; s2 += x2;
-          w1 += x1 * d[c][j]; w2 += x2 * d[c][j];
+          if (c < C) {
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+              const float x1 = ex2_fast(fmaf(e1[c][j], k2, n1[j])), x2 = ex2_fast(fmaf(e2[c][j], k2, n2[j]));
+              e1[c][j] = x1; e2[c][j] = x2;
+              s1[j] += x1; s2[j] += x2;
+              w1[j] = fmaf(x1, dz[c][j], w1[j]); w2[j] = fmaf(x2, dz[c][j], w2[j]);
+            }
+          }
         }
-        const float r1 = 1.f / s1, r2 = 1.f / s2;
-        const float delta = (m2 + logf(s2)) - (m1 + logf(s1));
-        const float kl12 = delta - w1 * r1, kl21 = w2 * r2 - delta;
-        lsum += kl12 + kl21;
-        const float gs = inv_T * scale;
+        float u1[PPT], u2[PPT], A1[PPT], A2[PPT];
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+          const float r1 = 1.f / s1[j], r2 = 1.f / s2[j];
+          // delta = logsumexp(z2/T) - logsumexp(z1/T);  d_c = (z2_c - z1_c)/T
+          const float delta = (m2[j] - m1[j]) * inv_T + (logf(s2[j]) - logf(s1[j]));
+          const float kl12 = delta - w1[j] * r1 * inv_T, kl21 = w2[j] * r2 * inv_T - delta;
+          lsum += kl12 + kl21;
+          u1[j] = gs * r1; u2[j] = gs * r2;
+          A1[j] = 1.f + delta - kl12; A2[j] = 1.f - delta - kl21;
+        }
 #pragma unroll
         for (int c = 0; c < CPAD; ++c) {
-          float p1 = e1[c][j] * r1, p2 = e2[c][j] * r2;
-          float D = d[c][j] - delta, q = p2 - p1;
-          e1[c][j] = (-q - p1 * (D + kl12)) * gs;
-          e2[c][j] = (q + p2 * (D - kl21)) * gs;
-        }
-      }
+          if (c < C) {
+            float g1[PPT], g2[PPT];
 #pragma unroll
-      for (int c = 0; c < CPAD; ++c) {
-        if (c < C) {
-          st_px<T, PPT>(pipe.row(k, 0, c), px, e1[c]);
-          st_px<T, PPT>(pipe.row(k, 1, c), px, e2[c]);
+            for (int j = 0; j < PPT; ++j) {
+              // g1 = gs*(p1*(A1 - d) - p2),  g2 = gs*(p2*(A2 + d) - p1)
+              const float x1 = e1[c][j] * u1[j], x2 = e2[c][j] * u2[j];
+              g1[j] = fmaf(x1, fmaf(dz[c][j], -inv_T, A1[j]), -x2);
+              g2[j] = fmaf(x2, fmaf(dz[c][j], inv_T, A2[j]), -x1);
+            }
+            st_px<T, PPT>(col1 + c * RS, 0, g1);
+            st_px<T, PPT>(col2 + c * RS, 0, g2);
+          }
         }
       }
+      pipe.release(k);
     }
-    pipe.release(k);
   }
   float v[1] = {lsum}, o[1];
   block_sum<1>(v, red, o);
@@ -831,6 +920,7 @@ __global__ void __launch_bounds__(pxstream::px_threads<PPT>(), 1)
 entropy_stream_kernel(const pxstream::PxIO io, double* __restrict__ acc, float scale) {
   using namespace pxstream;
   constexpr int NT = px_compute_threads<PPT>();
+  constexpr int RS = kPxTile * (int)sizeof(T);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* tail = smem + (size_t)io.stages * io.stage_bytes;
@@ -838,46 +928,62 @@ entropy_stream_kernel(const pxstream::PxIO io, double* __restrict__ acc, float s
   float* red = reinterpret_cast<float*>(tail + 64);
   const int C = io.C;
   float lsum = 0.f;
-  if (pipe.is_io()) pipe.io_loop();
-  else
-  for (int k = 0; k < pipe.n_my; ++k) {
-    pipe.wait(k);
-    const int px = threadIdx.x * PPT;
-    if (px < pipe.npix_of(k)) {
-      float e[CPAD][PPT], x[CPAD][PPT];
+  if (pipe.is_io()) {
+    pipe.io_loop();
+  } else {
+    for (int k = 0; k < pipe.n_my; ++k) {
+      pipe.wait(k);
+      const int px = threadIdx.x * PPT;
+      if (px < pipe.npix_of(k)) {
+        uint8_t* const col = pipe.stage(k) + (size_t)px * sizeof(T);
+        float e[CPAD][PPT], t[CPAD][PPT], m[PPT];
 #pragma unroll
-      for (int c = 0; c < CPAD; ++c) {
-        if (c < C) {
-          ld_px<T, PPT>(pipe.row(k, 0, c), px, x[c]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < PPT; ++j) x[c][j] = -INFINITY;
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < PPT; ++j) {
-        float m = x[0][j];
-#pragma unroll
-        for (int c = 1; c < CPAD; ++c) m = fmaxf(m, x[c][j]);
-        float s = 0.f, w = 0.f;
+        for (int j = 0; j < PPT; ++j) m[j] = -INFINITY;
 #pragma unroll
         for (int c = 0; c < CPAD; ++c) {
-          float xm = (c < C) ? x[c][j] - m : 0.f;
-          float ex = (c < C) ? exp2f(xm * kLog2e) : 0.f;
-          x[c][j] = xm; e[c][j] = ex;
-          s += ex; w += ex * xm;
+          if (c < C) {
+            ld_px<T, PPT>(col + c * RS, 0, t[c]);
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) m[j] = fmaxf(m[j], t[c][j]);
+          }
         }
-        const float r = 1.f / s, ls = logf(s);
-        const float H = ls - w * r;
-        lsum += H;
+        float s[PPT], w[PPT], nm[PPT];
 #pragma unroll
-        for (int c = 0; c < CPAD; ++c) e[c][j] = -scale * (e[c][j] * r) * ((x[c][j] - ls) + H);
+        for (int j = 0; j < PPT; ++j) { s[j] = 0.f; w[j] = 0.f; nm[j] = -m[j] * kLog2e; }
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) {
+          if (c < C) {
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) {
+              t[c][j] = fmaf(t[c][j], kLog2e, nm[j]);        // (x - max) in log2 units
+              e[c][j] = ex2_fast(t[c][j]);
+              s[j] += e[c][j];
+              w[j] = fmaf(e[c][j], t[c][j], w[j]);
+            }
+          }
+        }
+        float K[PPT], q0[PPT];
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+          const float r = 1.f / s[j], ls = logf(s[j]);
+          const float H = ls - w[j] * r * kLn2;
+          lsum += H;
+          // dH/dx_c = -p_c * ((x_c - max) - ls + H)
+          K[j] = -scale * r;
+          q0[j] = H - ls;
+        }
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) {
+          if (c < C) {
+            float g[PPT];
+#pragma unroll
+            for (int j = 0; j < PPT; ++j) g[j] = e[c][j] * K[j] * fmaf(t[c][j], kLn2, q0[j]);
+            st_px<T, PPT>(col + c * RS, 0, g);
+          }
+        }
       }
-#pragma unroll
-      for (int c = 0; c < CPAD; ++c)
-        if (c < C) st_px<T, PPT>(pipe.row(k, 0, c), px, e[c]);
+      pipe.release(k);
     }
-    pipe.release(k);
   }
   float v[1] = {lsum}, o[1];
   block_sum<1>(v, red, o);
