@@ -102,12 +102,65 @@ def test_tc_forward_and_dgrad(cfg):
     assert rel_err(dw.cpu(), 2 * dwr) < 2e-3
 
 
+@pytest.mark.parametrize("tile", ["1,128", "2,128", "1,256", "2,256"])
+@pytest.mark.parametrize("cfg", [(4, 16, 16, 256, 256, 3, 1, 1), (2, 32, 32, 128, 256, 3, 2, 1), (4, 16, 16, 384, 128, 3, 1, 1)],
+                         ids=["256to256", "128to256_s2", "384to128"])
+def test_tile_shapes_of_the_wide_layers(cfg, tile, monkeypatch):
+    """Every (pixel tile, channel tile) shape the persistent kernel's cost model can pick — 128/256 pixels x
+    128/256 channels, the last one with single-buffered TMEM — against the fp32 reference (forward with the fused
+    BatchNorm statistics, and dgrad with an addend)."""
+    ops = _ops()
+    B, H, W, Cin, Cout, k, s, p = cfg
+    if tile.endswith("256") and Cout % 256:
+        pytest.skip("channel tile wider than the layer")
+    monkeypatch.setenv("UDA_B200_TC_TILE", tile)
+    x = _rand((B, H, W, Cin), 11)
+    w = _rand((Cout, k, k, Cin), 12, (k * k * Cin) ** -0.5)
+    xg, wg = x.to(DEV), w.to(DEV)
+    yr = R.conv_fwd(x.float(), w.float(), None, s, p)
+    sums = torch.zeros(2 * Cout, dtype=torch.float64, device=DEV)
+    y = ops.conv_fwd(xg, wg, None, s, p, bn_sums=sums)
+    assert rel_err(y.float().cpu(), yr) < 1e-2
+    yf = y.double().reshape(-1, Cout)
+    assert rel_err(sums[Cout:].cpu(), (yf * yf).sum(0).cpu()) < 1e-4
+    assert (sums[:Cout].cpu() - yf.sum(0).cpu()).abs().max() < 1e-3 * float(yf.abs().sum(0).max())
+    dy = _rand(tuple(yr.shape), 13)
+    dxr = R.conv_dgrad(dy.float(), w.float(), x.shape, s, p)
+    add = _rand(tuple(x.shape), 14)
+    acc = add.clone().to(DEV)
+    out = ops.conv_dgrad(dy.to(DEV), wg, x.shape, s, p, addend=acc)
+    assert rel_err(out.float().cpu(), dxr + add.float()) < 1e-2
+
+
 def test_weight_flip_transpose():
     ops = _ops()
     w = _rand((6, 3, 3, 4), 5)
     wt = ops.weight_flip_transpose(w.to(DEV)).cpu()
     ref = w.flip(1, 2).permute(3, 1, 2, 0).contiguous()
     assert torch.equal(wt, ref)
+
+
+def test_weight_flip_transpose_batch():
+    """All conv weights of a network in one launch (64 x 64 shared-memory transposes): ragged channel counts
+    (3, 24, 100), 1x1 / 3x3 / 4x4 / 7x7 taps, several tiles per weight."""
+    ops = _ops()
+    shapes = [(64, 7, 7, 3), (24, 3, 3, 16), (128, 1, 1, 64), (256, 3, 3, 192), (100, 4, 4, 72), (8, 3, 3, 8)]
+    offs, rows, off = [], [], 0
+    for O, KH, KW, I in shapes:
+        offs.append(off)
+        rows.append([off, O, I, KH, KW])
+        off += (O * KH * KW * I + 7) // 8 * 8
+    g = torch.Generator().manual_seed(3)
+    base = torch.randn(off, generator=g).bfloat16()
+    out = torch.zeros(off, dtype=torch.bfloat16, device=DEV)
+    table = torch.tensor(rows, dtype=torch.int32, device=DEV)
+    ops.weight_flip_transpose_batch(base.to(DEV), out, table)
+    out = out.cpu()
+    for (O, KH, KW, I), o in zip(shapes, offs):
+        n = O * KH * KW * I
+        w = base[o:o + n].view(O, KH, KW, I)
+        ref = w.flip(1, 2).permute(3, 1, 2, 0).contiguous()
+        assert torch.equal(out[o:o + n].view(I, KH, KW, O), ref), (O, KH, KW, I)
 
 
 def test_unsupported_shapes_fall_back_loudly():

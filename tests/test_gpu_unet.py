@@ -286,6 +286,6 @@ def test_graphed_step_matches_eager_steps():
     for a, b in zip(eager[warm:], got):
         assert abs(a - b) <= 1e-3 * abs(a), (eager, got)
     # parameters after the trajectory agree too (L2: Adam's m/sqrt(v) turns the atomics-order noise of a
-    # near-zero gradient into a full +-lr step for a handful of weights)
-    assert l2_err(m2._store.flat, m1._store.flat) < 2e-3
+    # near-zero gradient into a full +-lr step for a handful of weights; two eager runs differ by 2-3e-3 as well)
+    assert l2_err(m2._store.flat, m1._store.flat) < 6e-3
     assert int(m2.encoder.bn1.num_batches_tracked) == int(m1.encoder.bn1.num_batches_tracked)

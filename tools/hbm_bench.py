@@ -57,7 +57,9 @@ z = torch.randn(B, 24, S, S, device=dev); t = torch.randint(0, 24, (B, S, S), de
 P = B * S * S
 line("CE fwd+bwd fp32", timeit(lambda: ops.seg_loss(z, t, ce_mode=1, use_dice=False)), 2 * P * 24 * 4 + 8 * P)
 line("CE+Dice fwd+bwd fp32", timeit(lambda: ops.seg_loss(z, t, ce_mode=1, use_dice=True)), 3 * P * 24 * 4 + 16 * P)
-line("consistency fp32", timeit(lambda: ops.consistency(z, z)), 4 * P * 24 * 4)
+z2 = torch.randn_like(z)
+line("consistency fp32", timeit(lambda: ops.consistency(z, z2)), 4 * P * 24 * 4)
+del z2
 line("entropy fp32", timeit(lambda: ops.entropy(z)), 2 * P * 24 * 4)
 line("argmax+confmat fp32 (i64 mask)", timeit(lambda: ops.argmax_confmat(z, t)), P * 24 * 4 + 16 * P)
 line("argmax+confmat fp32 (no mask)", timeit(lambda: ops.argmax_confmat(z, t, want_mask=False)), P * 24 * 4 + 8 * P)
@@ -65,5 +67,7 @@ line("nchw->nhwc dlogits", timeit(lambda: ops.nchw_to_nhwc(z, torch.bfloat16)), 
 zb = z.bfloat16()
 line("CE fwd+bwd bf16", timeit(lambda: ops.seg_loss(zb, t, ce_mode=1, use_dice=False)), 2 * P * 24 * 2 + 8 * P)
 line("CE+Dice fwd+bwd bf16", timeit(lambda: ops.seg_loss(zb, t, ce_mode=1, use_dice=True)), 3 * P * 24 * 2 + 16 * P)
-line("consistency bf16", timeit(lambda: ops.consistency(zb, zb)), 4 * P * 24 * 2)
+zb2 = torch.randn_like(zb)
+line("consistency bf16", timeit(lambda: ops.consistency(zb, zb2)), 4 * P * 24 * 2)
+del zb2
 line("argmax+confmat bf16 (u8 mask)", timeit(lambda: ops.argmax_confmat(zb, t, mask_dtype=torch.uint8)), P * 24 * 2 + 9 * P)

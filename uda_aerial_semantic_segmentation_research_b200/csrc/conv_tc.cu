@@ -223,23 +223,37 @@ __global__ void weight_flip_transpose_kernel(const bf16* __restrict__ w, bf16* _
   }
 }
 
-// all conv weights of a network in one launch: table[i] = {element offset, O, I, KH, KW}
-__global__ void weight_flip_transpose_batch_kernel(const bf16* __restrict__ base, bf16* __restrict__ out,
-                                                   const int* __restrict__ table) {
+// all conv weights of a network in one launch: table[i] = {element offset, O, I, KH, KW}.
+// Per tap the job is a [O][I] -> [I][O] matrix transpose: 64 x 64 tiles through shared memory, so both the
+// reads (64 consecutive ci of one co) and the writes (64 consecutive co of one ci) are full 128-byte segments.
+__global__ void __launch_bounds__(256) weight_flip_transpose_batch_kernel(const bf16* __restrict__ base,
+                                                                          bf16* __restrict__ out,
+                                                                          const int* __restrict__ table) {
+  __shared__ unsigned short tile[64][66];
   const int* e = table + 5 * blockIdx.y;
   const long long off = e[0];
   const int O = e[1], I = e[2], KH = e[3], KW = e[4];
-  const bf16* w = base + off;
-  bf16* wt = out + off;
-  const long long n = (long long)O * I * KH * KW;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int co = (int)(i % O);
-    long long t = i / O;
-    const int kw = (int)(t % KW); t /= KW;
-    const int kh = (int)(t % KH);
-    const int ci = (int)(t / KH);
-    wt[i] = w[(((long long)co * KH + (KH - 1 - kh)) * KW + (KW - 1 - kw)) * I + ci];
+  const unsigned short* w = reinterpret_cast<const unsigned short*>(base + off);
+  unsigned short* wt = reinterpret_cast<unsigned short*>(out + off);
+  const int taps = KH * KW, ot = (O + 63) / 64, it = (I + 63) / 64;
+  const int ntiles = taps * ot * it;
+  const int col = threadIdx.x & 63, row0 = threadIdx.x >> 6;   // 4 rows of 64 elements per pass
+  for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    const int tap = t % taps, o0 = ((t / taps) % ot) * 64, i0 = (t / taps / ot) * 64;
+    const int kh = tap / KW, kw = tap % KW;
+    const int src_tap = (KH - 1 - kh) * KW + (KW - 1 - kw);
+#pragma unroll 4
+    for (int r = row0; r < 64; r += 4) {
+      const int co = o0 + r, ci = i0 + col;
+      tile[r][col] = (co < O && ci < I) ? w[((long long)co * taps + src_tap) * I + ci] : (unsigned short)0;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int r = row0; r < 64; r += 4) {
+      const int ci = i0 + r, co = o0 + col;
+      if (ci < I && co < O) wt[((long long)ci * taps + tap) * O + co] = tile[col][r];
+    }
+    __syncthreads();
   }
 }
 

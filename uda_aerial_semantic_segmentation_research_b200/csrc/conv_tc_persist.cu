@@ -15,6 +15,7 @@
 //     high-resolution layers (decoder blocks 2-4, head, layer1) are HBM/issue bound, not FLOP bound;
 //   * stride-2 dgrad: the four output-parity classes are tiles of ONE launch.
 #include "conv_tc_internal.cuh"
+#include <stdlib.h>
 
 namespace uda {
 namespace tcconv {
@@ -50,7 +51,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   constexpr int kABytes = MT * 128 * KC * 2;
   constexpr int kBBytes = BN * KC * 2;
   constexpr uint32_t kAccCols = MT * BN;                      // one accumulator set
-  constexpr uint32_t kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;   // power of two for every (MT,BN)
+  constexpr int kSets = 2 * kAccCols <= 512 ? 2 : 1;          // 256 x 256 tiles fill TMEM: single-buffered
+  constexpr uint32_t kTmemCols = kSets * kAccCols < 32 ? 32 : kSets * kAccCols;   // power of two for every (MT,BN)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.stages;
@@ -132,8 +134,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
         const int ci = t / tiles_per_cls;
         const PClass& c = p.cls[ci];
-        const int q = j & 1;
-        mbar_wait(tempty_bar(q), ((j >> 1) & 1) ^ 1);   // epilogue has drained this accumulator set
+        const int q = j % kSets;
+        mbar_wait(tempty_bar(q), ((j / kSets) & 1) ^ 1);   // epilogue has drained this accumulator set
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)q * kAccCols;
         for (int tap = 0; tap < c.ntaps; ++tap) {
@@ -180,7 +182,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       const int grp = mt / tiles_per_group, tin = mt % tiles_per_group;
       const int b0 = grp * p.NB, h0 = (tin / p.tiles_w) * p.TH, w0 = (tin % p.tiles_w) * p.TW;
       const int oh = p.cls[ci].oh, ow = p.cls[ci].ow;
-      const int q = j & 1;
+      const int q = j % kSets;
       if (p.bn_sums && n0 != bn_n0) {   // channel tile changed: flush the partial statistics
         if (bn_n0 >= 0) {
 #pragma unroll
@@ -192,7 +194,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         }
         bn_n0 = n0;
       }
-      mbar_wait(tfull_bar(q), (j >> 1) & 1);
+      mbar_wait(tfull_bar(q), (j / kSets) & 1);
       tc_fence_after();
 #pragma unroll 1
       for (int sub = 0; sub < MT; ++sub) {
@@ -308,23 +310,73 @@ int launch_persist(const CUtensorMap& ma, const CUtensorMap& mb, PParams& p, int
   return UDA_OK;
 }
 
+bool big_tiles_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UDA_B200_TC_BIGTILES");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 }  // namespace
 
 int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
   const int MH = g.a_map ? g.a_MH : (g.src_s2 ? g.SH / 2 : g.SH), MW = g.a_map ? g.a_MW : (g.src_s2 ? g.SW / 2 : g.SW);
-  const int KC = g.a_map ? g.a_kc : pick_kc(g.Cred), BN = pick_bn(g.Cout);
+  const int KC = g.a_map ? g.a_kc : pick_kc(g.Cred);
+  int BN = pick_bn(g.Cout);
   UDA_REQUIRE(KC > 0 && g.ncls >= 1 && g.ncls <= kMaxClasses && g.Cout % 8 == 0, UDA_ERR_UNSUPPORTED,
               "conv_tc_persist: shape not covered (Cred=%d Cout=%d)", g.Cred, g.Cout);
-  const int n_tiles = (g.Cout + BN - 1) / BN;
+  int n_tiles = (g.Cout + BN - 1) / BN;
   // 256-pixel tiles when that still leaves at least two tiles per SM, else 128-pixel tiles
   TilePlan tp = plan_tiles(g.B, MH, MW, 256);
   int MT = 2;
   if (g.a_map) tp.ok = false;   // caller-built maps use 128-pixel boxes
+  const bool can256 = tp.ok;
   if (tp.ok) {
     const long long t2 = (long long)g.ncls * n_tiles * ((long long)g.B * MH * MW / 256);
     if (t2 < 2LL * num_sms()) tp.ok = false;
   }
   if (!tp.ok) { tp = plan_tiles(g.B, MH, MW, 128); MT = 1; }
+  // Wide layers whose weights cannot stay resident (layer2-4, decoder conv1/conv2 of blocks 0-1) stream
+  // (MT*128 + BN) operand rows per MT*128 x BN tile.  Measured on B200 (tools/conv_bench.py): whatever the tile
+  // shape, an SM takes in only ~30 B/clk through TMA (one 128-byte box row per ~4 clk), so these layers are bound
+  // by the operand bytes of the BUSIEST SM, not by the tensor pipe: pick the tile shape that minimises
+  // rounds x bytes per tile (vs the tensor-pipe time), among 128/256 pixels x 128/256 channels.
+  if (KC == 64 && g.Cout >= 128 && g.Cout % 128 == 0 && !g.a_map && big_tiles_enabled()) {
+    long long taps = 0;
+    for (int c = 0; c < g.ncls; ++c) taps += g.cls[c].ntaps;
+    const double K = (double)taps * g.Cred / g.ncls;   // average reduction length of a tile
+    const long long pixels = (long long)g.B * MH * MW;
+    double best = 1e30;
+    int best_mt = MT, best_bn = BN;
+    for (int mt = 1; mt <= 2; ++mt) {
+      if (mt == 2 && !can256) continue;
+      for (int bn = 128; bn <= 256; bn += 128) {
+        if (g.Cout % bn) continue;
+        if (pixels % (128 * mt)) continue;
+        const long long tiles = (pixels / (128 * mt)) * (g.Cout / bn) * g.ncls;
+        const int sms = num_sms();
+        const double rounds = (double)((tiles + sms - 1) / sms);
+        const double t_tma = rounds * K * 2.0 * (128 * mt + bn) / 30.0;
+        const double t_mma = rounds * (128.0 * mt) * bn * K / 4096.0;
+        const double t_epi = (2 * mt * bn > 512 ? rounds : 1.0) * mt * bn * 12.0;   // exposed epilogue
+        const double t = (t_tma > t_mma ? t_tma : t_mma) + t_epi + 1e-3 * mt * bn;  // ties: smaller tile
+        if (t < best) { best = t; best_mt = mt; best_bn = bn; }
+      }
+    }
+    // test hook: UDA_B200_TC_TILE="<MT>,<BN>" forces a tile shape (read on every call)
+    if (const char* e = getenv("UDA_B200_TC_TILE")) {
+      int fm = 0, fb = 0;
+      if (sscanf(e, "%d,%d", &fm, &fb) == 2 && (fm == 1 || (fm == 2 && can256)) && (fb == 128 || fb == 256) &&
+          g.Cout % fb == 0 && pixels % (128 * fm) == 0) {
+        best_mt = fm; best_bn = fb;
+      }
+    }
+    MT = best_mt; BN = best_bn;
+    n_tiles = g.Cout / BN;
+    tp = plan_tiles(g.B, MH, MW, 128 * MT);
+  }
   UDA_REQUIRE(tp.ok, UDA_ERR_UNSUPPORTED, "conv_tc_persist: pixel grid %dx%dx%d cannot be tiled", g.B, MH, MW);
   UDA_REQUIRE(aligned<bf16>(g.src, 16) && aligned<bf16>(g.wmat, 16) && (!g.out || aligned<bf16>(g.out, 16)) &&
                   (!g.addend || aligned<bf16>(g.addend, 16)),
@@ -376,7 +428,7 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
   if (KC == KCv && BN == BNv)                                                                      \
     return MT == 2 ? launch_persist<KCv, BNv, 2>(ma, mb, p, total_tiles, st)                       \
                    : launch_persist<KCv, BNv, 1>(ma, mb, p, total_tiles, st);
-  UDA_P(64, 128) UDA_P(64, 64) UDA_P(64, 32)
+  UDA_P(64, 256) UDA_P(64, 128) UDA_P(64, 64) UDA_P(64, 32)
   UDA_P(32, 128) UDA_P(32, 64) UDA_P(32, 32)
   UDA_P(16, 128) UDA_P(16, 64) UDA_P(16, 32)
 #undef UDA_P

@@ -625,10 +625,11 @@ int try_seg_stream(const SegLossParams& p, cudaStream_t st) {
   if (!pxstream::plan_px(io, ppt, 0)) return 0;
   int rc;
 #define UDA_SEG_STREAM(CP)                                                                         \
-  rc = (p.C == CP) ? launch_seg_stream_t<T, CP, 2, PASS, true>(p, io, st)                          \
-                   : launch_seg_stream_t<T, CP, 2, PASS, false>(p, io, st)
+  rc = (p.C == CP) ? ((ppt == 2) ? launch_seg_stream_t<T, CP, 2, PASS, true>(p, io, st)            \
+                                 : launch_seg_stream_t<T, CP, 1, PASS, true>(p, io, st))           \
+                   : ((ppt == 2) ? launch_seg_stream_t<T, CP, 2, PASS, false>(p, io, st)           \
+                                 : launch_seg_stream_t<T, CP, 1, PASS, false>(p, io, st))
   if (p.C <= 8) UDA_SEG_STREAM(8);
-  else if (p.C <= 16) UDA_SEG_STREAM(16);
   else if (p.C <= 24) UDA_SEG_STREAM(24);
   else UDA_SEG_STREAM(32);
 #undef UDA_SEG_STREAM

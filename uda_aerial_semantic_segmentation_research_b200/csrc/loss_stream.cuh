@@ -15,6 +15,7 @@ namespace pxstream {
 using namespace stream;
 
 constexpr size_t kSmemBudget = 220 * 1024;   // stages; coefficient / reduction scratch lives above it
+constexpr int kDefaultPpt = 2;
 constexpr int kPxTile = 512;                 // pixels per tile = compute threads x pixels per thread
 template <int PPT> constexpr int px_compute_threads() { return kPxTile / PPT; }
 template <int PPT> constexpr int px_threads() { return kPxTile / PPT + 32; }   // + the IO warp
@@ -167,10 +168,9 @@ inline bool plan_px(PxIO& io, int& ppt, size_t extra_smem) {
   if (io.target && (reinterpret_cast<uintptr_t>(io.target) & 15)) return false;
   if ((long long)io.B * io.C * io.HW * io.esize * io.nten < (1 << 20)) return false;
   (void)extra_smem;
-  // pixel pairs per thread (8 compute warps); UDA_B200_LOSS_PPT=1 selects the 16-warp variant (experimental:
-  // measured slower, and it fails the full-size CE+Dice linearity check)
+  // pixel pairs per thread (8 compute warps) or single pixels (16 compute warps); UDA_B200_LOSS_PPT overrides
   static const int forced = [] { const char* e = getenv("UDA_B200_LOSS_PPT"); return e ? atoi(e) : 0; }();
-  ppt = forced == 1 ? 1 : 2;
+  ppt = forced == 1 ? 1 : (forced == 2 ? 2 : kDefaultPpt);
   const size_t tp = kPxTile;
   const size_t sb = (size_t)io.nten * io.C * tp * io.esize + (io.target ? tp * 8 : 0);
   const int st = (int)(kSmemBudget / sb);

@@ -208,6 +208,25 @@ class Ctx:
     def __init__(self, store, dtype, training, tape):
         self.store, self.dtype, self.training, self.tape = store, dtype, training, tape
         self.sync = None  # optional gradient-sync object (ddp.GradSync): param_done(store, param)
+        self._pool, self._pool_used = None, 0   # zero-filled float64 scratch for the fused BatchNorm statistics
+        self._trackers = []                     # num_batches_tracked buffers to bump at the end of the forward
+
+    def stats_slot(self, n, device):
+        """``n`` zeroed float64 values for a conv epilogue's BatchNorm sums: slices of ONE zero-filled pool per
+        forward instead of one ``torch.zeros`` launch per layer."""
+        n_al = (n + 15) // 16 * 16
+        if self._pool is None or self._pool_used + n_al > self._pool.numel():
+            self._pool = torch.zeros(max(1 << 15, n_al), dtype=torch.float64, device=device)
+            self._pool_used = 0
+        out = self._pool[self._pool_used:self._pool_used + n]
+        self._pool_used += n_al
+        return out
+
+    def finish_forward(self):
+        """One fused increment of every BatchNorm's ``num_batches_tracked`` (instead of one launch per layer)."""
+        if self._trackers:
+            torch._foreach_add_(self._trackers, 1)
+            self._trackers = []
 
     def done(self, *params):
         """Tell the data-parallel layer that the gradients of ``params`` are final for this backward."""
@@ -238,7 +257,7 @@ def conv(ctx, xin, cp, nchw_out=False, bn=None):
     w = st.w(cp.weight, ctx.dtype)
     sums = None
     if bn is not None and _fused_stats_ok(ctx, xin, cp):
-        sums = torch.zeros(2 * cp.out_channels, dtype=torch.float64, device=w.device)
+        sums = ctx.stats_slot(2 * cp.out_channels, w.device)
     if xin.t is None:   # Cin = 3 stem on the tensor cores (see ops.stem_*)
         H, W = xin.nchw.shape[2:]
         K, pad = cp.kernel_size, cp.padding
@@ -284,12 +303,12 @@ def bn_act(ctx, zin, bn, slope=0.0, residual=None):
     if ctx.training and zin.sums is not None:
         a, mean, rstd, scale, shift = ops.bn_apply_fused(zin.t, zin.sums, bn.weight, bn.bias, bn.running_mean,
                                                          bn.running_var, bn.eps, bn.momentum, res_t, slope)
-        bn.num_batches_tracked += 1
+        ctx._trackers.append(bn.num_batches_tracked)
     else:
         if ctx.training:
             mean, rstd, scale, shift = ops.bn_stats(zin.t, bn.weight, bn.bias, bn.running_mean, bn.running_var,
                                                     bn.eps, bn.momentum)
-            bn.num_batches_tracked += 1
+            ctx._trackers.append(bn.num_batches_tracked)
         else:
             scale, shift = ops.bn_eval_coeffs(bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps)
             mean = rstd = None

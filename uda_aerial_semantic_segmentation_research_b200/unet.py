@@ -264,14 +264,17 @@ class Unet(nn.Module):
             in_vars = [xin]
             feats = self.encoder.run(ctx, xin)
             if part == "encoder":
+                ctx.finish_forward()
                 outs = [ops.nhwc_to_nchw(f.t) for f in feats[1:]]
                 return outs, tape, in_vars, feats[1:]
             dec = self.decoder.run(ctx, feats)
             logits = E.conv(ctx, dec, self.segmentation_head[0], nchw_out=True)
+            ctx.finish_forward()
             return [logits.t], tape, in_vars, [logits]
         if part == "decoder":
             in_vars = [None] + [Var(ops.nchw_to_nhwc(f.contiguous().float(), dtype)) for f in inputs[1:]]
             dec = self.decoder.run(ctx, in_vars)
+            ctx.finish_forward()
             return [ops.nhwc_to_nchw(dec.t)], tape, in_vars, [dec]
         if part == "head":
             xin = Var(ops.nchw_to_nhwc(inputs[0].contiguous().float(), dtype))
