@@ -84,7 +84,10 @@ def test_conv_direct(dtype, cfg):
 
 
 @pytest.mark.parametrize("dtype", DT)
-@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (3, 5, 7, 16), (1, 8, 8, 512), (2, 4, 4, 24), (1, 4, 4, 2048)])
+# the last two shapes are >= 1 MiB in bf16: the bulk-copy streaming kernels (several 16 KB tiles per CTA, a ragged
+# last tile for the 72x100 one)
+@pytest.mark.parametrize("shape", [(2, 16, 16, 64), (3, 5, 7, 16), (1, 8, 8, 512), (2, 4, 4, 24), (1, 4, 4, 2048),
+                                   (4, 64, 64, 128), (3, 72, 100, 32)])
 @pytest.mark.parametrize("slope", [0.0, 0.2, 1.0])
 def test_batchnorm(dtype, shape, slope):
     ops = _ops()
@@ -164,13 +167,16 @@ def test_pool_upcat_bias_colsum(dtype):
 
 
 @pytest.mark.parametrize("dtype", DT)
-def test_gap_linear_sigmoid(dtype):
+@pytest.mark.parametrize("hw", [4, 32])     # 32x32: the multi-CTA pooling / coalesced-fill kernels (bf16)
+def test_gap_linear_sigmoid(dtype, hw):
     ops = _ops()
-    x = _rand((3, 4, 4, 512), dtype, 18)
+    x = _rand((3, hw, hw, 512), dtype, 18)
     w, b = _rand((1, 512), torch.float32, 19, 0.05), torch.tensor([0.1])
     y, pooled = ops.gap_linear_sigmoid_fwd(x.to(DEV), w.to(DEV), b.to(DEV))
     yr, pr = R.gap_linear_sigmoid_fwd(x, w, b)
     assert y.shape == (3, 1) and rel_err(y.cpu(), yr) < 1e-5 and rel_err(pooled.cpu(), pr) < 1e-5
+    y2, pooled2 = ops.gap_linear_sigmoid_fwd(x.to(DEV), w.to(DEV), b.to(DEV))      # per-image counters are re-armed
+    assert torch.equal(y2, y) or rel_err(y2.cpu(), yr) < 1e-5
     dout = torch.tensor([[1.0], [-0.5], [2.0]])
     dw, db = torch.zeros(1, 512, device=DEV), torch.zeros(1, device=DEV)
     dx = ops.gap_linear_sigmoid_bwd(dout.to(DEV), y, pooled, w.to(DEV), dw, db, x.shape, dtype)

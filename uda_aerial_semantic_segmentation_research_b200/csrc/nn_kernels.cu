@@ -504,16 +504,16 @@ __global__ void sums_to_f32_kernel(const double* __restrict__ sums, float* __res
 // MaxPool 3x3 stride 2 pad 1 (NHWC).  idx stores the winning tap (kh*3+kw), first max in scan order
 // and NaN-propagating like torch.
 // ---------------------------------------------------------------------------------------------
-template <typename T, int VEC>
+template <typename T, int VEC, typename IT>
 __global__ void __launch_bounds__(kThreads)
 maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __restrict__ idx, int B, int H,
                    int W, int C, int Ho, int Wo) {
   const int cv = C / VEC;
-  const long long total = (long long)B * Ho * Wo * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  const IT total = (IT)B * Ho * Wo * cv;
+  for (IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (IT)gridDim.x * blockDim.x) {
     const int v = (int)(i % cv);
-    long long p = i / cv;
+    IT p = i / cv;
     const int wo = (int)(p % Wo); p /= Wo;
     const int ho = (int)(p % Ho);
     const int b = (int)(p / Ho);
@@ -548,23 +548,23 @@ maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __
   }
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, typename IT>
 __global__ void __launch_bounds__(kThreads)
 maxpool_bwd_kernel(const T* __restrict__ dy, const unsigned char* __restrict__ idx, const T* addend, T* dx, int B,
                    int H, int W, int C, int Ho, int Wo) {
   const int cv = C / VEC;
-  const long long total = (long long)B * H * W * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  const IT total = (IT)B * H * W * cv;
+  for (IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (IT)gridDim.x * blockDim.x) {
     const int v = (int)(i % cv);
-    long long p = i / cv;
+    IT p = i / cv;
     const int w = (int)(p % W); p /= W;
     const int h = (int)(p % H);
     const int b = (int)(p / H);
     float acc[VEC];
 #pragma unroll
     for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
-    if (addend) ld_vec<VEC>(addend + i * VEC, acc);  // may alias dx (same elements, same thread)
+    if (addend) ld_vec<VEC>(addend + (long long)i * VEC, acc);  // may alias dx (same elements, same thread)
 #pragma unroll
     for (int kh = 0; kh < 3; ++kh) {
       const int t = h + 1 - kh;
@@ -585,46 +585,46 @@ maxpool_bwd_kernel(const T* __restrict__ dy, const unsigned char* __restrict__ i
           if (idx[o + j] == kh * 3 + kw) acc[j] += dv[j];
       }
     }
-    st_vec<VEC>(dx + i * VEC, acc);
+    st_vec<VEC>(dx + (long long)i * VEC, acc);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // Decoder operand: out[b,h,w,:] = concat(x[b,h/2,w/2,:C1], skip[b,h,w,:C2])  (nearest x2)
 // ---------------------------------------------------------------------------------------------
-template <typename T, int VEC>
+template <typename T, int VEC, typename IT>
 __global__ void __launch_bounds__(kThreads)
 upcat_fwd_kernel(const T* __restrict__ x, const T* __restrict__ skip, T* __restrict__ out, int B, int H, int W,
                  int C1, int C2) {
   const int Ct = C1 + C2, cv = Ct / VEC;
-  const long long total = (long long)B * H * W * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
+  const IT total = (IT)B * H * W * cv;
+  for (IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (IT)gridDim.x * blockDim.x) {
     const int c = (int)(i % cv) * VEC;
-    long long p = i / cv;
+    IT p = i / cv;
     const int w = (int)(p % W); p /= W;
     const int h = (int)(p % H);
     const int b = (int)(p / H);
     float v[VEC];
     if (c < C1) ld_vec<VEC>(x + (((long long)b * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1)) * C1 + c, v);
     else ld_vec<VEC>(skip + (((long long)b * H + h) * W + w) * C2 + (c - C1), v);
-    st_vec<VEC>(out + i * VEC, v);
+    st_vec<VEC>(out + (long long)i * VEC, v);
   }
 }
 // dx[b,h2,w2,c] = sum of the 2x2 children of dout[..., c<C1];  dskip = dout[..., C1:]
-template <typename T, int VEC>
+template <typename T, int VEC, typename IT>
 __global__ void __launch_bounds__(kThreads)
 upcat_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dx, T* __restrict__ dskip, int B, int H, int W,
                  int C1, int C2) {
   const int Ct = C1 + C2;
   const int cv1 = C1 / VEC, cv2 = C2 / VEC;
-  const long long n1 = (long long)B * (H / 2) * (W / 2) * cv1;
-  const long long n2 = (long long)B * H * W * cv2;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2;
-       i += (long long)gridDim.x * blockDim.x) {
+  const IT n1 = (IT)B * (H / 2) * (W / 2) * cv1;
+  const IT n2 = (IT)B * H * W * cv2;
+  for (IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2;
+       i += (IT)gridDim.x * blockDim.x) {
     if (i < n1) {
       const int c = (int)(i % cv1) * VEC;
-      long long p = i / cv1;
+      IT p = i / cv1;
       const int w2 = (int)(p % (W / 2)); p /= (W / 2);
       const int h2 = (int)(p % (H / 2));
       const int b = (int)(p / (H / 2));
@@ -640,14 +640,14 @@ upcat_bwd_kernel(const T* __restrict__ dout, T* __restrict__ dx, T* __restrict__
 #pragma unroll
           for (int j = 0; j < VEC; ++j) acc[j] += v[j];
         }
-      st_vec<VEC>(dx + i * VEC, acc);
+      st_vec<VEC>(dx + (long long)i * VEC, acc);
     } else {
-      const long long k = i - n1;
+      const IT k = i - n1;
       const int c = (int)(k % cv2) * VEC;
-      const long long p = k / cv2;
+      const IT p = k / cv2;
       float v[VEC];
-      ld_vec<VEC>(dout + p * Ct + C1 + c, v);
-      st_vec<VEC>(dskip + k * VEC, v);
+      ld_vec<VEC>(dout + (long long)p * Ct + C1 + c, v);
+      st_vec<VEC>(dskip + (long long)k * VEC, v);
     }
   }
 }
@@ -697,6 +697,85 @@ __global__ void gap_linear_sigmoid_bwd_kernel(const float* __restrict__ dout, co
       float s = 0.f;
       for (int bb = 0; bb < B; ++bb) s += dout[bb] * y[bb] * (1.f - y[bb]);
       dbias[0] = (accumulate ? dbias[0] : 0.f) + s;
+    }
+  }
+}
+
+// Wide versions of the two kernels above for bf16 NHWC features with C % 8 == 0 and 256 % (C/8) == 0 (the
+// discriminator tail: [B,32,32,512] at 512x512 inputs).  The one-CTA-per-image kernels walk HW pixels serially per
+// channel (1.1 ms + 0.8 ms per adversarial step at B=8, ncu launch list); here the pooling is spread over
+// (image, pixel slice) CTAs with 16-byte loads, the last slice CTA of an image finishes Linear + sigmoid, and the
+// backward is a plain coalesced fill.
+__global__ void __launch_bounds__(256)
+gap_partial_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                   float* __restrict__ pooled, float* __restrict__ out, unsigned int* __restrict__ counters,
+                   int HW, int C) {
+  __shared__ float part[256 * 8];
+  __shared__ bool is_last;
+  __shared__ float red[32];
+  const int b = blockIdx.y, cvn = C / 8, rows = 256 / cvn;
+  const int cv = threadIdx.x % cvn, row = threadIdx.x / cvn;
+  const int per = (HW + gridDim.x - 1) / gridDim.x;
+  const int p0 = blockIdx.x * per, p1 = min(HW, p0 + per);
+  const bf16* xb = x + (long long)b * HW * C + cv * 8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  for (int p = p0 + row; p < p1; p += rows) {
+    float v[8];
+    ld_vec<8>(xb + (long long)p * C, v);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) part[threadIdx.x * 8 + j] = acc[j];
+  __syncthreads();
+  const float inv = 1.f / (float)HW;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    float sum = 0.f;
+    for (int r = 0; r < rows; ++r) sum += part[(r * cvn + c / 8) * 8 + (c & 7)];
+    atomicAdd(pooled + (long long)b * C + c, sum * inv);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = (atomicAdd(counters + b, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  float dot = 0.f;
+  for (int c = threadIdx.x; c < C; c += 256) dot += __ldcg(pooled + (long long)b * C + c) * w[c];
+  float v[1] = {dot}, o[1];
+  block_sum<1>(v, red, o);
+  if (threadIdx.x == 0) {
+    out[b] = 1.f / (1.f + expf(-(o[0] + bias[0])));
+    counters[b] = 0u;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+gap_bwd_fill_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ pooled,
+                    const float* __restrict__ w, float* __restrict__ dw, float* __restrict__ dbias,
+                    bf16* __restrict__ dx, int B, int HW, int C, int accumulate) {
+  const int b = blockIdx.y, cvn = C / 8;
+  const float dz = dout[b] * y[b] * (1.f - y[b]);
+  const float k = dz / (float)HW;
+  const int cv = threadIdx.x % cvn;   // 256 % cvn == 0: the channel vector of a thread is fixed
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = k * w[cv * 8 + j];
+  bf16* dxb = dx + (long long)b * HW * C;
+  const int nvec = HW * cvn;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < nvec; i += gridDim.x * 256) st_vec<8>(dxb + (long long)i * 8, v);
+  if (b == 0 && blockIdx.x == 0) {
+    for (int c = threadIdx.x; c < C; c += 256) {
+      float sacc = 0.f;
+      for (int bb = 0; bb < B; ++bb) sacc += dout[bb] * y[bb] * (1.f - y[bb]) * pooled[(long long)bb * C + c];
+      dw[c] = (accumulate ? dw[c] : 0.f) + sacc;
+    }
+    if (threadIdx.x == 0) {
+      float sacc = 0.f;
+      for (int bb = 0; bb < B; ++bb) sacc += dout[bb] * y[bb] * (1.f - y[bb]);
+      dbias[0] = (accumulate ? dbias[0] : 0.f) + sacc;
     }
   }
 }
@@ -1028,7 +1107,7 @@ extern "C" int uda_maxpool3x3s2_fwd(const void* x, void* y, unsigned char* idx, 
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   int vec = vec_for(dtype, C, x, y);
   const long long total = (long long)B * Ho * Wo * (C / vec);
-#define K(T, V) maxpool_fwd_kernel<T, V><<<grid_for(total), kThreads, 0, st>>>((const T*)x, (T*)y, idx, B, H, W, C, Ho, Wo)
+#define K(T, V) do { if (total * 8 < (1LL << 31)) maxpool_fwd_kernel<T, V, int><<<grid_for(total), kThreads, 0, st>>>((const T*)x, (T*)y, idx, B, H, W, C, Ho, Wo); else maxpool_fwd_kernel<T, V, long long><<<grid_for(total), kThreads, 0, st>>>((const T*)x, (T*)y, idx, B, H, W, C, Ho, Wo); } while (0)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV
@@ -1044,7 +1123,7 @@ extern "C" int uda_maxpool3x3s2_bwd(const void* dy, const unsigned char* idx, co
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   int vec = vec_for(dtype, C, dy, dx, addend);
   const long long total = (long long)B * H * W * (C / vec);
-#define K(T, V) maxpool_bwd_kernel<T, V><<<grid_for(total), kThreads, 0, st>>>((const T*)dy, idx, (const T*)addend, (T*)dx, B, H, W, C, Ho, Wo)
+#define K(T, V) do { if (total * 8 < (1LL << 31)) maxpool_bwd_kernel<T, V, int><<<grid_for(total), kThreads, 0, st>>>((const T*)dy, idx, (const T*)addend, (T*)dx, B, H, W, C, Ho, Wo); else maxpool_bwd_kernel<T, V, long long><<<grid_for(total), kThreads, 0, st>>>((const T*)dy, idx, (const T*)addend, (T*)dx, B, H, W, C, Ho, Wo); } while (0)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV
@@ -1063,7 +1142,7 @@ extern "C" int uda_upsample2x_concat_fwd(const void* x, const void* skip, void* 
   int vec = vec_for(dtype, C1, x, out);
   if (C2) { int v2 = vec_for(dtype, C2, skip); vec = vec < v2 ? vec : v2; }
   const long long total = (long long)B * H * W * ((C1 + C2) / vec);
-#define K(T, V) upcat_fwd_kernel<T, V><<<grid_for(total), kThreads, 0, st>>>((const T*)x, (const T*)skip, (T*)out, B, H, W, C1, C2)
+#define K(T, V) do { if (total * 8 < (1LL << 31)) upcat_fwd_kernel<T, V, int><<<grid_for(total), kThreads, 0, st>>>((const T*)x, (const T*)skip, (T*)out, B, H, W, C1, C2); else upcat_fwd_kernel<T, V, long long><<<grid_for(total), kThreads, 0, st>>>((const T*)x, (const T*)skip, (T*)out, B, H, W, C1, C2); } while (0)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV
@@ -1080,7 +1159,7 @@ extern "C" int uda_upsample2x_concat_bwd(const void* dout, void* dx, void* dskip
   int vec = vec_for(dtype, C1, dout, dx);
   if (C2) { int v2 = vec_for(dtype, C2, dskip); vec = vec < v2 ? vec : v2; }
   const long long total = (long long)B * (H / 2) * (W / 2) * (C1 / vec) + (long long)B * H * W * (C2 / vec);
-#define K(T, V) upcat_bwd_kernel<T, V><<<grid_for(total), kThreads, 0, st>>>((const T*)dout, (T*)dx, (T*)dskip, B, H, W, C1, C2)
+#define K(T, V) do { if (total * 8 < (1LL << 31)) upcat_bwd_kernel<T, V, int><<<grid_for(total), kThreads, 0, st>>>((const T*)dout, (T*)dx, (T*)dskip, B, H, W, C1, C2); else upcat_bwd_kernel<T, V, long long><<<grid_for(total), kThreads, 0, st>>>((const T*)dout, (T*)dx, (T*)dskip, B, H, W, C1, C2); } while (0)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
 #undef KV
@@ -1093,6 +1172,23 @@ extern "C" int uda_gap_linear_sigmoid_fwd(const void* x, int dtype, const float*
                                           float* out, int B, long long HW, int C, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   UDA_REQUIRE(x && w && bias && pooled && out && B > 0 && HW > 0 && C > 0, UDA_ERR_BAD_ARG, "gap_linear: bad argument");
+  if (dtype == UDA_BF16 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0 && HW >= 64 && HW < (1 << 24) && B <= 1024 &&
+      aligned<bf16>(x, 16)) {
+    static unsigned int* counters = nullptr;   // one "slices done" counter per image, left at zero by every launch
+    if (!counters) {
+      UDA_CUDA_OK(cudaMalloc(&counters, 1024 * sizeof(unsigned int)));
+      UDA_CUDA_OK(cudaMemset(counters, 0, 1024 * sizeof(unsigned int)));
+    }
+    UDA_CUDA_OK(cudaMemsetAsync(pooled, 0, (size_t)B * C * sizeof(float), st));
+    int slices = (int)(HW / 32);
+    const int cap = (2 * num_sms() + B - 1) / B;
+    if (slices > cap) slices = cap;
+    if (slices < 1) slices = 1;
+    gap_partial_kernel<<<dim3((unsigned)slices, (unsigned)B), 256, 0, st>>>((const bf16*)x, w, bias, pooled, out, counters,
+                                                                           (int)HW, C);
+    UDA_LAUNCH_OK("gap_partial_kernel");
+    return UDA_OK;
+  }
 #define K(T, ...) gap_linear_sigmoid_kernel<T><<<B, 256, 0, st>>>((const T*)x, w, bias, pooled, out, HW, C)
   UDA_DT(dtype, K, 0);
 #undef K
@@ -1105,6 +1201,16 @@ extern "C" int uda_gap_linear_sigmoid_bwd(const float* dout, const float* y, con
                                           int accumulate, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   UDA_REQUIRE(dout && y && pooled && w && dw && dbias && dx && B > 0, UDA_ERR_BAD_ARG, "gap_linear_bwd: bad argument");
+  if (dtype == UDA_BF16 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0 && HW * (C / 8) < (1LL << 30) &&
+      aligned<bf16>(dx, 16)) {
+    long long blocks = (HW * (C / 8) + 255) / 256;
+    const long long cap = (8LL * num_sms() + B - 1) / B;
+    if (blocks > cap) blocks = cap;
+    gap_bwd_fill_kernel<<<dim3((unsigned)blocks, (unsigned)B), 256, 0, st>>>(dout, y, pooled, w, dw, dbias, (bf16*)dx, B,
+                                                                            (int)HW, C, accumulate);
+    UDA_LAUNCH_OK("gap_bwd_fill_kernel");
+    return UDA_OK;
+  }
 #define K(T, ...) gap_linear_sigmoid_bwd_kernel<T><<<B, 256, 0, st>>>(dout, y, pooled, w, dw, dbias, (T*)dx, B, HW, C, accumulate)
   UDA_DT(dtype, K, 0);
 #undef K

@@ -319,7 +319,7 @@ int stream_launch_geometry(StreamIO& io, size_t extra_smem, int* grid, size_t* s
 
 template <typename K>
 int set_smem_attr(K kernel) {
-  UDA_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  UDA_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   return UDA_OK;
 }
 
