@@ -183,6 +183,21 @@ int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtype, const fl
                const float* rstd, const float* scale, const float* shift, void* dx, void* dres, int dres_accumulate,
                float* dgamma, float* dbeta, int param_accumulate, long long M, int C, float slope, void* workspace,
                void* stream);
+/* BatchNorm backward with the reduction fused into the producer of dy: uda_conv2d_tc_dgrad_bnstats (the dgrad of the
+ * convolution that consumed a = act(BN(z) (+res)), reference: autograd of nn.BatchNorm2d inside smp.Unet) adds
+ * sums[c] += sum g, sums[C+c] += sum g*v over its output, g = dy*(a > 0 ? 1 : slope), v = z (v_is_z = 1, z given) or
+ * the pre-activation recovered from a (v_is_z = 0; non-residual layers: xhat = (v - beta)/gamma).  sums (double[2C])
+ * must be zero before the dgrad.  uda_bn_bwd_apply_fused then finalizes per channel in its prologue (dgamma, dbeta,
+ * coefficients) and applies dx (+ the residual-branch gradient) in ONE launch.  bf16, power-of-two C, >= 1 MiB. */
+int uda_conv2d_tc_dgrad_bnstats(const void* dy, const void* w_ft, const void* addend, void* dx, int B, int H, int W,
+                                int Cin, int Cout, int KH, int KW, int stride, int pad, const void* a, const void* z,
+                                float slope, double* sums, void* stream);
+int uda_bn_bwd_fused_supported(int dtype, long long M, int C);
+int uda_bn_bwd_apply_fused(const void* dy, const void* x, const void* a, int dtype, const double* sums, int v_is_z,
+                           const float* gamma, const float* beta, const float* mean, const float* rstd,
+                           const float* scale, const float* shift, void* dx, void* dres, int dres_accumulate,
+                           float* dgamma, float* dbeta, int param_accumulate, long long M, int C, float slope,
+                           void* stream);
 int uda_act_bwd(const void* dy, const void* a, void* dx, int dtype, long long n, float slope, void* stream);
 int uda_bias_act(const void* x, const float* bias, void* y, int dtype, long long M, int C, float slope, void* stream);
 int uda_colsum(const void* x, int dtype, float* out, long long M, int C, float scale, int accumulate,

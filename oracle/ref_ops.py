@@ -16,6 +16,11 @@ LAUNCHES = 0
 USE_TC = False
 
 
+def dgrad_bnstats_supported(*a):
+    """The oracle has no fused epilogues: the engine then takes the separate BatchNorm-backward reduce path."""
+    return False
+
+
 def stem_supported(*a):
     return False
 #: arithmetic dtype of the restatements; tests switch it to float64 to check the engine's backward
@@ -66,7 +71,7 @@ def conv_fwd(x, w, bias=None, stride=1, pad=1, nchw_out=False, bn_sums=None, for
     return _nhwc(y).to(x.dtype)
 
 
-def conv_dgrad(dy, w, x_shape, stride=1, pad=1, addend=None, force_direct=False, w_ft=None):
+def conv_dgrad(dy, w, x_shape, stride=1, pad=1, addend=None, force_direct=False, w_ft=None, bn_stats=None):
     B, H, W, Cin = x_shape
     dx = torch.nn.grad.conv2d_input((B, Cin, H, W), _w_oihw(w), _nchw(dy.to(_F)), stride, pad)
     dx = _nhwc(dx)

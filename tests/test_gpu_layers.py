@@ -133,6 +133,60 @@ def test_batchnorm(dtype, shape, slope):
     assert rel_err(sc.cpu(), scr) < 1e-5 and rel_err(sf.cpu(), sfr) < 1e-5
 
 
+@pytest.mark.parametrize("residual", [False, True])
+@pytest.mark.parametrize("cfg", [
+    # B, H, W, C (channels of a), Cout of the consumer conv, k, stride, pad, slope
+    (4, 32, 32, 64, 128, 3, 1, 1, 0.0),     # persistent kernel, 128-pixel tiles
+    (2, 64, 64, 128, 64, 3, 2, 1, 0.0),     # stride-2 consumer: four output-parity classes in one launch
+    (2, 128, 128, 32, 32, 3, 1, 1, 0.0),    # halo kernel
+    (4, 32, 32, 64, 128, 4, 2, 1, 0.2),     # discriminator-style 4x4 stride 2, LeakyReLU
+    (1, 256, 128, 16, 24, 3, 1, 1, 0.0),    # head-like: 16-channel a (late reduction path)
+])
+def test_bn_backward_reduction_fused_into_dgrad(cfg, residual, monkeypatch):
+    """The dgrad that produces dL/da also accumulates the BatchNorm-backward sums (uda_conv2d_tc_dgrad_bnstats) and
+    uda_bn_bwd_apply_fused finalizes + applies in one launch: same dz / dgamma / dbeta / residual gradient as the
+    separate reduce + apply path (which the oracle tests above pin), including a pre-existing gradient (addend)."""
+    ops = _ops()
+    monkeypatch.setattr(ops, "FUSE_BN_BWD", True)      # opt-in path (see ops.FUSE_BN_BWD)
+    B, H, W, C, Co, k, s, p, slope = cfg
+    dtype = torch.bfloat16
+    z = (_rand((B, H, W, C), dtype, 21, 2.0) + 0.3).to(DEV)
+    res = _rand((B, H, W, C), dtype, 22).to(DEV) if residual else None
+    gamma, beta = (torch.rand(C) + 0.5).to(DEV), torch.randn(C).to(DEV)
+    rm, rv = torch.zeros(C, device=DEV), torch.ones(C, device=DEV)
+    mean, rstd, scale, shift = ops.bn_stats(z, gamma, beta, rm, rv, 1e-5, 0.1)
+    a = ops.bn_apply(z, scale, shift, res, slope)
+    w = (_rand((Co, k, k, C), dtype, 23) * (k * k * C) ** -0.5).to(DEV)
+    Ho, Wo = (H, W) if s == 1 else (H // 2, W // 2)
+    dy = _rand((B, Ho, Wo, Co), dtype, 24).to(DEV)
+    if not ops.dgrad_bnstats_supported(a.shape, w.shape, s, p, dtype):
+        pytest.skip("fused path not available for this shape")
+    for with_addend in (False, True):
+        add = _rand((B, H, W, C), dtype, 25).to(DEV) if with_addend else None
+        # reference: separate passes
+        da_ref = ops.conv_dgrad(dy, w, a.shape, s, p, addend=add.clone() if with_addend else None)
+        dg_r, db_r = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        dres_r = torch.empty_like(z) if residual else None
+        use_a = residual and slope != 1.0
+        zm = (not residual) and slope != 1.0
+        dz_r = ops.bn_bwd(da_ref, z, a if use_a else None, gamma, mean, rstd, slope, dg_r, db_r, dres=dres_r,
+                          scale=scale if zm else None, shift=shift if zm else None)
+        # fused
+        sums = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
+        da = ops.conv_dgrad(dy, w, a.shape, s, p, addend=add.clone() if with_addend else None,
+                            bn_stats=(a, z if residual else None, slope, sums))
+        assert torch.equal(da, da_ref)
+        dg, db = torch.zeros(C, device=DEV), torch.zeros(C, device=DEV)
+        dres = torch.empty_like(z) if residual else None
+        dz = ops.bn_bwd_apply_fused(da, z, a if use_a else None, sums, residual, gamma, beta, mean, rstd, slope, dg, db,
+                                    dres=dres, scale=scale if zm else None, shift=shift if zm else None)
+        # non-residual layers recover xhat from the bf16-ROUNDED output a (2^-9 per element): dgamma to 5e-3
+        assert rel_err(db.cpu(), db_r.cpu()) < 1e-3 and rel_err(dg.cpu(), dg_r.cpu()) < (2e-3 if residual else 5e-3), (with_addend,)
+        assert rel_err(dz.float().cpu(), dz_r.float().cpu()) < 1e-2
+        if residual:
+            assert torch.equal(dres, dres_r)
+
+
 @pytest.mark.parametrize("dtype", DT)
 def test_pool_upcat_bias_colsum(dtype):
     ops = _ops()

@@ -82,4 +82,9 @@ int bn_apply_stream(const void* x, const void* residual, void* y, const float* s
 int bn_bwd_stream(const void* dy, const void* x, const void* a, const float* mean, const float* rstd,
                   const float* scale, const float* shift, void* dx, void* dres, int dres_accumulate, double* sums,
                   float* coef, const bn::BnBwdFinal& fin, long long M, int C, float slope, cudaStream_t st);
+int bn_bwd_apply_fused_stream(const void* dy, const void* x, const void* a, const double* sums, int v_is_z,
+                              const float* gamma, const float* beta, const float* mean, const float* rstd,
+                              const float* scale, const float* shift, void* dx, void* dres, int dres_accumulate,
+                              float* dgamma, float* dbeta, int param_accumulate, long long M, int C, float slope,
+                              cudaStream_t st);
 }  // namespace uda

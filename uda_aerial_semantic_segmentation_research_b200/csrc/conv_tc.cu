@@ -413,11 +413,16 @@ bool dgrad_shape_ok(int B, int H, int W, int Cin, int Cout, int KH, int KW, int 
 // with kh = ph+pad (mod 2) read dY[i + (ph+pad-kh)/2, ...] and write dX[2i+ph, 2j+pw] (every dX pixel is
 // produced by exactly one launch; parities without any tap are zero).
 int run_dgrad(const void* dy, const void* w_ft, const void* addend, void* dx, int B, int H, int W, int Cin, int Cout,
-              int KH, int KW, int stride, int pad, cudaStream_t st) {
+              int KH, int KW, int stride, int pad, cudaStream_t st, const void* st_a = nullptr,
+              const void* st_z = nullptr, float st_slope = 0.f, double* st_sums = nullptr) {
   UDA_REQUIRE(dgrad_shape_ok(B, H, W, Cin, Cout, KH, KW, stride, pad), UDA_ERR_UNSUPPORTED,
               "conv_tc_dgrad: shape not covered (B=%d H=%d W=%d Cin=%d Cout=%d k=%d s=%d p=%d)", B, H, W, Cin, Cout,
               KH, stride, pad);
+  UDA_REQUIRE(!st_sums || (use_persistent() && st_a && !(stride == 2 && KH < 2)), UDA_ERR_UNSUPPORTED,
+              "conv_tc_dgrad: BatchNorm-backward statistics need the persistent kernels, `a`, and a dgrad that "
+              "writes every input pixel (not 1x1 stride 2)");
   GemmConv g{};
+  g.st_a = st_a; g.st_z = st_z; g.st_slope = st_slope; g.st_sums = st_sums;
   g.src = dy; g.B = B; g.Cred = Cout; g.src_s2 = 0;
   g.wmat = w_ft; g.Cout = Cin; g.wtaps = KH * KW;
   g.OH = H; g.OW = W; g.bias = nullptr; g.addend = addend; g.out = dx; g.out_nchw = nullptr;
@@ -926,6 +931,16 @@ extern "C" int uda_conv2d_tc_dgrad(const void* dy, const void* w_ft, const void*
                                    int Cin, int Cout, int KH, int KW, int stride, int pad, void* stream) {
   UDA_REQUIRE(dy && w_ft && dx, UDA_ERR_BAD_ARG, "conv_tc_dgrad: null pointer");
   return run_dgrad(dy, w_ft, addend, dx, B, H, W, Cin, Cout, KH, KW, stride, pad, (cudaStream_t)stream);
+}
+
+// dgrad that also accumulates the BatchNorm-backward statistics of the tensor it produces (include/uda_b200.h)
+extern "C" int uda_conv2d_tc_dgrad_bnstats(const void* dy, const void* w_ft, const void* addend, void* dx, int B, int H,
+                                           int W, int Cin, int Cout, int KH, int KW, int stride, int pad, const void* a,
+                                           const void* z, float slope, double* sums, void* stream) {
+  UDA_REQUIRE(dy && w_ft && dx && a && sums, UDA_ERR_BAD_ARG, "conv_tc_dgrad_bnstats: null pointer");
+  UDA_REQUIRE(aligned<bf16>(a, 16) && (!z || aligned<bf16>(z, 16)), UDA_ERR_BAD_ARG,
+              "conv_tc_dgrad_bnstats: a / z must be 16-byte aligned");
+  return run_dgrad(dy, w_ft, addend, dx, B, H, W, Cin, Cout, KH, KW, stride, pad, (cudaStream_t)stream, a, z, slope, sums);
 }
 
 extern "C" int uda_conv2d_weight_flip_transpose(const void* w, void* w_ft, int Cout, int Cin, int KH, int KW,

@@ -28,6 +28,7 @@ struct HParams {
   int stages;
   bf16* out; float* out_nchw; const float* bias; const bf16* addend;
   double* bn_sums;
+  const bf16* st_a; const bf16* st_z; float st_slope; double* st_sums;   // GemmConv::st_*
 };
 
 template <int KC, int BN, int R>
@@ -144,6 +145,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     float late_s[kLate ? 32 : 1], late_q[kLate ? 32 : 1];
 #pragma unroll
     for (int k = 0; k < (kLate ? 32 : 1); ++k) { late_s[k] = 0.f; late_q[k] = 0.f; }
+    double* const sums_out = p.bn_sums ? p.bn_sums : p.st_sums;   // forward statistics or BN-backward statistics
+    const float inv_slope = p.st_slope != 0.f ? 1.f / p.st_slope : 0.f;
     int j = 0;
     for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
       const int b = t / tiles_per_img, tin = t % tiles_per_img;
@@ -171,6 +174,18 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             for (int k = 0; k < 32; ++k)
               if (c0 + k < p.Cout) f[k] += __ldg(p.bias + c0 + k);
           }
+          if (p.addend) {
+            const bf16* add = p.addend + pix * p.Cout + c0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              if (c0 + k < p.Cout) {
+                float a8[8];
+                ld_vec<8>(add + k, a8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[k + e] += a8[e];
+              }
+            }
+          }
           if (p.bn_sums) {
             if constexpr (kLate) {
 #pragma unroll
@@ -182,22 +197,26 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             } else {
               bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);
             }
+          } else if (p.st_sums) {
+            float g[32], gv[32];
+            const long long off = pix * p.Cout + c0;
+            bn_bwd_chunk_terms(f, p.st_a + off, p.st_z ? p.st_z + off : nullptr, p.st_slope, inv_slope, p.Cout - c0, g, gv);
+            if constexpr (kLate) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) { late_s[k] += g[k]; late_q[k] += gv[k]; }
+            } else {
+              bn_s[c0 / 32] += warp_column_sums(g, lane);
+              bn_q[c0 / 32] += warp_column_sums(gv, lane);
+            }
           }
           if (p.out) {
             bf16* dst = p.out + pix * p.Cout + c0;
-            const bf16* add = p.addend ? p.addend + pix * p.Cout + c0 : nullptr;
 #pragma unroll
             for (int k = 0; k < 32; k += 8) {
               if (c0 + k < p.Cout) {
                 float o[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[e] = f[k + e];
-                if (add) {
-                  float a8[8];
-                  ld_vec<8>(add + k, a8);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) o[e] += a8[e];
-                }
                 st_vec<8>(dst + k, o);
               }
             }
@@ -215,7 +234,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(q));
     }
-    if (p.bn_sums) {
+    if (sums_out) {
       if constexpr (kLate) {
         float ts[32], tq[32];
 #pragma unroll
@@ -226,7 +245,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
       for (int cc = 0; cc < kChunks; ++cc) {
         const int col = cc * 32 + lane;
-        if (col < p.Cout) { atomicAdd(p.bn_sums + col, (double)bn_s[cc]); atomicAdd(p.bn_sums + p.Cout + col, (double)bn_q[cc]); }
+        if (col < p.Cout) { atomicAdd(sums_out + col, (double)bn_s[cc]); atomicAdd(sums_out + p.Cout + col, (double)bn_q[cc]); }
       }
     }
   }
@@ -291,6 +310,8 @@ int run_gemm_conv_halo(const GemmConv& g, cudaStream_t st) {
   p.Cout = g.Cout; p.Cred = g.Cred; p.kchunks = kchunks;
   p.out = (bf16*)g.out; p.out_nchw = g.out_nchw; p.bias = g.bias; p.addend = (const bf16*)g.addend;
   p.bn_sums = g.bn_sums;
+  p.st_a = (const bf16*)g.st_a; p.st_z = (const bf16*)g.st_z; p.st_slope = g.st_slope; p.st_sums = g.st_sums;
+  if (g.st_sums && (!g.st_a || !g.out || g.bn_sums)) return UDA_ERR_UNSUPPORTED;
   CUtensorMap ma, mb;
   {
     const uint64_t C = (uint64_t)g.Cred;

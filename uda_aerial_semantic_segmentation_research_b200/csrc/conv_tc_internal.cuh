@@ -45,6 +45,12 @@ struct GemmConv {
   int OH, OW, os;
   const float* bias; const void* addend; void* out; float* out_nchw;
   double* bn_sums;   // optional [2*Cout]: += per-channel sum / sum of squares of the bf16-rounded outputs
+  // optional BatchNorm-BACKWARD statistics of the tensor this launch produces (it is the dgrad of the convolution
+  // that consumed a = act(BN(z) (+res)), so `out` is dL/da):  st_sums[c] += sum g,  st_sums[Cout+c] += sum g*v  over
+  // all output pixels, with g = out * (a > 0 ? 1 : slope) and v = z when st_z is given, else v = the pre-activation
+  // recovered from a (a > 0 ? a : a/slope) — see uda_bn_bwd_apply_fused for how the finalize turns them into
+  // sum g*xhat.  Every output pixel must be written by exactly one epilogue row (not 1x1 stride-2 dgrads).
+  const void* st_a; const void* st_z; float st_slope; double* st_sums;
   // optional: caller-built A-operand tensor map (rank-5 coordinate form {c, w, ph, h, b}) over an M-grid of
   // MH x MW pixels — used by the Cin=3 stem, whose A operand is a padded 4-channel row view of the image
   const CUtensorMap* a_map; int a_MH, a_MW, a_kc;
@@ -86,6 +92,32 @@ __device__ __forceinline__ void bn_chunk_stats(const float (&f)[32], int lane, f
   for (int k = 0; k < 32; ++k) u[k] = t[k] * t[k];
   s += warp_column_sums(t, lane);
   q += warp_column_sums(u, lane);
+}
+// BatchNorm-backward partial sums of one 32-column chunk (GemmConv::st_*): o = the final output values of this
+// thread's row (after the addend), a_row / z_row = the row's 32 channels of a / z (z_row may be null).
+__device__ __forceinline__ void bn_bwd_chunk_terms(const float (&o)[32], const bf16* a_row, const bf16* z_row,
+                                                   float slope, float inv_slope, int ncols, float (&g)[32],
+                                                   float (&gv)[32]) {
+#pragma unroll
+  for (int k = 0; k < 32; k += 8) {
+    float av[8], zv[8];
+    if (k < ncols) {
+      ld_vec<8>(a_row + k, av);
+      if (z_row) ld_vec<8>(z_row + k, zv);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float gg = 0.f, vv = 0.f;
+      if (k < ncols) {
+        const float ob = __bfloat162float(__float2bfloat16_rn(o[k + e]));
+        const bool pos = av[e] > 0.f;
+        gg = pos ? ob : ob * slope;
+        vv = z_row ? zv[e] : (pos ? av[e] : av[e] * inv_slope);
+      }
+      g[k + e] = gg;
+      gv[k + e] = gg * vv;
+    }
+  }
 }
 #endif
 

@@ -42,6 +42,7 @@ struct PParams {
   PClass cls[kMaxClasses];
   bf16* out; float* out_nchw; const float* bias; const bf16* addend;
   double* bn_sums;
+  const bf16* st_a; const bf16* st_z; float st_slope; double* st_sums;   // GemmConv::st_*
 };
 
 template <int KC, int BN, int MT>
@@ -175,6 +176,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 #pragma unroll
     for (int k = 0; k < (kLate ? 32 : 1); ++k) { late_s[k] = 0.f; late_q[k] = 0.f; }
     int bn_n0 = -1;
+    double* const sums_out = p.bn_sums ? p.bn_sums : p.st_sums;   // forward statistics or BN-backward statistics
+    const float inv_slope = p.st_slope != 0.f ? 1.f / p.st_slope : 0.f;
     int j = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
       const int ci = t / tiles_per_cls, rem = t % tiles_per_cls;
@@ -183,12 +186,12 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       const int b0 = grp * p.NB, h0 = (tin / p.tiles_w) * p.TH, w0 = (tin % p.tiles_w) * p.TW;
       const int oh = p.cls[ci].oh, ow = p.cls[ci].ow;
       const int q = j % kSets;
-      if (p.bn_sums && n0 != bn_n0) {   // channel tile changed: flush the partial statistics
+      if (sums_out && n0 != bn_n0) {   // channel tile changed: flush the partial statistics
         if (bn_n0 >= 0) {
 #pragma unroll
           for (int cc = 0; cc < kChunks; ++cc) {
             const int col = bn_n0 + cc * 32 + lane;
-            if (col < p.Cout) { atomicAdd(p.bn_sums + col, (double)bn_s[cc]); atomicAdd(p.bn_sums + p.Cout + col, (double)bn_q[cc]); }
+            if (col < p.Cout) { atomicAdd(sums_out + col, (double)bn_s[cc]); atomicAdd(sums_out + p.Cout + col, (double)bn_q[cc]); }
             bn_s[cc] = 0.f; bn_q[cc] = 0.f;
           }
         }
@@ -219,6 +222,18 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             for (int k = 0; k < 32; ++k)
               if (nbase + k < p.Cout) f[k] += __ldg(p.bias + nbase + k);
           }
+          if (p.addend) {
+            const bf16* add = p.addend + pix * p.Cout + nbase;
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              if (nbase + k < p.Cout) {
+                float a8[8];
+                ld_vec<8>(add + k, a8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[k + e] += a8[e];
+              }
+            }
+          }
           if (p.bn_sums) {
             if constexpr (kLate) {
 #pragma unroll
@@ -230,22 +245,27 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             } else {
               bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);
             }
+          } else if (p.st_sums) {
+            float g[32], gv[32];
+            const long long off = pix * p.Cout + nbase;
+            bn_bwd_chunk_terms(f, p.st_a + off, p.st_z ? p.st_z + off : nullptr, p.st_slope, inv_slope,
+                               p.Cout - nbase, g, gv);
+            if constexpr (kLate) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) { late_s[k] += g[k]; late_q[k] += gv[k]; }
+            } else {
+              bn_s[c0 / 32] += warp_column_sums(g, lane);
+              bn_q[c0 / 32] += warp_column_sums(gv, lane);
+            }
           }
           if (p.out) {
             bf16* dst = p.out + pix * p.Cout + nbase;
-            const bf16* add = p.addend ? p.addend + pix * p.Cout + nbase : nullptr;
 #pragma unroll
             for (int k = 0; k < 32; k += 8) {
               if (nbase + k < p.Cout) {
                 float o[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[e] = f[k + e];
-                if (add) {
-                  float a8[8];
-                  ld_vec<8>(add + k, a8);
-#pragma unroll
-                  for (int e = 0; e < 8; ++e) o[e] += a8[e];
-                }
                 st_vec<8>(dst + k, o);
               }
             }
@@ -263,7 +283,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(q));
     }
-    if (p.bn_sums && bn_n0 >= 0) {
+    if (sums_out && bn_n0 >= 0) {
       if constexpr (kLate) {   // BN = 32: a single channel tile, nothing was flushed before
         float ts[32], tq[32];
 #pragma unroll
@@ -274,7 +294,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 #pragma unroll
       for (int cc = 0; cc < kChunks; ++cc) {
         const int col = bn_n0 + cc * 32 + lane;
-        if (col < p.Cout) { atomicAdd(p.bn_sums + col, (double)bn_s[cc]); atomicAdd(p.bn_sums + p.Cout + col, (double)bn_q[cc]); }
+        if (col < p.Cout) { atomicAdd(sums_out + col, (double)bn_s[cc]); atomicAdd(sums_out + p.Cout + col, (double)bn_q[cc]); }
       }
     }
   }
@@ -400,6 +420,9 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
   }
   p.out = (bf16*)g.out; p.out_nchw = g.out_nchw; p.bias = g.bias; p.addend = (const bf16*)g.addend;
   p.bn_sums = g.bn_sums;
+  p.st_a = (const bf16*)g.st_a; p.st_z = (const bf16*)g.st_z; p.st_slope = g.st_slope; p.st_sums = g.st_sums;
+  UDA_REQUIRE(!(g.bn_sums && g.st_sums), UDA_ERR_BAD_ARG, "conv_tc_persist: forward and backward statistics are exclusive");
+  UDA_REQUIRE(!g.st_sums || (g.st_a && g.out), UDA_ERR_BAD_ARG, "conv_tc_persist: backward statistics need `a` and an NHWC output");
 
   CUtensorMap ma, mb;
   const uint64_t C = (uint64_t)g.Cred, H = (uint64_t)g.SH, W = (uint64_t)g.SW;

@@ -995,6 +995,25 @@ extern "C" int uda_bn_apply_fused(const void* x, const void* residual, void* y, 
 }
 
 // workspace: 2*C doubles + 3*C floats
+extern "C" int uda_bn_bwd_fused_supported(int dtype, long long M, int C) {
+  return (use_stream() && bn_stream_ok(dtype, M, C)) ? 1 : 0;
+}
+
+// BatchNorm backward apply with the statistics from uda_conv2d_tc_dgrad_bnstats (include/uda_b200.h)
+extern "C" int uda_bn_bwd_apply_fused(const void* dy, const void* x, const void* a, int dtype, const double* sums,
+                                      int v_is_z, const float* gamma, const float* beta, const float* mean,
+                                      const float* rstd, const float* scale, const float* shift, void* dx, void* dres,
+                                      int dres_accumulate, float* dgamma, float* dbeta, int param_accumulate,
+                                      long long M, int C, float slope, void* stream) {
+  UDA_REQUIRE(dy && x && sums && mean && rstd && dx, UDA_ERR_BAD_ARG, "bn_bwd_apply_fused: null pointer");
+  UDA_REQUIRE((scale == nullptr) == (shift == nullptr), UDA_ERR_BAD_ARG, "bn_bwd_apply_fused: scale and shift go together");
+  UDA_REQUIRE(a || scale || slope == 1.f, UDA_ERR_BAD_ARG, "bn_bwd_apply_fused: the activation mask needs a or scale/shift");
+  UDA_REQUIRE(uda_bn_bwd_fused_supported(dtype, M, C), UDA_ERR_UNSUPPORTED,
+              "bn_bwd_apply_fused: bf16, power-of-two C <= 2048 and >= 1 MiB tensors only (M=%lld C=%d)", M, C);
+  return bn_bwd_apply_fused_stream(dy, x, a, sums, v_is_z, gamma, beta, mean, rstd, scale, shift, dx, dres,
+                                   dres_accumulate, dgamma, dbeta, param_accumulate, M, C, slope, (cudaStream_t)stream);
+}
+
 extern "C" int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtype, const float* gamma,
                           const float* mean, const float* rstd, const float* scale, const float* shift, void* dx,
                           void* dres, int dres_accumulate,

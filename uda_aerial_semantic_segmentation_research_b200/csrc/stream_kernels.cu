@@ -251,6 +251,10 @@ struct BwdApplyParams {
   StreamIO io;   // in: dy, x (, a) (, dres when accumulating)   out: dx (, dres)
   const float* coef; const float* scale; const float* shift;
   int C; float slope; int has_a, res_in;   // res_in: index of the dres input (accumulate) or -1
+  // fused finalize (uda_bn_bwd_apply_fused): sums = [sum g | sum g*v] from the producing dgrad epilogue
+  const double* sums; int v_is_z;
+  const float* gamma; const float* beta; const float* mean; const float* rstd;
+  float* dgamma; float* dbeta; int accumulate; long long M;
 };
 
 __global__ void __launch_bounds__(kCta, 1) bn_bwd_apply_stream_kernel(const BwdApplyParams p) {
@@ -263,11 +267,39 @@ __global__ void __launch_bounds__(kCta, 1) bn_bwd_apply_stream_kernel(const BwdA
   const int c = (threadIdx.x * 8) % C;
   const bool zmask = !p.has_a && p.scale != nullptr;
   float kA[8], kB[8], kC[8], sc[8], sf[8];
+  if (p.sums) {
+    // finalize fused into the apply pass: the per-channel sums come from the epilogue of the dgrad that produced dy.
+    //   s1 = sum g;   s2 = sum g*xhat = rstd*(S2 - mean*s1)   (v = z)      or  (S2 - beta*s1)/gamma   (v = the
+    //   pre-activation recovered from a:  xhat = (v - beta)/gamma)
+    //   dx = A*g + Bc*x + Cc  with  k0 = gamma*rstd,  A = k0,  Bc = -k0*s2/M*rstd,  Cc = -k0*s1/M - Bc*mean
+    float* s_coef = reinterpret_cast<float*>(bars + 2 * kMaxStages);
+    const double inv_m = 1.0 / (double)p.M;
+    for (int ch = threadIdx.x; ch < C; ch += kCompute) {
+      const double s1 = p.sums[ch], S2 = p.sums[C + ch];
+      const float g = p.gamma ? p.gamma[ch] : 1.f, b = p.beta ? p.beta[ch] : 0.f;
+      const float rs = p.rstd[ch], mu = p.mean[ch];
+      double s2;
+      if (p.v_is_z) s2 = (double)rs * (S2 - (double)mu * s1);
+      else s2 = g != 0.f ? (S2 - (double)b * s1) / (double)g : 0.0;
+      const float k0 = g * rs;
+      const float k1 = k0 * (float)(s1 * inv_m), k2 = k0 * (float)(s2 * inv_m);
+      s_coef[ch] = k0;
+      s_coef[C + ch] = -k2 * rs;
+      s_coef[2 * C + ch] = -k1 + k2 * rs * mu;
+      if (blockIdx.x == 0) {
+        if (p.dgamma) p.dgamma[ch] = (p.accumulate ? p.dgamma[ch] : 0.f) + (float)s2;
+        if (p.dbeta) p.dbeta[ch] = (p.accumulate ? p.dbeta[ch] : 0.f) + (float)s1;
+      }
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kCompute) : "memory");   // compute warps only
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    kA[j] = p.coef[c + j]; kB[j] = p.coef[C + c + j]; kC[j] = p.coef[2 * C + c + j];
-    sc[j] = zmask ? p.scale[c + j] : 0.f; sf[j] = zmask ? p.shift[c + j] : 0.f;
+    for (int j = 0; j < 8; ++j) { kA[j] = s_coef[c + j]; kB[j] = s_coef[C + c + j]; kC[j] = s_coef[2 * C + c + j]; }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { kA[j] = p.coef[c + j]; kB[j] = p.coef[C + c + j]; kC[j] = p.coef[2 * C + c + j]; }
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = zmask ? p.scale[c + j] : 0.f; sf[j] = zmask ? p.shift[c + j] : 0.f; }
   const bool wres = p.io.nout > 1;
   for (int k = 0; k < pipe.n_my; ++k) {
     pipe.wait(k);
@@ -381,6 +413,35 @@ int bn_bwd_stream(const void* dy, const void* x, const void* a, const float* mea
     bn_bwd_apply_stream_kernel<<<grid, kCta, smem, st>>>(p);
     UDA_LAUNCH_OK("bn_bwd_apply_stream_kernel");
   }
+  return UDA_OK;
+}
+
+// BatchNorm backward whose reduction already happened in the dgrad epilogue (GemmConv::st_sums): one apply launch
+// with the per-channel finalize in its prologue.
+int bn_bwd_apply_fused_stream(const void* dy, const void* x, const void* a, const double* sums, int v_is_z,
+                              const float* gamma, const float* beta, const float* mean, const float* rstd,
+                              const float* scale, const float* shift, void* dx, void* dres, int dres_accumulate,
+                              float* dgamma, float* dbeta, int param_accumulate, long long M, int C, float slope,
+                              cudaStream_t st) {
+  BwdApplyParams p{};
+  int n = 0;
+  p.io.in[n++] = (const uint8_t*)dy; p.io.in[n++] = (const uint8_t*)x;
+  if (a) { p.io.in[2] = (const uint8_t*)a; n = 3; }
+  p.res_in = -1;
+  if (dres && dres_accumulate) { p.res_in = a ? 3 : 2; p.io.in[p.res_in] = (const uint8_t*)dres; n = p.res_in + 1; }
+  p.io.nin = n;
+  p.io.out[0] = (uint8_t*)dx; p.io.out[1] = (uint8_t*)dres; p.io.nout = dres ? 2 : 1;
+  p.io.out_slot[0] = 0; p.io.out_slot[1] = 1;
+  p.io.nbytes = M * (long long)C * 2;
+  p.coef = nullptr; p.scale = scale; p.shift = shift; p.C = C; p.slope = slope; p.has_a = a ? 1 : 0;
+  p.sums = sums; p.v_is_z = v_is_z; p.gamma = gamma; p.beta = beta; p.mean = mean; p.rstd = rstd;
+  p.dgamma = dgamma; p.dbeta = dbeta; p.accumulate = param_accumulate; p.M = M;
+  int grid; size_t smem;
+  if (int rc = stream_launch_geometry(p.io, 3 * (size_t)C * sizeof(float), &grid, &smem)) return rc;
+  static bool cfg = false;
+  if (!cfg) { if (int rc = set_smem_attr(bn_bwd_apply_stream_kernel)) return rc; cfg = true; }
+  bn_bwd_apply_stream_kernel<<<grid, kCta, smem, st>>>(p);
+  UDA_LAUNCH_OK("bn_bwd_apply_stream_kernel");
   return UDA_OK;
 }
 

@@ -18,13 +18,16 @@ from . import ops
 class Var:
     """An activation (NHWC tensor) plus its gradient slot on the tape.  A network input that feeds a
     tensor-core stem keeps the raw fp32 NCHW image in ``nchw`` instead (``t`` is None)."""
-    __slots__ = ("t", "g", "nchw", "sums")
+    __slots__ = ("t", "g", "nchw", "sums", "uses", "bn_req", "bwd_sums")
 
     def __init__(self, t, nchw=None):
         self.t = t
         self.g = None
         self.nchw = nchw
         self.sums = None   # BatchNorm batch statistics emitted by the producing conv epilogue (double[2C])
+        self.uses = 0      # consumers still to contribute to .g during backward (counted at forward time)
+        self.bn_req = None     # (z tensor or None, slope): this Var is a = act(BN(z) (+res)); set by bn_act
+        self.bwd_sums = None   # BatchNorm-backward sums of .g, filled by the dgrad that made the LAST contribution
 
 
 def input_var(x, dtype, cp, need_grad):
@@ -216,7 +219,7 @@ class Ctx:
         forward instead of one ``torch.zeros`` launch per layer."""
         n_al = (n + 15) // 16 * 16
         if self._pool is None or self._pool_used + n_al > self._pool.numel():
-            self._pool = torch.zeros(max(1 << 15, n_al), dtype=torch.float64, device=device)
+            self._pool = torch.zeros(max(1 << 16, n_al), dtype=torch.float64, device=device)
             self._pool_used = 0
         out = self._pool[self._pool_used:self._pool_used + n]
         self._pool_used += n_al
@@ -280,9 +283,12 @@ def conv(ctx, xin, cp, nchw_out=False, bn=None):
     out = Var(y)
     out.sums = sums
     if ctx.tape is not None:
+        xin.uses += 1
+
         def bwd():
             dy = out.g
             out.g = None
+            xin.uses -= 1
             if dy is None:
                 return
             if cp.bias is not None:
@@ -290,7 +296,14 @@ def conv(ctx, xin, cp, nchw_out=False, bn=None):
             ops.conv_wgrad(dy, xin.t, st.g(cp.weight), cp.stride, cp.padding)
             if xin.g is not False:  # False marks "no gradient needed" (network input)
                 wft = st.w_ft(cp.weight) if (ctx.dtype == torch.bfloat16 and ops.USE_TC) else None
-                xin.g = ops.conv_dgrad(dy, w, xin.t.shape, cp.stride, cp.padding, addend=xin.g, w_ft=wft)
+                stats = None
+                # last contribution to dL/da of a BatchNorm output: its epilogue also reduces the BN-backward sums
+                if (xin.uses == 0 and xin.bn_req is not None
+                        and ops.dgrad_bnstats_supported(xin.t.shape, w.shape, cp.stride, cp.padding, ctx.dtype)):
+                    z, slope = xin.bn_req
+                    xin.bwd_sums = ctx.stats_slot(2 * xin.t.shape[-1], xin.t.device)
+                    stats = (xin.t, z, slope, xin.bwd_sums)
+                xin.g = ops.conv_dgrad(dy, w, xin.t.shape, cp.stride, cp.padding, addend=xin.g, w_ft=wft, bn_stats=stats)
             ctx.done(cp.weight, cp.bias)
         ctx.tape.push(bwd)
     return out
@@ -318,10 +331,18 @@ def bn_act(ctx, zin, bn, slope=0.0, residual=None):
         if not ctx.training:
             raise RuntimeError("uda_b200: backward through eval-mode BatchNorm is not supported "
                                "(the reference never trains in eval mode)")
+        if residual is not None:
+            residual.uses += 1
+        # the dgrad that completes dL/da may reduce this layer's backward sums in its epilogue: residual layers need
+        # z for xhat (a - res is not the BN output), the others recover the pre-activation from a alone
+        if slope != 1.0 or residual is None:
+            out.bn_req = (zin.t if residual is not None else None, slope)
 
         def bwd():
             da = out.g
             out.g = None
+            if residual is not None:
+                residual.uses -= 1
             if da is None:
                 return
             dres = None
@@ -334,9 +355,16 @@ def bn_act(ctx, zin, bn, slope=0.0, residual=None):
             # activation mask: non-residual layers recompute it from z (no read of `a`); residual ones need `a`
             use_a = slope != 1.0 and residual is not None
             zm = slope != 1.0 and residual is None
-            zin.g = ops.bn_bwd(da, zin.t, a if use_a else None, bn.weight, mean, rstd, slope,
-                               st.g(bn.weight), st.g(bn.bias), dres=dres, dres_accumulate=acc,
-                               scale=scale if zm else None, shift=shift if zm else None)
+            if out.bwd_sums is not None:
+                zin.g = ops.bn_bwd_apply_fused(da, zin.t, a if use_a else None, out.bwd_sums, residual is not None,
+                                               bn.weight, bn.bias, mean, rstd, slope, st.g(bn.weight), st.g(bn.bias),
+                                               dres=dres, dres_accumulate=acc,
+                                               scale=scale if zm else None, shift=shift if zm else None)
+                out.bwd_sums = None
+            else:
+                zin.g = ops.bn_bwd(da, zin.t, a if use_a else None, bn.weight, mean, rstd, slope,
+                                   st.g(bn.weight), st.g(bn.bias), dres=dres, dres_accumulate=acc,
+                                   scale=scale if zm else None, shift=shift if zm else None)
             if residual is not None:
                 residual.g = dres
             ctx.done(bn.weight, bn.bias)
@@ -349,7 +377,10 @@ def bias_act(ctx, zin, slope):
     a = ops.bias_act(zin.t, None, slope)
     out = Var(a)
     if ctx.tape is not None:
+        zin.uses += 1
+
         def bwd():
+            zin.uses -= 1
             if out.g is not None:
                 zin.g = ops.act_bwd(out.g, a, slope)
             out.g = None
@@ -361,7 +392,10 @@ def maxpool(ctx, xin):
     y, idx = ops.maxpool_fwd(xin.t)
     out = Var(y)
     if ctx.tape is not None:
+        xin.uses += 1
+
         def bwd():
+            xin.uses -= 1
             if out.g is not None:
                 xin.g = ops.maxpool_bwd(out.g, idx, xin.t.shape, addend=xin.g)
             out.g = None
@@ -375,8 +409,14 @@ def upcat(ctx, xin, skip):
     if ctx.tape is not None:
         C1 = xin.t.shape[-1]
         C2 = skip.t.shape[-1] if skip is not None else 0
+        xin.uses += 1
+        if skip is not None:
+            skip.uses += 1
 
         def bwd():
+            xin.uses -= 1
+            if skip is not None:
+                skip.uses -= 1
             if out.g is None:
                 return
             dx, dskip = ops.upcat_bwd(out.g, C1, C2)

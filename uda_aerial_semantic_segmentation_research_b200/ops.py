@@ -18,6 +18,12 @@ _WS = {}
 USE_TC = os.environ.get("UDA_B200_USE_TC", "1") != "0"
 #: BatchNorm batch statistics from the tensor-core conv epilogue (set "0" to use the separate bn_stats pass)
 FUSE_BN_STATS = os.environ.get("UDA_B200_FUSE_BN_STATS", "1") != "0"
+#: BatchNorm-backward reduction in the epilogue of the dgrad that produces dL/da.  OFF by default: measured on B200
+#: (B=16, 512x512) the extra epilogue work (reading `a`/`z`, 62 shuffles per 32x32 chunk, not overlapped when a CTA
+#: owns one or two tiles) costs +1.2 ms of dgrad time per step and saves only 0.8 ms of bn_bwd_reduce launches.
+FUSE_BN_BWD = os.environ.get("UDA_B200_FUSE_BN_BWD", "0") == "1"
+#: the persistent / halo tensor-core kernels are the ones with the fused epilogues (UDA_B200_TC_PERSIST=0 disables)
+TC_PERSIST = os.environ.get("UDA_B200_TC_PERSIST", "1") != "0"
 #: counts launches issued through this module (bench.py reports it as gpu_launches)
 LAUNCHES = 0
 #: algorithmic FLOPs (2*M*N*K) and call count of the convolutions routed to the tcgen05 kernels
@@ -228,10 +234,21 @@ def weight_flip_transpose_batch(base, out, table):
     return out
 
 
-def conv_dgrad(dy, w, x_shape, stride=1, pad=1, addend=None, force_direct=False, w_ft=None):
+def dgrad_bnstats_supported(x_shape, w_shape, stride, pad, dtype):
+    """Can the tensor-core dgrad of this convolution also emit the BatchNorm-backward statistics of its output?"""
+    B, H, W, Cin, Cout, KH, KW, Ho, Wo = _geom(x_shape, w_shape, stride, pad)
+    if not (USE_TC and TC_PERSIST and FUSE_BN_BWD and dtype == torch.bfloat16) or (stride == 2 and KH < 2):
+        return False
+    return bool(tc_supported(1, B, H, W, Cin, Cout, KH, KW, stride, pad)
+                and _lib.lib().uda_bn_bwd_fused_supported(ci(BF16), ll(B * H * W), ci(Cin)))
+
+
+def conv_dgrad(dy, w, x_shape, stride=1, pad=1, addend=None, force_direct=False, w_ft=None, bn_stats=None):
     """dx = conv_transpose(dy, w) (+ addend, accumulated in place into ``addend``'s buffer when given).
 
-    ``w_ft`` (optional): cached ``weight_flip_transpose(w)`` for the tensor-core path."""
+    ``w_ft`` (optional): cached ``weight_flip_transpose(w)`` for the tensor-core path.
+    ``bn_stats`` = (a, z_or_None, slope, sums): also accumulate the BatchNorm-backward sums of dx (see
+    ``uda_conv2d_tc_dgrad_bnstats``); tensor-core path only."""
     _chk(dy, "conv_dgrad.dy"); _chk(w, "conv_dgrad.w")
     B, H, W, Cin, Cout, KH, KW, Ho, Wo = _geom(x_shape, w.shape, stride, pad)
     if tuple(dy.shape) != (B, Ho, Wo, Cout):
@@ -248,9 +265,19 @@ def conv_dgrad(dy, w, x_shape, stride=1, pad=1, addend=None, force_direct=False,
     if use_tc:
         if w_ft is None:
             w_ft = weight_flip_transpose(w)
-        call("conv2d_tc_dgrad", ptr(dy), ptr(w_ft), ptr(addend), ptr(dx), ci(B), ci(H), ci(W), ci(Cin), ci(Cout), ci(KH), ci(KW),
-             ci(stride), ci(pad), _stream())
+        if bn_stats is not None:
+            a, z, slope, sums = bn_stats
+            _chk(a, "conv_dgrad.bn_stats.a", dy.dtype)
+            if tuple(a.shape) != (B, H, W, Cin) or sums.dtype != torch.float64 or sums.numel() != 2 * Cin:
+                raise _lib.UdaError("conv_dgrad: bn_stats shape mismatch")
+            call("conv2d_tc_dgrad_bnstats", ptr(dy), ptr(w_ft), ptr(addend), ptr(dx), ci(B), ci(H), ci(W), ci(Cin), ci(Cout),
+                 ci(KH), ci(KW), ci(stride), ci(pad), ptr(a), ptr(z), float(slope), ptr(sums), _stream())
+        else:
+            call("conv2d_tc_dgrad", ptr(dy), ptr(w_ft), ptr(addend), ptr(dx), ci(B), ci(H), ci(W), ci(Cin), ci(Cout), ci(KH),
+                 ci(KW), ci(stride), ci(pad), _stream())
         _tc_account(B, Ho, Wo, Cout, Cin, KH, KW)
+    elif bn_stats is not None:
+        raise _lib.UdaError("conv_dgrad: bn_stats needs the tensor-core path")
     else:
         call("conv2d_direct_dgrad", ptr(dy), ci(dt(dy)), ptr(w), ci(dt(w)), ptr(addend), ptr(dx), ci(B), ci(H), ci(W), ci(Cin),
              ci(Cout), ci(KH), ci(KW), ci(stride), ci(pad), _stream())
@@ -343,6 +370,21 @@ def bn_bwd(dy, x, a, gamma, mean, rstd, slope, dgamma, dbeta, dres=None, dres_ac
          ci(1 if dres_accumulate else 0), ptr(dgamma), ptr(dbeta), ci(1 if param_accumulate else 0), ll(M), ci(C),
          float(slope), ptr(ws), _stream())
     _count(2)
+    return dx
+
+
+def bn_bwd_apply_fused(dy, x, a, sums, v_is_z, gamma, beta, mean, rstd, slope, dgamma, dbeta, dres=None,
+                       dres_accumulate=False, param_accumulate=True, scale=None, shift=None):
+    """BatchNorm(+activation) backward whose per-channel sums were produced by the dgrad epilogue
+    (``conv_dgrad(bn_stats=...)``): finalize + apply in one launch."""
+    _chk(dy, "bn_bwd_apply_fused.dy"); _chk(x, "bn_bwd_apply_fused.x", dy.dtype)
+    C = x.shape[-1]
+    M = x.numel() // C
+    dx = torch.empty_like(x)
+    call("bn_bwd_apply_fused", ptr(dy), ptr(x), ptr(a), ci(dt(x)), ptr(sums), ci(1 if v_is_z else 0), ptr(gamma), ptr(beta),
+         ptr(mean), ptr(rstd), ptr(scale), ptr(shift), ptr(dx), ptr(dres), ci(1 if dres_accumulate else 0), ptr(dgamma),
+         ptr(dbeta), ci(1 if param_accumulate else 0), ll(M), ci(C), float(slope), _stream())
+    _count()
     return dx
 
 
