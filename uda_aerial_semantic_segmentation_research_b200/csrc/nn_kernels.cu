@@ -596,19 +596,44 @@ template <typename T, int VEC, typename IT>
 __global__ void __launch_bounds__(kThreads)
 upcat_fwd_kernel(const T* __restrict__ x, const T* __restrict__ skip, T* __restrict__ out, int B, int H, int W,
                  int C1, int C2) {
-  const int Ct = C1 + C2, cv = Ct / VEC;
-  const IT total = (IT)B * H * W * cv;
-  for (IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (IT)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cv) * VEC;
-    IT p = i / cv;
-    const int w = (int)(p % W); p /= W;
-    const int h = (int)(p % H);
-    const int b = (int)(p / H);
-    float v[VEC];
-    if (c < C1) ld_vec<VEC>(x + (((long long)b * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1)) * C1 + c, v);
-    else ld_vec<VEC>(skip + (((long long)b * H + h) * W + w) * C2 + (c - C1), v);
-    st_vec<VEC>(out + (long long)i * VEC, v);
+  // Work items: one low-resolution vector of x (-> its 2x2 children: one load, four stores), then groups of four
+  // skip vectors of one pixel row segment (four independent loads in flight before the stores).  The first
+  // version moved one vector per loop trip with a dependent load -> store and sat at ~50 % of the HBM roofline.
+  const int Ct = C1 + C2, cv1 = C1 / VEC, cv2 = C2 / VEC;
+  const int H2 = H / 2, W2 = W / 2;
+  const IT n1 = (IT)B * H2 * W2 * cv1;
+  const IT n2 = ((IT)B * H * W * cv2 + 3) / 4;
+  const IT nskip = (IT)B * H * W * cv2;
+  for (IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x; i < n1 + n2; i += (IT)gridDim.x * blockDim.x) {
+    if (i < n1) {
+      const int c = (int)(i % cv1) * VEC;
+      IT p = i / cv1;
+      const int w2 = (int)(p % W2); p /= W2;
+      const int h2 = (int)(p % H2);
+      const int b = (int)(p / H2);
+      float v[VEC];
+      ld_vec<VEC>(x + (long long)i * VEC, v);
+      T* o = out + (((long long)b * H + 2 * h2) * W + 2 * w2) * Ct + c;
+      st_vec<VEC>(o, v);
+      st_vec<VEC>(o + Ct, v);
+      st_vec<VEC>(o + (long long)W * Ct, v);
+      st_vec<VEC>(o + (long long)W * Ct + Ct, v);
+    } else {
+      const IT k0 = (i - n1) * 4;
+      float v[4][VEC];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (k0 + u < nskip) ld_vec<VEC>(skip + (long long)(k0 + u) * VEC, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const IT k = k0 + u;
+        if (k < nskip) {
+          const int c = (int)(k % cv2) * VEC;
+          const IT p = k / cv2;
+          st_vec<VEC>(out + (long long)p * Ct + C1 + c, v[u]);
+        }
+      }
+    }
   }
 }
 // dx[b,h2,w2,c] = sum of the 2x2 children of dout[..., c<C1];  dskip = dout[..., C1:]
@@ -1160,7 +1185,7 @@ extern "C" int uda_upsample2x_concat_fwd(const void* x, const void* skip, void* 
   UDA_REQUIRE(H % 2 == 0 && W % 2 == 0, UDA_ERR_BAD_ARG, "upcat_fwd: output size must be even");
   int vec = vec_for(dtype, C1, x, out);
   if (C2) { int v2 = vec_for(dtype, C2, skip); vec = vec < v2 ? vec : v2; }
-  const long long total = (long long)B * H * W * ((C1 + C2) / vec);
+  const long long total = (long long)B * H * W * ((C1 + C2) / vec);   // bound for the index type; work items are fewer
 #define K(T, V) do { if (total * 8 < (1LL << 31)) upcat_fwd_kernel<T, V, int><<<grid_for(total), kThreads, 0, st>>>((const T*)x, (const T*)skip, (T*)out, B, H, W, C1, C2); else upcat_fwd_kernel<T, V, long long><<<grid_for(total), kThreads, 0, st>>>((const T*)x, (const T*)skip, (T*)out, B, H, W, C1, C2); } while (0)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
   UDA_DT(dtype, KV, 0);
