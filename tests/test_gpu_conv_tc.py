@@ -132,6 +132,39 @@ def test_tile_shapes_of_the_wide_layers(cfg, tile, monkeypatch):
     assert rel_err(out.float().cpu(), dxr + add.float()) < 1e-2
 
 
+@pytest.mark.parametrize("cfg", [(2, 32, 32, 128, 128), (2, 32, 32, 256, 256), (1, 64, 64, 128, 128), (3, 32, 32, 64, 64),
+                                 (2, 16, 32, 64, 128), (1, 64, 64, 192, 64), (5, 24, 64, 64, 128)],
+                         ids=lambda c: "B%d_%dx%d_%dto%d" % c)
+def test_pitched_halo_kernel(cfg, monkeypatch):
+    """conv_tc_phalo.cu (3x3 stride 1 on W = 32 / 64 images: pitched positions, one halo box for nine taps): forward
+    with the fused BatchNorm statistics and dgrad with an addend against the fp32 reference and the persistent
+    kernel; ragged cases: an odd number of blocks (last tile partly empty), a last block that is mostly junk
+    positions, tiles that straddle images."""
+    ops = _ops()
+    B, H, W, Cin, Cout = cfg
+    x = _rand((B, H, W, Cin), 31)
+    w = _rand((Cout, 3, 3, Cin), 32, (9 * Cin) ** -0.5)
+    xg, wg = x.to(DEV), w.to(DEV)
+    yr = R.conv_fwd(x.float(), w.float(), None, 1, 1)
+    monkeypatch.setenv("UDA_B200_TC_PHALO", "0")
+    y_persist = ops.conv_fwd(xg, wg, None, 1, 1)
+    monkeypatch.setenv("UDA_B200_TC_PHALO", "2")
+    sums = torch.zeros(2 * Cout, dtype=torch.float64, device=DEV)
+    y = ops.conv_fwd(xg, wg, None, 1, 1, bn_sums=sums)
+    assert rel_err(y.float().cpu(), yr) < 1e-2
+    assert rel_err(y.float().cpu(), y_persist.float().cpu()) < 4e-3      # same products, different summation order
+    yf = y.double().reshape(-1, Cout)
+    assert rel_err(sums[Cout:].cpu(), (yf * yf).sum(0).cpu()) < 1e-4
+    assert (sums[:Cout].cpu() - yf.sum(0).cpu()).abs().max() < 1e-3 * float(yf.abs().sum(0).max())
+    dy = _rand(tuple(yr.shape), 33)
+    dxr = R.conv_dgrad(dy.float(), w.float(), x.shape, 1, 1)
+    add = _rand(tuple(x.shape), 34)
+    acc = add.clone().to(DEV)
+    out = ops.conv_dgrad(dy.to(DEV), wg, x.shape, 1, 1, addend=acc)
+    assert out.data_ptr() == acc.data_ptr()
+    assert rel_err(out.float().cpu(), dxr + add.float()) < 1e-2
+
+
 def test_weight_flip_transpose():
     ops = _ops()
     w = _rand((6, 3, 3, 4), 5)

@@ -349,7 +349,9 @@ bool use_halo() {
 int run_gemm_conv(const GemmConv& g, cudaStream_t st) {
   if (use_persistent()) {
     if (use_halo()) {
-      const int rc = run_gemm_conv_halo(g, st);
+      int rc = run_gemm_conv_halo(g, st);
+      if (rc != UDA_ERR_UNSUPPORTED) return rc;
+      rc = run_gemm_conv_phalo(g, st);
       if (rc != UDA_ERR_UNSUPPORTED) return rc;
     }
     return run_gemm_conv_persistent(g, st);

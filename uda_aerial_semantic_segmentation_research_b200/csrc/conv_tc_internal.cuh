@@ -126,6 +126,9 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st);
 // conv_tc_halo.cu: halo-tile kernel for 3x3 stride-1 convolutions on wide images; returns UDA_ERR_UNSUPPORTED
 // (no message) when the shape does not qualify
 int run_gemm_conv_halo(const GemmConv& g, cudaStream_t st);
+// conv_tc_phalo.cu: pitched-halo kernel for 3x3 stride-1 convolutions on narrow images (W = 32 / 64) with 64-multiple
+// channel counts; UDA_ERR_UNSUPPORTED (no message) otherwise
+int run_gemm_conv_phalo(const GemmConv& g, cudaStream_t st);
 // conv_tc_wgrad_halo.cu: halo-tile wgrad (3x3 stride 1 pad 1, W % 128 == 0); UDA_ERR_UNSUPPORTED otherwise
 int run_wgrad_halo(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, cudaStream_t st);
 // conv_tc_wgrad_big.cu: multi-accumulator wgrad sharing one dY tile (Cin, Cout multiples of 64); UDA_ERR_UNSUPPORTED otherwise

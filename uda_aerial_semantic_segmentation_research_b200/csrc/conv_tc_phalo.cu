@@ -1,0 +1,341 @@
+// Pitched-halo tcgen05 convolution for 3x3 stride-1 "same" convolutions on NARROW images (W <= 64) with many
+// channels (layer2 / layer3, decoder blocks 0-1, and their dgrads), sm_100a.
+//
+// conv_tc_persist.cu loads every input pixel nine times (one TMA box per tap) and, for these layers, is bound by
+// the operand rows an SM can take in through TMA (~one 128-byte box row per 4-5 clk), not by the tensor pipe.
+// conv_tc_halo.cu removes the nine-fold re-read for wide images, where one image row is one 128-row MMA block.
+// Here the same trick works for narrow images by making the GEMM-M index a PITCHED position: an image of H x W
+// pixels is walked as H rows of P = W + 2 positions (the two extra positions per row are junk outputs that are
+// never written), 128 consecutive positions = one MMA block.  The halo of a block — the image rows it touches
+// plus one above / below, each with one extra pixel left / right — is ONE zero-filled TMA box {KC, P, HR, 1};
+// in it, tap (kh, kw) of position m sits exactly (kh*P + kw) rows after the block's first row, so the nine taps
+// are nine MMA descriptors at shifted start addresses inside the same shared-memory tile (the swizzle is a
+// function of absolute shared-memory address bits: tools/exp/halo_desc_test.cu).  A-operand rows per tile drop
+// ~5x (W = 32) / ~3.5x (W = 64); the weight tiles are streamed per (channel chunk, tap) through a second ring.
+// A CTA tile is NBLK consecutive blocks (of the whole batch: blocks never straddle images, tiles may) x BN
+// output channels; TMEM is double-buffered when 2*NBLK*BN <= 512 columns.
+#include "conv_tc_internal.cuh"
+#include <stdlib.h>
+
+namespace uda {
+namespace tcconv {
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 192;
+constexpr int kSmemBudget = 218 * 1024;
+constexpr int kAStages = 2;
+constexpr int kMaxBStages = 8;
+
+struct PHParams {
+  int H, W, P, B;
+  int nb_img, total_blocks, m_tiles, n_tiles;
+  int Cout, Cred, kchunks;
+  int HR, halo_bytes, halo_stride, b_stages;
+  bf16* out; const bf16* addend; double* bn_sums;
+};
+
+template <int KC, int BN, int NBLK>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                     const PHParams p) {
+  constexpr int kRowB = KC * 2;
+  constexpr int kBBytes = BN * KC * 2;
+  constexpr uint32_t kAccCols = NBLK * BN;
+  constexpr int kSets = 2 * kAccCols <= 512 ? 2 : 1;
+  constexpr uint32_t kTmemCols = kSets * kAccCols < 32 ? 32 : kSets * kAccCols;
+  static_assert(kAccCols <= 512, "accumulators exceed TMEM");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int SB = p.b_stages;
+  const int a_stage_bytes = NBLK * p.halo_stride;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kAStages * a_stage_bytes + SB * kBBytes);
+  // bars: a_full[2], a_empty[2], b_full[8], b_empty[8], tmem_full[2], tmem_empty[2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+  const uint32_t a_base = smem_u32(smem);
+  const uint32_t b_base = a_base + kAStages * a_stage_bytes;
+  const uint32_t bar_base = smem_u32(bars);
+  auto afull = [&](int s) { return bar_base + 8u * s; };
+  auto aempty = [&](int s) { return bar_base + 8u * (2 + s); };
+  auto bfull = [&](int s) { return bar_base + 8u * (4 + s); };
+  auto bempty = [&](int s) { return bar_base + 8u * (12 + s); };
+  auto tfull = [&](int q) { return bar_base + 8u * (20 + q); };
+  auto tempty = [&](int q) { return bar_base + 8u * (22 + q); };
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < kAStages; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
+      for (int s = 0; s < SB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
+      for (int q = 0; q < 2; ++q) { mbar_init(tfull(q), 1); mbar_init(tempty(q), 4); }
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer: per channel chunk one halo box per block, then nine weight tiles =====
+    if (elect_one()) {
+      int ita = 0, itb = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int mt = t % p.m_tiles, n0 = (t / p.m_tiles) * BN;
+        const int gb0 = mt * NBLK;
+        const int nblk = min(NBLK, p.total_blocks - gb0);
+        for (int kc = 0; kc < p.kchunks; ++kc, ++ita) {
+          const int sa = ita % kAStages;
+          mbar_wait(aempty(sa), ((ita / kAStages) & 1) ^ 1);
+          mbar_expect_tx(afull(sa), (uint32_t)nblk * p.halo_bytes);
+          for (int j = 0; j < nblk; ++j) {
+            const int gb = gb0 + j, b = gb / p.nb_img, m0 = (gb % p.nb_img) * 128;
+            const int row0 = m0 / p.P;
+            tma_load_4d(a_base + sa * a_stage_bytes + j * p.halo_stride, &map_a, afull(sa), kc * KC, -1, row0 - 1, b);
+          }
+          for (int tap = 0; tap < 9; ++tap, ++itb) {
+            const int sb = itb % SB;
+            mbar_wait(bempty(sb), ((itb / SB) & 1) ^ 1);
+            mbar_expect_tx(bfull(sb), kBBytes);
+            tma_load_2d(b_base + sb * kBBytes, &map_b, bfull(sb), tap * p.Cred + kc * KC, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+      int ita = 0, itb = 0, j = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+        const int mt = t % p.m_tiles;
+        const int gb0 = mt * NBLK;
+        const int nblk = min(NBLK, p.total_blocks - gb0);
+        uint32_t off[NBLK];   // first halo row of each block's positions (tap (0,0))
+#pragma unroll
+        for (int i = 0; i < NBLK; ++i) {
+          const int m0 = ((gb0 + i) % p.nb_img) * 128;
+          off[i] = (uint32_t)(m0 - (m0 / p.P) * p.P);
+        }
+        const int q = j % kSets;
+        mbar_wait(tempty(q), ((j / kSets) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t acc = tmem_base + (uint32_t)q * kAccCols;
+        for (int kc = 0; kc < p.kchunks; ++kc, ++ita) {
+          const int sa = ita % kAStages;
+          mbar_wait(afull(sa), (ita / kAStages) & 1);
+          tc_fence_after();
+          const uint32_t halo = a_base + sa * a_stage_bytes;
+#pragma unroll 1
+          for (int tap = 0; tap < 9; ++tap, ++itb) {
+            const int sb = itb % SB;
+            mbar_wait(bfull(sb), (itb / SB) & 1);
+            tc_fence_after();
+            const int kh = tap / 3, kw = tap - 3 * kh;
+            const uint64_t bdesc = make_kmajor_desc(b_base + sb * kBBytes, kRowB);
+#pragma unroll
+            for (int i = 0; i < NBLK; ++i) {
+              if (i < nblk) {
+                const uint64_t adesc =
+                    make_kmajor_desc(halo + i * p.halo_stride + (off[i] + kh * p.P + kw) * kRowB, kRowB);
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k)
+                  umma_bf16(acc + (uint32_t)i * BN, adesc + 2ull * k, bdesc + 2ull * k, idesc,
+                            (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+              }
+            }
+            umma_commit(bempty(sb));
+          }
+          umma_commit(aempty(sa));
+        }
+        umma_commit(tfull(q));
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps): 128 pitched positions per block, junk columns skipped ==========
+    const int qw = warp & 3;
+    constexpr int kChunks = (BN + 31) / 32;
+    float bn_s[kChunks], bn_q[kChunks];
+#pragma unroll
+    for (int cc = 0; cc < kChunks; ++cc) { bn_s[cc] = 0.f; bn_q[cc] = 0.f; }
+    int bn_n0 = -1;
+    int j = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+      const int mt = t % p.m_tiles, n0 = (t / p.m_tiles) * BN;
+      const int gb0 = mt * NBLK;
+      const int nblk = min(NBLK, p.total_blocks - gb0);
+      const int q = j % kSets;
+      if (p.bn_sums && n0 != bn_n0) {   // channel tile changed: flush the partial statistics
+        if (bn_n0 >= 0) {
+#pragma unroll
+          for (int cc = 0; cc < kChunks; ++cc) {
+            const int col = bn_n0 + cc * 32 + lane;
+            if (col < p.Cout) { atomicAdd(p.bn_sums + col, (double)bn_s[cc]); atomicAdd(p.bn_sums + p.Cout + col, (double)bn_q[cc]); }
+            bn_s[cc] = 0.f; bn_q[cc] = 0.f;
+          }
+        }
+        bn_n0 = n0;
+      }
+      mbar_wait(tfull(q), (j / kSets) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int i = 0; i < nblk; ++i) {
+        const int gb = gb0 + i, b = gb / p.nb_img;
+        const int m = (gb % p.nb_img) * 128 + qw * 32 + lane;
+        const int r = m / p.P, c = m - r * p.P;
+        const bool valid = c < p.W && r < p.H;
+        const long long pix = ((long long)b * p.H + r) * p.W + c;
+        const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)q * kAccCols + (uint32_t)i * BN;
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          const int nbase = n0 + c0;
+          if (nbase >= p.Cout) break;   // warp-uniform
+          uint32_t v[32];
+          tmem_ld_32x32(tbase + (uint32_t)c0, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) f[k] = valid ? __uint_as_float(v[k]) : 0.f;
+          if (p.addend && valid) {
+            const bf16* add = p.addend + pix * p.Cout + nbase;
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              if (nbase + k < p.Cout) {
+                float a8[8];
+                ld_vec<8>(add + k, a8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[k + e] += a8[e];
+              }
+            }
+          }
+          if (p.bn_sums) bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);   // junk rows contribute zeros
+          if (valid) {
+            bf16* dst = p.out + pix * p.Cout + nbase;
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              if (nbase + k < p.Cout) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = f[k + e];
+                st_vec<8>(dst + k, o);
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty(q));
+    }
+    if (p.bn_sums && bn_n0 >= 0) {
+#pragma unroll
+      for (int cc = 0; cc < kChunks; ++cc) {
+        const int col = bn_n0 + cc * 32 + lane;
+        if (col < p.Cout) { atomicAdd(p.bn_sums + col, (double)bn_s[cc]); atomicAdd(p.bn_sums + p.Cout + col, (double)bn_q[cc]); }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// UDA_B200_TC_PHALO: 0 = off, 1 (default) = on for layers with at least half a wave of tiles, 2 = always (tests)
+int phalo_mode() {
+  const char* e = getenv("UDA_B200_TC_PHALO");   // read on every call: the tests switch it
+  return e ? atoi(e) : 1;
+}
+
+template <int KC, int BN, int NBLK>
+int launch_phalo(const CUtensorMap& ma, const CUtensorMap& mb, PHParams& p, cudaStream_t st) {
+  constexpr int kBBytes = BN * KC * 2;
+  p.halo_bytes = p.HR * p.P * KC * 2;
+  p.halo_stride = (p.halo_bytes + 1023) / 1024 * 1024;
+  const int a_bytes = kAStages * NBLK * p.halo_stride;
+  int SB = (kSmemBudget - a_bytes) / kBBytes;
+  if (SB > kMaxBStages) SB = kMaxBStages;
+  if (SB < 3) return UDA_ERR_UNSUPPORTED;   // caller falls back
+  p.b_stages = SB;
+  p.m_tiles = (p.total_blocks + NBLK - 1) / NBLK;
+  const int smem = a_bytes + SB * kBBytes + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    UDA_CUDA_OK(cudaFuncSetAttribute(conv_tc_phalo_kernel<KC, BN, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     227 * 1024));
+    configured = true;
+  }
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
+  conv_tc_phalo_kernel<KC, BN, NBLK><<<grid, kThreads, smem, st>>>(ma, mb, p);
+  UDA_LAUNCH_OK("conv_tc_phalo_kernel");
+  return UDA_OK;
+}
+
+}  // namespace
+
+// Returns UDA_ERR_UNSUPPORTED (without an error message the caller would surface) when the shape is not a 3x3
+// stride-1 "same" convolution on a narrow image with 64-multiple channel counts.
+int run_gemm_conv_phalo(const GemmConv& g, cudaStream_t st) {
+  const int mode = phalo_mode();
+  if (mode == 0) return UDA_ERR_UNSUPPORTED;
+  if (g.ncls != 1 || g.src_s2 || g.a_map || g.os != 1 || g.wtaps != 9 || g.cls[0].ntaps != 9) return UDA_ERR_UNSUPPORTED;
+  const TapClass& c = g.cls[0];
+  if (c.oh != 0 || c.ow != 0) return UDA_ERR_UNSUPPORTED;
+  for (int t = 0; t < 9; ++t)
+    if (c.dh[t] != t / 3 - 1 || c.dw[t] != t % 3 - 1 || c.wtap[t] != t) return UDA_ERR_UNSUPPORTED;
+  const int H = g.SH, W = g.SW;
+  if (g.OH != H || g.OW != W || g.bias || g.out_nchw || !g.out || g.st_sums) return UDA_ERR_UNSUPPORTED;
+  if (g.Cred % 64 || g.Cout % 64 || g.Cout < 64) return UDA_ERR_UNSUPPORTED;
+  // W = 64 (330-row halos: 64-byte rows, four blocks per tile) is implemented and tested, but measured slower than
+  // the persistent kernel's 256 x 128 tiles (33.6 vs 30.7 us on layer2 at B=16): default on for W = 32 only
+  if (!(W == 32 || (W == 64 && mode == 2)) || H < 8) return UDA_ERR_UNSUPPORTED;
+  if (!(aligned<bf16>(g.src, 16) && aligned<bf16>(g.wmat, 16) && aligned<bf16>(g.out, 16) &&
+        (!g.addend || aligned<bf16>(g.addend, 16))))
+    return UDA_ERR_UNSUPPORTED;
+  const int BN = g.Cout % 128 == 0 ? 128 : 64;
+  const int KC = W == 32 ? 64 : 32;        // W = 64: 330-row halos, four blocks per tile -> 64-byte rows
+  PHParams p{};
+  p.H = H; p.W = W; p.P = W + 2; p.B = g.B;
+  p.nb_img = (H * p.P + 127) / 128;
+  p.total_blocks = g.B * p.nb_img;
+  p.n_tiles = g.Cout / BN;
+  p.Cout = g.Cout; p.Cred = g.Cred; p.kchunks = g.Cred / KC;
+  p.HR = (128 + p.P - 1) / p.P + 3;
+  p.out = (bf16*)g.out; p.addend = (const bf16*)g.addend; p.bn_sums = g.bn_sums;
+  // enough work for a full wave, else the persistent kernel's smaller tiles are the better fit
+  const int nblk = W == 32 ? 2 : 4;
+  if (mode != 2 && (long long)((p.total_blocks + nblk - 1) / nblk) * p.n_tiles < num_sms() / 2) return UDA_ERR_UNSUPPORTED;
+  CUtensorMap ma, mb;
+  {
+    const uint64_t C = (uint64_t)g.Cred;
+    uint64_t dims[4] = {C, (uint64_t)W, (uint64_t)H, (uint64_t)g.B};
+    uint64_t str[3] = {C * 2, (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[4] = {(uint32_t)KC, (uint32_t)p.P, (uint32_t)p.HR, 1};
+    if (int rc = make_tmap_bf16(&ma, g.src, 4, dims, str, box, KC * 2)) return rc;
+  }
+  {
+    const uint64_t Kt = (uint64_t)9 * g.Cred;
+    uint64_t dims[2] = {Kt, (uint64_t)g.Cout};
+    uint64_t str[1] = {Kt * 2};
+    uint32_t box[2] = {(uint32_t)KC, (uint32_t)BN};
+    if (int rc = make_tmap_bf16(&mb, g.wmat, 2, dims, str, box, KC * 2)) return rc;
+  }
+  if (W == 32) {
+    if (BN == 128) return launch_phalo<64, 128, 2>(ma, mb, p, st);
+    return launch_phalo<64, 64, 2>(ma, mb, p, st);
+  }
+  if (BN == 128) return launch_phalo<32, 128, 4>(ma, mb, p, st);
+  return launch_phalo<32, 64, 4>(ma, mb, p, st);
+}
+
+}  // namespace tcconv
+}  // namespace uda
