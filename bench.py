@@ -195,9 +195,13 @@ def run_ours(args):
         adv = AdversarialLoss(0.001)
     opt = FusedAdam(model, lr=1e-3, capturable=graph_adv)
     crit = CrossEntropyLoss()
+    graph_adv_dp = adversarial and world > 1 and not args.no_graph
     if world > 1:
         from uda_aerial_semantic_segmentation_research_b200.ddp import GradSync
-        GradSync(nets)
+        gsync = GradSync(nets)
+        if graph_adv_dp:   # captured phases: the all-reduce runs on the flat gradient buffers between the graphs
+            for n in nets:
+                n._grad_sync = None
     Bs = B // 2 if adversarial else B
     x, t = synthetic_batch(Bs, size, 1234 + rank, dev)
     xt = synthetic_batch(Bs, size, 4321 + rank, dev)[0] if adversarial else None
@@ -234,6 +238,30 @@ def run_ours(args):
     if graph_adv:
         from uda_aerial_semantic_segmentation_research_b200.graph import GraphedFn
         graphed = GraphedFn(eager_step, [x, t, xt], [model, disc])
+    if graph_adv_dp:
+        from uda_aerial_semantic_segmentation_research_b200.graph import GraphedPhases
+
+        def d_compute(xs, ts, xtg):   # src/models/adversarial_trainer.py:84-95
+            dopt.zero_grad()
+            d_loss = adv.discriminator_loss(disc(xs), disc(xtg))
+            d_loss.backward()
+            return d_loss.detach()
+
+        def d_finish():
+            dist.all_reduce(disc._store.grad, op=dist.ReduceOp.AVG)
+            dopt.step()
+
+        def g_compute(xs, ts, xtg):   # src/models/adversarial_trainer.py:98-114
+            opt.zero_grad()
+            total = crit(model(xs), ts) + adv.generator_loss(disc(xtg))
+            total.backward()
+            return total.detach()
+
+        def g_finish():
+            dist.all_reduce(model._store.grad, op=dist.ReduceOp.AVG)
+            opt.step()
+
+        graphed = GraphedPhases([(d_compute, d_finish), (g_compute, g_finish)], [x, t, xt], [model, disc])
 
     def sync():
         if world > 1:
@@ -360,7 +388,8 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": wl, "global_batch": B * world, "image_size": size, "classes": CLASSES,
                        "parallelism": f"dp{world}", "l2": "inputs+activations per step (>3 GB) exceed the 126 MB L2",
-                       "launch": ("cuda-graph replay of the whole D/G step" if adversarial else
+                       "launch": (("cuda-graph replay of the D-step and G-step compute phases, all-reduce + fused Adam "
+                                   "after each" if world > 1 else "cuda-graph replay of the whole D/G step") if adversarial else
                                   "cuda-graph replay of fwd+loss+bwd, then all-reduce + fused Adam") if graphed is not None
                                  else "eager launches"},
             "e2e": e2e, "gpu_launches": launches, "clocks": sampler.result(),

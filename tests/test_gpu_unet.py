@@ -289,3 +289,52 @@ def test_graphed_step_matches_eager_steps():
     # near-zero gradient into a full +-lr step for a handful of weights; two eager runs differ by 2-3e-3 as well)
     assert l2_err(m2._store.flat, m1._store.flat) < 6e-3
     assert int(m2.encoder.bn1.num_batches_tracked) == int(m1.encoder.bn1.num_batches_tracked)
+
+
+def test_graphed_phases_match_eager_adversarial_steps():
+    """graph.GraphedPhases (D-step graph -> optimizer -> G-step graph -> optimizer: the data-parallel form of the
+    adversarial step, here without the all-reduce) walks the same loss trajectory as the eager D/G steps of
+    src/models/adversarial_trainer.py:84-114 (fp32 mode)."""
+    U = _pkg()
+    from uda_aerial_semantic_segmentation_research_b200.graph import GraphedPhases
+    from uda_aerial_semantic_segmentation_research_b200.optim import FusedAdam
+    from uda_aerial_semantic_segmentation_research_b200.losses import CrossEntropyLoss, AdversarialLoss
+    from uda_aerial_semantic_segmentation_research_b200.discriminator import DomainDiscriminator
+    g = torch.Generator().manual_seed(9)
+    xs = torch.randn(2, 3, 64, 64, generator=g).to(DEV)
+    xt = torch.randn(2, 3, 64, 64, generator=g).to(DEV)
+    ts = torch.randint(0, 6, (2, 64, 64), generator=g).to(DEV)
+    warm, steps = 2, 3
+
+    def make():
+        torch.manual_seed(4)
+        m = U.Unet("resnet18", encoder_weights=None, classes=6, compute_dtype=torch.float32).to(DEV).train()
+        d = DomainDiscriminator(3, compute_dtype=torch.float32).to(DEV).train()
+        return m, d, FusedAdam(m, lr=1e-3), FusedAdam(d, lr=1e-4), CrossEntropyLoss(), AdversarialLoss(0.001)
+
+    def phases(m, d, o, do, c, adv):
+        def d_compute(a, t, b):
+            do.zero_grad()
+            loss = adv.discriminator_loss(d(a), d(b))
+            loss.backward()
+            return loss.detach()
+
+        def g_compute(a, t, b):
+            o.zero_grad()
+            total = c(m(a), t) + adv.generator_loss(d(b))
+            total.backward()
+            return total.detach()
+        return [(d_compute, do.step), (g_compute, o.step)]
+
+    ph = phases(*make())
+    eager = []
+    for _ in range(warm + 1 + steps):            # GraphedPhases: warm-up steps + one trajectory step while capturing
+        for compute, finish in ph:
+            out = compute(xs, ts, xt)
+            finish()
+        eager.append(float(out))
+    step = GraphedPhases(phases(*make()), [xs, ts, xt], [], warmup=warm)
+    got = [float(step(xs, ts, xt)) for _ in range(steps)]
+    assert step.launches_per_step > 60
+    for a, b in zip(eager[warm + 1:], got):
+        assert abs(a - b) <= 2e-3 * abs(a), (eager, got)

@@ -138,3 +138,56 @@ class GraphedFn:
             dst.copy_(src, non_blocking=True)
         self.graph.replay()
         return self.out
+
+
+class GraphedPhases:
+    """A training step made of several captured compute phases with eager glue in between — the data-parallel form
+    of the adversarial step (``src/models/adversarial_trainer.py:84-114``): D-step compute graph -> all-reduce of the
+    discriminator gradients + its optimizer step -> G-step compute graph -> all-reduce of the segmentation network's
+    gradients + its optimizer step.  ``phases`` = [(compute_fn, finish_fn), ...]; every ``compute_fn(*inputs)`` does
+    zero_grad / forward / loss / backward on the device and returns a tensor; ``finish_fn()`` runs right after the
+    replay (collectives, optimizer).  The networks must not carry an overlapping ``GradSync`` (the bucketed hooks
+    are host logic that a graph cannot replay): reduce ``net._store.grad`` in ``finish_fn`` instead.
+    """
+
+    def __init__(self, phases, example_inputs, networks, warmup=2):
+        dev = example_inputs[0].device
+        if dev.type != "cuda":
+            raise RuntimeError("GraphedPhases needs CUDA example inputs")
+        for m in networks:
+            if getattr(m, "_grad_sync", None) is not None:
+                raise RuntimeError("GraphedPhases: detach GradSync (net._grad_sync = None) and all-reduce in finish_fn")
+        self.inputs = [t.clone() for t in example_inputs]
+        self.finish = [f for _, f in phases]
+        s = torch.cuda.Stream(device=dev)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(warmup):
+                for compute, finish in phases:
+                    compute(*self.inputs)
+                    finish()
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        from . import ops
+        self.graphs, self.outs, self.launches_per_step = [], [], 0
+        for compute, finish in phases:
+            for m in networks:                 # every phase refreshes the bf16 shadow weights it reads
+                m._store.shadow_version = None
+                m._store.shadow_ft_version = None
+            g = torch.cuda.CUDAGraph()
+            l0 = ops.LAUNCHES
+            with torch.cuda.graph(g):
+                out = compute(*self.inputs)
+            self.launches_per_step += ops.LAUNCHES - l0 + 1
+            self.graphs.append(g)
+            self.outs.append(out)
+            g.replay()                         # capturing does not execute: run the phase once for real so that the
+            finish()                           # next phase is captured (and later replayed) on a consistent trajectory
+
+    def __call__(self, *inputs):
+        for dst, src in zip(self.inputs, inputs):
+            dst.copy_(src, non_blocking=True)
+        for g, finish in zip(self.graphs, self.finish):
+            g.replay()
+            finish()
+        return self.outs[-1]
