@@ -295,14 +295,15 @@ int run_gemm_conv_phalo(const GemmConv& g, cudaStream_t st) {
   const int H = g.SH, W = g.SW;
   if (g.OH != H || g.OW != W || g.bias || g.out_nchw || !g.out || g.st_sums) return UDA_ERR_UNSUPPORTED;
   if (g.Cred % 64 || g.Cout % 64 || g.Cout < 64) return UDA_ERR_UNSUPPORTED;
-  // W = 64 (330-row halos: 64-byte rows, four blocks per tile) is implemented and tested, but measured slower than
-  // the persistent kernel's 256 x 128 tiles (33.6 vs 30.7 us on layer2 at B=16): default on for W = 32 only
+  // W = 64 (330-row halos) is implemented and tested, but measured no faster than the persistent kernel's
+  // 256 x 128 tiles (30.8 vs 30.7 us on layer2 at B=16, although it moves half the operand bytes): default on for
+  // W = 32 only
   if (!(W == 32 || (W == 64 && mode == 2)) || H < 8) return UDA_ERR_UNSUPPORTED;
   if (!(aligned<bf16>(g.src, 16) && aligned<bf16>(g.wmat, 16) && aligned<bf16>(g.out, 16) &&
         (!g.addend || aligned<bf16>(g.addend, 16))))
     return UDA_ERR_UNSUPPORTED;
   const int BN = g.Cout % 128 == 0 ? 128 : 64;
-  const int KC = W == 32 ? 64 : 32;        // W = 64: 330-row halos, four blocks per tile -> 64-byte rows
+  const int KC = 64;
   PHParams p{};
   p.H = H; p.W = W; p.P = W + 2; p.B = g.B;
   p.nb_img = (H * p.P + 127) / 128;
@@ -312,7 +313,7 @@ int run_gemm_conv_phalo(const GemmConv& g, cudaStream_t st) {
   p.HR = (128 + p.P - 1) / p.P + 3;
   p.out = (bf16*)g.out; p.addend = (const bf16*)g.addend; p.bn_sums = g.bn_sums;
   // enough work for a full wave, else the persistent kernel's smaller tiles are the better fit
-  const int nblk = W == 32 ? 2 : 4;
+  const int nblk = 2;
   if (mode != 2 && (long long)((p.total_blocks + nblk - 1) / nblk) * p.n_tiles < num_sms() / 2) return UDA_ERR_UNSUPPORTED;
   CUtensorMap ma, mb;
   {
@@ -329,12 +330,8 @@ int run_gemm_conv_phalo(const GemmConv& g, cudaStream_t st) {
     uint32_t box[2] = {(uint32_t)KC, (uint32_t)BN};
     if (int rc = make_tmap_bf16(&mb, g.wmat, 2, dims, str, box, KC * 2)) return rc;
   }
-  if (W == 32) {
-    if (BN == 128) return launch_phalo<64, 128, 2>(ma, mb, p, st);
-    return launch_phalo<64, 64, 2>(ma, mb, p, st);
-  }
-  if (BN == 128) return launch_phalo<32, 128, 4>(ma, mb, p, st);
-  return launch_phalo<32, 64, 4>(ma, mb, p, st);
+  if (BN == 128) return launch_phalo<64, 128, 2>(ma, mb, p, st);
+  return launch_phalo<64, 64, 2>(ma, mb, p, st);
 }
 
 }  // namespace tcconv

@@ -542,8 +542,15 @@ maxpool_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, unsigned char* __
     const long long o = (((long long)b * Ho + ho) * Wo + wo) * C + v * VEC;
     st_vec<VEC>(y + o, best);
     if (idx) {
+      if constexpr (VEC == 8) {
+        uint2 iv;
+        iv.x = (unsigned)bi[0] | ((unsigned)bi[1] << 8) | ((unsigned)bi[2] << 16) | ((unsigned)bi[3] << 24);
+        iv.y = (unsigned)bi[4] | ((unsigned)bi[5] << 8) | ((unsigned)bi[6] << 16) | ((unsigned)bi[7] << 24);
+        *reinterpret_cast<uint2*>(idx + o) = iv;
+      } else {
 #pragma unroll
-      for (int j = 0; j < VEC; ++j) idx[o + j] = (unsigned char)bi[j];
+        for (int j = 0; j < VEC; ++j) idx[o + j] = (unsigned char)bi[j];
+      }
     }
   }
 }
@@ -580,9 +587,18 @@ maxpool_bwd_kernel(const T* __restrict__ dy, const unsigned char* __restrict__ i
         const long long o = (((long long)b * Ho + ho) * Wo + wo) * C + v * VEC;
         float dv[VEC];
         ld_vec<VEC>(dy + o, dv);
+        if constexpr (VEC == 8) {   // the eight winning-tap bytes in one 8-byte load
+          const uint2 iv = *reinterpret_cast<const uint2*>(idx + o);
 #pragma unroll
-        for (int j = 0; j < VEC; ++j)
-          if (idx[o + j] == kh * 3 + kw) acc[j] += dv[j];
+          for (int j = 0; j < 8; ++j) {
+            const unsigned int b = ((j < 4 ? iv.x : iv.y) >> (8 * (j & 3))) & 0xffu;
+            if (b == (unsigned int)(kh * 3 + kw)) acc[j] += dv[j];
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < VEC; ++j)
+            if (idx[o + j] == kh * 3 + kw) acc[j] += dv[j];
+        }
       }
     }
     st_vec<VEC>(dx + (long long)i * VEC, acc);
