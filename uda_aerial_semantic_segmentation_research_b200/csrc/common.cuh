@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "../../include/uda_b200.h"
 
@@ -124,6 +125,36 @@ template <int VEC> __device__ __forceinline__ void st_vec(bf16* p, const float (
           make_uint4(pack_bf16x2(v[i], v[i + 1]), pack_bf16x2(v[i + 2], v[i + 3]),
                      pack_bf16x2(v[i + 4], v[i + 5]), pack_bf16x2(v[i + 6], v[i + 7]));
   }
+}
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------
+// A training step is ~300 dependent launches of 20-60 us each; with plain stream order every launch pays the drain of
+// its predecessor, the launch latency and its own prologue (barrier init, TMEM allocation, descriptor prefetch).
+// Kernels launched through launch_pdl() may start as soon as every CTA of the predecessor has executed
+// pdl_launch_dependents() (they do so first thing) and an SM is free; pdl_wait() — executed by EVERY CTA before it
+// touches global memory and before it exits, so that completion stays transitive along the stream — blocks until
+// the predecessor grid has completed and its writes are visible.  Without the launch attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UDA_B200_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // ---- reductions ------------------------------------------------------------------------------

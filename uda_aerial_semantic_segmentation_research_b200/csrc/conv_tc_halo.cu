@@ -60,6 +60,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
   if (warp == 1) {
     if (lane == 0) {
@@ -76,6 +77,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ===================== TMA producer: weights once, then one halo box per (tile, channel chunk) ==========
@@ -274,7 +276,7 @@ int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, HParams& p, cudaSt
     configured = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_tc_halo_kernel<KC, BN, R><<<grid, kThreads, smem, st>>>(ma, mb, p);
+  UDA_CUDA_OK(launch_pdl(conv_tc_halo_kernel<KC, BN, R>, dim3(grid), dim3(kThreads), smem, st, ma, mb, p));
   UDA_LAUNCH_OK("conv_tc_halo_kernel");
   return UDA_OK;
 }

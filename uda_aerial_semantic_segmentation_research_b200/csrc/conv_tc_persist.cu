@@ -43,6 +43,7 @@ struct PParams {
   bf16* out; float* out_nchw; const float* bias; const bf16* addend;
   double* bn_sums;
   const bf16* st_a; const bf16* st_z; float st_slope; double* st_sums;   // GemmConv::st_*
+  int debug;   // UDA_B200_TC_DEBUG bit mask (timing experiments only): 1 = no epilogue stores, 2 = no MMAs, 4 = no TMA loads
 };
 
 template <int KC, int BN, int MT>
@@ -76,6 +77,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const int total_tiles = p.ncls * tiles_per_cls;
   const int tiles_per_group = p.tiles_w * p.tiles_h;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
   if (warp == 1) {
     if (lane == 0) {
@@ -92,6 +94,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -115,6 +118,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             const uint32_t phs = (it / S) & 1;
             mbar_wait(empty_bar(s), phs ^ 1);
             const uint32_t a_dst = ring_base + s * stage_bytes;
+            if (p.debug & 4) { mbar_arrive(full_bar(s)); continue; }
             mbar_expect_tx(full_bar(s), stage_bytes);
             if (p.rank5)
               tma_load_5d(a_dst, &map_a, full_bar(s), c.pw[tap] * p.Cred + kc * KC, w0 + c.dw[tap], c.ph[tap],
@@ -148,13 +152,15 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             const uint32_t a_addr = ring_base + s * stage_bytes;
             const uint32_t b_addr = p.ws ? ws_base + (c.wtap[tap] * p.kchunks + kc) * kBBytes : a_addr + kABytes;
             const uint64_t bdesc = make_kmajor_desc(b_addr, KC * 2);
+            if (!(p.debug & 2)) {
 #pragma unroll
-            for (int sub = 0; sub < MT; ++sub) {
-              const uint64_t adesc = make_kmajor_desc(a_addr + sub * (128 * KC * 2), KC * 2);
+              for (int sub = 0; sub < MT; ++sub) {
+                const uint64_t adesc = make_kmajor_desc(a_addr + sub * (128 * KC * 2), KC * 2);
 #pragma unroll
-              for (int k = 0; k < KC / 16; ++k)
-                umma_bf16(acc + (uint32_t)sub * BN, adesc + 2ull * k, bdesc + 2ull * k, idesc,
-                          (tap > 0 || kc > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < KC / 16; ++k)
+                  umma_bf16(acc + (uint32_t)sub * BN, adesc + 2ull * k, bdesc + 2ull * k, idesc,
+                            (tap > 0 || kc > 0 || k > 0) ? 1u : 0u);
+              }
             }
             umma_commit(empty_bar(s));
           }
@@ -258,7 +264,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
               bn_q[c0 / 32] += warp_column_sums(gv, lane);
             }
           }
-          if (p.out) {
+          if (p.out && !(p.debug & 1)) {
             bf16* dst = p.out + pix * p.Cout + nbase;
 #pragma unroll
             for (int k = 0; k < 32; k += 8) {
@@ -325,7 +331,7 @@ int launch_persist(const CUtensorMap& ma, const CUtensorMap& mb, PParams& p, int
     configured = 227 * 1024;
   }
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  conv_tc_persist_kernel<KC, BN, MT><<<grid, kThreads, smem, st>>>(ma, mb, p);
+  UDA_CUDA_OK(launch_pdl(conv_tc_persist_kernel<KC, BN, MT>, dim3(grid), dim3(kThreads), smem, st, ma, mb, p));
   UDA_LAUNCH_OK("conv_tc_persist_kernel");
   return UDA_OK;
 }
@@ -420,6 +426,7 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
   }
   p.out = (bf16*)g.out; p.out_nchw = g.out_nchw; p.bias = g.bias; p.addend = (const bf16*)g.addend;
   p.bn_sums = g.bn_sums;
+  { const char* e = getenv("UDA_B200_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
   p.st_a = (const bf16*)g.st_a; p.st_z = (const bf16*)g.st_z; p.st_slope = g.st_slope; p.st_sums = g.st_sums;
   UDA_REQUIRE(!(g.bn_sums && g.st_sums), UDA_ERR_BAD_ARG, "conv_tc_persist: forward and backward statistics are exclusive");
   UDA_REQUIRE(!g.st_sums || (g.st_a && g.out), UDA_ERR_BAD_ARG, "conv_tc_persist: backward statistics need `a` and an NHWC output");

@@ -65,6 +65,7 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
   if (warp == 1) {
     if (lane == 0) {
@@ -81,6 +82,7 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible from here on
 
   if (warp == 0) {
     // ===================== TMA producer: per channel chunk one halo box per block, then nine weight tiles =====
@@ -275,7 +277,7 @@ int launch_phalo(const CUtensorMap& ma, const CUtensorMap& mb, PHParams& p, cuda
   }
   const int total_tiles = p.m_tiles * p.n_tiles;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  conv_tc_phalo_kernel<KC, BN, NBLK><<<grid, kThreads, smem, st>>>(ma, mb, p);
+  UDA_CUDA_OK(launch_pdl(conv_tc_phalo_kernel<KC, BN, NBLK>, dim3(grid), dim3(kThreads), smem, st, ma, mb, p));
   UDA_LAUNCH_OK("conv_tc_phalo_kernel");
   return UDA_OK;
 }

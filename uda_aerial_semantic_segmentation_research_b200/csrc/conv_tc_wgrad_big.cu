@@ -76,6 +76,7 @@ conv_tc_wgrad_big_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
   const int n_iters = st_end - st_begin;   // >= 1 by construction of the grid
   const int tiles_per_group = p.tiles_w * p.tiles_h;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_dy); }
   if (warp == 1) {
     if (lane == 0) {
@@ -91,6 +92,7 @@ conv_tc_wgrad_big_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible from here on
 
   if (warp == 0) {
     if (elect_one()) {
@@ -196,7 +198,7 @@ int launch_big(const CUtensorMap& mx, const CUtensorMap& mdy, const WBParams& p,
     configured = true;
   }
   dim3 grid((unsigned)groups, (unsigned)n_tiles, (unsigned)splits);
-  conv_tc_wgrad_big_kernel<BN><<<grid, kThreads, smem, st>>>(mx, mdy, p);
+  UDA_CUDA_OK(launch_pdl(conv_tc_wgrad_big_kernel<BN>, grid, dim3(kThreads), smem, st, mx, mdy, p));
   UDA_LAUNCH_OK("conv_tc_wgrad_big_kernel");
   return UDA_OK;
 }

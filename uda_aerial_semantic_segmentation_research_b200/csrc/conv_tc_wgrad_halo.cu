@@ -80,6 +80,7 @@ conv_tc_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
   int t_end = t_begin + p.tiles_per_cta;
   if (t_end > p.total_tiles) t_end = p.total_tiles;
 
+  pdl_launch_dependents();
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_dy); }
   if (warp == 1) {
     if (lane == 0) {
@@ -95,6 +96,7 @@ conv_tc_wgrad_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __gri
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible from here on
 
   if (warp == 0) {
     if (elect_one()) {
@@ -218,7 +220,7 @@ int launch_wh(const void* x, const void* dy, WHParams& p, cudaStream_t st) {
                                      cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
-  conv_tc_wgrad_halo_kernel<AA, CA, AB, BN, R><<<ctas, kThreads, smem, st>>>(mx, mdy, p);
+  UDA_CUDA_OK(launch_pdl(conv_tc_wgrad_halo_kernel<AA, CA, AB, BN, R>, dim3(ctas), dim3(kThreads), smem, st, mx, mdy, p));
   UDA_LAUNCH_OK("conv_tc_wgrad_halo_kernel");
   return UDA_OK;
 }

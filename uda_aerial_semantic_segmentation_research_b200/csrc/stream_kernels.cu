@@ -42,11 +42,13 @@ struct Pipe {
     done_base = full_base + 8u * kMaxStages;
     total_tiles = (io.nbytes + kTile - 1) / kTile;
     n_my = total_tiles > blockIdx.x ? (int)((total_tiles - blockIdx.x - 1) / gridDim.x + 1) : 0;
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
       for (int s = 0; s < io.stages; ++s) { mbar_init(full_base + 8u * s, 1); mbar_init(done_base + 8u * s, kCompute); }
       fence_barrier_init();
     }
     __syncthreads();
+    pdl_wait();   // barrier setup overlapped the predecessor's tail; its outputs are visible from here on
   }
   __device__ __forceinline__ bool is_io() const { return threadIdx.x >= kCompute; }
   __device__ __forceinline__ long long tile_of(int k) const { return (long long)blockIdx.x + (long long)k * gridDim.x; }
@@ -372,7 +374,7 @@ int bn_apply_stream(const void* x, const void* residual, void* y, const float* s
   if (int rc = stream_launch_geometry(p.io, 2 * (size_t)C * sizeof(float), &grid, &smem)) return rc;
   static bool cfg = false;
   if (!cfg) { if (int rc = set_smem_attr(bn_apply_stream_kernel)) return rc; cfg = true; }
-  bn_apply_stream_kernel<<<grid, kCta, smem, st>>>(p);
+  UDA_CUDA_OK(launch_pdl(bn_apply_stream_kernel, dim3(grid), dim3(kCta), smem, st, p));
   UDA_LAUNCH_OK("bn_apply_stream_kernel");
   return UDA_OK;
 }
@@ -391,7 +393,7 @@ int bn_bwd_stream(const void* dy, const void* x, const void* a, const float* mea
     if (int rc = stream_launch_geometry(p.io, kCompute * 16 * sizeof(float), &grid, &smem)) return rc;
     static bool cfg = false;
     if (!cfg) { if (int rc = set_smem_attr(bn_bwd_reduce_stream_kernel)) return rc; cfg = true; }
-    bn_bwd_reduce_stream_kernel<<<grid, kCta, smem, st>>>(p);
+    UDA_CUDA_OK(launch_pdl(bn_bwd_reduce_stream_kernel, dim3(grid), dim3(kCta), smem, st, p));
     UDA_LAUNCH_OK("bn_bwd_reduce_stream_kernel");
   }
   {
@@ -410,7 +412,7 @@ int bn_bwd_stream(const void* dy, const void* x, const void* a, const float* mea
     if (int rc = stream_launch_geometry(p.io, 0, &grid, &smem)) return rc;
     static bool cfg = false;
     if (!cfg) { if (int rc = set_smem_attr(bn_bwd_apply_stream_kernel)) return rc; cfg = true; }
-    bn_bwd_apply_stream_kernel<<<grid, kCta, smem, st>>>(p);
+    UDA_CUDA_OK(launch_pdl(bn_bwd_apply_stream_kernel, dim3(grid), dim3(kCta), smem, st, p));
     UDA_LAUNCH_OK("bn_bwd_apply_stream_kernel");
   }
   return UDA_OK;
@@ -440,7 +442,7 @@ int bn_bwd_apply_fused_stream(const void* dy, const void* x, const void* a, cons
   if (int rc = stream_launch_geometry(p.io, 3 * (size_t)C * sizeof(float), &grid, &smem)) return rc;
   static bool cfg = false;
   if (!cfg) { if (int rc = set_smem_attr(bn_bwd_apply_stream_kernel)) return rc; cfg = true; }
-  bn_bwd_apply_stream_kernel<<<grid, kCta, smem, st>>>(p);
+  UDA_CUDA_OK(launch_pdl(bn_bwd_apply_stream_kernel, dim3(grid), dim3(kCta), smem, st, p));
   UDA_LAUNCH_OK("bn_bwd_apply_stream_kernel");
   return UDA_OK;
 }
