@@ -28,6 +28,22 @@ FWD_GFLOP_PER_IMG_512 = 64.248
 TRAIN_GFLOP_PER_IMG_512 = 191.51
 
 
+def conv_traffic_from_profile():
+    """Average DRAM bytes per tensor-core convolution launch from the committed ncu launch list of this workload
+    (profiles/r01_launch_shares_final.csv: dram__bytes_read.sum + dram__bytes_write.sum per kernel), or None."""
+    path = os.path.join(ROOT, "profiles", "r01_launch_shares_final.csv")
+    try:
+        n, tot = 0, 0.0
+        for line in open(path).read().splitlines()[1:]:
+            f = line.split(",")
+            if f[0].startswith("conv_tc_") and f[4] and f[5]:
+                n += int(f[1])
+                tot += (float(f[4]) + float(f[5])) * 1e6
+        return tot / n if n else None
+    except Exception:
+        return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -358,7 +374,8 @@ def run_ours(args):
             roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolution family (conv_tc_persist / conv_tc_halo / "
                                                  "conv_tc_wgrad[_halo] kernels: fwd + dgrad + wgrad launches)",
                     "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["bf16_tflops_sustained"], "traffic": None,
+                    "frac": ach / pk["bf16_tflops_sustained"], "traffic": conv_traffic_from_profile(),
+                    "traffic_note": "average DRAM bytes per conv launch, ncu launch list under profiles/ (cold cache)",
                     "peak_source": pk["which"] + " (sustained: kernels timed inside a long step)",
                     "gflop_per_step": tc_gflop, "ms_per_step": tc_ms, "launches_per_step": tc_n,
                     "top_entry_point_by_time": top}

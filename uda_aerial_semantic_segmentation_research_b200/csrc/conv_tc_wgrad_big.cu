@@ -215,7 +215,17 @@ int run_wgrad_big(const void* dy, const void* x, float* dw, int B, int H, int W,
   WBParams p{};
   p.Cin = Cin; p.Cout = Cout; p.ntaps = KH * KW; p.cchunks = Cin / 64; p.rank5 = stride == 2;
   p.total_atoms = p.ntaps * p.cchunks;
-  const int max_atoms = 2 * (512 / BN);                     // TMEM: NACC x BN <= 512 columns
+  int max_atoms = 2 * (512 / BN);                           // TMEM: NACC x BN <= 512 columns
+  // ... and three stages of 64-pixel steps must fit: (2*NACC + BN/64) atoms of 8 KB <= ring/3.  Measured: with
+  // 32-pixel steps (twice the barrier round trips per byte) dec1.c1 takes 131 us, with six atoms per group 84 us.
+  if (plan_tiles(B, Ho, Wo, 64).ok) {
+    const int cap = 2 * ((kSmemRing / 3 / (64 * 128) - BN / 64) / 2);
+    if (cap >= 2 && cap < max_atoms) max_atoms = cap;
+  }
+  if (const char* e = getenv("UDA_B200_WGRAD_APG")) {       // experiment hook: cap the atoms per group
+    const int v = atoi(e);
+    if (v >= 2 && v < max_atoms) max_atoms = v;
+  }
   const int groups = (p.total_atoms + max_atoms - 1) / max_atoms;
   p.apg = (p.total_atoms + groups - 1) / groups;
   p.nacc = (p.apg + 1) / 2;
