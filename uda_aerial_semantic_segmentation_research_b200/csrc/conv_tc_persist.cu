@@ -366,7 +366,7 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
   if (!tp.ok) { tp = plan_tiles(g.B, MH, MW, 128); MT = 1; }
   // Wide layers whose weights cannot stay resident (layer2-4, decoder conv1/conv2 of blocks 0-1) stream
   // (MT*128 + BN) operand rows per MT*128 x BN tile.  Measured on B200 (tools/conv_bench.py): whatever the tile
-  // shape, an SM takes in only ~30 B/clk through TMA (one 128-byte box row per ~4 clk), so these layers are bound
+  // shape, an SM takes in only ~30 B/clk of operands (3-4 ring slots against the slot round-trip latency), so these layers are bound
   // by the operand bytes of the BUSIEST SM, not by the tensor pipe: pick the tile shape that minimises
   // rounds x bytes per tile (vs the tensor-pipe time), among 128/256 pixels x 128/256 channels.
   if (KC == 64 && g.Cout >= 128 && g.Cout % 128 == 0 && !g.a_map && big_tiles_enabled()) {

@@ -2,7 +2,7 @@
 // channels (layer2 / layer3, decoder blocks 0-1, and their dgrads), sm_100a.
 //
 // conv_tc_persist.cu loads every input pixel nine times (one TMA box per tap) and, for these layers, is bound by
-// the operand rows an SM can take in through TMA (~one 128-byte box row per 4-5 clk), not by the tensor pipe.
+// the operand bytes an SM can take in (~30 B/clk with 3-4 ring slots against the slot latency), not by the tensor pipe.
 // conv_tc_halo.cu removes the nine-fold re-read for wide images, where one image row is one 128-row MMA block.
 // Here the same trick works for narrow images by making the GEMM-M index a PITCHED position: an image of H x W
 // pixels is walked as H rows of P = W + 2 positions (the two extra positions per row are junk outputs that are
