@@ -285,9 +285,11 @@ def test_graphed_step_matches_eager_steps():
     assert step.launches_per_step > 50
     for a, b in zip(eager[warm:], got):
         assert abs(a - b) <= 1e-3 * abs(a), (eager, got)
-    # parameters after the trajectory agree too (L2: Adam's m/sqrt(v) turns the atomics-order noise of a
-    # near-zero gradient into a full +-lr step for a handful of weights; two eager runs differ by 2-3e-3 as well)
-    assert l2_err(m2._store.flat, m1._store.flat) < 6e-3
+    # parameters after the trajectory agree too — loosely: Adam's m/sqrt(v) turns the atomics-order noise of a
+    # near-zero gradient into a full +-lr step per iteration for those weights, so two runs of the SAME eager code
+    # already differ by 2e-3..1e-2 in relative L2; a skipped or doubled update would show up as >= 1e-1
+    assert l2_err(m2._store.flat, m1._store.flat) < 3e-2
+    assert float((m2._store.flat - m1._store.flat).abs().max()) <= 2 * (warm + 4) * 3.2e-3   # |Adam step| <= 3.2 lr
     assert int(m2.encoder.bn1.num_batches_tracked) == int(m1.encoder.bn1.num_batches_tracked)
 
 
