@@ -283,8 +283,8 @@ def test_graphed_step_matches_eager_steps():
         step.stage(xs[i].pin_memory(), ts[i].pin_memory())
         got.append(float(step()))
     assert step.launches_per_step > 50
-    for a, b in zip(eager[warm:], got):
-        assert abs(a - b) <= 1e-3 * abs(a), (eager, got)
+    for i, (a, b) in enumerate(zip(eager[warm:], got)):   # same state at the first step; noise compounds afterwards
+        assert abs(a - b) <= (1e-3 if i == 0 else 5e-3) * abs(a), (eager, got)
     # parameters after the trajectory agree too — loosely: Adam's m/sqrt(v) turns the atomics-order noise of a
     # near-zero gradient into a full +-lr step per iteration for those weights, so two runs of the SAME eager code
     # already differ by 2e-3..1e-2 in relative L2; a skipped or doubled update would show up as >= 1e-1
@@ -339,4 +339,4 @@ def test_graphed_phases_match_eager_adversarial_steps():
     got = [float(step(xs, ts, xt)) for _ in range(steps)]
     assert step.launches_per_step > 60
     for a, b in zip(eager[warm + 1:], got):
-        assert abs(a - b) <= 2e-3 * abs(a), (eager, got)
+        assert abs(a - b) <= 5e-3 * abs(a), (eager, got)
