@@ -426,7 +426,15 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
   }
   p.out = (bf16*)g.out; p.out_nchw = g.out_nchw; p.bias = g.bias; p.addend = (const bf16*)g.addend;
   p.bn_sums = g.bn_sums;
-  { const char* e = getenv("UDA_B200_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }
+  {
+    const char* e = getenv("UDA_B200_TC_DEBUG");
+    p.debug = e ? atoi(e) : 0;
+    static bool warned = false;
+    if (p.debug && !warned) {
+      fprintf(stderr, "uda_b200: UDA_B200_TC_DEBUG=%d is a TIMING EXPERIMENT (work is skipped): convolution results are WRONG\n", p.debug);
+      warned = true;
+    }
+  }
   p.st_a = (const bf16*)g.st_a; p.st_z = (const bf16*)g.st_z; p.st_slope = g.st_slope; p.st_sums = g.st_sums;
   UDA_REQUIRE(!(g.bn_sums && g.st_sums), UDA_ERR_BAD_ARG, "conv_tc_persist: forward and backward statistics are exclusive");
   UDA_REQUIRE(!g.st_sums || (g.st_a && g.out), UDA_ERR_BAD_ARG, "conv_tc_persist: backward statistics need `a` and an NHWC output");
