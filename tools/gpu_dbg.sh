@@ -1,5 +1,8 @@
 #!/bin/bash
-for a in 0 6 4; do
-  echo "== UDA_B200_WGRAD_APG=$a =="
-  UDA_B200_WGRAD_APG=$a timeout 300 python tools/conv_bench.py 2>&1 | awk -F'|' '{print $1, $4}' | grep -E "layer2|layer3|layer4|dec0|dec1|dec2.c1|l2.0|l3.0|l4.0|totals"
+# in-graph cost of kernel families: step time with their work removed (timing experiments, wrong numerics)
+for cfg in "0 0" "0 1" "7 0" "7 1"; do
+  set -- $cfg
+  UDA_B200_TC_DEBUG=$1 UDA_B200_BN_DEBUG=$2 timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('TC_DEBUG=$1 BN_DEBUG=$2  ms/step', round(d['ms_per_step'],3))"
 done
