@@ -8,6 +8,10 @@ One step = one pass of the hot path over one batch of synthetic input:
               zero_grad, forward, cross-entropy, backward, Adam step   (reference src/models/train.py:336-346)
   adversarial (configs[2]): the reference's discriminator step + generator step on a source and a target
               batch (src/models/adversarial_trainer.py:76-114), 8+8 images per GPU
+  finetune    (configs[3]): unsupervised target-domain fine-tuning — two views of a target batch through the
+              network, FineTuningLoss (ramped symmetric-KL consistency + domain confusion,
+              src/models/losses.py:256-342) + entropy minimisation, clip_grad_norm 1.0, Adam
+              (src/models/unsupervised_trainer.py:99-150); 4 images per GPU (global 32 on 8 GPUs)
 For N>1 the script is launched by torchrun (one rank per GPU, NCCL); each rank processes its own batch
 (weak scaling) and gradients are all-reduced in buckets overlapped with backward.  Rank 0 prints ONE JSON line.
 `--impl reference` times the reference's own CPU path (oracle port: fp32 PyTorch on all host cores).
@@ -203,13 +207,22 @@ def run_ours(args):
     model = U.Unet("resnet34", encoder_weights=None, in_channels=3, classes=CLASSES).to(dev).train()
     nets = [model]
     adversarial = args.workload == "adversarial"
+    finetune = args.workload == "finetune"
+    if finetune:
+        B = args.batch = min(args.batch, 4) if args.batch == 16 else args.batch   # configs[3]: 4 images per GPU
     graph_adv = adversarial and world == 1 and not args.no_graph
     if adversarial:
         disc = DomainDiscriminator(3).to(dev).train()
         nets.append(disc)
         dopt = FusedAdam(disc, lr=1e-4, capturable=graph_adv)
         adv = AdversarialLoss(0.001)
-    opt = FusedAdam(model, lr=1e-3, capturable=graph_adv)
+    if finetune:
+        from uda_aerial_semantic_segmentation_research_b200.losses import FineTuningLoss, EntropyMinimizationLoss
+        disc = DomainDiscriminator(3).to(dev).train()      # frozen critic: only its prediction enters the loss
+        for q in disc.parameters():
+            q.requires_grad_(False)
+        ft_loss, ent_loss = FineTuningLoss(), EntropyMinimizationLoss(0.1)
+    opt = FusedAdam(model, lr=1e-3, capturable=graph_adv, max_grad_norm=1.0 if finetune else None)
     crit = CrossEntropyLoss()
     graph_adv_dp = adversarial and world > 1 and not args.no_graph
     if world > 1:
@@ -223,18 +236,40 @@ def run_ours(args):
     xt = synthetic_batch(Bs, size, 4321 + rank, dev)[0] if adversarial else None
     hx, ht = synthetic_batch(Bs, size, 1234 + rank, pinned=True)
     hxt = synthetic_batch(Bs, size, 4321 + rank, pinned=True)[0] if adversarial else None
+    if finetune:   # second view = flipped + jittered copy (stand-in for the strong augmentation)
+        gq = torch.Generator().manual_seed(77 + rank)
+        hxt = (hx.flip(-1) + 0.1 * torch.randn(hx.shape, generator=gq)).pin_memory()
+        xt = hxt.to(dev)
 
     graphed = None
-    if not adversarial and not args.no_graph:
+    if not adversarial and not finetune and not args.no_graph:
         from uda_aerial_semantic_segmentation_research_b200.graph import GraphedStep
         graphed = GraphedStep(model, crit, opt, x, t)
 
     def step(xs, ts, xtg):
         if graphed is not None:
-            return graphed(xs, ts, xtg) if adversarial else graphed(xs, ts)
+            return graphed(xs, ts, xtg) if (adversarial or finetune) else graphed(xs, ts)
         return eager_step(xs, ts, xtg)
 
+    def ft_compute(xs, ts, xtg):   # src/models/unsupervised_trainer.py:99-150
+        opt.zero_grad()
+        p1, p2 = model(xs), model(xtg)
+        with torch.no_grad():
+            dpred = disc(xs)
+        total = ft_loss(p1, p2, dpred, 40)["total"] + ent_loss(p1)
+        total.backward()
+        return total.detach()
+
+    def ft_finish():
+        if world > 1:
+            dist.all_reduce(model._store.grad, op=dist.ReduceOp.AVG)
+        opt.step()
+
     def eager_step(xs, ts, xtg):
+        if finetune:
+            out = ft_compute(xs, ts, xtg)
+            ft_finish()
+            return out
         if adversarial:   # src/models/adversarial_trainer.py:84-114
             dopt.zero_grad()
             d_loss = adv.discriminator_loss(disc(xs), disc(xtg))
@@ -254,6 +289,11 @@ def run_ours(args):
     if graph_adv:
         from uda_aerial_semantic_segmentation_research_b200.graph import GraphedFn
         graphed = GraphedFn(eager_step, [x, t, xt], [model, disc])
+    if finetune and not args.no_graph:
+        from uda_aerial_semantic_segmentation_research_b200.graph import GraphedPhases
+        for n in nets:
+            n._grad_sync = None
+        graphed = GraphedPhases([(ft_compute, ft_finish)], [x, t, xt], [model, disc])
     if graph_adv_dp:
         from uda_aerial_semantic_segmentation_research_b200.graph import GraphedPhases
 
@@ -316,7 +356,7 @@ def run_ours(args):
     def e2e_step():
         xs = hx.to(dev, non_blocking=True)
         ts = ht.to(dev, non_blocking=True)
-        xtg = hxt.to(dev, non_blocking=True) if adversarial else None
+        xtg = hxt.to(dev, non_blocking=True) if (adversarial or finetune) else None
         return step(xs, ts, xtg).item()
 
     def e2e_pipelined(steps):
@@ -328,14 +368,14 @@ def run_ours(args):
                 graphed.stage(hx, ht)
             loss.item()
 
-    if graphed is not None and not adversarial:
+    if graphed is not None and not adversarial and not finetune:
         e2e_pipelined(2)
         ms_e2e = timed(lambda: e2e_pipelined(args.steps), 1)
     else:
         for _ in range(2):
             e2e_step()
         ms_e2e = timed(e2e_step, args.steps)
-    h2d = hx.numel() * 4 + ht.numel() * 8 + (hxt.numel() * 4 if adversarial else 0)
+    h2d = hx.numel() * 4 + ht.numel() * 8 + (hxt.numel() * 4 if (adversarial or finetune) else 0)
     e2e = {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
 
     # ---- per-kernel CUDA-event profile of a few steps (rank 0): roofline of the dominant kernel ----
@@ -383,20 +423,29 @@ def run_ours(args):
     # HBM-bound loss kernel (second half of BASELINE's metric): algorithmic bytes 2*P*C*4 + 8*P (fp32 NCHW logits read,
     # int64 targets read, fp32 gradient written) over its CUDA-event time inside the profiled steps
     hbm_kernels = None
-    if rank == 0 and "seg_loss_fwd_bwd" in breakdown and breakdown["seg_loss_fwd_bwd"]["ms_per_step"] > 0:
-        P = Bs * size * size
-        nbytes = 2.0 * P * CLASSES * 4 + 8.0 * P
-        t_ms = breakdown["seg_loss_fwd_bwd"]["ms_per_step"]
-        gbs = nbytes / (t_ms * 1e-3) / 1e9
-        hbm_kernels = {"seg_loss_fwd_bwd": {"bound": "hbm", "achieved": gbs, "peak": peaks()["hbm_gbs"], "unit": "GB/s",
-                                            "frac": gbs / peaks()["hbm_gbs"], "frac_of_8TBs_nominal": gbs / 8000.0,
-                                            "algorithmic_mb_per_launch": nbytes / 1e6, "ms_per_step": t_ms,
-                                            "note": "includes the finalize / rescale launches of the entry point"}}
+    if rank == 0:
+        P = float(Bs * size * size)
+        # algorithmic bytes per launch, fp32 NCHW logits as the reference passes them
+        alg = {"seg_loss_fwd_bwd": 2.0 * P * CLASSES * 4 + 8.0 * P,      # CE: logits read, targets read, gradient written
+               "consistency_fwd_bwd": 4.0 * P * CLASSES * 4,             # two logit tensors read, two gradients written
+               "entropy_fwd_bwd": 2.0 * P * CLASSES * 4}
+        for name, nbytes in alg.items():
+            if name in breakdown and breakdown[name]["ms_per_step"] > 0:
+                n_launch = max(breakdown[name]["launches_per_step"], 1.0)
+                t_ms = breakdown[name]["ms_per_step"] / n_launch
+                gbs = nbytes / (t_ms * 1e-3) / 1e9
+                hbm_kernels = hbm_kernels or {}
+                hbm_kernels[name] = {"bound": "hbm", "achieved": gbs, "peak": peaks()["hbm_gbs"], "unit": "GB/s",
+                                     "frac": gbs / peaks()["hbm_gbs"], "frac_of_8TBs_nominal": gbs / 8000.0,
+                                     "algorithmic_mb_per_launch": nbytes / 1e6, "ms_per_launch": t_ms,
+                                     "note": "includes the finalize / rescale launches of the entry point"}
 
     out = None
     if rank == 0:
         wl = (f"supervised source-domain training, U-Net resnet34, batch {B}/GPU @{size}x{size}, {CLASSES} classes, "
-              "CE loss + Adam (BASELINE configs[1])") if not adversarial else \
+              "CE loss + Adam (BASELINE configs[1])") if not (adversarial or finetune) else \
+             (f"unsupervised target-domain fine-tuning (two views, FineTuningLoss consistency + domain confusion + entropy "
+              f"minimisation, clip 1.0, Adam), U-Net resnet34, {B} images/GPU @{size}x{size} (BASELINE configs[3])") if finetune else \
              (f"adversarial UDA step (D step + G step), U-Net resnet34 + image discriminator, {Bs}+{Bs} images/GPU "
               f"@{size}x{size} (BASELINE configs[2])")
         out = {
@@ -407,6 +456,7 @@ def run_ours(args):
                        "parallelism": f"dp{world}", "l2": "inputs+activations per step (>3 GB) exceed the 126 MB L2",
                        "launch": (("cuda-graph replay of the D-step and G-step compute phases, all-reduce + fused Adam "
                                    "after each" if world > 1 else "cuda-graph replay of the whole D/G step") if adversarial else
+                                  "cuda-graph replay of the compute phase, then all-reduce + clip + fused Adam" if finetune else
                                   "cuda-graph replay of fwd+loss+bwd, then all-reduce + fused Adam") if graphed is not None
                                  else "eager launches"},
             "e2e": e2e, "gpu_launches": launches, "clocks": sampler.result(),
@@ -428,7 +478,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="supervised", choices=["supervised", "adversarial"])
+    ap.add_argument("--workload", default="supervised", choices=["supervised", "adversarial", "finetune"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--ref-batch", type=int, default=2, help="bounded sample batch of the reference arm")

@@ -287,7 +287,7 @@ class FineTuningLoss(nn.Module):
             consistency = consistency_t.detach()
         domain_confusion = self.domain_loss.generator_loss(domain_pred)
         total = weighted_consistency + domain_confusion * float(self.domain_weight * ramp)
-        supervised = torch.tensor(0.0, device=pred1.device)
+        supervised = torch.zeros((), device=pred1.device)   # (a fill kernel: capturable in a CUDA graph)
         if supervised_pred is not None and supervised_target is not None:
             if supervised_target.dtype != torch.long:
                 supervised_target = supervised_target.long()
