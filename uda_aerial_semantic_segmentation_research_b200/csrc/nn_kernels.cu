@@ -1234,11 +1234,17 @@ extern "C" int uda_gap_linear_sigmoid_fwd(const void* x, int dtype, const float*
   UDA_REQUIRE(x && w && bias && pooled && out && B > 0 && HW > 0 && C > 0, UDA_ERR_BAD_ARG, "gap_linear: bad argument");
   if (dtype == UDA_BF16 && C % 8 == 0 && C / 8 <= 256 && 256 % (C / 8) == 0 && HW >= 64 && HW < (1 << 24) && B <= 1024 &&
       aligned<bf16>(x, 16)) {
-    static unsigned int* counters = nullptr;   // one "slices done" counter per image, left at zero by every launch
-    if (!counters) {
-      UDA_CUDA_OK(cudaMalloc(&counters, 1024 * sizeof(unsigned int)));
-      UDA_CUDA_OK(cudaMemset(counters, 0, 1024 * sizeof(unsigned int)));
+    // one "slices done" counter per image, left at zero by every launch; one array per device (allocated on first
+    // use, which GraphedStep / GraphedFn / GraphedPhases guarantee to happen in their eager warm-up, not under capture)
+    static unsigned int* counters_of[64] = {};
+    int devid = 0;
+    UDA_CUDA_OK(cudaGetDevice(&devid));
+    UDA_REQUIRE(devid >= 0 && devid < 64, UDA_ERR_UNSUPPORTED, "gap_linear: device index %d", devid);
+    if (!counters_of[devid]) {
+      UDA_CUDA_OK(cudaMalloc(&counters_of[devid], 1024 * sizeof(unsigned int)));
+      UDA_CUDA_OK(cudaMemset(counters_of[devid], 0, 1024 * sizeof(unsigned int)));
     }
+    unsigned int* counters = counters_of[devid];
     UDA_CUDA_OK(cudaMemsetAsync(pooled, 0, (size_t)B * C * sizeof(float), st));
     int slices = (int)(HW / 32);
     const int cap = (2 * num_sms() + B - 1) / B;
