@@ -187,3 +187,100 @@ def test_ddp_gloo_world2():
     for p in procs:
         p.join(60)
     assert same_grads and same_weights and gsum > 0 and nb > 1
+
+
+def test_shadow_freshness_key_tracks_parameter_writes(cpu_engine):
+    """parameters are views of the flat buffer with their OWN version counters — the key that
+    decides whether the bf16 shadow weights are stale must move on in-place writes through the nn.Parameter
+    (torch.optim.Adam as at reference train.py:461, load_state_dict as at phase_manager.py:140, p.copy_)."""
+    U = cpu_engine
+    torch.manual_seed(5)
+    m = U.Unet("resnet18", classes=3, compute_dtype=torch.float64)
+    st = m._store
+    st.ensure_flat(torch.device("cpu"))
+    k0 = st.param_version()
+    with torch.no_grad():
+        next(m.parameters()).add_(1.0)
+    k1 = st.param_version()
+    assert k1 != k0
+    m.load_state_dict(RefUnet("resnet18", classes=3).state_dict())
+    k2 = st.param_version()
+    assert k2 != k1
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    F.cross_entropy(m(torch.randn(1, 3, 32, 32)).double(), torch.randint(0, 3, (1, 32, 32))).backward()
+    opt.step()
+    assert st.param_version() != k2
+    # the parameters still live in the flat buffer after all of that (no silent re-allocation)
+    base = st.flat.data_ptr()
+    assert all(p.data_ptr() == base + st.flat.element_size() * st.offsets[id(p)] for p in st.params)
+
+
+def test_decoder_standalone_with_detached_features(cpu_engine):
+    """model.decoder(*features) on features that need no gradient (frozen / no_grad encoder),
+    followed by backward, must train the decoder instead of raising in upcat's backward."""
+    U = cpu_engine
+    torch.manual_seed(6)
+    ref = RefUnet("resnet18", classes=3)
+    m = U.Unet("resnet18", classes=3, compute_dtype=torch.float64)
+    m.load_state_dict(ref.state_dict())
+    ref = ref.double()
+    x = torch.randn(1, 3, 64, 64)
+    with torch.no_grad():
+        feats = m.encoder(x)
+        feats_r = ref.encoder(x.double())
+    assert not any(f.requires_grad for f in feats)
+    z = m.segmentation_head(m.decoder(*feats))
+    zr = ref.segmentation_head(ref.decoder(*feats_r))
+    assert rel_err(z.detach(), zr.detach()) < 1e-6
+    (z.double() ** 2).sum().backward()
+    (zr ** 2).sum().backward()
+    got = dict(m.named_parameters())
+    for n, p2 in ref.named_parameters():
+        if n.startswith("encoder."):
+            continue
+        assert rel_err(got[n].grad, p2.grad) < 1e-5, n
+
+
+def test_fused_adam_is_a_torch_optimizer(cpu_engine, monkeypatch):
+    """the reference trainers read optimizer.param_groups[0]['lr'] (train.py:361,
+    adversarial_trainer.py:58), LR schedulers write it, and checkpoints hold optimizer.state_dict()
+    (train.py:496,678) — FusedAdam must honour all three, and a restored optimizer must continue identically."""
+    U = cpu_engine
+    from uda_aerial_semantic_segmentation_research_b200 import optim
+    monkeypatch.setattr(optim, "ops", ref_ops)
+    torch.manual_seed(8)
+    m = U.Unet("resnet18", classes=3, compute_dtype=torch.float64)
+    opt = optim.FusedAdam(m, lr=1e-3)
+    assert isinstance(opt, torch.optim.Optimizer)
+    assert opt.param_groups[0]["lr"] == 1e-3 and opt.param_groups[0]["betas"] == (0.9, 0.999)
+    sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.5)
+    x, t = torch.randn(1, 3, 32, 32), torch.randint(0, 3, (1, 32, 32))
+
+    def one_step(o):
+        o.zero_grad()
+        F.cross_entropy(m(x).double(), t).backward()
+        o.step()
+
+    one_step(opt)
+    sched.step()
+    assert opt.param_groups[0]["lr"] == 5e-4 and opt.lr == 5e-4
+    one_step(opt)
+    sd = opt.state_dict()
+    assert sd["state"][0]["step"] == 2 and sd["param_groups"][0]["lr"] == 5e-4
+    w = m._store.flat.clone()
+    one_step(opt)
+    w_next = m._store.flat.clone()
+    # restore parameters + optimizer state into a fresh optimizer: the third step must repeat exactly
+    with torch.no_grad():
+        m._store.flat.copy_(w)
+    opt2 = optim.FusedAdam(m, lr=123.0)
+    opt2.load_state_dict(sd)
+    assert opt2.param_groups[0]["lr"] == 5e-4 and opt2.step_count == 2
+    one_step(opt2)
+    assert torch.equal(m._store.flat, w_next)
+    # step() without a backward after zero_grad() is refused (no stale gradients)
+    opt2.zero_grad()
+    with pytest.raises(RuntimeError):
+        opt2.step()
+    with pytest.raises(TypeError):
+        optim.FusedAdam(list(m.parameters()))

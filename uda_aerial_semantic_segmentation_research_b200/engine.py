@@ -127,6 +127,7 @@ class ParamStore:
         self.shadow = None
         self.shadow_version = None
         self.grad = None
+        self.grad_dropped = False   # zero_grad() since the last backward (FusedAdam refuses to step on stale gradients)
 
     # -- parameters -------------------------------------------------------------------------
     def _view_like(self, flat, p):
@@ -156,26 +157,36 @@ class ParamStore:
         self.shadow_ft_version = None
         self._ft_table = None
 
+    def param_version(self):
+        """Freshness key of the bf16 shadow copies.  The parameters are re-pointed into the flat buffer with
+        ``p.data = view``, so every ``nn.Parameter`` keeps its OWN version counter: in-place writes through the
+        parameter (``torch.optim.Adam``, ``load_state_dict``, ``p.copy_``) bump ``p._version`` and never
+        ``flat._version``.  The key is therefore the sum over the parameters (plus the flat buffer's, for writes
+        through it); the fused Adam kernel refreshes the shadow itself and calls ``mark_shadow_fresh``."""
+        return self.flat._version + sum(p._version for p in self.params)
+
     def refresh_shadow(self, force=False):
-        ver = self.flat._version
+        ver = self.param_version()
         if force or self.shadow_version != ver:
             ops.cast_f32(self.flat, self.shadow)
             self.shadow_version = ver
+            self.shadow_ft_version = None
 
     def mark_shadow_fresh(self):
-        self.shadow_version = self.flat._version
+        self.shadow_version = self.param_version()
         self.shadow_ft_version = None
 
     def w_ft(self, p):
         """[Cin][KH][KW][Cout] flipped/transposed bf16 copy of conv weight ``p`` (dgrad on the tensor cores);
         all copies are refreshed together, lazily, the first time a backward needs them after an update."""
-        if self.shadow_ft_version != self.flat._version or self.shadow_ft_version is None:
+        ver = self.param_version()
+        if self.shadow_ft_version != ver or self.shadow_ft_version is None:
             if self._ft_table is None:
                 rows = [[self.offsets[id(q)]] + [q.shape[0], q.shape[1], q.shape[2], q.shape[3]]
                         for q in self.params if q.dim() == 4]
                 self._ft_table = torch.tensor(rows, dtype=torch.int32, device=self.flat.device).contiguous()
             ops.weight_flip_transpose_batch(self.shadow, self.shadow_ft, self._ft_table)
-            self.shadow_ft_version = self.flat._version
+            self.shadow_ft_version = ver
         off = self.offsets[id(p)]
         O, I, KH, KW = p.shape
         return self.shadow_ft[off:off + p.numel()].view(I, KH, KW, O)
@@ -190,6 +201,7 @@ class ParamStore:
     # -- gradients --------------------------------------------------------------------------
     def new_grad(self):
         self.grad = torch.zeros(self.total, dtype=torch.float32, device=self.flat.device)
+        self.grad_dropped = False
         return self.grad
 
     def g(self, p):
@@ -421,10 +433,12 @@ def upcat(ctx, xin, skip):
                 return
             dx, dskip = ops.upcat_bwd(out.g, C1, C2)
             out.g = None
-            if xin.g is not None or (skip is not None and skip.g is not None):
+            # `False` marks an input that needs no gradient (detached features given to the stand-alone decoder)
+            if isinstance(xin.g, torch.Tensor) or (skip is not None and isinstance(skip.g, torch.Tensor)):
                 raise RuntimeError("upcat: inputs are expected to have no earlier gradient on the tape")
-            xin.g = dx
-            if skip is not None:
+            if xin.g is not False:
+                xin.g = dx
+            if skip is not None and skip.g is not False:
                 skip.g = dskip
         ctx.tape.push(bwd)
     return out

@@ -94,6 +94,8 @@ class GraphedStep:
             self.staged_free.record()
             self._staged = False
         self.graph.replay()
+        for m in self.models:
+            m._store.grad_dropped = False    # the replayed backward refilled the flat gradient buffers
         self._finish()
         return self.loss
 
@@ -158,6 +160,7 @@ class GraphedPhases:
             if getattr(m, "_grad_sync", None) is not None:
                 raise RuntimeError("GraphedPhases: detach GradSync (net._grad_sync = None) and all-reduce in finish_fn")
         self.inputs = [t.clone() for t in example_inputs]
+        self.networks = list(networks)
         self.finish = [f for _, f in phases]
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream())
@@ -189,5 +192,7 @@ class GraphedPhases:
             dst.copy_(src, non_blocking=True)
         for g, finish in zip(self.graphs, self.finish):
             g.replay()
+            for m in self.networks:
+                m._store.grad_dropped = False
             finish()
         return self.outs[-1]

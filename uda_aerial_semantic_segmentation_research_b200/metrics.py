@@ -28,17 +28,25 @@ class SegmentationMetrics:
         self.num_classes = num_classes
         self.ignore_index = ignore_index
 
-    def hist_tensor(self, pred: torch.Tensor, true: torch.Tensor, hist: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def hist_tensor(self, pred: torch.Tensor, true: torch.Tensor, hist: Optional[torch.Tensor] = None,
+                    return_bad: bool = False):
         """Device-resident int64 [C,C] confusion matrix (rows = true, cols = pred); accumulates into
-        ``hist`` when given — no host synchronisation."""
+        ``hist`` when given — no host synchronisation.  ``return_bad``: also return the device counter of pixels
+        whose PREDICTION is outside [0, C) (the reference's ``bincount(...).reshape(C, C)`` raises on those)."""
         p = _idx(pred, "SegmentationMetrics")
         t = _idx(true, "SegmentationMetrics").long()
-        h, _bad = ops.confmat(p, t, self.num_classes, self.ignore_index, hist=hist)
-        return h
+        h, bad = ops.confmat(p, t, self.num_classes, self.ignore_index, hist=hist)
+        return (h, bad) if return_bad else h
 
     def _fast_hist(self, pred: torch.Tensor, true: torch.Tensor) -> np.ndarray:
         """``metrics.py:17-27``: bincount(C*true+pred) over pixels with 0 <= true < C (and != ignore)."""
-        return self.hist_tensor(pred, true).cpu().numpy()
+        h, bad = self.hist_tensor(pred, true, return_bad=True)
+        h = h.cpu().numpy()
+        nbad = int(bad.item())
+        if nbad:
+            raise ValueError(f"SegmentationMetrics: {nbad} predictions lie outside [0, {self.num_classes}) "
+                             "(the reference's bincount/reshape fails on such input)")
+        return h
 
     def batch_iou(self, predictions: torch.Tensor, targets: torch.Tensor) -> dict:
         """``metrics.py:29-42``."""

@@ -65,11 +65,20 @@ def _chk(t, name, dtype=None):
     return t
 
 
+_WS_RETIRED = []
+
+
 def workspace(nbytes, device):
-    """Stream-ordered scratch (re-used by consecutive launches on the same stream)."""
-    key = (device.index if device.index is not None else torch.cuda.current_device())
+    """Stream-ordered scratch (re-used by consecutive launches on the same stream).  One block per (device, stream):
+    launches on different streams never share scratch.  A block that has to grow is RETIRED, not freed — a captured
+    CUDA graph may have baked its address in, and handing the memory back to the caching allocator would let graph
+    replays scribble over somebody else's tensor."""
+    dev = device.index if device.index is not None else torch.cuda.current_device()
+    key = (dev, torch.cuda.current_stream(dev).cuda_stream)
     ws = _WS.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            _WS_RETIRED.append(ws)
         ws = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
         _WS[key] = ws
     return ws
@@ -575,6 +584,13 @@ def bce_logits(x, label, scale=1.0, out=None, accumulate=False, want_grad=True):
     return out, grad
 
 
+def _chk_hist(hist, C, who):
+    """A caller-supplied accumulator is indexed as C*C int64 by the kernels: anything else is out of bounds."""
+    _chk(hist, f"{who}.hist", torch.int64)
+    if tuple(hist.shape) != (C, C):
+        raise _lib.UdaError(f"{who}: hist must be an int64 [{C},{C}] tensor (got {tuple(hist.shape)})")
+
+
 def argmax_confmat(logits, target=None, num_classes=None, ignore_index=None, want_mask=True, mask_dtype=torch.int64,
                    hist=None):
     """argmax over dim 1 (+ confusion matrix against ``target``).  Returns (mask | None, hist | None)."""
@@ -598,6 +614,8 @@ def argmax_confmat(logits, target=None, num_classes=None, ignore_index=None, wan
         if hist is None:
             hist = torch.empty((C, C), dtype=torch.int64, device=logits.device)
             zero = 1
+        else:
+            _chk_hist(hist, C, "argmax_confmat")
     call("argmax_confmat", ptr(logits), ci(dt(logits)), ptr(target), ptr(mask64), ptr(mask8),
          ptr(hist) if target is not None else ptr(None), ci(B), ci(C), ll(HW),
          ll(ignore_index if ignore_index is not None else 0), ci(0 if ignore_index is None else 1), ci(zero), _stream())
@@ -619,6 +637,8 @@ def confmat(pred, target, num_classes, ignore_index=None, hist=None):
     if hist is None:
         hist = torch.empty((num_classes, num_classes), dtype=torch.int64, device=pred.device)
         zero = 1
+    else:
+        _chk_hist(hist, num_classes, "confmat")
     bad = torch.empty(1, dtype=torch.int64, device=pred.device)
     call("confmat", ptr(pred), ci(pd), ptr(target), ptr(hist), ptr(bad), ll(pred.numel()), ci(num_classes),
          ll(ignore_index if ignore_index is not None else 0), ci(0 if ignore_index is None else 1), ci(zero), _stream())

@@ -56,7 +56,7 @@ def sliding_window_evaluate(model, tile, target, num_classes, window=512, batch=
     masks = []
     for i in range(0, wins.shape[0], batch):
         logits = model(wins[i:i + batch].contiguous())
-        m, _ = ops.argmax_confmat(logits.contiguous(), tw[i:i + batch].contiguous().long(),
+        m, _ = ops.argmax_confmat(logits.contiguous(), tw[i:i + batch].contiguous().long(), num_classes=num_classes,
                                   ignore_index=ignore_index, want_mask=return_mask, hist=hist)
         if return_mask:
             masks.append(m)
