@@ -38,8 +38,13 @@ def golden_dir():
 def rel_err(a, b):
     """max-norm relative error  ||a-b||_inf / (||b||_inf + eps)  (SURVEY.md 8d parity metric)."""
     import torch
-    a = torch.as_tensor(a).double().cpu()
-    b = torch.as_tensor(b).double().cpu()
+    a, b = torch.as_tensor(a), torch.as_tensor(b)
+    if a.is_cuda and b.is_cuda and a.device == b.device:   # large tensors: reduce on the device
+        d = float((a.double() - b.double()).abs().max()) if a.dtype == torch.float64 or a.numel() < (1 << 24) \
+            else float((a.float() - b.float()).abs().max())
+        return d / (float(b.abs().max()) + 1e-30)
+    a = a.double().cpu()
+    b = b.double().cpu()
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 

@@ -1,0 +1,104 @@
+"""GPU parity AT THE BENCHMARKED SHAPE ("no parity test at the benchmarked shape"): every convolution
+family of U-Net r34 at B = 16 and its true H x W for a 512 x 512 input — the shapes for which the tile / kernel
+selection in the launchers (persistent 256x128 / 128x256 / 256x256 tiles, weight-stationary mode, halo rows,
+pitched halo, pair kernels, multi-accumulator wgrad groups) is the one ``bench.py`` times.  Reference = the oracle op
+(``oracle/ref_ops``: F.conv2d / torch.nn.grad in fp32, TF32 off) executed ON THE DEVICE on the same bf16 inputs.
+Tolerances as in test_gpu_conv_tc.py: bf16 outputs 1e-2 of the tensor's max, fp32 weight gradients 2e-3."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import ref_ops as R
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+B, S = 16, 512
+s2, s4, s8, s16, s32 = S // 2, S // 4, S // 8, S // 16, S // 32
+FAMILIES = [
+    # name, H(=W), Cin, Cout, k, stride
+    ("layer1", s4, 64, 64, 3, 1), ("l2.0_s2", s4, 64, 128, 3, 2), ("l2_ds_1x1_s2", s4, 64, 128, 1, 2),
+    ("layer2", s8, 128, 128, 3, 1), ("l3.0_s2", s8, 128, 256, 3, 2), ("layer3", s16, 256, 256, 3, 1),
+    ("l4.0_s2", s16, 256, 512, 3, 2), ("layer4", s32, 512, 512, 3, 1), ("dec0.c1", s16, 768, 256, 3, 1),
+    ("dec0.c2", s16, 256, 256, 3, 1), ("dec1.c1", s8, 384, 128, 3, 1), ("dec1.c2", s8, 128, 128, 3, 1),
+    ("dec2.c1", s4, 192, 64, 3, 1), ("dec2.c2", s4, 64, 64, 3, 1), ("dec3.c1", s2, 128, 32, 3, 1),
+    ("dec3.c2", s2, 32, 32, 3, 1), ("dec4.c1", S, 32, 16, 3, 1), ("dec4.c2", S, 16, 16, 3, 1),
+    ("head", S, 16, 24, 3, 1),
+]
+
+
+@pytest.fixture(autouse=True)
+def _true_fp32():
+    a, b = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = a, b
+    torch.cuda.empty_cache()
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    return (torch.randn(shape, generator=g, device=DEV) * scale).bfloat16()
+
+
+@pytest.mark.parametrize("fam", FAMILIES, ids=[f[0] for f in FAMILIES])
+def test_conv_family_at_benchmark_shape(fam):
+    from uda_aerial_semantic_segmentation_research_b200 import ops
+    name, H, Cin, Cout, k, s = fam
+    p = (k - 1) // 2
+    assert ops.tc_supported(0, B, H, H, Cin, Cout, k, k, s, p)
+    x = _rand((B, H, H, Cin), 1)
+    w = _rand((Cout, k, k, Cin), 2, (k * k * Cin) ** -0.5)
+    # forward with the fused BatchNorm statistics (what the training step launches)
+    yr = R.conv_fwd(x.float(), w.float(), None, s, p)
+    sums = torch.zeros(2 * Cout, dtype=torch.float64, device=DEV)
+    y = ops.conv_fwd(x, w, None, s, p, bn_sums=sums)
+    assert rel_err(y.float(), yr) < 1e-2, name
+    yf = y.double().reshape(-1, Cout)
+    assert rel_err(sums[Cout:], (yf * yf).sum(0)) < 1e-4
+    assert float((sums[:Cout] - yf.sum(0)).abs().max()) < 1e-3 * float(yf.abs().sum(0).max())
+    if name == "head":      # fp32 NCHW edge output with bias
+        bias = torch.randn(Cout, device=DEV)
+        yn = ops.conv_fwd(x, w, bias, s, p, nchw_out=True)
+        assert rel_err(yn, R.conv_fwd(x.float(), w.float(), bias, s, p, nchw_out=True)) < 2e-3
+    del yf
+    # dgrad accumulating into an existing gradient (residual / skip consumers)
+    dy = _rand(tuple(yr.shape), 3)
+    del yr, y
+    dxr = R.conv_dgrad(dy.float(), w.float(), x.shape, s, p)
+    add = _rand(tuple(x.shape), 4)
+    acc = add.clone()
+    out = ops.conv_dgrad(dy, w, x.shape, s, p, addend=acc)
+    assert out.data_ptr() == acc.data_ptr()
+    assert rel_err(out.float(), dxr + add.float()) < 1e-2, name
+    dx = ops.conv_dgrad(dy, w, x.shape, s, p)
+    assert rel_err(dx.float(), dxr) < 1e-2, name
+    del dxr, add, acc, out, dx
+    # wgrad (fp32 accumulation over B*Ho*Wo pixels, atomics across pixel splits)
+    dwr = R.conv_wgrad(dy.float(), x.float(), torch.zeros(Cout, k, k, Cin, device=DEV), s, p)
+    dw = torch.zeros((Cout, k, k, Cin), device=DEV)
+    ops.conv_wgrad(dy, x, dw, s, p)
+    assert rel_err(dw, dwr) < 2e-3, name
+
+
+def test_stem_at_benchmark_shape():
+    """U-Net stem 7x7 stride 2 (Cin = 3) on the tensor cores, B = 16 @ 512 x 512."""
+    from uda_aerial_semantic_segmentation_research_b200 import ops
+    if not ops.stem_supported(B, S, S, 3, 64, 7, 2, 3):
+        pytest.skip("stem path disabled")
+    g = torch.Generator(device=DEV).manual_seed(11)
+    x = torch.randn(B, 3, S, S, generator=g, device=DEV).bfloat16().float()
+    w = _rand((64, 7, 7, 3), 12, 0.1)
+    xs = ops.stem_pack_input(x, 3)
+    sums = torch.zeros(128, dtype=torch.float64, device=DEV)
+    y = ops.stem_fwd(xs, ops.stem_pack_weight(w), None, S, S, 7, 3, bn_sums=sums)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    yr = R.conv_fwd(x_nhwc, w.float(), None, 2, 3)
+    assert rel_err(y.float(), yr) < 1e-2
+    yf = y.double().reshape(-1, 64)
+    assert rel_err(sums[64:], (yf * yf).sum(0)) < 1e-4
+    dy = _rand(tuple(yr.shape), 13)
+    dw = torch.zeros((64, 7, 7, 3), device=DEV)
+    ops.stem_wgrad(dy, xs, dw, S, S, 7, 3)
+    dwr = R.conv_wgrad(dy.float(), x_nhwc, torch.zeros(64, 7, 7, 3, device=DEV), 2, 3)
+    assert rel_err(dw, dwr) < 2e-3

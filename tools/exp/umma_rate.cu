@@ -100,7 +100,9 @@ static int run_check(int N) {
 // ------------------------------------------------------------------------------------------------------------
 struct RateOut { long long mma_clk, tma_clk; };
 
-template <int CG>
+// CE / WE (compile-time powers of two, 0 = never): a tcgen05.commit every CE MMAs, an mbarrier wait + fence every WE MMAs
+// — the issuing thread is ONE in-order thread: whatever it executes between MMAs (runtime divisions!) throttles the pipe
+template <int CG, int CE, int WE>
 __global__ void __launch_bounds__(128, 1)
 rate_kernel(const __grid_constant__ CUtensorMap map_s, RateOut* out, int N, int n_mma, int n_loads, int nboxes) {
   extern __shared__ uint8_t smem_raw[];
@@ -108,13 +110,17 @@ rate_kernel(const __grid_constant__ CUtensorMap map_s, RateOut* out, int N, int 
   const uint32_t a_smem = smem_u32(smem), b_smem = a_smem + 16384, ring = b_smem + 32768;
   uint64_t* bars = (uint64_t*)(smem + 16384 + 32768 + 4 * 16384);
   uint32_t* tmem_slot = (uint32_t*)(bars + 8);
-  const uint32_t done_bar = smem_u32(bars), sbar0 = done_bar + 8;
+  const uint32_t done_bar = smem_u32(bars), sbar0 = done_bar + 8, cbar = done_bar + 40, wbar = done_bar + 48;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t r = CG == 2 ? cluster_ctarank() : 0;
   for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += 128) ((uint32_t*)smem)[i] = 0x3c003c00u;  // small bf16 values
   fence_proxy_async();
   if (warp == 0) {
-    if (lane == 0) { mbar_init(done_bar, 1); for (int s = 0; s < 4; ++s) mbar_init(sbar0 + 8 * s, 1); fence_barrier_init(); }
+    if (lane == 0) {
+      mbar_init(done_bar, 1); for (int s = 0; s < 4; ++s) mbar_init(sbar0 + 8 * s, 1);
+      mbar_init(cbar, 1); mbar_init(wbar, 1); mbar_arrive(wbar);   // wbar: phase 0 already complete
+      fence_barrier_init();
+    }
     __syncwarp();
     if (CG == 2) { tmem_alloc_pair(smem_u32(tmem_slot), 512); tmem_relinquish_pair(); }
     else { tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish(); }
@@ -128,6 +134,7 @@ rate_kernel(const __grid_constant__ CUtensorMap map_s, RateOut* out, int N, int 
       const uint64_t adesc = make_kmajor_desc(a_smem, 128), bdesc = make_kmajor_desc(b_smem, 128);
       const long long t0 = clock64();
       for (int i = 0; i < n_mma; i += 4) {
+        if (WE && (i & (WE - 1)) == 0) { mbar_wait(wbar, 0); tc_fence_after(); }   // as in a real main loop
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           // two accumulators alternate so that consecutive MMAs are independent, as in a two-block tile
@@ -135,6 +142,8 @@ rate_kernel(const __grid_constant__ CUtensorMap map_s, RateOut* out, int N, int 
           if (CG == 2) umma_bf16_pair(acc, adesc + 2ull * k, bdesc + 2ull * k, idesc, 1u);
           else umma_bf16(acc, adesc + 2ull * k, bdesc + 2ull * k, idesc, 1u);
         }
+        // a per-stage "slot free" commit as the pipelined kernels issue it (nobody waits on cbar)
+        if (CE && ((i + 4) & (CE - 1)) == 0) { if (CG == 2) umma_commit_pair(cbar); else umma_commit(cbar); }
       }
       if (CG == 2) umma_commit_pair(done_bar); else umma_commit(done_bar);
       mbar_wait(done_bar, 0);
@@ -163,15 +172,16 @@ rate_kernel(const __grid_constant__ CUtensorMap map_s, RateOut* out, int N, int 
   if (warp == 0) { tc_fence_after(); if (CG == 2) tmem_dealloc_pair(tmem, 512); else tmem_dealloc(tmem, 512); }
 }
 
-template <int CG>
+template <int CG, int CE = 0, int WE = 0>
 static void run_rate(const CUtensorMap& ms, int nboxes, int N, int n_mma, int n_loads, int sms) {
+  const int commit_every = CE, wait_every = WE;
   RateOut* dout; CK(cudaMalloc(&dout, sms * sizeof(RateOut))); CK(cudaMemset(dout, 0, sms * sizeof(RateOut)));
   const size_t smem = 16384 + 32768 + 4 * 16384 + 1024 + 256;
-  CK(cudaFuncSetAttribute(rate_kernel<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CK(cudaFuncSetAttribute(rate_kernel<CG, CE, WE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = CG == 2 ? sms / 2 * 2 : sms;
   for (int rep = 0; rep < 2; ++rep) {
-    if (CG == 2) CK(launch_pair(rate_kernel<CG>, dim3(grid), dim3(128), smem, 0, false, ms, dout, N, n_mma, n_loads, nboxes));
-    else { rate_kernel<CG><<<grid, 128, smem>>>(ms, dout, N, n_mma, n_loads, nboxes); CK(cudaGetLastError()); }
+    if (CG == 2) CK(launch_pair(rate_kernel<CG, CE, WE>, dim3(grid), dim3(128), smem, 0, false, ms, dout, N, n_mma, n_loads, nboxes));
+    else { rate_kernel<CG, CE, WE><<<grid, 128, smem>>>(ms, dout, N, n_mma, n_loads, nboxes); CK(cudaGetLastError()); }
     CK(cudaDeviceSynchronize());
   }
   std::vector<RateOut> h(sms);
@@ -181,7 +191,7 @@ static void run_rate(const CUtensorMap& ms, int nboxes, int N, int n_mma, int n_
     if (h[i].mma_clk) { mma += h[i].mma_clk; ++nm; mmax = std::max(mmax, h[i].mma_clk); }
     if (h[i].tma_clk) { tma += h[i].tma_clk; ++nt; tmax = std::max(tmax, h[i].tma_clk); }
   }
-  printf("rate M=%3d N=%3d mma=%5d loads=%4d :", 128 * CG, N, n_mma, n_loads);
+  printf("rate M=%3d N=%3d mma=%5d loads=%4d commit/%-3d wait/%-3d:", 128 * CG, N, n_mma, n_loads, commit_every, wait_every);
   if (nm) {
     const double clk = mma / nm / n_mma;
     printf("  %.1f clk/MMA (max %.1f)  = %.0f%% of the %d-clk floor", clk, (double)mmax / n_mma, 100.0 * (N / 2.0) / clk, N / 2);
@@ -205,6 +215,18 @@ int main(int argc, char** argv) {
   printf("--- MMA only (operands resident in shared memory)\n");
   for (int N : {16, 32, 64, 128, 256}) run_rate<1>(ms, nboxes, N, 4096, 0, sms);
   for (int N : {32, 64, 128, 256}) run_rate<2>(ms, nboxes, N, 4096, 0, sms);
+  printf("--- MMA with a tcgen05.commit every c MMAs / an (already complete) mbarrier wait + fence every w MMAs\n");
+  run_rate<1, 4, 0>(ms, nboxes, 128, 4096, 0, sms); run_rate<1, 8, 0>(ms, nboxes, 128, 4096, 0, sms);
+  run_rate<1, 16, 0>(ms, nboxes, 128, 4096, 0, sms); run_rate<1, 32, 0>(ms, nboxes, 128, 4096, 0, sms);
+  run_rate<1, 4, 0>(ms, nboxes, 256, 4096, 0, sms); run_rate<1, 8, 0>(ms, nboxes, 256, 4096, 0, sms);
+  run_rate<1, 0, 4>(ms, nboxes, 128, 4096, 0, sms); run_rate<1, 0, 8>(ms, nboxes, 128, 4096, 0, sms);
+  run_rate<1, 0, 16>(ms, nboxes, 128, 4096, 0, sms);
+  run_rate<1, 4, 4>(ms, nboxes, 128, 4096, 0, sms); run_rate<1, 8, 8>(ms, nboxes, 128, 4096, 0, sms);
+  run_rate<1, 16, 16>(ms, nboxes, 128, 4096, 0, sms);
+  run_rate<1, 4, 4>(ms, nboxes, 64, 4096, 0, sms); run_rate<1, 8, 8>(ms, nboxes, 64, 4096, 0, sms);
+  run_rate<2, 4, 4>(ms, nboxes, 128, 4096, 0, sms); run_rate<2, 8, 8>(ms, nboxes, 128, 4096, 0, sms);
+  run_rate<2, 4, 4>(ms, nboxes, 256, 4096, 0, sms); run_rate<2, 8, 8>(ms, nboxes, 256, 4096, 0, sms);
+  run_rate<1, 8, 8>(ms, nboxes, 128, 4096, 768, sms); run_rate<2, 8, 8>(ms, nboxes, 256, 2048, 768, sms);
   printf("--- TMA only (16 KB boxes of a 16 MB L2-resident buffer, 4 in flight per SM)\n");
   run_rate<1>(ms, nboxes, 128, 0, 1024, sms);
   printf("--- both\n");

@@ -865,6 +865,12 @@ int run_stem_wgrad(const void* dy, const void* xs, float* dws, int B, int H, int
 using namespace uda;
 
 // ---- Cin = 3 stem entry points (xs: packed input of uda_stem_pack_input; ws: uda_stem_pack_weight) ----
+#ifdef UDA_B200_EXPERIMENTS
+namespace uda { namespace tcconv { long long* g_trace_buf = nullptr; } }
+// experiment builds only: device buffer of 16 int64 per CTA (see conv_tc_internal.cuh), or null to switch tracing off
+extern "C" int uda_exp_set_trace(void* buf) { uda::tcconv::g_trace_buf = (long long*)buf; return 0; }
+#endif
+
 extern "C" int uda_stem_tc_supported(int B, int H, int W, int Cin, int Cout, int K, int stride, int pad) {
   if (!uda_device_supported() || !use_persistent()) return 0;
   return stem_shape_ok(B, H, W, Cin, Cout, K, stride, pad) ? 1 : 0;

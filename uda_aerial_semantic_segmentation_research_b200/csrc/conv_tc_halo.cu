@@ -29,6 +29,7 @@ struct HParams {
   bf16* out; float* out_nchw; const float* bias; const bf16* addend;
   double* bn_sums;
   const bf16* st_a; const bf16* st_z; float st_slope; double* st_sums;   // GemmConv::st_*
+  long long* trace;   // experiment builds only: per-CTA trace records (conv_tc_internal.cuh)
 };
 
 template <int KC, int BN, int R>
@@ -60,6 +61,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
+  UDA_TR(const long long tr0 = clock64(); long long* const trp = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;)
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
   if (warp == 1) {
@@ -78,10 +80,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible from here on
+  UDA_TR(if (trp && threadIdx.x == 0) { trp[0] = tr0; trp[1] = clock64() - tr0; })
 
   if (warp == 0) {
     // ===================== TMA producer: weights once, then one halo box per (tile, channel chunk) ==========
     if (elect_one()) {
+      UDA_TR(long long tr_w = 0;)
       mbar_expect_tx(ws_bar, ws_bytes);
       for (int t = 0; t < 9; ++t)
         for (int kc = 0; kc < p.kchunks; ++kc)
@@ -92,27 +96,30 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int h0 = (tin / p.tiles_w) * R, w0 = (tin % p.tiles_w) * 128;
         for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
           const int s = it % S;
-          mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1);
+          UDA_TR_WAIT(tr_w, mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1))
           mbar_expect_tx(full_bar(s), kHaloBytes);
           tma_load_4d(ring_base + s * kHaloStride, &map_a, full_bar(s), kc * KC, w0 - 1, h0 - 1, b);
         }
       }
+      UDA_TR(if (trp) { trp[2] = tr_w; trp[3] = clock64() - tr0; })
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN);
-      mbar_wait(ws_bar, 0);
+      UDA_TR(long long tr_wf = 0, tr_we = 0, tr_first = 0;)
+      UDA_TR_WAIT(tr_wf, mbar_wait(ws_bar, 0))
       tc_fence_after();
       int it = 0, j = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++j) {
         const int q = j & 1;
-        mbar_wait(tempty_bar(q), ((j >> 1) & 1) ^ 1);
+        UDA_TR_WAIT(tr_we, mbar_wait(tempty_bar(q), ((j >> 1) & 1) ^ 1))
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)q * kAccCols;
         for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
           const int s = it % S;
-          mbar_wait(full_bar(s), (it / S) & 1);
+          UDA_TR_WAIT(tr_wf, mbar_wait(full_bar(s), (it / S) & 1))
+          UDA_TR(if (!tr_first) tr_first = clock64() - tr0;)
           tc_fence_after();
           const uint32_t halo = ring_base + s * kHaloStride;
 #pragma unroll 1
@@ -133,9 +140,11 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         umma_commit(tfull_bar(q));
       }
+      UDA_TR(if (trp) { trp[4] = tr_wf; trp[5] = tr_we; trp[6] = tr_first; trp[7] = clock64() - tr0; trp[12] = j; })
     }
   } else {
     // ===================== epilogue (4 warps): one image row of 128 pixels per sub-tile =====================
+    UDA_TR(long long tr_wt = 0, tr_busy = 0;)
     const int qw = warp & 3;
     constexpr int kChunks = (BN + 31) / 32;
     float bn_s[kChunks], bn_q[kChunks];
@@ -154,7 +163,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int b = t / tiles_per_img, tin = t % tiles_per_img;
       const int h0 = (tin / p.tiles_w) * R, w0 = (tin % p.tiles_w) * 128;
       const int q = j & 1;
-      mbar_wait(tfull_bar(q), (j >> 1) & 1);
+      UDA_TR_WAIT(tr_wt, mbar_wait(tfull_bar(q), (j >> 1) & 1))
+      UDA_TR(const long long tr_b0 = clock64();)
       tc_fence_after();
       const int w = w0 + qw * 32 + lane;
 #pragma unroll 1
@@ -235,7 +245,9 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(q));
+      UDA_TR(tr_busy += clock64() - tr_b0;)
     }
+    UDA_TR(if (trp && warp == 2 && lane == 0) { trp[8] = tr_wt; trp[9] = tr_busy; trp[10] = clock64() - tr0; })
     if (sums_out) {
       if constexpr (kLate) {
         float ts[32], tq[32];
@@ -253,6 +265,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
+  UDA_TR(if (trp && threadIdx.x == 0) trp[11] = clock64() - tr0;)
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -314,6 +327,7 @@ int run_gemm_conv_halo(const GemmConv& g, cudaStream_t st) {
   p.bn_sums = g.bn_sums;
   p.st_a = (const bf16*)g.st_a; p.st_z = (const bf16*)g.st_z; p.st_slope = g.st_slope; p.st_sums = g.st_sums;
   if (g.st_sums && (!g.st_a || !g.out || g.bn_sums)) return UDA_ERR_UNSUPPORTED;
+  UDA_TR(p.trace = g_trace_buf;)
   CUtensorMap ma, mb;
   {
     const uint64_t C = (uint64_t)g.Cred;

@@ -65,6 +65,21 @@ inline int pick_kc(int c) {
 }
 inline int pick_bn(int cout) { return cout > 64 ? 128 : (cout > 32 ? 64 : 32); }
 
+// ---- experiment builds (make EXPERIMENTS=1): per-CTA phase / wait-time trace of the warp roles --------------------
+// One record of 16 int64 clocks per CTA, written to the buffer given to uda_exp_set_trace():
+//   0 entry  1 after griddepcontrol.wait  2 producer: clocks waiting for free ring slots  3 producer: last TMA issued
+//   4 MMA thread: clocks waiting for operands (full barriers)  5 MMA thread: clocks waiting for a drained accumulator
+//   6 first MMA issued  7 last commit issued  8 epilogue warp 2: clocks waiting for accumulators  9 epilogue: busy clocks
+//   10 epilogue done  11 CTA exit  12 tiles of this CTA     (all times relative to 0)
+#ifdef UDA_B200_EXPERIMENTS
+extern long long* g_trace_buf;
+#define UDA_TR(...) __VA_ARGS__
+#define UDA_TR_WAIT(acc, ...) { const long long _t0 = clock64(); __VA_ARGS__; acc += clock64() - _t0; }
+#else
+#define UDA_TR(...)
+#define UDA_TR_WAIT(acc, ...) { __VA_ARGS__; }
+#endif
+
 #ifdef __CUDACC__
 // Column sums over the 32 rows a warp holds (one row per lane, 32 values per lane): recursive halving,
 // 31 shuffles; afterwards lane L holds the sum of column L in v[0].

@@ -43,8 +43,14 @@ struct PParams {
   bf16* out; float* out_nchw; const float* bias; const bf16* addend;
   double* bn_sums;
   const bf16* st_a; const bf16* st_z; float st_slope; double* st_sums;   // GemmConv::st_*
-  int debug;   // UDA_B200_TC_DEBUG bit mask (timing experiments only): 1 = no epilogue stores, 2 = no MMAs, 4 = no TMA loads
+  long long* trace;   // experiment builds only: per-CTA trace records (conv_tc_internal.cuh)
+  int debug;   // experiment builds only (UDA_B200_TC_DEBUG bit mask): 1 = no epilogue stores, 2 = no MMAs, 4 = no TMA loads
 };
+#ifdef UDA_B200_EXPERIMENTS
+#define UDA_TC_DBG(p, bit) ((p).debug & (bit))
+#else
+#define UDA_TC_DBG(p, bit) false
+#endif
 
 template <int KC, int BN, int MT>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -77,6 +83,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const int total_tiles = p.ncls * tiles_per_cls;
   const int tiles_per_group = p.tiles_w * p.tiles_h;
 
+  UDA_TR(const long long tr0 = clock64(); long long* const trp = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;)
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
   if (warp == 1) {
@@ -95,10 +102,12 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible from here on
+  UDA_TR(if (trp && threadIdx.x == 0) { trp[0] = tr0; trp[1] = clock64() - tr0; })
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
+      UDA_TR(long long tr_w = 0;)
       if (p.ws) {
         mbar_expect_tx(ws_bar, ws_bytes);
         for (int wt = 0; wt < p.wtaps; ++wt)
@@ -116,9 +125,9 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
           for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
             const int s = it % S;
             const uint32_t phs = (it / S) & 1;
-            mbar_wait(empty_bar(s), phs ^ 1);
+            UDA_TR_WAIT(tr_w, mbar_wait(empty_bar(s), phs ^ 1))
             const uint32_t a_dst = ring_base + s * stage_bytes;
-            if (p.debug & 4) { mbar_arrive(full_bar(s)); continue; }
+            if (UDA_TC_DBG(p, 4)) { mbar_arrive(full_bar(s)); continue; }
             mbar_expect_tx(full_bar(s), stage_bytes);
             if (p.rank5)
               tma_load_5d(a_dst, &map_a, full_bar(s), c.pw[tap] * p.Cred + kc * KC, w0 + c.dw[tap], c.ph[tap],
@@ -129,30 +138,33 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
           }
         }
       }
+      UDA_TR(if (trp) { trp[2] = tr_w; trp[3] = clock64() - tr0; })
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN);
-      if (p.ws) { mbar_wait(ws_bar, 0); tc_fence_after(); }
+      UDA_TR(long long tr_wf = 0, tr_we = 0, tr_first = 0;)
+      if (p.ws) { UDA_TR_WAIT(tr_wf, mbar_wait(ws_bar, 0)) tc_fence_after(); }
       int it = 0, j = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
         const int ci = t / tiles_per_cls;
         const PClass& c = p.cls[ci];
         const int q = j % kSets;
-        mbar_wait(tempty_bar(q), ((j / kSets) & 1) ^ 1);   // epilogue has drained this accumulator set
+        UDA_TR_WAIT(tr_we, mbar_wait(tempty_bar(q), ((j / kSets) & 1) ^ 1))   // epilogue has drained this accumulator set
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)q * kAccCols;
         for (int tap = 0; tap < c.ntaps; ++tap) {
           for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
             const int s = it % S;
             const uint32_t phs = (it / S) & 1;
-            mbar_wait(full_bar(s), phs);
+            UDA_TR_WAIT(tr_wf, mbar_wait(full_bar(s), phs))
+            UDA_TR(if (!tr_first) tr_first = clock64() - tr0;)
             tc_fence_after();
             const uint32_t a_addr = ring_base + s * stage_bytes;
             const uint32_t b_addr = p.ws ? ws_base + (c.wtap[tap] * p.kchunks + kc) * kBBytes : a_addr + kABytes;
             const uint64_t bdesc = make_kmajor_desc(b_addr, KC * 2);
-            if (!(p.debug & 2)) {
+            if (!UDA_TC_DBG(p, 2)) {
 #pragma unroll
               for (int sub = 0; sub < MT; ++sub) {
                 const uint64_t adesc = make_kmajor_desc(a_addr + sub * (128 * KC * 2), KC * 2);
@@ -167,9 +179,11 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         }
         umma_commit(tfull_bar(q));
       }
+      UDA_TR(if (trp) { trp[4] = tr_wf; trp[5] = tr_we; trp[6] = tr_first; trp[7] = clock64() - tr0; trp[12] = j; })
     }
   } else {
     // ===================== epilogue (4 warps) =====================
+    UDA_TR(long long tr_wt = 0, tr_busy = 0;)
     const int qw = warp & 3;
     constexpr int kChunks = (BN + 31) / 32;
     float bn_s[kChunks], bn_q[kChunks];
@@ -203,7 +217,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         }
         bn_n0 = n0;
       }
-      mbar_wait(tfull_bar(q), (j / kSets) & 1);
+      UDA_TR_WAIT(tr_wt, mbar_wait(tfull_bar(q), (j / kSets) & 1))
+      UDA_TR(const long long tr_b0 = clock64();)
       tc_fence_after();
 #pragma unroll 1
       for (int sub = 0; sub < MT; ++sub) {
@@ -264,7 +279,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
               bn_q[c0 / 32] += warp_column_sums(gv, lane);
             }
           }
-          if (p.out && !(p.debug & 1)) {
+          if (p.out && !UDA_TC_DBG(p, 1)) {
             bf16* dst = p.out + pix * p.Cout + nbase;
 #pragma unroll
             for (int k = 0; k < 32; k += 8) {
@@ -288,7 +303,9 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar(q));
+      UDA_TR(tr_busy += clock64() - tr_b0;)
     }
+    UDA_TR(if (trp && warp == 2 && lane == 0) { trp[8] = tr_wt; trp[9] = tr_busy; trp[10] = clock64() - tr0; })
     if (sums_out && bn_n0 >= 0) {
       if constexpr (kLate) {   // BN = 32: a single channel tile, nothing was flushed before
         float ts[32], tq[32];
@@ -306,6 +323,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  UDA_TR(if (trp && threadIdx.x == 0) trp[11] = clock64() - tr0;)
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -426,7 +444,11 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
   }
   p.out = (bf16*)g.out; p.out_nchw = g.out_nchw; p.bias = g.bias; p.addend = (const bf16*)g.addend;
   p.bn_sums = g.bn_sums;
-  {
+  p.debug = 0;
+  p.trace = nullptr;
+  UDA_TR(p.trace = g_trace_buf;)
+#ifdef UDA_B200_EXPERIMENTS
+  {   // timing experiments that SKIP WORK: compiled only into experiment builds (make EXPERIMENTS=1)
     const char* e = getenv("UDA_B200_TC_DEBUG");
     p.debug = e ? atoi(e) : 0;
     static bool warned = false;
@@ -435,6 +457,7 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
       warned = true;
     }
   }
+#endif
   p.st_a = (const bf16*)g.st_a; p.st_z = (const bf16*)g.st_z; p.st_slope = g.st_slope; p.st_sums = g.st_sums;
   UDA_REQUIRE(!(g.bn_sums && g.st_sums), UDA_ERR_BAD_ARG, "conv_tc_persist: forward and backward statistics are exclusive");
   UDA_REQUIRE(!g.st_sums || (g.st_a && g.out), UDA_ERR_BAD_ARG, "conv_tc_persist: backward statistics need `a` and an NHWC output");

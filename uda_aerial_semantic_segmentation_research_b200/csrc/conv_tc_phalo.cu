@@ -34,6 +34,7 @@ struct PHParams {
   int Cout, Cred, kchunks;
   int HR, halo_bytes, halo_stride, b_stages;
   bf16* out; const bf16* addend; double* bn_sums;
+  long long* trace;   // experiment builds only: per-CTA trace records (conv_tc_internal.cuh)
 };
 
 template <int KC, int BN, int NBLK>
@@ -65,6 +66,7 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
+  UDA_TR(const long long tr0 = clock64(); long long* const trp = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;)
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
   if (warp == 1) {
@@ -83,10 +85,12 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible from here on
+  UDA_TR(if (trp && threadIdx.x == 0) { trp[0] = tr0; trp[1] = clock64() - tr0; })
 
   if (warp == 0) {
     // ===================== TMA producer: per channel chunk one halo box per block, then nine weight tiles =====
     if (elect_one()) {
+      UDA_TR(long long tr_w = 0;)
       int ita = 0, itb = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int mt = t % p.m_tiles, n0 = (t / p.m_tiles) * BN;
@@ -94,7 +98,7 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         const int nblk = min(NBLK, p.total_blocks - gb0);
         for (int kc = 0; kc < p.kchunks; ++kc, ++ita) {
           const int sa = ita % kAStages;
-          mbar_wait(aempty(sa), ((ita / kAStages) & 1) ^ 1);
+          UDA_TR_WAIT(tr_w, mbar_wait(aempty(sa), ((ita / kAStages) & 1) ^ 1))
           mbar_expect_tx(afull(sa), (uint32_t)nblk * p.halo_bytes);
           for (int j = 0; j < nblk; ++j) {
             const int gb = gb0 + j, b = gb / p.nb_img, m0 = (gb % p.nb_img) * 128;
@@ -103,17 +107,19 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           }
           for (int tap = 0; tap < 9; ++tap, ++itb) {
             const int sb = itb % SB;
-            mbar_wait(bempty(sb), ((itb / SB) & 1) ^ 1);
+            UDA_TR_WAIT(tr_w, mbar_wait(bempty(sb), ((itb / SB) & 1) ^ 1))
             mbar_expect_tx(bfull(sb), kBBytes);
             tma_load_2d(b_base + sb * kBBytes, &map_b, bfull(sb), tap * p.Cred + kc * KC, n0);
           }
         }
       }
+      UDA_TR(if (trp) { trp[2] = tr_w; trp[3] = clock64() - tr0; })
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN);
+      UDA_TR(long long tr_wf = 0, tr_we = 0, tr_first = 0, tr_wa = 0;)
       int ita = 0, itb = 0, j = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
         const int mt = t % p.m_tiles;
@@ -126,18 +132,19 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           off[i] = (uint32_t)(m0 - (m0 / p.P) * p.P);
         }
         const int q = j % kSets;
-        mbar_wait(tempty(q), ((j / kSets) & 1) ^ 1);
+        UDA_TR_WAIT(tr_we, mbar_wait(tempty(q), ((j / kSets) & 1) ^ 1))
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)q * kAccCols;
         for (int kc = 0; kc < p.kchunks; ++kc, ++ita) {
           const int sa = ita % kAStages;
-          mbar_wait(afull(sa), (ita / kAStages) & 1);
+          UDA_TR_WAIT(tr_wa, mbar_wait(afull(sa), (ita / kAStages) & 1))
           tc_fence_after();
           const uint32_t halo = a_base + sa * a_stage_bytes;
 #pragma unroll 1
           for (int tap = 0; tap < 9; ++tap, ++itb) {
             const int sb = itb % SB;
-            mbar_wait(bfull(sb), (itb / SB) & 1);
+            UDA_TR_WAIT(tr_wf, mbar_wait(bfull(sb), (itb / SB) & 1))
+            UDA_TR(if (!tr_first) tr_first = clock64() - tr0;)
             tc_fence_after();
             const int kh = tap / 3, kw = tap - 3 * kh;
             const uint64_t bdesc = make_kmajor_desc(b_base + sb * kBBytes, kRowB);
@@ -158,9 +165,11 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
         umma_commit(tfull(q));
       }
+      UDA_TR(if (trp) { trp[4] = tr_wf; trp[5] = tr_we; trp[6] = tr_first; trp[7] = clock64() - tr0; trp[12] = j; trp[13] = tr_wa; })
     }
   } else {
     // ===================== epilogue (4 warps): 128 pitched positions per block, junk columns skipped ==========
+    UDA_TR(long long tr_wt = 0, tr_busy = 0;)
     const int qw = warp & 3;
     constexpr int kChunks = (BN + 31) / 32;
     float bn_s[kChunks], bn_q[kChunks];
@@ -184,7 +193,8 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
         bn_n0 = n0;
       }
-      mbar_wait(tfull(q), (j / kSets) & 1);
+      UDA_TR_WAIT(tr_wt, mbar_wait(tfull(q), (j / kSets) & 1))
+      UDA_TR(const long long tr_b0 = clock64();)
       tc_fence_after();
 #pragma unroll 1
       for (int i = 0; i < nblk; ++i) {
@@ -234,7 +244,9 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty(q));
+      UDA_TR(tr_busy += clock64() - tr_b0;)
     }
+    UDA_TR(if (trp && warp == 2 && lane == 0) { trp[8] = tr_wt; trp[9] = tr_busy; trp[10] = clock64() - tr0; })
     if (p.bn_sums && bn_n0 >= 0) {
 #pragma unroll
       for (int cc = 0; cc < kChunks; ++cc) {
@@ -245,6 +257,7 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  UDA_TR(if (trp && threadIdx.x == 0) trp[11] = clock64() - tr0;)
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -314,6 +327,7 @@ int run_gemm_conv_phalo(const GemmConv& g, cudaStream_t st) {
   p.Cout = g.Cout; p.Cred = g.Cred; p.kchunks = g.Cred / KC;
   p.HR = (128 + p.P - 1) / p.P + 3;
   p.out = (bf16*)g.out; p.addend = (const bf16*)g.addend; p.bn_sums = g.bn_sums;
+  UDA_TR(p.trace = g_trace_buf;)
   // enough work for a full wave, else the persistent kernel's smaller tiles are the better fit
   const int nblk = 2;
   if (mode != 2 && (long long)((p.total_blocks + nblk - 1) / nblk) * p.n_tiles < num_sms() / 2) return UDA_ERR_UNSUPPORTED;

@@ -337,7 +337,9 @@ __global__ void __launch_bounds__(kCta, 1) bn_bwd_apply_stream_kernel(const BwdA
 
 // one CTA per SM; as many stages (<= 4) as fit beside `extra_smem`; small tensors get >= 2 tiles per CTA
 int stream_launch_geometry(StreamIO& io, size_t extra_smem, int* grid, size_t* smem) {
-  {   // UDA_B200_BN_DEBUG=1: timing experiment — the kernels launch but move no data (results are WRONG)
+#ifdef UDA_B200_EXPERIMENTS
+  {   // UDA_B200_BN_DEBUG=1: timing experiment — the kernels launch but move no data (results are WRONG).  Compiled
+      // only into experiment builds (make EXPERIMENTS=1); the product library has no work-skipping switch.
     static const bool skip = [] {
       const char* e = getenv("UDA_B200_BN_DEBUG");
       const bool on = e && e[0] == '1';
@@ -346,6 +348,7 @@ int stream_launch_geometry(StreamIO& io, size_t extra_smem, int* grid, size_t* s
     }();
     if (skip) io.nbytes = 0;
   }
+#endif
   const size_t stage = (size_t)io.nin * kTile;
   int st = (int)((208 * 1024 - extra_smem) / stage);
   if (st > kMaxStages) st = kMaxStages;
