@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the segmentation-training hot path (BASELINE.json metric: UDA train images/s @512x512).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload supervised|adversarial]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload supervised|adversarial|finetune]
 
 One step = one pass of the hot path over one batch of synthetic input:
   supervised  (BASELINE configs[1], default): U-Net r34, batch 16 @512x512 bf16, 24 classes —
@@ -13,7 +13,9 @@ One step = one pass of the hot path over one batch of synthetic input:
               src/models/losses.py:256-342) + entropy minimisation, clip_grad_norm 1.0, Adam
               (src/models/unsupervised_trainer.py:99-150); 4 images per GPU (global 32 on 8 GPUs)
 For N>1 the script is launched by torchrun (one rank per GPU, NCCL); each rank processes its own batch
-(weak scaling) and gradients are all-reduced in buckets overlapped with backward.  Rank 0 prints ONE JSON line.
+(weak scaling) and gradients are all-reduced in ~25 MB buckets overlapped with backward — the NCCL kernels are
+captured into the step's CUDA graph on a side stream.  Rank 0 prints ONE JSON line; the supervised (default) line
+carries an `adversarial` sub-record (configs[2], the workload the north-star's scaling target is written for).
 `--impl reference` times the reference's own CPU path (oracle port: fp32 PyTorch on all host cores).
 """
 import argparse
@@ -30,22 +32,6 @@ CLASSES = 24
 # algorithmic conv FLOPs of U-Net r34 / 24 classes per 512x512 image (counted on the oracle)
 FWD_GFLOP_PER_IMG_512 = 64.248
 TRAIN_GFLOP_PER_IMG_512 = 191.51
-
-
-def conv_traffic_from_profile():
-    """Average DRAM bytes per tensor-core convolution launch from the committed ncu launch list of this workload
-    (profiles/r01_launch_shares_final.csv: dram__bytes_read.sum + dram__bytes_write.sum per kernel), or None."""
-    path = os.path.join(ROOT, "profiles", "r01_launch_shares_final.csv")
-    try:
-        n, tot = 0, 0.0
-        for line in open(path).read().splitlines()[1:]:
-            f = line.split(",")
-            if f[0].startswith("conv_tc_") and f[4] and f[5]:
-                n += int(f[1])
-                tot += (float(f[4]) + float(f[5])) * 1e6
-        return tot / n if n else None
-    except Exception:
-        return None
 
 
 def peaks():
@@ -185,7 +171,29 @@ def cpu_baseline(size, budget_s=20.0):
 # ------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------
-def run_ours(args):
+def conv_traffic_from_profile():
+    """Average DRAM bytes per tensor-core convolution launch from the newest committed ncu launch list of this workload
+    (profiles/r*_launch_shares*.csv: dram__bytes_read.sum + dram__bytes_write.sum per kernel).  Returns (bytes, file)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_launch_shares*.csv")))
+    for path in reversed(files):
+        try:
+            n, tot = 0, 0.0
+            for line in open(path).read().splitlines()[1:]:
+                f = line.split(",")
+                if f[0].startswith("conv_tc_") and f[4] and f[5]:
+                    n += int(f[1])
+                    tot += (float(f[4]) + float(f[5])) * 1e6
+            if n:
+                return tot / n, os.path.relpath(path, ROOT)
+        except Exception:
+            continue
+    return None, None
+
+
+def measure_workload(args, workload, env, full):
+    """Build the networks / optimizers / captured step of one workload, time K steps device-resident and end to end,
+    and (``full``) profile the kernel families.  Returns the result dict (rank 0) or None."""
     import torch
     import torch.distributed as dist
     import uda_aerial_semantic_segmentation_research_b200 as U
@@ -193,28 +201,23 @@ def run_ours(args):
     from uda_aerial_semantic_segmentation_research_b200.losses import CrossEntropyLoss, AdversarialLoss
     from uda_aerial_semantic_segmentation_research_b200.optim import FusedAdam
     from uda_aerial_semantic_segmentation_research_b200.discriminator import DomainDiscriminator
+    from uda_aerial_semantic_segmentation_research_b200.graph import GraphedStep, GraphedFn, GraphedPhases
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        import datetime
-        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    world, rank, local, dev = env["world"], env["rank"], env["local"], env["dev"]
     torch.manual_seed(0)
     size, B = args.size, args.batch
+    adversarial, finetune = workload == "adversarial", workload == "finetune"
+    if finetune and args.batch == 16:
+        B = 4                                               # configs[3]: 32 images on 8 GPUs
+    use_graph = not args.no_graph
     model = U.Unet("resnet34", encoder_weights=None, in_channels=3, classes=CLASSES).to(dev).train()
     nets = [model]
-    adversarial = args.workload == "adversarial"
-    finetune = args.workload == "finetune"
-    if finetune:
-        B = args.batch = min(args.batch, 4) if args.batch == 16 else args.batch   # configs[3]: 4 images per GPU
-    graph_adv = adversarial and world == 1 and not args.no_graph
+    crit = CrossEntropyLoss()
+    opt = FusedAdam(model, lr=1e-3, capturable=use_graph and adversarial, max_grad_norm=1.0 if finetune else None)
     if adversarial:
         disc = DomainDiscriminator(3).to(dev).train()
         nets.append(disc)
-        dopt = FusedAdam(disc, lr=1e-4, capturable=graph_adv)
+        dopt = FusedAdam(disc, lr=1e-4, capturable=use_graph)
         adv = AdversarialLoss(0.001)
     if finetune:
         from uda_aerial_semantic_segmentation_research_b200.losses import FineTuningLoss, EntropyMinimizationLoss
@@ -222,38 +225,72 @@ def run_ours(args):
         for q in disc.parameters():
             q.requires_grad_(False)
         ft_loss, ent_loss = FineTuningLoss(), EntropyMinimizationLoss(0.1)
-    opt = FusedAdam(model, lr=1e-3, capturable=graph_adv, max_grad_norm=1.0 if finetune else None)
-    crit = CrossEntropyLoss()
-    graph_adv_dp = adversarial and world > 1 and not args.no_graph
     if world > 1:
         from uda_aerial_semantic_segmentation_research_b200.ddp import GradSync
-        gsync = GradSync(nets)
-        if graph_adv_dp:   # captured phases: the all-reduce runs on the flat gradient buffers between the graphs
+        GradSync(nets)                                      # bucketed all-reduce, overlapped with backward
+        if use_graph and args.nccl_outside_graph:           # A/B switch: one flat all-reduce after the replay
             for n in nets:
                 n._grad_sync = None
+
+    def flat_allreduce(net):
+        if world > 1 and net._grad_sync is None:
+            dist.all_reduce(net._store.grad, op=dist.ReduceOp.AVG)
+
+    # ---- inputs ------------------------------------------------------------------------------------------------
     Bs = B // 2 if adversarial else B
-    x, t = synthetic_batch(Bs, size, 1234 + rank, dev)
-    xt = synthetic_batch(Bs, size, 4321 + rank, dev)[0] if adversarial else None
     hx, ht = synthetic_batch(Bs, size, 1234 + rank, pinned=True)
-    hxt = synthetic_batch(Bs, size, 4321 + rank, pinned=True)[0] if adversarial else None
+    host = [hx, ht]
+    if adversarial:
+        host.append(synthetic_batch(Bs, size, 4321 + rank, pinned=True)[0])
     if finetune:   # second view = flipped + jittered copy (stand-in for the strong augmentation)
         gq = torch.Generator().manual_seed(77 + rank)
-        hxt = (hx.flip(-1) + 0.1 * torch.randn(hx.shape, generator=gq)).pin_memory()
-        xt = hxt.to(dev)
+        hx2 = hx.flip(-1) + 0.1 * torch.randn(hx.shape, generator=gq)
+        host = [torch.cat([hx, hx2]).pin_memory(), ht] if args.ft_views == "pooled" else [hx, ht, hx2.pin_memory()]
+    devin = [h.to(dev) for h in host]
 
-    graphed = None
-    if not adversarial and not finetune and not args.no_graph:
-        from uda_aerial_semantic_segmentation_research_b200.graph import GraphedStep
-        graphed = GraphedStep(model, crit, opt, x, t)
-
-    def step(xs, ts, xtg):
-        if graphed is not None:
-            return graphed(xs, ts, xtg) if (adversarial or finetune) else graphed(xs, ts)
-        return eager_step(xs, ts, xtg)
-
-    def ft_compute(xs, ts, xtg):   # src/models/unsupervised_trainer.py:99-150
+    # ---- the step (reference semantics) ------------------------------------------------------------------------
+    def sup_step(xs, ts):                # src/models/train.py:336-346
         opt.zero_grad()
-        p1, p2 = model(xs), model(xtg)
+        loss = crit(model(xs), ts)
+        loss.backward()
+        flat_allreduce(model)
+        opt.step()
+        return loss.detach()
+
+    def adv_step(xs, ts, xtg):           # src/models/adversarial_trainer.py:84-114
+        dopt.zero_grad()
+        d_loss = adv.discriminator_loss(disc(xs), disc(xtg))
+        d_loss.backward()
+        flat_allreduce(disc)
+        dopt.step()
+        opt.zero_grad()
+        total = crit(model(xs), ts) + adv.generator_loss(disc(xtg))
+        total.backward()
+        flat_allreduce(model)
+        opt.step()
+        return total.detach()
+
+    class SplitViews(torch.autograd.Function):
+        """logits [2B,...] -> the two views; backward re-joins the two logit gradients with one copy (autograd's own
+        slice backward would materialise two zero-padded full-size tensors and add them)."""
+
+        @staticmethod
+        def forward(ctx, p):
+            return p[:B], p[B:]
+
+        @staticmethod
+        def backward(ctx, g1, g2):
+            return torch.cat([g1, g2])
+
+    def ft_compute(*inp):                # src/models/unsupervised_trainer.py:99-150
+        opt.zero_grad()
+        if args.ft_views == "pooled":    # both views in ONE pass of 2B images, split at the loss
+            xv, ts = inp
+            p1, p2 = SplitViews.apply(model(xv))
+            xs = xv[:B]
+        else:
+            xs, ts, x2 = inp
+            p1, p2 = model(xs), model(x2)
         with torch.no_grad():
             dpred = disc(xs)
         total = ft_loss(p1, p2, dpred, 40)["total"] + ent_loss(p1)
@@ -261,63 +298,45 @@ def run_ours(args):
         return total.detach()
 
     def ft_finish():
-        if world > 1:
-            dist.all_reduce(model._store.grad, op=dist.ReduceOp.AVG)
+        flat_allreduce(model)
         opt.step()
 
-    def eager_step(xs, ts, xtg):
+    def ft_step(*inp):
+        out = ft_compute(*inp)
+        ft_finish()
+        return out
+
+    eager = ft_step if finetune else adv_step if adversarial else sup_step
+    graphed, launch = None, "eager launches"
+    nccl = "" if world == 1 else (" + one flat all-reduce after the replay" if args.nccl_outside_graph else
+                                  "; bucketed NCCL all-reduce captured inside the graph on a side stream (overlaps backward)")
+    if use_graph:
         if finetune:
-            out = ft_compute(xs, ts, xtg)
-            ft_finish()
-            return out
-        if adversarial:   # src/models/adversarial_trainer.py:84-114
-            dopt.zero_grad()
-            d_loss = adv.discriminator_loss(disc(xs), disc(xtg))
-            d_loss.backward()
-            dopt.step()
-            opt.zero_grad()
-            total = crit(model(xs), ts) + adv.generator_loss(disc(xtg))
-            total.backward()
-            opt.step()
-            return total.detach()
-        opt.zero_grad()
-        loss = crit(model(xs), ts)
-        loss.backward()
-        opt.step()
-        return loss
+            graphed = GraphedPhases([(ft_compute, ft_finish)], devin, [model, disc])
+            launch = "cuda-graph replay of fwd+loss+bwd, then clip + fused Adam" + nccl
+        elif adversarial and not (world > 1 and args.nccl_outside_graph):
+            graphed = GraphedFn(adv_step, devin, nets)
+            launch = "ONE cuda-graph replay of the whole D step + G step (both fused Adam steps captured)" + nccl
+        elif adversarial:
+            def d_compute(xs, ts, xtg):
+                dopt.zero_grad()
+                d_loss = adv.discriminator_loss(disc(xs), disc(xtg))
+                d_loss.backward()
+                return d_loss.detach()
 
-    if graph_adv:
-        from uda_aerial_semantic_segmentation_research_b200.graph import GraphedFn
-        graphed = GraphedFn(eager_step, [x, t, xt], [model, disc])
-    if finetune and not args.no_graph:
-        from uda_aerial_semantic_segmentation_research_b200.graph import GraphedPhases
-        for n in nets:
-            n._grad_sync = None
-        graphed = GraphedPhases([(ft_compute, ft_finish)], [x, t, xt], [model, disc])
-    if graph_adv_dp:
-        from uda_aerial_semantic_segmentation_research_b200.graph import GraphedPhases
+            def g_compute(xs, ts, xtg):
+                opt.zero_grad()
+                total = crit(model(xs), ts) + adv.generator_loss(disc(xtg))
+                total.backward()
+                return total.detach()
 
-        def d_compute(xs, ts, xtg):   # src/models/adversarial_trainer.py:84-95
-            dopt.zero_grad()
-            d_loss = adv.discriminator_loss(disc(xs), disc(xtg))
-            d_loss.backward()
-            return d_loss.detach()
-
-        def d_finish():
-            dist.all_reduce(disc._store.grad, op=dist.ReduceOp.AVG)
-            dopt.step()
-
-        def g_compute(xs, ts, xtg):   # src/models/adversarial_trainer.py:98-114
-            opt.zero_grad()
-            total = crit(model(xs), ts) + adv.generator_loss(disc(xtg))
-            total.backward()
-            return total.detach()
-
-        def g_finish():
-            dist.all_reduce(model._store.grad, op=dist.ReduceOp.AVG)
-            opt.step()
-
-        graphed = GraphedPhases([(d_compute, d_finish), (g_compute, g_finish)], [x, t, xt], [model, disc])
+            graphed = GraphedPhases([(d_compute, lambda: (flat_allreduce(disc), dopt.step())),
+                                     (g_compute, lambda: (flat_allreduce(model), opt.step()))], devin, nets)
+            launch = "cuda-graph replay of the D-step and G-step compute phases, all-reduce + fused Adam after each"
+        else:
+            graphed = GraphedStep(model, crit, opt, devin[0], devin[1])
+            launch = "cuda-graph replay of fwd+loss+bwd, then fused Adam" + nccl
+    step = graphed if graphed is not None else eager
 
     def sync():
         if world > 1:
@@ -337,13 +356,13 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- device-resident arm -----------------------------------------------------------------
+    # ---- device-resident arm -----------------------------------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
-        step(x, t, xt)
+        step(*devin)
     sampler = ClockSampler(local)
     sampler.start()
     l0 = ops.LAUNCHES
-    ms = timed(lambda: step(x, t, xt), args.steps)
+    ms = timed(lambda: step(*devin), args.steps)
     launches = ops.LAUNCHES - l0
     if graphed is not None:
         launches = graphed.launches_per_step * args.steps
@@ -352,47 +371,57 @@ def run_ours(args):
     imgs = B * world * args.steps
     value = imgs / (ms * 1e-3)
 
-    # ---- end-to-end arm: pinned host inputs, H2D inside the timed region, loss read back ------
-    def e2e_step():
-        xs = hx.to(dev, non_blocking=True)
-        ts = ht.to(dev, non_blocking=True)
-        xtg = hxt.to(dev, non_blocking=True) if (adversarial or finetune) else None
-        return step(xs, ts, xtg).item()
+    # ---- end-to-end arm: pinned host inputs, H2D inside the timed region, loss read back ------------------------
+    def e2e_eager():
+        return step(*[h.to(dev, non_blocking=True) for h in host]).item()
 
     def e2e_pipelined(steps):
         # same bytes per step; the H2D copy of batch i+1 runs on a side stream under the compute of batch i
-        graphed.stage(hx, ht)
+        graphed.stage(*host)
         for i in range(steps):
             loss = graphed()
             if i + 1 < steps:
-                graphed.stage(hx, ht)
+                graphed.stage(*host)
             loss.item()
 
-    if graphed is not None and not adversarial and not finetune:
+    if graphed is not None:
         e2e_pipelined(2)
         ms_e2e = timed(lambda: e2e_pipelined(args.steps), 1)
     else:
         for _ in range(2):
-            e2e_step()
-        ms_e2e = timed(e2e_step, args.steps)
-    h2d = hx.numel() * 4 + ht.numel() * 8 + (hxt.numel() * 4 if (adversarial or finetune) else 0)
+            e2e_eager()
+        ms_e2e = timed(e2e_eager, args.steps)
+    h2d = sum(h.numel() * h.element_size() for h in host)
     e2e = {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
 
-    # ---- per-kernel CUDA-event profile of a few steps (rank 0): roofline of the dominant kernel ----
-    roof = None
-    breakdown = {}
-    # every rank runs the profiled steps (they contain the gradient all-reduce); only rank 0 records events
+    wl = (f"supervised source-domain training, U-Net resnet34, batch {B}/GPU @{size}x{size}, {CLASSES} classes, "
+          "CE loss + Adam (BASELINE configs[1])") if not (adversarial or finetune) else \
+         (f"unsupervised target-domain fine-tuning (two views, FineTuningLoss consistency + domain confusion + entropy "
+          f"minimisation, clip 1.0, Adam), U-Net resnet34, {B} images/GPU @{size}x{size} (BASELINE configs[3]); "
+          + ("both views run as ONE pass of 2B images split at the loss (BatchNorm statistics pooled over the two views); "
+             if args.ft_views == "pooled" else "two separate passes of B images; ")
+          + "deviation from src/models/unsupervised_trainer.py:116-122: its third, unused segmentation forward of the "
+            "un-augmented batch is not run, the critic is frozen") if finetune else \
+         (f"adversarial UDA step (D step + G step), U-Net resnet34 + image discriminator, {Bs}+{Bs} images/GPU "
+          f"@{size}x{size} (BASELINE configs[2])")
+    res = {"value": value, "ms_per_step": ms / args.steps, "e2e": e2e, "gpu_launches": launches,
+           "clocks": sampler.result(), "workload": wl, "launch": launch, "global_batch": B * world}
+    if not full:
+        del model, nets, graphed, step
+        torch.cuda.empty_cache()
+        return res if rank == 0 else None
+
+    # ---- per-kernel CUDA-event profile of a few steps (rank 0): roofline of the dominant kernel -----------------
+    roof, breakdown = None, {}
     prof_steps = 3
     if rank == 0:
         _lib.PROFILE = {}
     sync()
     f0 = ops.TC_FLOPS
-    saved_graphed, graphed = graphed, None      # the per-entry-point profile needs eager launches
-    for _ in range(prof_steps):
+    for _ in range(prof_steps):                 # every rank runs them (they contain the gradient all-reduce)
         torch.cuda._sleep(int(60e-3 * 1.9e9))   # let the host run ahead: event pairs then bracket pure device time
-        step(x, t, xt)
+        eager(*devin)
     torch.cuda.synchronize()
-    graphed = saved_graphed
     if rank == 0:
         prof, _lib.PROFILE = _lib.PROFILE, None
         for name, evs in prof.items():
@@ -403,7 +432,6 @@ def run_ours(args):
                 last = [round(a.elapsed_time(b) * 1e3, 1) for a, b in evs[-per:]]
                 print(f"[profile] {name}: {last}", file=sys.stderr)
         pk = peaks()
-        # tensor-core convolution family: algorithmic FLOPs routed through the tcgen05 kernels
         tc_keys = ("conv2d_tc_fwd", "conv2d_tc_dgrad", "conv2d_tc_wgrad", "stem_tc_fwd", "stem_tc_wgrad")
         tc_ms = sum(breakdown.get(k, {}).get("ms_per_step", 0.0) for k in tc_keys)
         tc_n = sum(breakdown.get(k, {}).get("launches_per_step", 0.0) for k in tc_keys)
@@ -411,17 +439,17 @@ def run_ours(args):
         top = max(breakdown.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if breakdown else None
         if tc_ms > 0:
             ach = tc_gflop / tc_ms  # GFLOP / ms == TFLOP/s
+            traffic, tfile = conv_traffic_from_profile()
             roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM convolution family (conv_tc_persist / conv_tc_halo / "
-                                                 "conv_tc_wgrad[_halo] kernels: fwd + dgrad + wgrad launches)",
+                                                 "conv_tc_phalo / conv_tc_wgrad[_big|_halo] kernels: fwd + dgrad + wgrad launches)",
                     "achieved": ach, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                    "frac": ach / pk["bf16_tflops_sustained"], "traffic": conv_traffic_from_profile(),
-                    "traffic_note": "average DRAM bytes per conv launch, ncu launch list under profiles/ (cold cache)",
+                    "frac": ach / pk["bf16_tflops_sustained"], "traffic": traffic,
+                    "traffic_note": f"average DRAM bytes per conv launch (dram__bytes_read.sum + dram__bytes_write.sum) from the "
+                                    f"committed ncu launch list {tfile} (cold cache, same command); not re-measured in this run",
                     "peak_source": pk["which"] + " (sustained: kernels timed inside a long step)",
                     "gflop_per_step": tc_gflop, "ms_per_step": tc_ms, "launches_per_step": tc_n,
+                    "whole_step_frac": tc_gflop / (ms / args.steps) / pk["bf16_tflops_sustained"],
                     "top_entry_point_by_time": top}
-
-    # HBM-bound loss kernel (second half of BASELINE's metric): algorithmic bytes 2*P*C*4 + 8*P (fp32 NCHW logits read,
-    # int64 targets read, fp32 gradient written) over its CUDA-event time inside the profiled steps
     hbm_kernels = None
     if rank == 0:
         P = float(Bs * size * size)
@@ -439,31 +467,55 @@ def run_ours(args):
                                      "frac": gbs / peaks()["hbm_gbs"], "frac_of_8TBs_nominal": gbs / 8000.0,
                                      "algorithmic_mb_per_launch": nbytes / 1e6, "ms_per_launch": t_ms,
                                      "note": "includes the finalize / rescale launches of the entry point"}
+    res.update({"roofline": roof, "hbm_kernels": hbm_kernels,
+                "kernel_breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in
+                                                 sorted(breakdown.items(), key=lambda kv: -kv[1]["ms_per_step"])}})
+    del model, nets, graphed, step
+    torch.cuda.empty_cache()
+    return res if rank == 0 else None
 
-    out = None
+
+def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:   # NCCL collectives are captured into the CUDA graphs (PyTorch's rule for that)
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "0")
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
+    env = {"world": world, "rank": rank, "local": local, "dev": dev}
+    size = args.size
+    head = measure_workload(args, args.workload, env, full=True)
+    sub = None
+    if args.workload == "supervised" and not args.no_sub:
+        # the north-star's scaling target is written for the adversarial UDA step: measure it in the same line
+        sub = measure_workload(args, "adversarial", env, full=False)
     if rank == 0:
-        wl = (f"supervised source-domain training, U-Net resnet34, batch {B}/GPU @{size}x{size}, {CLASSES} classes, "
-              "CE loss + Adam (BASELINE configs[1])") if not (adversarial or finetune) else \
-             (f"unsupervised target-domain fine-tuning (two views, FineTuningLoss consistency + domain confusion + entropy "
-              f"minimisation, clip 1.0, Adam), U-Net resnet34, {B} images/GPU @{size}x{size} (BASELINE configs[3])") if finetune else \
-             (f"adversarial UDA step (D step + G step), U-Net resnet34 + image discriminator, {Bs}+{Bs} images/GPU "
-              f"@{size}x{size} (BASELINE configs[2])")
         out = {
-            "metric": "train_images_per_s", "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": "train_images_per_s", "value": head["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": wl, "global_batch": B * world, "image_size": size, "classes": CLASSES,
-                       "parallelism": f"dp{world}", "l2": "inputs+activations per step (>3 GB) exceed the 126 MB L2",
-                       "launch": (("cuda-graph replay of the D-step and G-step compute phases, all-reduce + fused Adam "
-                                   "after each" if world > 1 else "cuda-graph replay of the whole D/G step") if adversarial else
-                                  "cuda-graph replay of the compute phase, then all-reduce + clip + fused Adam" if finetune else
-                                  "cuda-graph replay of fwd+loss+bwd, then all-reduce + fused Adam") if graphed is not None
-                                 else "eager launches"},
-            "e2e": e2e, "gpu_launches": launches, "clocks": sampler.result(),
-            "roofline": roof, "hbm_kernels": hbm_kernels, "kernel_breakdown_ms_per_step": {k: round(v["ms_per_step"], 4) for k, v in
-                                                               sorted(breakdown.items(), key=lambda kv: -kv[1]["ms_per_step"])},
-            "fraction_of_flop_roofline": value / world / (peaks()["bf16_tflops"] * 1e3 / TRAIN_GFLOP_PER_IMG_512 * (512 / size) ** 2),
+            "config": {"workload": head["workload"], "global_batch": head["global_batch"], "image_size": size,
+                       "classes": CLASSES, "parallelism": f"dp{world}",
+                       "l2": "inputs+activations per step (>3 GB) exceed the 126 MB L2", "launch": head["launch"]},
+            "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": head["clocks"],
+            "roofline": head["roofline"], "hbm_kernels": head["hbm_kernels"],
+            "kernel_breakdown_ms_per_step": head["kernel_breakdown_ms_per_step"],
+            "fraction_of_flop_roofline": head["value"] / world / (peaks()["bf16_tflops"] * 1e3 / TRAIN_GFLOP_PER_IMG_512 * (512 / size) ** 2),
+            # every UDA_B200_* switch present in the environment of this run (none = the shipped defaults)
+            "env": {k: v for k, v in sorted(os.environ.items()) if k.startswith("UDA_B200_")},
         }
+        if sub is not None:
+            out["adversarial"] = {"metric": "train_images_per_s", "value": sub["value"], "unit": "images/s",
+                                  "ms_per_step": sub["ms_per_step"], "e2e": sub["e2e"], "gpu_launches": sub["gpu_launches"],
+                                  "n_gpus": world, "scaling": "weak",
+                                  "config": {"workload": sub["workload"], "global_batch": sub["global_batch"],
+                                             "launch": sub["launch"]}}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(size)
         print(json.dumps(out))
@@ -484,6 +536,11 @@ def main():
     ap.add_argument("--ref-batch", type=int, default=2, help="bounded sample batch of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-sub", action="store_true", help="skip the adversarial sub-record of the supervised line")
+    ap.add_argument("--nccl-outside-graph", action="store_true",
+                    help="A/B switch (N>1): one flat all-reduce after the graph replay instead of the captured, overlapped buckets")
+    ap.add_argument("--ft-views", default="pooled", choices=["pooled", "separate"],
+                    help="finetune workload: both views as one 2B pass (default) or two B passes")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -131,6 +131,16 @@ int uda_conv2d_tc_supported(int op, int B, int H, int W, int Cin, int Cout, int 
 int uda_conv2d_tc_fwd(const void* x, const void* w, const float* bias, void* y_nhwc, float* y_nchw_f32,
                       double* bn_sums, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
                       void* stream);
+/* Inference form of the forward convolution: y = act(conv(x, w) + bias (+ addend)) in one launch; act_slope 0 = ReLU,
+ * 0.2 = LeakyReLU, 1 = none.  With uda_bn_fold_conv (w' = w * gamma / sqrt(var + eps) in bf16, bias' = beta + (b - mean)
+ * * gamma / sqrt(var + eps); w fp32 [Cout][per_out]) an eval-mode conv + BatchNorm (+ residual) + ReLU chain
+ * (reference src/models/predict.py:113-130: model.eval(); model(images)) runs without any BatchNorm pass. */
+int uda_conv2d_tc_fwd_fused(const void* x, const void* w, const float* bias, const void* addend, float act_slope,
+                            void* y_nhwc, float* y_nchw_f32, int B, int H, int W, int Cin, int Cout, int KH, int KW,
+                            int stride, int pad, void* stream);
+int uda_bn_fold_conv(const float* w, const float* conv_bias, const float* gamma, const float* beta,
+                     const float* running_mean, const float* running_var, float eps, void* w_folded, float* bias_folded,
+                     int Cout, int per_out, void* stream);
 /* dgrad takes w_ft = uda_conv2d_weight_flip_transpose(w): [Cin][KH][KW][Cout] bf16 (the weights of the
  * equivalent forward convolution of dy); addend as in uda_conv2d_direct_dgrad. */
 int uda_conv2d_weight_flip_transpose(const void* w, void* w_ft, int Cout, int Cin, int KH, int KW, void* stream);
@@ -153,6 +163,8 @@ int uda_stem_pack_input(const float* x_nchw, void* xs, int B, int H, int W, int 
 int uda_stem_pack_weight(const void* w, void* ws, int Cout, int K, void* stream);
 int uda_stem_tc_fwd(const void* xs, const void* ws, const float* bias, void* y, double* bn_sums, int B, int H, int W,
                     int Cout, int K, int pad, void* stream);
+int uda_stem_tc_fwd_act(const void* xs, const void* ws, const float* bias, void* y, float act_slope, int B, int H, int W,
+                        int Cout, int K, int pad, void* stream);
 int uda_stem_tc_wgrad(const void* dy, const void* xs, float* dw, float* dws_scratch, int B, int H, int W, int Cout,
                       int K, int pad, void* stream);
 

@@ -340,3 +340,192 @@ def test_graphed_phases_match_eager_adversarial_steps():
     assert step.launches_per_step > 60
     for a, b in zip(eager[warm + 1:], got):
         assert abs(a - b) <= 5e-3 * abs(a), (eager, got)
+
+
+def test_shadow_weights_follow_parameter_writes():
+    """in bf16 mode the tensor-core convolutions read a bf16 shadow copy of the weights; it must be
+    refreshed after (a) ``load_state_dict`` on a model that has already run (reference phase_manager.py:140,
+    test_system.py:260) and (b) a stock ``torch.optim.Adam`` step (reference train.py:461)."""
+    U = _pkg()
+    torch.manual_seed(21)
+    m = U.Unet("resnet18", classes=5).to(DEV).eval()
+    x = torch.randn(2, 3, 64, 64, device=DEV)
+    with torch.no_grad():
+        y0 = m(x).clone()
+    # (a) load different weights into the used model: must equal a FRESH model built from the same state
+    torch.manual_seed(22)
+    other = U.Unet("resnet18", classes=5)
+    sd = {k: v.clone() for k, v in other.state_dict().items()}
+    m.load_state_dict(sd)
+    fresh = U.Unet("resnet18", classes=5)
+    fresh.load_state_dict(sd)
+    fresh = fresh.to(DEV).eval()
+    with torch.no_grad():
+        y1, yf = m(x), fresh(x)
+    assert torch.equal(y1, yf) and not torch.allclose(y1, y0)
+    # (b) torch.optim.Adam writes through the nn.Parameters: conv outputs must move, and equal a fresh model's
+    m.train()
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2)
+    t = torch.randint(0, 5, (2, 64, 64), device=DEV)
+    F.cross_entropy(m(x), t).backward()
+    opt.step()
+    m.eval()
+    fresh2 = U.Unet("resnet18", classes=5)
+    fresh2.load_state_dict({k: v.detach().cpu().clone() for k, v in m.state_dict().items()})
+    fresh2 = fresh2.to(DEV).eval()
+    with torch.no_grad():
+        y2, yf2 = m(x), fresh2(x)
+    assert torch.equal(y2, yf2)
+    assert rel_err(y2, y1) > 1e-3          # the convolution weights really changed (not only BatchNorm affine / biases)
+
+
+def test_fused_adam_checkpoint_and_graph_replay_after_zero_grad():
+    """ADVICE r1 (medium): FusedAdam exposes param_groups / state_dict / load_state_dict (reference train.py:361,496);
+    a GraphedStep replay after a user-side zero_grad() steps normally."""
+    U = _pkg()
+    from uda_aerial_semantic_segmentation_research_b200.optim import FusedAdam
+    from uda_aerial_semantic_segmentation_research_b200.losses import CrossEntropyLoss
+    from uda_aerial_semantic_segmentation_research_b200.graph import GraphedStep
+    torch.manual_seed(5)
+    m = U.Unet("resnet18", classes=4, compute_dtype=torch.float32).to(DEV).train()
+    opt = FusedAdam(m, lr=1e-3)
+    assert opt.param_groups[0]["lr"] == 1e-3
+    crit = CrossEntropyLoss()
+    x, t = torch.randn(2, 3, 64, 64, device=DEV), torch.randint(0, 4, (2, 64, 64), device=DEV)
+    for _ in range(2):
+        opt.zero_grad(); crit(m(x), t).backward(); opt.step()
+    sd = opt.state_dict()
+    assert sd["state"][0]["step"] == 2
+    w = m._store.flat.clone()
+    rs = {k: v.clone() for k, v in m.state_dict().items() if "running" in k or "num_batches" in k}
+    opt.zero_grad(); crit(m(x), t).backward(); opt.step()
+    w_next = m._store.flat.clone()
+    with torch.no_grad():
+        m._store.flat.copy_(w)
+    m.load_state_dict(rs, strict=False)
+    opt2 = FusedAdam(m, lr=5.0)
+    opt2.load_state_dict(sd)
+    assert opt2.param_groups[0]["lr"] == 1e-3
+    opt2.zero_grad(); crit(m(x), t).backward(); opt2.step()
+    assert l2_err(m._store.flat, w_next) < 1e-5      # same update up to the atomics order of the gradient sums
+    step = GraphedStep(m, crit, opt2, x, t, warmup=1)
+    l1 = float(step(x, t))
+    opt2.zero_grad()                                  # user-side zero_grad between replays
+    l2 = float(step(x, t))
+    assert l2 < l1 * 1.5 and np.isfinite(l2)
+
+
+def test_eval_mode_folded_batchnorm_matches_unfolded_path():
+    """Inference (reference predict.py:113-130): BatchNorm folded into the convolution weights / bias, residual add and
+    ReLU in the conv epilogue — against the unfolded path (normalise pass per layer), the bf16 reference and fp32."""
+    from oracle.ref_unet import emulate_bf16
+    from uda_aerial_semantic_segmentation_research_b200 import ops
+    m, ref = _pair("resnet34", 24, torch.bfloat16, seed=6)
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(2, 3, 128, 128, generator=g)
+    ref.train()
+    with torch.no_grad():
+        for _ in range(3):
+            ref(x + 0.1 * torch.randn(x.shape, generator=g))
+    m.load_state_dict(ref.state_dict())
+    m.eval(); ref.eval()
+    with torch.no_grad():
+        l0 = ops.LAUNCHES
+        y_fold = m(x.to(DEV)).cpu()
+        n_fold = ops.LAUNCHES - l0
+        ops.FOLD_BN_EVAL = False
+        try:
+            l0 = ops.LAUNCHES
+            y_plain = m(x.to(DEV)).cpu()
+            n_plain = ops.LAUNCHES - l0
+        finally:
+            ops.FOLD_BN_EVAL = True
+        yr, yr16 = ref(x), emulate_bf16(ref).eval()(x)
+        l0 = ops.LAUNCHES
+        m(x.to(DEV))
+        n_cached = ops.LAUNCHES - l0
+    nat = rel_err(yr16, yr)
+    e_fold, e_plain = rel_err(y_fold, yr), rel_err(y_plain, yr)
+    print(f"eval logits vs fp32 oracle: folded {e_fold:.3e}  unfolded {e_plain:.3e}  bf16 reference {nat:.3e}; "
+          f"launches folded {n_fold} (cached weights {n_cached}) vs unfolded {n_plain}")
+    assert e_fold < 1.5 * nat + 2e-2 and rel_err(y_fold, yr16) < max(2 * nat, 2e-2)
+    assert rel_err(y_fold, y_plain) < max(2 * nat, 2e-2)
+    assert n_cached < n_plain - 80          # 46 BatchNorm passes + their coefficient launches are gone
+    # folded weights follow the running statistics: a training forward must invalidate the cache
+    m.train()
+    with torch.no_grad():
+        m(x.to(DEV))
+    m.eval()
+    with torch.no_grad():
+        y_after = m(x.to(DEV)).cpu()
+        ops.FOLD_BN_EVAL = False
+        try:
+            y_after_plain = m(x.to(DEV)).cpu()
+        finally:
+            ops.FOLD_BN_EVAL = True
+    assert rel_err(y_after, y_after_plain) < max(2 * nat, 2e-2) and not torch.equal(y_after, y_fold)
+
+
+def test_bf16_discriminator_matches_bf16_reference():
+    """the bf16 discriminator path against the oracle discriminator with bf16 storage rounding at the
+    same points (input, conv weights, every conv output, every activation) — forward 1e-2, gradients in L2."""
+    from uda_aerial_semantic_segmentation_research_b200.discriminator import DomainDiscriminator
+    import copy
+    torch.manual_seed(12)
+    ref = RefDomainDiscriminator(3)
+    D = DomainDiscriminator(3)
+    D.load_state_dict(ref.state_dict())
+    D = D.to(DEV).train()
+    r16 = copy.deepcopy(ref).train()
+    with torch.no_grad():
+        for mod in r16.modules():
+            if isinstance(mod, torch.nn.Conv2d):
+                mod.weight.copy_(mod.weight.bfloat16().float())
+    rnd = lambda _m, _i, out: out.bfloat16().float()
+    for mod in r16.features:
+        if isinstance(mod, (torch.nn.Conv2d, torch.nn.LeakyReLU)):
+            mod.register_forward_hook(rnd)
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(4, 3, 128, 128, generator=g).bfloat16().float()
+    y = D(x.to(DEV))
+    yr = r16(x)
+    assert rel_err(y.detach().cpu(), yr.detach()) < 1e-2
+    w = torch.tensor([[1.0], [-1.0], [0.5], [2.0]])
+    (y * w.to(DEV)).sum().backward()
+    (yr * w).sum().backward()
+    worst = 0.0
+    for (n, p), (_, p2) in zip(D.named_parameters(), r16.named_parameters()):
+        if p2.grad.abs().max() < 1e-9:        # conv bias in front of a BatchNorm: analytically zero
+            continue
+        worst = max(worst, l2_err(p.grad.cpu(), p2.grad))
+    print(f"bf16 discriminator: y {rel_err(y.detach().cpu(), yr.detach()):.2e}, worst parameter-gradient L2 error {worst:.2e}")
+    assert worst < 5e-2      # three train-mode BatchNorm + LeakyReLU layers: mask flips at bf16 ties (see test_gpu_stages)
+
+
+def test_domain_adaptation_model_wrap():
+    """the reference's DomainAdaptationModel (src/models/domain_model.py:4-83; restated and pinned in
+    oracle/ref_domain_model.py because the GPU box has no reference tree) around U.Unet + DomainDiscriminator."""
+    U = _pkg()
+    from uda_aerial_semantic_segmentation_research_b200.discriminator import DomainDiscriminator
+    from oracle.ref_domain_model import RefDomainAdaptationModel
+    torch.manual_seed(14)
+    rseg, rdisc = RefUnet("resnet18", classes=4), RefDomainDiscriminator()
+    seg = U.Unet("resnet18", classes=4, compute_dtype=torch.float32)
+    disc = DomainDiscriminator(compute_dtype=torch.float32)
+    seg.load_state_dict(rseg.state_dict()); disc.load_state_dict(rdisc.state_dict())
+    ours = RefDomainAdaptationModel(seg, disc).to(DEV).eval()
+    ref = RefDomainAdaptationModel(rseg, rdisc).eval()
+    x = torch.randn(2, 3, 64, 64)
+    with torch.no_grad():
+        (s1, d1), (s2, d2) = ours(x.to(DEV), domain_adaptation=True), ref(x, domain_adaptation=True)
+        assert rel_err(s1.cpu(), s2) < 1e-4 and rel_err(d1.cpu(), d2) < 1e-4
+        f1, f2 = ours.get_features(x.to(DEV)), ref.get_features(x)
+        assert len(f1) == 6 and all(rel_err(a.cpu(), b) < 1e-4 for a, b in zip(f1, f2))
+        assert rel_err(ours(x.to(DEV)).cpu(), ref(x)) < 1e-4
+    assert len(ours.parameters()) == len(ref.parameters()) and all(p.is_cuda for p in ours.parameters())
+    ours.train()
+    assert seg.training and disc.training
+    opt = torch.optim.Adam(ours.parameters(), lr=1e-4)          # the reference's optimizer over both members
+    seg_pred, dom = ours(x.to(DEV), domain_adaptation=True)
+    (seg_pred.mean() + dom.mean()).backward()
+    opt.step()

@@ -136,3 +136,97 @@ def test_unet_oracle_structure():
     m50.eval()
     with torch.no_grad():
         assert m50(torch.zeros(1, 3, 64, 64)).shape == (1, 23, 64, 64)
+
+
+@pytest.mark.parametrize("name", ["resnet18", "resnet34", "resnet50"])
+def test_encoder_oracle_equals_torchvision_resnet(name):
+    """Pins the U-Net oracle's encoder to the real third-party dependency: smp's ResNet encoders ARE torchvision
+    ResNets without avgpool/fc.  The restatement loads torchvision's state_dict unchanged and must
+    reproduce its feature maps bit for bit (train mode, so BatchNorm batch statistics and the running-stat updates are
+    covered too)."""
+    tv = pytest.importorskip("torchvision")
+    from oracle.ref_unet import RefResNetEncoder
+    torch.manual_seed(0)
+    net = getattr(tv.models, name)(weights=None)
+    enc = RefResNetEncoder(name)
+    sd = {k: v for k, v in net.state_dict().items() if not k.startswith("fc.")}
+    assert sorted(sd.keys()) == sorted(enc.state_dict().keys())
+    enc.load_state_dict(sd)
+    x = torch.randn(2, 3, 64, 64)
+    net.train(); enc.train()
+    f = enc(x)
+    y = net.relu(net.bn1(net.conv1(x)))
+    assert torch.equal(f[0], x) and torch.equal(f[1], y)
+    y = net.maxpool(y)
+    for li in range(1, 5):
+        y = getattr(net, f"layer{li}")(y)
+        assert torch.equal(f[li + 1], y), (name, li)
+    for k, v in net.state_dict().items():            # running statistics advanced identically
+        if "running" in k and not k.startswith("fc."):
+            assert torch.equal(v, enc.state_dict()[k]), k
+    assert enc.out_channels == ((3, 64, 64, 128, 256, 512) if name != "resnet50" else (3, 64, 256, 512, 1024, 2048))
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "src")), reason="reference tree not present")
+def test_domain_model_restatement_matches_reference():
+    """oracle.ref_domain_model.RefDomainAdaptationModel == the reference's DomainAdaptationModel
+    (src/models/domain_model.py:4-83) on the same members: forward with and without domain adaptation,
+    get_features, train / eval propagation, parameters()."""
+    sys.path.insert(0, REFERENCE)
+    try:
+        from src.models.domain_model import DomainAdaptationModel
+    finally:
+        sys.path.remove(REFERENCE)
+    from oracle.ref_domain_model import RefDomainAdaptationModel
+    from oracle.ref_unet import RefUnet
+    from oracle.ref_discriminator import RefDomainDiscriminator
+    torch.manual_seed(1)
+    seg, disc = RefUnet("resnet18", classes=5).eval(), RefDomainDiscriminator().eval()
+    a, b = DomainAdaptationModel(seg, disc), RefDomainAdaptationModel(seg, disc)
+    x = torch.randn(2, 3, 64, 64)
+    with torch.no_grad():
+        assert torch.equal(a(x), b(x))
+        (s1, d1), (s2, d2) = a(x, domain_adaptation=True), b(x, domain_adaptation=True)
+        assert torch.equal(s1, s2) and torch.equal(d1, d2)
+        assert all(torch.equal(u, v) for u, v in zip(a.get_features(x), b.get_features(x)))
+        assert torch.equal(DomainAdaptationModel(seg)(x, domain_adaptation=True),
+                           RefDomainAdaptationModel(seg)(x, domain_adaptation=True))
+    assert [id(p) for p in a.parameters()] == [id(p) for p in b.parameters()]
+    assert b.train() is b and seg.training and disc.training
+    assert b.eval() is b and not seg.training and not disc.training
+    assert RefDomainAdaptationModel(torch.nn.Identity()).get_features(x) is None
+
+
+@pytest.mark.skipif(not os.path.isdir(os.path.join(REFERENCE, "src")), reason="reference tree not present")
+def test_reference_domain_model_wraps_uda_b200_networks(monkeypatch):
+    """The reference's OWN DomainAdaptationModel around the uda_b200 Unet + DomainDiscriminator (engine executed by the
+    oracle ops on the CPU — the GPU twin of this test is tests/test_gpu_unet.py::test_domain_adaptation_model_wrap)."""
+    sys.path.insert(0, REFERENCE)
+    try:
+        from src.models.domain_model import DomainAdaptationModel
+    finally:
+        sys.path.remove(REFERENCE)
+    import uda_aerial_semantic_segmentation_research_b200 as U
+    from uda_aerial_semantic_segmentation_research_b200 import unet, engine, discriminator
+    from oracle import ref_ops
+    from oracle.ref_unet import RefUnet
+    from oracle.ref_discriminator import RefDomainDiscriminator
+    for mod in (unet, engine, discriminator):
+        monkeypatch.setattr(mod, "ops", ref_ops)
+    monkeypatch.setattr(unet.Unet, "_prepare", lambda self, device: self._store.ensure_flat(device))
+    monkeypatch.setattr(discriminator.DomainDiscriminator, "_prepare", lambda self, device: self._store.ensure_flat(device))
+    torch.manual_seed(2)
+    rseg, rdisc = RefUnet("resnet18", classes=4), RefDomainDiscriminator()
+    seg = U.Unet("resnet18", classes=4, compute_dtype=torch.float32)
+    disc = discriminator.DomainDiscriminator(compute_dtype=torch.float32)
+    seg.load_state_dict(rseg.state_dict()); disc.load_state_dict(rdisc.state_dict())
+    ours, ref = DomainAdaptationModel(seg, disc).eval(), DomainAdaptationModel(rseg, rdisc).eval()
+    x = torch.randn(2, 3, 64, 64)
+    with torch.no_grad():
+        (s1, d1), (s2, d2) = ours(x, domain_adaptation=True), ref(x, domain_adaptation=True)
+        assert torch.allclose(s1, s2, atol=1e-4) and torch.allclose(d1, d2, atol=1e-5)
+        f1, f2 = ours.get_features(x), ref.get_features(x)
+        assert len(f1) == 6 and all(torch.allclose(u, v, atol=1e-4) for u, v in zip(f1, f2))
+    assert len(ours.parameters()) == len(ref.parameters())
+    ours.train()
+    assert seg.training and disc.training

@@ -201,6 +201,64 @@ static void run_rate(const CUtensorMap& ms, int nboxes, int N, int n_mma, int n_
   cudaFree(dout);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// issuers: is the ~55-clock floor per tcgen05.mma a limit of the issuing THREAD or of the SM's tensor front end?
+// NW warps (one elected lane each) issue n_mma MMAs each into their own accumulators.
+// ------------------------------------------------------------------------------------------------------------
+template <int NW>
+__global__ void __launch_bounds__(32 * (NW + 1), 1)
+issuers_kernel(RateOut* out, int N, int n_mma) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~uintptr_t(1023));
+  const uint32_t a_smem = smem_u32(smem), b_smem = a_smem + 16384;
+  uint64_t* bars = (uint64_t*)(smem + 16384 + 32768);
+  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+  const uint32_t bar0 = smem_u32(bars);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < (16384 + 32768) / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0x3c003c00u;
+  fence_proxy_async();
+  if (warp == 0) {
+    if (lane == 0) { for (int w = 0; w < NW; ++w) mbar_init(bar0 + 8 * w, 1); fence_barrier_init(); }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), 512); tmem_relinquish();
+  }
+  tc_fence_before(); __syncthreads(); tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  long long clk = 0;
+  if (warp >= 1 && lane == 0) {
+    const int w = warp - 1;
+    const uint32_t idesc = make_idesc_bf16(128, N);
+    const uint64_t adesc = make_kmajor_desc(a_smem, 128), bdesc = make_kmajor_desc(b_smem, 128);
+    const uint32_t acc = tmem + (uint32_t)(w * (512 / NW));
+    const long long t0 = clock64();
+    for (int i = 0; i < n_mma; i += 4) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(acc + (uint32_t)(((i >> 2) & 1) * N), adesc + 2ull * k, bdesc + 2ull * k, idesc, 1u);
+    }
+    umma_commit(bar0 + 8 * w);
+    mbar_wait(bar0 + 8 * w, 0);
+    clk = clock64() - t0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 32) out[blockIdx.x].mma_clk = clk;
+  tc_fence_before(); __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+template <int NW>
+static void run_issuers(int N, int n_mma, int sms) {
+  RateOut* dout; CK(cudaMalloc(&dout, sms * sizeof(RateOut))); CK(cudaMemset(dout, 0, sms * sizeof(RateOut)));
+  const size_t smem = 16384 + 32768 + 1024 + 256;
+  CK(cudaFuncSetAttribute(issuers_kernel<NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  for (int rep = 0; rep < 2; ++rep) { issuers_kernel<NW><<<sms, 32 * (NW + 1), smem>>>(dout, N, n_mma); CK(cudaGetLastError()); CK(cudaDeviceSynchronize()); }
+  std::vector<RateOut> h(sms);
+  CK(cudaMemcpy(h.data(), dout, sms * sizeof(RateOut), cudaMemcpyDeviceToHost));
+  double t = 0; for (int i = 0; i < sms; ++i) t += h[i].mma_clk;
+  printf("issuers %d x %5d MMAs  M=128 N=%3d : %.1f clk per MMA of the SM (pipe floor %d)\n", NW, n_mma, N, t / sms / (NW * (double)n_mma), N / 2);
+  cudaFree(dout);
+}
+
 int main(int argc, char** argv) {
   int dev = 0, sms = 0;
   CK(cudaGetDevice(&dev));
@@ -227,6 +285,8 @@ int main(int argc, char** argv) {
   run_rate<2, 4, 4>(ms, nboxes, 128, 4096, 0, sms); run_rate<2, 8, 8>(ms, nboxes, 128, 4096, 0, sms);
   run_rate<2, 4, 4>(ms, nboxes, 256, 4096, 0, sms); run_rate<2, 8, 8>(ms, nboxes, 256, 4096, 0, sms);
   run_rate<1, 8, 8>(ms, nboxes, 128, 4096, 768, sms); run_rate<2, 8, 8>(ms, nboxes, 256, 2048, 768, sms);
+  printf("--- one / two / four issuing warps\n");
+  for (int N : {16, 32, 64, 128}) { run_issuers<1>(N, 4096, sms); run_issuers<2>(N, 4096, sms); if (N <= 64) run_issuers<4>(N, 4096, sms); }
   printf("--- TMA only (16 KB boxes of a 16 MB L2-resident buffer, 4 in flight per SM)\n");
   run_rate<1>(ms, nboxes, 128, 0, 1024, sms);
   printf("--- both\n");

@@ -58,3 +58,5 @@ for name, H, Cin, Cout, k, s in SHAPES:
     run(f"{name} fwd+stats", lambda: ops.conv_fwd(x, w, None, s, p, bn_sums=sums))
     run(f"{name} fwd", lambda: ops.conv_fwd(x, w, None, s, p))
     run(f"{name} dgrad", lambda: ops.conv_dgrad(dy, w, x.shape, s, p, w_ft=wft))
+    dw = torch.zeros(Cout, k, k, Cin, device="cuda")
+    run(f"{name} wgrad", lambda: ops.conv_wgrad(dy, x, dw, s, p))

@@ -376,7 +376,7 @@ bool fwd_shape_ok(int B, int H, int W, int Cin, int Cout, int KH, int KW, int st
 // x: [B,H,W,Cin] bf16; w: [Cout][KH*KW][Cin] bf16; "same" (stride 1) or halving (stride 2) forward convolution
 int run_fwd(const void* x, const void* w, const float* bias, const void* addend, void* y, float* y_nchw,
             double* bn_sums, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-            cudaStream_t st) {
+            cudaStream_t st, int act = 0, float act_slope = 0.f) {
   UDA_REQUIRE(fwd_shape_ok(B, H, W, Cin, Cout, KH, KW, stride, pad), UDA_ERR_UNSUPPORTED,
               "conv_tc: shape not covered by the tensor-core kernel (B=%d H=%d W=%d Cin=%d Cout=%d k=%d s=%d p=%d)",
               B, H, W, Cin, Cout, KH, stride, pad);
@@ -398,6 +398,7 @@ int run_fwd(const void* x, const void* w, const float* bias, const void* addend,
     }
   g.OH = stride == 1 ? H : H / 2; g.OW = stride == 1 ? W : W / 2; g.os = 1;
   g.bias = bias; g.addend = addend; g.out = y; g.out_nchw = y_nchw; g.bn_sums = bn_sums;
+  g.act = act; g.act_slope = act_slope;
   return run_gemm_conv(g, st);
 }
 
@@ -812,7 +813,8 @@ int make_stem_map(CUtensorMap* m, const void* xs, int B, int H, int W, int K, co
   return make_tmap_bf16(m, xs, 5, dims, str, box, KS * 8);
 }
 
-int run_stem_fwd(const void* xs, const void* ws, const float* bias, void* y, double* bn_sums, int B, int H, int W,
+int run_stem_fwd(const void* xs, const void* ws, const float* bias, void* y, double* bn_sums, int act, float act_slope,
+                 int B, int H, int W,
                  int Cout, int K, cudaStream_t st) {
   const TilePlan tp = plan_tiles(B, H / 2, W / 2);
   CUtensorMap ma;
@@ -825,6 +827,7 @@ int run_stem_fwd(const void* xs, const void* ws, const float* bias, void* y, dou
   for (int kh = 0; kh < K; ++kh) { c.dh[kh] = kh >> 1; c.ph[kh] = kh & 1; c.dw[kh] = 0; c.pw[kh] = 0; c.wtap[kh] = kh; }
   g.OH = H / 2; g.OW = W / 2; g.os = 1;
   g.bias = bias; g.addend = nullptr; g.out = y; g.out_nchw = nullptr; g.bn_sums = bn_sums;
+  g.act = act; g.act_slope = act_slope;
   g.a_map = &ma; g.a_MH = H / 2; g.a_MW = W / 2; g.a_kc = stem_slots(K) * 4;
   return run_gemm_conv_persistent(g, st);
 }
@@ -898,7 +901,14 @@ extern "C" int uda_stem_tc_fwd(const void* xs, const void* ws, const float* bias
                                int H, int W, int Cout, int K, int pad, void* stream) {
   UDA_REQUIRE(xs && ws && y, UDA_ERR_BAD_ARG, "stem_tc_fwd: null pointer");
   UDA_REQUIRE(stem_shape_ok(B, H, W, 3, Cout, K, 2, pad), UDA_ERR_UNSUPPORTED, "stem_tc_fwd: shape not covered");
-  return run_stem_fwd(xs, ws, bias, y, bn_sums, B, H, W, Cout, K, (cudaStream_t)stream);
+  return run_stem_fwd(xs, ws, bias, y, bn_sums, 0, 0.f, B, H, W, Cout, K, (cudaStream_t)stream);
+}
+// stem forward with the activation in the epilogue (eval mode: BatchNorm folded into ws / bias)
+extern "C" int uda_stem_tc_fwd_act(const void* xs, const void* ws, const float* bias, void* y, float act_slope, int B,
+                                   int H, int W, int Cout, int K, int pad, void* stream) {
+  UDA_REQUIRE(xs && ws && y, UDA_ERR_BAD_ARG, "stem_tc_fwd_act: null pointer");
+  UDA_REQUIRE(stem_shape_ok(B, H, W, 3, Cout, K, 2, pad), UDA_ERR_UNSUPPORTED, "stem_tc_fwd_act: shape not covered");
+  return run_stem_fwd(xs, ws, bias, y, nullptr, 1, act_slope, B, H, W, Cout, K, (cudaStream_t)stream);
 }
 // dw [Cout][K][K][3] fp32 += wgrad; dws_scratch: fp32 [Cout][K][KS*4] scratch (KS = 8 for K = 7, 4 for K = 4)
 extern "C" int uda_stem_tc_wgrad(const void* dy, const void* xs, float* dw, float* dws_scratch, int B, int H, int W,
@@ -934,6 +944,19 @@ extern "C" int uda_conv2d_tc_fwd(const void* x, const void* w, const float* bias
                  (cudaStream_t)stream);
 }
 
+// Inference form: y = act(conv(x, w) + bias (+ addend)) in ONE launch — with BatchNorm folded into w / bias
+// (uda_bn_fold_conv) this is conv + BN (+ residual) + ReLU of an eval-mode network.  act_slope: 0 = ReLU,
+// 0.2 = LeakyReLU, 1 = no activation.
+extern "C" int uda_conv2d_tc_fwd_fused(const void* x, const void* w, const float* bias, const void* addend,
+                                       float act_slope, void* y_nhwc, float* y_nchw_f32, int B, int H, int W, int Cin,
+                                       int Cout, int KH, int KW, int stride, int pad, void* stream) {
+  UDA_REQUIRE(x && w && (y_nhwc || y_nchw_f32), UDA_ERR_BAD_ARG, "conv_tc_fwd_fused: null pointer");
+  UDA_REQUIRE(use_persistent(), UDA_ERR_UNSUPPORTED, "conv_tc_fwd_fused: the fused epilogue needs the persistent kernels");
+  UDA_REQUIRE(!addend || aligned<bf16>(addend, 16), UDA_ERR_BAD_ARG, "conv_tc_fwd_fused: addend must be 16-byte aligned");
+  return run_fwd(x, w, bias, addend, y_nhwc, y_nchw_f32, nullptr, B, H, W, Cin, Cout, KH, KW, stride, pad,
+                 (cudaStream_t)stream, act_slope != 1.f ? 1 : 0, act_slope);
+}
+
 // w_ft: weights from uda_conv2d_weight_flip_transpose ([Cin][KH][KW][Cout] bf16)
 extern "C" int uda_conv2d_tc_dgrad(const void* dy, const void* w_ft, const void* addend, void* dx, int B, int H, int W,
                                    int Cin, int Cout, int KH, int KW, int stride, int pad, void* stream) {
@@ -949,6 +972,28 @@ extern "C" int uda_conv2d_tc_dgrad_bnstats(const void* dy, const void* w_ft, con
   UDA_REQUIRE(aligned<bf16>(a, 16) && (!z || aligned<bf16>(z, 16)), UDA_ERR_BAD_ARG,
               "conv_tc_dgrad_bnstats: a / z must be 16-byte aligned");
   return run_dgrad(dy, w_ft, addend, dx, B, H, W, Cin, Cout, KH, KW, stride, pad, (cudaStream_t)stream, a, z, slope, sums);
+}
+
+// ---- eval-mode BatchNorm folding:  w'[o] = w[o] * gamma[o] / sqrt(var[o] + eps),  b' = beta - mean * gamma / sqrt(...) (+ b * ...)
+__global__ void bn_fold_conv_kernel(const float* __restrict__ w, const float* __restrict__ conv_bias,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ mean, const float* __restrict__ var, float eps,
+                                    bf16* __restrict__ w_out, float* __restrict__ bias_out, int Cout, int per_out) {
+  const int o = blockIdx.x;
+  const float s = gamma[o] * rsqrtf(var[o] + eps);
+  for (int i = threadIdx.x; i < per_out; i += blockDim.x)
+    w_out[(size_t)o * per_out + i] = __float2bfloat16_rn(w[(size_t)o * per_out + i] * s);
+  if (threadIdx.x == 0) bias_out[o] = beta[o] + ((conv_bias ? conv_bias[o] : 0.f) - mean[o]) * s;
+}
+extern "C" int uda_bn_fold_conv(const float* w, const float* conv_bias, const float* gamma, const float* beta,
+                                const float* running_mean, const float* running_var, float eps, void* w_folded,
+                                float* bias_folded, int Cout, int per_out, void* stream) {
+  UDA_REQUIRE(w && gamma && beta && running_mean && running_var && w_folded && bias_folded && Cout > 0 && per_out > 0,
+              UDA_ERR_BAD_ARG, "bn_fold_conv: bad argument");
+  bn_fold_conv_kernel<<<Cout, 128, 0, (cudaStream_t)stream>>>(w, conv_bias, gamma, beta, running_mean, running_var, eps,
+                                                               (bf16*)w_folded, bias_folded, Cout, per_out);
+  UDA_LAUNCH_OK("bn_fold_conv_kernel");
+  return UDA_OK;
 }
 
 extern "C" int uda_conv2d_weight_flip_transpose(const void* w, void* w_ft, int Cout, int Cin, int KH, int KW,

@@ -28,6 +28,7 @@ struct HParams {
   int stages;
   bf16* out; float* out_nchw; const float* bias; const bf16* addend;
   double* bn_sums;
+  int act; float act_slope;            // GemmConv::act
   const bf16* st_a; const bf16* st_z; float st_slope; double* st_sums;   // GemmConv::st_*
   long long* trace;   // experiment builds only: per-CTA trace records (conv_tc_internal.cuh)
 };
@@ -198,6 +199,10 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               }
             }
           }
+          if (p.act) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) f[k] = f[k] > 0.f ? f[k] : f[k] * p.act_slope;
+          }
           if (p.bn_sums) {
             if constexpr (kLate) {
 #pragma unroll
@@ -325,6 +330,7 @@ int run_gemm_conv_halo(const GemmConv& g, cudaStream_t st) {
   p.Cout = g.Cout; p.Cred = g.Cred; p.kchunks = kchunks;
   p.out = (bf16*)g.out; p.out_nchw = g.out_nchw; p.bias = g.bias; p.addend = (const bf16*)g.addend;
   p.bn_sums = g.bn_sums;
+  p.act = g.act; p.act_slope = g.act_slope;
   p.st_a = (const bf16*)g.st_a; p.st_z = (const bf16*)g.st_z; p.st_slope = g.st_slope; p.st_sums = g.st_sums;
   if (g.st_sums && (!g.st_a || !g.out || g.bn_sums)) return UDA_ERR_UNSUPPORTED;
   UDA_TR(p.trace = g_trace_buf;)

@@ -44,6 +44,9 @@ struct GemmConv {
   int ncls; TapClass cls[kMaxClasses];
   int OH, OW, os;
   const float* bias; const void* addend; void* out; float* out_nchw;
+  // optional activation applied LAST in the epilogue (after bias and addend): v = v > 0 ? v : act_slope * v; act = 0: none.
+  // Eval-mode inference folds BatchNorm into the weights / bias, so conv + BN (+ residual) + ReLU is ONE launch.
+  int act; float act_slope;
   double* bn_sums;   // optional [2*Cout]: += per-channel sum / sum of squares of the bf16-rounded outputs
   // optional BatchNorm-BACKWARD statistics of the tensor this launch produces (it is the dgrad of the convolution
   // that consumed a = act(BN(z) (+res)), so `out` is dL/da):  st_sums[c] += sum g,  st_sums[Cout+c] += sum g*v  over

@@ -42,6 +42,7 @@ struct PParams {
   PClass cls[kMaxClasses];
   bf16* out; float* out_nchw; const float* bias; const bf16* addend;
   double* bn_sums;
+  int act; float act_slope;            // GemmConv::act
   const bf16* st_a; const bf16* st_z; float st_slope; double* st_sums;   // GemmConv::st_*
   long long* trace;   // experiment builds only: per-CTA trace records (conv_tc_internal.cuh)
   int debug;   // experiment builds only (UDA_B200_TC_DEBUG bit mask): 1 = no epilogue stores, 2 = no MMAs, 4 = no TMA loads
@@ -114,7 +115,9 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
           for (int kc = 0; kc < p.kchunks; ++kc)
             tma_load_2d(ws_base + (wt * p.kchunks + kc) * kBBytes, &map_b, ws_bar, wt * p.Cred + kc * KC, 0);
       }
-      int it = 0;
+      // ring position kept as (slot, phase) counters: no integer division in the per-stage loop
+      int s = 0; uint32_t phs = 0;
+      uint32_t a_dst = ring_base;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int ci = t / tiles_per_cls, rem = t % tiles_per_cls;
         const int mt = rem % p.m_tiles, n0 = (rem / p.m_tiles) * BN;
@@ -122,19 +125,21 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const int b0 = grp * p.NB, h0 = (tin / p.tiles_w) * p.TH, w0 = (tin % p.tiles_w) * p.TW;
         const PClass& c = p.cls[ci];
         for (int tap = 0; tap < c.ntaps; ++tap) {
-          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-            const int s = it % S;
-            const uint32_t phs = (it / S) & 1;
+          const int cw = c.pw[tap] * p.Cred, xw = w0 + c.dw[tap], xh = h0 + c.dh[tap], ph = c.ph[tap];
+          const int bw = c.wtap[tap] * p.Cred;
+          for (int kc = 0; kc < p.kchunks; ++kc) {
             UDA_TR_WAIT(tr_w, mbar_wait(empty_bar(s), phs ^ 1))
-            const uint32_t a_dst = ring_base + s * stage_bytes;
-            if (UDA_TC_DBG(p, 4)) { mbar_arrive(full_bar(s)); continue; }
-            mbar_expect_tx(full_bar(s), stage_bytes);
-            if (p.rank5)
-              tma_load_5d(a_dst, &map_a, full_bar(s), c.pw[tap] * p.Cred + kc * KC, w0 + c.dw[tap], c.ph[tap],
-                          h0 + c.dh[tap], b0);
-            else
-              tma_load_4d(a_dst, &map_a, full_bar(s), kc * KC, w0 + c.dw[tap], h0 + c.dh[tap], b0);
-            if (!p.ws) tma_load_2d(a_dst + kABytes, &map_b, full_bar(s), c.wtap[tap] * p.Cred + kc * KC, n0);
+            if (UDA_TC_DBG(p, 4)) {
+              mbar_arrive(full_bar(s));
+            } else {
+              mbar_expect_tx(full_bar(s), stage_bytes);
+              if (p.rank5)
+                tma_load_5d(a_dst, &map_a, full_bar(s), cw + kc * KC, xw, ph, xh, b0);
+              else
+                tma_load_4d(a_dst, &map_a, full_bar(s), kc * KC, xw, xh, b0);
+              if (!p.ws) tma_load_2d(a_dst + kABytes, &map_b, full_bar(s), bw + kc * KC, n0);
+            }
+            if (++s == S) { s = 0; phs ^= 1; a_dst = ring_base; } else { a_dst += stage_bytes; }
           }
         }
       }
@@ -146,7 +151,16 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       constexpr uint32_t idesc = make_idesc_bf16(128, BN < 16 ? 16 : BN);
       UDA_TR(long long tr_wf = 0, tr_we = 0, tr_first = 0;)
       if (p.ws) { UDA_TR_WAIT(tr_wf, mbar_wait(ws_bar, 0)) tc_fence_after(); }
-      int it = 0, j = 0;
+      // The issuing thread is ONE in-order thread: at N = 128 a tcgen05.mma occupies the tensor pipe for 64 clocks and
+      // the thread needs ~55 clocks to issue one, so every extra instruction per stage (integer divisions for the ring
+      // index, descriptor construction, parameter loads) used to throttle the pipe (measured: ~100-140 clk per MMA,
+      // tools/exp/umma_rate.cu, profiles/r02_trace_conv.txt).  Ring slot / phase are counters, descriptors are a
+      // constant high word plus a low word that is only ever added to.
+      const uint32_t dhi = kmajor_desc_hi(KC * 2);
+      const uint32_t ring_lo = kmajor_desc_lo(ring_base), ws_lo = kmajor_desc_lo(ws_base);
+      const uint32_t stage_step = (uint32_t)stage_bytes >> 4;
+      int s = 0, j = 0; uint32_t phs = 0;
+      uint32_t a_lo = ring_lo;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
         const int ci = t / tiles_per_cls;
         const PClass& c = p.cls[ci];
@@ -155,26 +169,23 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)q * kAccCols;
         for (int tap = 0; tap < c.ntaps; ++tap) {
-          for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
-            const int s = it % S;
-            const uint32_t phs = (it / S) & 1;
+          const uint32_t wt_lo = ws_lo + (((uint32_t)c.wtap[tap] * p.kchunks * kBBytes) >> 4);
+          for (int kc = 0; kc < p.kchunks; ++kc) {
             UDA_TR_WAIT(tr_wf, mbar_wait(full_bar(s), phs))
             UDA_TR(if (!tr_first) tr_first = clock64() - tr0;)
             tc_fence_after();
-            const uint32_t a_addr = ring_base + s * stage_bytes;
-            const uint32_t b_addr = p.ws ? ws_base + (c.wtap[tap] * p.kchunks + kc) * kBBytes : a_addr + kABytes;
-            const uint64_t bdesc = make_kmajor_desc(b_addr, KC * 2);
+            const uint32_t b_lo = p.ws ? wt_lo + (uint32_t)kc * (kBBytes >> 4) : a_lo + (kABytes >> 4);
             if (!UDA_TC_DBG(p, 2)) {
 #pragma unroll
               for (int sub = 0; sub < MT; ++sub) {
-                const uint64_t adesc = make_kmajor_desc(a_addr + sub * (128 * KC * 2), KC * 2);
 #pragma unroll
                 for (int k = 0; k < KC / 16; ++k)
-                  umma_bf16(acc + (uint32_t)sub * BN, adesc + 2ull * k, bdesc + 2ull * k, idesc,
-                            (tap > 0 || kc > 0 || k > 0) ? 1u : 0u);
+                  umma_bf16(acc + (uint32_t)sub * BN, desc64(a_lo + sub * ((128 * KC * 2) >> 4) + 2 * k, dhi),
+                            desc64(b_lo + 2 * k, dhi), idesc, (tap > 0 || kc > 0 || k > 0) ? 1u : 0u);
               }
             }
             umma_commit(empty_bar(s));
+            if (++s == S) { s = 0; phs ^= 1; a_lo = ring_lo; } else { a_lo += stage_step; }
           }
         }
         umma_commit(tfull_bar(q));
@@ -254,6 +265,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 for (int e = 0; e < 8; ++e) f[k + e] += a8[e];
               }
             }
+          }
+          if (p.act) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) f[k] = f[k] > 0.f ? f[k] : f[k] * p.act_slope;
           }
           if (p.bn_sums) {
             if constexpr (kLate) {
@@ -444,6 +459,7 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
   }
   p.out = (bf16*)g.out; p.out_nchw = g.out_nchw; p.bias = g.bias; p.addend = (const bf16*)g.addend;
   p.bn_sums = g.bn_sums;
+  p.act = g.act; p.act_slope = g.act_slope;
   p.debug = 0;
   p.trace = nullptr;
   UDA_TR(p.trace = g_trace_buf;)

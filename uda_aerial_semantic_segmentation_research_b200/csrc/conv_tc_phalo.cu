@@ -34,6 +34,7 @@ struct PHParams {
   int Cout, Cred, kchunks;
   int HR, halo_bytes, halo_stride, b_stages;
   bf16* out; const bf16* addend; double* bn_sums;
+  const float* bias; int act; float act_slope;   // GemmConv::bias / act
   long long* trace;   // experiment builds only: per-CTA trace records (conv_tc_internal.cuh)
 };
 
@@ -91,25 +92,31 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // ===================== TMA producer: per channel chunk one halo box per block, then nine weight tiles =====
     if (elect_one()) {
       UDA_TR(long long tr_w = 0;)
-      int ita = 0, itb = 0;
+      // ring positions are (slot, phase) counters: no integer division in the per-stage loops
+      int sa = 0, sb = 0; uint32_t pha = 0, phb = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int mt = t % p.m_tiles, n0 = (t / p.m_tiles) * BN;
         const int gb0 = mt * NBLK;
         const int nblk = min(NBLK, p.total_blocks - gb0);
-        for (int kc = 0; kc < p.kchunks; ++kc, ++ita) {
-          const int sa = ita % kAStages;
-          UDA_TR_WAIT(tr_w, mbar_wait(aempty(sa), ((ita / kAStages) & 1) ^ 1))
+        int hb[NBLK], hrow[NBLK];   // image / first halo row of each block
+#pragma unroll
+        for (int j = 0; j < NBLK; ++j) {
+          const int gb = gb0 + j, b = gb / p.nb_img, m0 = (gb - b * p.nb_img) * 128;
+          hb[j] = b; hrow[j] = m0 / p.P - 1;
+        }
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          UDA_TR_WAIT(tr_w, mbar_wait(aempty(sa), pha ^ 1))
           mbar_expect_tx(afull(sa), (uint32_t)nblk * p.halo_bytes);
-          for (int j = 0; j < nblk; ++j) {
-            const int gb = gb0 + j, b = gb / p.nb_img, m0 = (gb % p.nb_img) * 128;
-            const int row0 = m0 / p.P;
-            tma_load_4d(a_base + sa * a_stage_bytes + j * p.halo_stride, &map_a, afull(sa), kc * KC, -1, row0 - 1, b);
-          }
-          for (int tap = 0; tap < 9; ++tap, ++itb) {
-            const int sb = itb % SB;
-            UDA_TR_WAIT(tr_w, mbar_wait(bempty(sb), ((itb / SB) & 1) ^ 1))
+#pragma unroll
+          for (int j = 0; j < NBLK; ++j)
+            if (j < nblk)
+              tma_load_4d(a_base + sa * a_stage_bytes + j * p.halo_stride, &map_a, afull(sa), kc * KC, -1, hrow[j], hb[j]);
+          if (++sa == kAStages) { sa = 0; pha ^= 1; }
+          for (int tap = 0; tap < 9; ++tap) {
+            UDA_TR_WAIT(tr_w, mbar_wait(bempty(sb), phb ^ 1))
             mbar_expect_tx(bfull(sb), kBBytes);
             tma_load_2d(b_base + sb * kBBytes, &map_b, bfull(sb), tap * p.Cred + kc * KC, n0);
+            if (++sb == SB) { sb = 0; phb ^= 1; }
           }
         }
       }
@@ -120,48 +127,53 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc_bf16(128, BN);
       UDA_TR(long long tr_wf = 0, tr_we = 0, tr_first = 0, tr_wa = 0;)
-      int ita = 0, itb = 0, j = 0;
+      // one in-order thread issues every MMA: keep its per-stage instruction count minimal — ring
+      // positions are counters, descriptors a constant high word plus a low word that is only added to
+      const uint32_t dhi = kmajor_desc_hi(kRowB);
+      const uint32_t a_lo0 = kmajor_desc_lo(a_base), b_lo0 = kmajor_desc_lo(b_base);
+      const uint32_t row16 = kRowB >> 4;                    // one pixel row in descriptor address units
+      int sa = 0, sb = 0, j = 0; uint32_t pha = 0, phb = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
         const int mt = t % p.m_tiles;
         const int gb0 = mt * NBLK;
         const int nblk = min(NBLK, p.total_blocks - gb0);
-        uint32_t off[NBLK];   // first halo row of each block's positions (tap (0,0))
+        uint32_t off[NBLK];   // descriptor offset of each block's tap (0,0) window inside its halo
 #pragma unroll
         for (int i = 0; i < NBLK; ++i) {
           const int m0 = ((gb0 + i) % p.nb_img) * 128;
-          off[i] = (uint32_t)(m0 - (m0 / p.P) * p.P);
+          off[i] = (uint32_t)(i * p.halo_stride) / 16u + (uint32_t)(m0 - (m0 / p.P) * p.P) * row16;
         }
         const int q = j % kSets;
         UDA_TR_WAIT(tr_we, mbar_wait(tempty(q), ((j / kSets) & 1) ^ 1))
         tc_fence_after();
         const uint32_t acc = tmem_base + (uint32_t)q * kAccCols;
-        for (int kc = 0; kc < p.kchunks; ++kc, ++ita) {
-          const int sa = ita % kAStages;
-          UDA_TR_WAIT(tr_wa, mbar_wait(afull(sa), (ita / kAStages) & 1))
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          UDA_TR_WAIT(tr_wa, mbar_wait(afull(sa), pha))
           tc_fence_after();
-          const uint32_t halo = a_base + sa * a_stage_bytes;
+          const uint32_t halo_lo = a_lo0 + (uint32_t)(sa * a_stage_bytes) / 16u;
+          uint32_t tap_lo = 0;                              // (kh * P + kw) rows
 #pragma unroll 1
-          for (int tap = 0; tap < 9; ++tap, ++itb) {
-            const int sb = itb % SB;
-            UDA_TR_WAIT(tr_wf, mbar_wait(bfull(sb), (itb / SB) & 1))
+          for (int tap = 0; tap < 9; ++tap) {
+            UDA_TR_WAIT(tr_wf, mbar_wait(bfull(sb), phb))
             UDA_TR(if (!tr_first) tr_first = clock64() - tr0;)
             tc_fence_after();
-            const int kh = tap / 3, kw = tap - 3 * kh;
-            const uint64_t bdesc = make_kmajor_desc(b_base + sb * kBBytes, kRowB);
+            const uint32_t b_lo = b_lo0 + (uint32_t)sb * (kBBytes >> 4);
 #pragma unroll
             for (int i = 0; i < NBLK; ++i) {
               if (i < nblk) {
-                const uint64_t adesc =
-                    make_kmajor_desc(halo + i * p.halo_stride + (off[i] + kh * p.P + kw) * kRowB, kRowB);
+                const uint32_t a_lo = halo_lo + off[i] + tap_lo;
 #pragma unroll
                 for (int k = 0; k < KC / 16; ++k)
-                  umma_bf16(acc + (uint32_t)i * BN, adesc + 2ull * k, bdesc + 2ull * k, idesc,
+                  umma_bf16(acc + (uint32_t)i * BN, desc64(a_lo + 2 * k, dhi), desc64(b_lo + 2 * k, dhi), idesc,
                             (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
               }
             }
             umma_commit(bempty(sb));
+            if (++sb == SB) { sb = 0; phb ^= 1; }
+            tap_lo += (tap == 2 || tap == 5) ? (uint32_t)(p.P - 2) * row16 : row16;   // next kw, or next kh row
           }
           umma_commit(aempty(sa));
+          if (++sa == kAStages) { sa = 0; pha ^= 1; }
         }
         umma_commit(tfull(q));
       }
@@ -214,6 +226,11 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
           float f[32];
 #pragma unroll
           for (int k = 0; k < 32; ++k) f[k] = valid ? __uint_as_float(v[k]) : 0.f;
+          if (p.bias && valid) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k)
+              if (nbase + k < p.Cout) f[k] += __ldg(p.bias + nbase + k);
+          }
           if (p.addend && valid) {
             const bf16* add = p.addend + pix * p.Cout + nbase;
 #pragma unroll
@@ -225,6 +242,10 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                 for (int e = 0; e < 8; ++e) f[k + e] += a8[e];
               }
             }
+          }
+          if (p.act) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) f[k] = f[k] > 0.f ? f[k] : f[k] * p.act_slope;
           }
           if (p.bn_sums) bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);   // junk rows contribute zeros
           if (valid) {
@@ -308,7 +329,7 @@ int run_gemm_conv_phalo(const GemmConv& g, cudaStream_t st) {
   for (int t = 0; t < 9; ++t)
     if (c.dh[t] != t / 3 - 1 || c.dw[t] != t % 3 - 1 || c.wtap[t] != t) return UDA_ERR_UNSUPPORTED;
   const int H = g.SH, W = g.SW;
-  if (g.OH != H || g.OW != W || g.bias || g.out_nchw || !g.out || g.st_sums) return UDA_ERR_UNSUPPORTED;
+  if (g.OH != H || g.OW != W || g.out_nchw || !g.out || g.st_sums) return UDA_ERR_UNSUPPORTED;
   if (g.Cred % 64 || g.Cout % 64 || g.Cout < 64) return UDA_ERR_UNSUPPORTED;
   // W = 64 (330-row halos) is implemented and tested, but measured no faster than the persistent kernel's
   // 256 x 128 tiles (30.8 vs 30.7 us on layer2 at B=16, although it moves half the operand bytes): default on for
@@ -327,6 +348,7 @@ int run_gemm_conv_phalo(const GemmConv& g, cudaStream_t st) {
   p.Cout = g.Cout; p.Cred = g.Cred; p.kchunks = g.Cred / KC;
   p.HR = (128 + p.P - 1) / p.P + 3;
   p.out = (bf16*)g.out; p.addend = (const bf16*)g.addend; p.bn_sums = g.bn_sums;
+  p.bias = g.bias; p.act = g.act; p.act_slope = g.act_slope;
   UDA_TR(p.trace = g_trace_buf;)
   // enough work for a full wave, else the persistent kernel's smaller tiles are the better fit
   const int nblk = 2;

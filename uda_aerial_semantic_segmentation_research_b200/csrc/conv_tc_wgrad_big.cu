@@ -32,6 +32,7 @@ struct WBParams {
   int total_atoms, apg, nacc;           // atoms per group (<= 8), accumulators per CTA
   int n_steps, steps_per_split, stages;
   float* dw_out;                        // [Cout][ntaps][Cin] fp32
+  long long* trace;                     // experiment builds only: per-CTA trace records (conv_tc_internal.cuh)
 };
 
 __device__ __forceinline__ uint64_t mn_desc128(uint32_t addr, uint32_t lbo_bytes) {
@@ -76,6 +77,8 @@ conv_tc_wgrad_big_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
   const int n_iters = st_end - st_begin;   // >= 1 by construction of the grid
   const int tiles_per_group = p.tiles_w * p.tiles_h;
 
+  UDA_TR(const long long tr0 = clock64(); const int tr_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+         long long* const trp = (p.trace && tr_cta < 148) ? p.trace + (size_t)tr_cta * 16 : nullptr;)
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_dy); }
   if (warp == 1) {
@@ -93,31 +96,50 @@ conv_tc_wgrad_big_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible from here on
+  UDA_TR(if (trp && threadIdx.x == 0) { trp[0] = tr0; trp[1] = clock64() - tr0; trp[12] = n_iters; })
 
   if (warp == 0) {
     if (elect_one()) {
+      UDA_TR(long long tr_w = 0;)
+      // The producer is ONE thread issuing up to 16 + 4 TMA instructions per 64-pixel step: anything it computes per
+      // instruction is on the critical path (measured: with two integer divisions per atom and four per step the MMA
+      // thread waited for operands half of the time).  Atom coordinates are decoded once, the pixel-tile position is a
+      // set of counters.
+      constexpr int kMaxAtoms = 16;
+      int at_c[kMaxAtoms], at_sh[kMaxAtoms];      // channel coordinate; packed (dw, dh, ph) shifts
+#pragma unroll
+      for (int a = 0; a < kMaxAtoms; ++a) {
+        const int gidx = atom0 + (a < valid_atoms ? a : 0);
+        const int tap = gidx / p.cchunks, c0 = (gidx - tap * p.cchunks) * 64;
+        at_c[a] = p.rank5 ? p.pw[tap] * p.Cin + c0 : c0;
+        at_sh[a] = (p.dw[tap] & 0xff) | ((p.dh[tap] & 0xff) << 8) | ((p.ph[tap] & 0xff) << 16);
+      }
+      int grp = st_begin / tiles_per_group, tin = st_begin - grp * tiles_per_group;
+      int th = tin / p.tiles_w, tw = tin - th * p.tiles_w;
+      int s = 0; uint32_t phs = 0;
       for (int it = 0; it < n_iters; ++it) {
-        const int s = it % S;
-        mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1);
-        const int tile = st_begin + it;
-        const int grp = tile / tiles_per_group, tin = tile % tiles_per_group;
-        const int b0 = grp * p.NB, h0 = (tin / p.tiles_w) * p.TH, w0 = (tin % p.tiles_w) * p.TW;
+        UDA_TR_WAIT(tr_w, mbar_wait(empty_bar(s), phs ^ 1))
+        const int b0 = grp * p.NB, h0 = th * p.TH, w0 = tw * p.TW;
         const uint32_t a_dst = smem_base + s * stage_bytes;
         const uint32_t b_dst = a_dst + a_bytes;
         mbar_expect_tx(full_bar(s), (uint32_t)(valid_atoms + kBAtoms) * atom_bytes);
 #pragma unroll
         for (int j = 0; j < kBAtoms; ++j)
           tma_load_4d(b_dst + j * atom_bytes, &map_dy, full_bar(s), n0 + j * 64, w0, h0, b0);
-        for (int a = 0; a < valid_atoms; ++a) {
-          const int gidx = atom0 + a;
-          const int tap = gidx / p.cchunks, c0 = (gidx % p.cchunks) * 64;
-          if (p.rank5)
-            tma_load_5d(a_dst + a * atom_bytes, &map_x, full_bar(s), p.pw[tap] * p.Cin + c0, w0 + p.dw[tap],
-                        p.ph[tap], h0 + p.dh[tap], b0);
-          else
-            tma_load_4d(a_dst + a * atom_bytes, &map_x, full_bar(s), c0, w0 + p.dw[tap], h0 + p.dh[tap], b0);
+#pragma unroll
+        for (int a = 0; a < kMaxAtoms; ++a) {
+          if (a < valid_atoms) {
+            const int dw = (int)(signed char)(at_sh[a] & 0xff), dh = (int)(signed char)((at_sh[a] >> 8) & 0xff);
+            if (p.rank5)
+              tma_load_5d(a_dst + a * atom_bytes, &map_x, full_bar(s), at_c[a], w0 + dw, (at_sh[a] >> 16) & 0xff, h0 + dh, b0);
+            else
+              tma_load_4d(a_dst + a * atom_bytes, &map_x, full_bar(s), at_c[a], w0 + dw, h0 + dh, b0);
+          }
         }
+        if (++s == S) { s = 0; phs ^= 1; }
+        if (++tw == p.tiles_w) { tw = 0; if (++th == p.tiles_h) { th = 0; ++grp; } }
       }
+      UDA_TR(if (trp) { trp[2] = tr_w; trp[3] = clock64() - tr0; })
     }
   } else if (warp == 1) {
     if (elect_one()) {
@@ -125,30 +147,40 @@ conv_tc_wgrad_big_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
       constexpr uint32_t idesc = make_idesc_bf16(128, BN) | (1u << 15) | (1u << 16);
       const int nacc = (valid_atoms + 1) >> 1;
       const int ksteps = p.KP >> 4;   // 16 pixels per MMA
+      // lean issue loop (one in-order thread feeds the tensor pipe): ring slot / phase as counters, descriptors as a
+      // constant high word plus a low word that is only added to
+      const uint64_t d0 = mn_desc128(0, atom_bytes);
+      const uint32_t dhi = (uint32_t)(d0 >> 32), dlo0 = (uint32_t)d0;      // start-address field zero
+      const uint32_t stage16 = stage_bytes >> 4, a16 = a_bytes >> 4, atom16 = atom_bytes >> 4;
+      uint32_t st_lo = (smem_base & 0x3FFFFu) >> 4;
+      const uint32_t ring_lo = st_lo;
+      int s = 0; uint32_t phs = 0;
+      UDA_TR(long long tr_wf = 0, tr_first = 0;)
       for (int it = 0; it < n_iters; ++it) {
-        const int s = it % S;
-        mbar_wait(full_bar(s), (it / S) & 1);
+        UDA_TR_WAIT(tr_wf, mbar_wait(full_bar(s), phs))
+        UDA_TR(if (!tr_first) tr_first = clock64() - tr0;)
         tc_fence_after();
-        const uint32_t a_addr = smem_base + s * stage_bytes;
-        const uint32_t b_addr = a_addr + a_bytes;
+        const uint32_t b_lo = dlo0 + st_lo + a16;
         for (int acc = 0; acc < nacc; ++acc) {
-          const uint32_t aa = a_addr + (uint32_t)(2 * acc) * atom_bytes;
+          const uint32_t a_lo = dlo0 + st_lo + (uint32_t)(2 * acc) * atom16;
 #pragma unroll 4
-          for (int k = 0; k < ksteps; ++k) {
-            const uint64_t adesc = mn_desc128(aa + k * 2048, atom_bytes);
-            const uint64_t bdesc = mn_desc128(b_addr + k * 2048, atom_bytes);
-            umma_bf16(tmem_base + (uint32_t)(acc * BN), adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < ksteps; ++k)
+            umma_bf16(tmem_base + (uint32_t)(acc * BN), desc64(a_lo + k * 128, dhi), desc64(b_lo + k * 128, dhi), idesc,
+                      (it > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(empty_bar(s));
+        if (++s == S) { s = 0; phs ^= 1; st_lo = ring_lo; } else { st_lo += stage16; }
       }
       umma_commit(tmem_full_bar);
+      UDA_TR(if (trp) { trp[4] = tr_wf; trp[6] = tr_first; trp[7] = clock64() - tr0; })
     }
   } else {
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const int nacc = (valid_atoms + 1) >> 1;
-    mbar_wait(tmem_full_bar, 0);
+    UDA_TR(long long tr_wt = 0;)
+    UDA_TR_WAIT(tr_wt, mbar_wait(tmem_full_bar, 0))
+    UDA_TR(const long long tr_b0 = clock64();)
     tc_fence_after();
 #pragma unroll 1
     for (int acc = 0; acc < nacc; ++acc) {
@@ -171,6 +203,7 @@ conv_tc_wgrad_big_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
       }
     }
     tc_fence_before();
+    UDA_TR(if (trp && warp == 2 && lane == 0) { trp[8] = tr_wt; trp[9] = clock64() - tr_b0; trp[10] = clock64() - tr0; trp[11] = trp[10]; })
   }
   __syncthreads();
   if (warp == 1) {
@@ -257,6 +290,7 @@ int run_wgrad_big(const void* dy, const void* x, float* dw, int B, int H, int W,
     }
   p.n_steps = (B / tp.NB) * p.tiles_w * p.tiles_h;
   p.dw_out = dw;
+  UDA_TR(p.trace = g_trace_buf;)
   // at most one wave: groups x n_tiles x splits <= SMs
   int splits = num_sms() / (groups * n_tiles);
   if (splits < 1) splits = 1;

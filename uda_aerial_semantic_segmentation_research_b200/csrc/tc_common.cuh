@@ -37,9 +37,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(done)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 // Parity wait with a watchdog: a protocol bug traps (reported as a launch failure) instead of hanging
-// the GPU.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+// the GPU.  The watchdog (clock reads, printf) lives out of line so that the single MMA-issuing / TMA-issuing
+// threads — whose instruction count per pipeline stage bounds the tensor pipe — only pay a try_wait.
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   long long t0 = 0;
   for (uint32_t spin = 0;; ++spin) {
@@ -61,6 +73,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       }
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (!mbar_try_wait(bar, parity)) mbar_wait_slow(bar, parity);
 }
 
 // ---- TMA loads (global -> shared, completion on an mbarrier) ----
@@ -141,6 +156,18 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t smem_addr, uint32_
   d |= (uint64_t)((8u * row_bytes) >> 4) << 32;        // SBO            [32,46)
   d |= (uint64_t)1 << 46;                              // descriptor version (Blackwell)
   d |= layout << 61;                                   // swizzle mode   [61,64)
+  return d;
+}
+// The same descriptor as two 32-bit words: only the low word (start address >> 4, LBO) changes between ring slots,
+// K steps (+2 = 32 bytes) and shifted halo windows, so issue loops keep `lo` in a register and add to it.
+__device__ __forceinline__ uint32_t kmajor_desc_lo(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t kmajor_desc_hi(uint32_t row_bytes) {
+  const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+  return ((8u * row_bytes) >> 4) | (1u << 14) | (layout << 29);
+}
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
   return d;
 }
 // kind::f16 instruction descriptor: bf16 A/B (K-major), fp32 accumulate, M x N tile

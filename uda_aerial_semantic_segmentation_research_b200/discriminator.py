@@ -86,7 +86,7 @@ class DomainDiscriminator(nn.Module):
         f = self.features
         y = E.bias_act(ctx, E.conv(ctx, xin, f[0]), 0.2)
         for ci, bi in ((2, 3), (5, 6), (8, 9)):
-            y = E.bn_act(ctx, E.conv(ctx, y, f[ci], bn=f[bi]), f[bi], slope=0.2)
+            y = E.conv_bn_act(ctx, y, f[ci], f[bi], slope=0.2)
         ctx.finish_forward()
         lin = self.classifier[2]
         out, pooled = ops.gap_linear_sigmoid_fwd(y.t, self._store.w2d(lin.weight), lin.bias)

@@ -128,6 +128,8 @@ class ParamStore:
         self.shadow_version = None
         self.grad = None
         self.grad_dropped = False   # zero_grad() since the last backward (FusedAdam refuses to step on stale gradients)
+        self.stats_epoch = 0        # training forwards so far (running statistics are updated by kernels)
+        self._fold_cache = {}
 
     # -- parameters -------------------------------------------------------------------------
     def _view_like(self, flat, p):
@@ -198,6 +200,23 @@ class ParamStore:
         src = self.shadow if dtype == torch.bfloat16 else self.flat
         return src[off:off + p.numel()].view(O, KH, KW, I)
 
+    # -- eval-mode BatchNorm folding ----------------------------------------------------------------
+    def fold_key(self):
+        """Freshness key of the folded (conv x BatchNorm) inference weights: parameters, BatchNorm buffers (in-place
+        loads bump their versions) and the number of training forwards (the kernels update the running statistics
+        without torch noticing)."""
+        return (self.param_version(), sum(b._version for b in self.module.buffers()), self.stats_epoch)
+
+    def folded(self, key, cp, bn):
+        """(bf16 OHWI weights, fp32 bias) of ``cp`` with ``bn`` folded in; cached until ``key`` changes."""
+        hit = self._fold_cache.get(id(cp))
+        if hit is not None and hit[0] == key:
+            return hit[1], hit[2]
+        w, b = ops.bn_fold_conv(self.w(cp.weight, torch.float32), cp.bias, bn.weight, bn.bias, bn.running_mean,
+                                bn.running_var, bn.eps)
+        self._fold_cache[id(cp)] = (key, w, b)
+        return w, b
+
     # -- gradients --------------------------------------------------------------------------
     def new_grad(self):
         self.grad = torch.zeros(self.total, dtype=torch.float32, device=self.flat.device)
@@ -223,6 +242,7 @@ class Ctx:
     def __init__(self, store, dtype, training, tape):
         self.store, self.dtype, self.training, self.tape = store, dtype, training, tape
         self.sync = None  # optional gradient-sync object (ddp.GradSync): param_done(store, param)
+        self.fold_key = None                    # eval mode: freshness key of the folded weights, taken once per forward
         self._pool, self._pool_used = None, 0   # zero-filled float64 scratch for the fused BatchNorm statistics
         self._trackers = []                     # num_batches_tracked buffers to bump at the end of the forward
 
@@ -242,6 +262,7 @@ class Ctx:
         if self._trackers:
             torch._foreach_add_(self._trackers, 1)
             self._trackers = []
+            self.store.stats_epoch += 1
 
     def done(self, *params):
         """Tell the data-parallel layer that the gradients of ``params`` are final for this backward."""
@@ -319,6 +340,29 @@ def conv(ctx, xin, cp, nchw_out=False, bn=None):
             ctx.done(cp.weight, cp.bias)
         ctx.tape.push(bwd)
     return out
+
+
+def conv_bn_act(ctx, xin, cp, bn, slope=0.0, residual=None):
+    """a = act(BN(conv(x)) (+ residual)).  Training: convolution with the BatchNorm statistics in its epilogue, then the
+    normalise + activation pass.  Eval mode on the tensor cores (inference, ``src/models/predict.py:113-130``): the
+    BatchNorm is FOLDED into the weights / bias and the residual add + activation run in the convolution's epilogue —
+    one launch, no BatchNorm pass, no intermediate tensor."""
+    if (not ctx.training and ctx.tape is None and ctx.dtype == torch.bfloat16 and ops.USE_TC and ops.TC_PERSIST
+            and ops.FOLD_BN_EVAL):
+        st = ctx.store
+        if ctx.fold_key is None:
+            ctx.fold_key = st.fold_key()
+        if xin.t is None:   # Cin = 3 stem
+            H, W = xin.nchw.shape[2:]
+            w, b = st.folded(ctx.fold_key, cp, bn)
+            xs = ops.stem_pack_input(xin.nchw, cp.padding)
+            return Var(ops.stem_fwd(xs, ops.stem_pack_weight(w), b, H, W, cp.kernel_size, cp.padding, act_slope=slope))
+        B, H, W, Cin = xin.t.shape
+        if ops.tc_supported(0, B, H, W, Cin, cp.out_channels, cp.kernel_size, cp.kernel_size, cp.stride, cp.padding):
+            w, b = st.folded(ctx.fold_key, cp, bn)
+            return Var(ops.conv_fwd_fused(xin.t, w, b, slope, addend=residual.t if residual is not None else None,
+                                          stride=cp.stride, pad=cp.padding))
+    return bn_act(ctx, conv(ctx, xin, cp, bn=bn), bn, slope=slope, residual=residual)
 
 
 def bn_act(ctx, zin, bn, slope=0.0, residual=None):

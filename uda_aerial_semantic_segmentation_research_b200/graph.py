@@ -1,5 +1,11 @@
 """CUDA-graph capture of the training step.
 
+Data-parallel runs capture the gradient all-reduce INSIDE the graph: the engine's per-parameter "gradient final"
+notifications make ``ddp.GradSync`` fork a communication stream after the last wgrad of every ~25 MB bucket and issue
+``ncclAllReduce`` there (stream fork / join become graph dependencies), so on replay the NCCL kernels run under the
+remaining backward kernels and only the last bucket is exposed.  (PyTorch's rules for capturing NCCL apply: NCCL >=
+2.9.6 and ``TORCH_NCCL_ASYNC_ERROR_HANDLING=0`` set before ``init_process_group``.)
+
 One training step of the hot path is ~900 kernel launches; issued one by one from Python the host needs
 ~13 ms per step — as long as the B200 needs to execute them.  ``GraphedStep`` captures
 ``zero_grad -> forward -> loss -> backward`` once into a CUDA graph (all kernels, memsets and TMA
@@ -16,8 +22,54 @@ import torch
 import torch.distributed as dist
 
 
-class GraphedStep:
-    def __init__(self, model, criterion, optimizer, example_images, example_masks, warmup=3, extra_models=()):
+def _capture_kwargs(with_nccl):
+    """NCCL's watchdog thread may touch the CUDA API while a capture is open: relax the capture error mode to the
+    capturing thread when collectives are captured."""
+    return {"capture_error_mode": "thread_local"} if with_nccl else {}
+
+
+class _Staging:
+    """Double-buffered input staging shared by the captured-step classes: ``stage(*batch)`` starts the asynchronous
+    host->device copy of the NEXT batch (pinned host or device tensors) on a side stream while the current step runs;
+    calling the step without arguments consumes the staged batch."""
+
+    def _init_staging(self, inputs):
+        self._in = inputs
+        dev = inputs[0].device
+        self._stg = [torch.empty_like(t) for t in inputs]
+        self.copy_stream = torch.cuda.Stream(device=dev)
+        self.staged_ready, self.staged_free = torch.cuda.Event(), torch.cuda.Event()
+        self.staged_free.record()
+        self._staged = False
+
+    def stage(self, *batch):
+        if len(batch) != len(self._stg):
+            raise ValueError(f"stage(): expected {len(self._stg)} tensors")
+        self.copy_stream.wait_event(self.staged_free)
+        with torch.cuda.stream(self.copy_stream):
+            for dst, src in zip(self._stg, batch):
+                dst.copy_(src, non_blocking=True)
+            self.staged_ready.record()
+        self._staged = True
+
+    def _load_inputs(self, batch):
+        """Copy ``batch`` (or, when empty, the staged batch) into the captured input buffers."""
+        staged = len(batch) == 0 or batch[0] is None
+        if staged:
+            if not self._staged:
+                raise RuntimeError("captured step called without a batch and none staged")
+            torch.cuda.current_stream().wait_event(self.staged_ready)
+            batch = self._stg
+        for dst, src in zip(self._in, batch):
+            dst.copy_(src, non_blocking=True)
+        if staged:
+            self.staged_free.record()
+            self._staged = False
+
+
+class GraphedStep(_Staging):
+    def __init__(self, model, criterion, optimizer, example_images, example_masks, warmup=3, extra_models=(),
+                 sync_in_graph=True):
         dev = next(model.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("GraphedStep needs the model on a CUDA device")
@@ -26,11 +78,13 @@ class GraphedStep:
         self.x = example_images.to(dev, non_blocking=True).clone()
         self.t = example_masks.to(dev, non_blocking=True).clone()
         self.sync = getattr(model, "_grad_sync", None)
-        # the bucketed all-reduce hooks are host-side logic; under capture the all-reduce runs once on the flat
-        # gradient buffer after the replay instead
+        # sync_in_graph: the bucketed, backward-overlapped all-reduce is captured with the step (module docstring);
+        # otherwise the hooks are detached and ONE all-reduce of the flat gradient buffer runs after the replay
+        self.sync_in_graph = bool(sync_in_graph and self.sync is not None and self.sync.overlap)
         saved = [(m, m._grad_sync) for m in self.models]
-        for m in self.models:
-            m._grad_sync = None
+        if not self.sync_in_graph:
+            for m in self.models:
+                m._grad_sync = None
         try:
             s = torch.cuda.Stream(device=dev)
             s.wait_stream(torch.cuda.current_stream())
@@ -47,18 +101,14 @@ class GraphedStep:
             self.optimizer.zero_grad(set_to_none=True)
             from . import ops
             l0 = ops.LAUNCHES
-            with torch.cuda.graph(self.graph):
+            with torch.cuda.graph(self.graph, **_capture_kwargs(self.sync_in_graph)):
                 self.loss = self._fwd_bwd()
             self.launches_per_step = ops.LAUNCHES - l0 + 1      # captured launches + the fused Adam launch
         finally:
             for m, gs in saved:
                 m._grad_sync = gs
         # staging buffers: the next batch is copied host->device on a side stream while this step runs
-        self.xs, self.ts = torch.empty_like(self.x), torch.empty_like(self.t)
-        self.copy_stream = torch.cuda.Stream(device=dev)
-        self.staged_ready, self.staged_free = torch.cuda.Event(), torch.cuda.Event()
-        self.staged_free.record()
-        self._staged = False
+        self._init_staging([self.x, self.t])
 
     def _fwd_bwd(self):
         self.optimizer.zero_grad(set_to_none=True)
@@ -67,32 +117,14 @@ class GraphedStep:
         return loss.detach()
 
     def _finish(self):
-        if self.sync is not None:
+        if self.sync is not None and not self.sync_in_graph:
             for m in self.models:
                 if m._store.grad is not None:
                     dist.all_reduce(m._store.grad, op=dist.ReduceOp.AVG, group=self.sync.group)
         self.optimizer.step()
 
-    def stage(self, images, masks):
-        """Start the asynchronous copy of the NEXT batch (pinned host or device tensors) into the staging buffers."""
-        self.copy_stream.wait_event(self.staged_free)
-        with torch.cuda.stream(self.copy_stream):
-            self.xs.copy_(images, non_blocking=True)
-            self.ts.copy_(masks, non_blocking=True)
-            self.staged_ready.record()
-        self._staged = True
-
     def __call__(self, images=None, masks=None):
-        if images is None:
-            if not self._staged:
-                raise RuntimeError("GraphedStep(): no batch given and none staged")
-            torch.cuda.current_stream().wait_event(self.staged_ready)
-            images, masks = self.xs, self.ts
-        self.x.copy_(images, non_blocking=True)
-        self.t.copy_(masks, non_blocking=True)
-        if images is self.xs:
-            self.staged_free.record()
-            self._staged = False
+        self._load_inputs(() if images is None else (images, masks))
         self.graph.replay()
         for m in self.models:
             m._store.grad_dropped = False    # the replayed backward refilled the flat gradient buffers
@@ -100,23 +132,22 @@ class GraphedStep:
         return self.loss
 
 
-class GraphedFn:
+class GraphedFn(_Staging):
     """Capture an arbitrary training-step function (e.g. the adversarial D/G step of
     ``src/models/adversarial_trainer.py:84-114``) into one CUDA graph.
 
     ``fn(*inputs)`` must do everything of the step on the device - zero_grad, forward, losses, backward and
-    ``FusedAdam(..., capturable=True).step()`` - and return a tensor (or tuple of tensors); single-process only
-    (no collective is captured).  ``networks`` are the uda_b200 networks used, so that the captured step refreshes
-    their bf16 shadow weights itself.
+    ``FusedAdam(..., capturable=True).step()`` - and return a tensor (or tuple of tensors).  Networks that carry a
+    ``ddp.GradSync`` get their bucketed gradient all-reduce captured with the step (overlapped with backward, see the
+    module docstring), so the same class serves single-GPU and data-parallel runs.  ``networks`` are the uda_b200
+    networks used, so that the captured step refreshes their bf16 shadow weights itself.
     """
 
     def __init__(self, fn, example_inputs, networks, warmup=3):
         dev = example_inputs[0].device
         if dev.type != "cuda":
             raise RuntimeError("GraphedFn needs CUDA example inputs")
-        for m in networks:
-            if getattr(m, "_grad_sync", None) is not None:
-                raise RuntimeError("GraphedFn does not capture the gradient all-reduce; use GraphedStep")
+        with_nccl = any(getattr(m, "_grad_sync", None) is not None for m in networks)
         self.inputs = [t.clone() for t in example_inputs]
         s = torch.cuda.Stream(device=dev)
         s.wait_stream(torch.cuda.current_stream())
@@ -131,18 +162,18 @@ class GraphedFn:
         from . import ops
         l0 = ops.LAUNCHES
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        with torch.cuda.graph(self.graph, **_capture_kwargs(with_nccl)):
             self.out = fn(*self.inputs)
         self.launches_per_step = ops.LAUNCHES - l0
+        self._init_staging(self.inputs)
 
     def __call__(self, *inputs):
-        for dst, src in zip(self.inputs, inputs):
-            dst.copy_(src, non_blocking=True)
+        self._load_inputs(inputs)
         self.graph.replay()
         return self.out
 
 
-class GraphedPhases:
+class GraphedPhases(_Staging):
     """A training step made of several captured compute phases with eager glue in between — the data-parallel form
     of the adversarial step (``src/models/adversarial_trainer.py:84-114``): D-step compute graph -> all-reduce of the
     discriminator gradients + its optimizer step -> G-step compute graph -> all-reduce of the segmentation network's
@@ -156,9 +187,8 @@ class GraphedPhases:
         dev = example_inputs[0].device
         if dev.type != "cuda":
             raise RuntimeError("GraphedPhases needs CUDA example inputs")
-        for m in networks:
-            if getattr(m, "_grad_sync", None) is not None:
-                raise RuntimeError("GraphedPhases: detach GradSync (net._grad_sync = None) and all-reduce in finish_fn")
+        # networks that still carry a GradSync get their bucketed all-reduce captured inside the phase graphs
+        with_nccl = any(getattr(m, "_grad_sync", None) is not None for m in networks)
         self.inputs = [t.clone() for t in example_inputs]
         self.networks = list(networks)
         self.finish = [f for _, f in phases]
@@ -179,17 +209,17 @@ class GraphedPhases:
                 m._store.shadow_ft_version = None
             g = torch.cuda.CUDAGraph()
             l0 = ops.LAUNCHES
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, **_capture_kwargs(with_nccl)):
                 out = compute(*self.inputs)
             self.launches_per_step += ops.LAUNCHES - l0 + 1
             self.graphs.append(g)
             self.outs.append(out)
             g.replay()                         # capturing does not execute: run the phase once for real so that the
             finish()                           # next phase is captured (and later replayed) on a consistent trajectory
+        self._init_staging(self.inputs)
 
     def __call__(self, *inputs):
-        for dst, src in zip(self.inputs, inputs):
-            dst.copy_(src, non_blocking=True)
+        self._load_inputs(inputs)
         for g, finish in zip(self.graphs, self.finish):
             g.replay()
             for m in self.networks:

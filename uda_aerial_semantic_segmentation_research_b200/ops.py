@@ -24,6 +24,9 @@ FUSE_BN_STATS = os.environ.get("UDA_B200_FUSE_BN_STATS", "1") != "0"
 FUSE_BN_BWD = os.environ.get("UDA_B200_FUSE_BN_BWD", "0") == "1"
 #: the persistent / halo tensor-core kernels are the ones with the fused epilogues (UDA_B200_TC_PERSIST=0 disables)
 TC_PERSIST = os.environ.get("UDA_B200_TC_PERSIST", "1") != "0"
+#: eval mode: fold BatchNorm into the convolution weights and run conv + BN (+ residual) + activation as one launch
+#: (set "0" to run the separate normalise pass, e.g. to A/B the two inference paths)
+FOLD_BN_EVAL = os.environ.get("UDA_B200_FOLD_BN_EVAL", "1") != "0"
 #: counts launches issued through this module (bench.py reports it as gpu_launches)
 LAUNCHES = 0
 #: algorithmic FLOPs (2*M*N*K) and call count of the convolutions routed to the tcgen05 kernels
@@ -173,6 +176,39 @@ def conv_fwd(x, w, bias=None, stride=1, pad=1, nchw_out=False, bn_sums=None, for
     return y_nchw if nchw_out else y_nhwc
 
 
+def conv_fwd_fused(x, w, bias, act_slope, addend=None, nchw_out=False, stride=1, pad=1):
+    """Inference form: y = act(conv(x, w) + bias (+ addend)) in one launch (``act_slope`` 0 = ReLU, 0.2 = LeakyReLU,
+    1 = none).  With BatchNorm folded into ``w`` / ``bias`` (``bn_fold_conv``) this is an eval-mode conv + BN (+ residual)
+    + activation.  Tensor-core path only (bf16); the caller checks ``tc_supported``."""
+    _chk(x, "conv_fwd_fused.x", torch.bfloat16); _chk(w, "conv_fwd_fused.w", torch.bfloat16)
+    B, H, W, Cin, Cout, KH, KW, Ho, Wo = _geom(x.shape, w.shape, stride, pad)
+    if bias is not None:
+        _chk(bias, "conv_fwd_fused.bias", torch.float32)
+    if addend is not None:
+        _chk(addend, "conv_fwd_fused.addend", torch.bfloat16)
+        if tuple(addend.shape) != (B, Ho, Wo, Cout):
+            raise _lib.UdaError("conv_fwd_fused: addend must have the output's shape")
+    y_nhwc = None if nchw_out else torch.empty((B, Ho, Wo, Cout), dtype=x.dtype, device=x.device)
+    y_nchw = torch.empty((B, Cout, Ho, Wo), dtype=torch.float32, device=x.device) if nchw_out else None
+    call("conv2d_tc_fwd_fused", ptr(x), ptr(w), ptr(bias), ptr(addend), float(act_slope), ptr(y_nhwc), ptr(y_nchw), ci(B),
+         ci(H), ci(W), ci(Cin), ci(Cout), ci(KH), ci(KW), ci(stride), ci(pad), _stream())
+    _tc_account(B, Ho, Wo, Cout, Cin, KH, KW)
+    _count()
+    return y_nchw if nchw_out else y_nhwc
+
+
+def bn_fold_conv(w_f32, conv_bias, gamma, beta, running_mean, running_var, eps=1e-5):
+    """Eval-mode BatchNorm folded into a convolution: returns (bf16 OHWI weights scaled per output channel, fp32 bias)."""
+    _chk(w_f32, "bn_fold_conv.w", torch.float32)
+    O = w_f32.shape[0]
+    w_out = torch.empty(w_f32.shape, dtype=torch.bfloat16, device=w_f32.device)
+    b_out = torch.empty(O, dtype=torch.float32, device=w_f32.device)
+    call("bn_fold_conv", ptr(w_f32), ptr(conv_bias), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+         float(eps), ptr(w_out), ptr(b_out), ci(O), ci(w_f32.numel() // O), _stream())
+    _count()
+    return w_out, b_out
+
+
 def weight_flip_transpose(w, out=None):
     """OHWI bf16 weights -> [Cin][KH][KW][Cout] flipped copy (the forward-conv weights of dgrad)."""
     _chk(w, "weight_flip_transpose.w", torch.bfloat16)
@@ -214,11 +250,17 @@ def stem_pack_weight(w):
     return ws
 
 
-def stem_fwd(xs, ws, bias, H, W, K, pad, bn_sums=None):
+def stem_fwd(xs, ws, bias, H, W, K, pad, bn_sums=None, act_slope=None):
+    """``act_slope`` (eval mode, BatchNorm folded into ws / bias): activation in the epilogue."""
     B = xs.shape[0]
     O = ws.shape[0]
     y = torch.empty((B, H // 2, W // 2, O), dtype=torch.bfloat16, device=xs.device)
-    call("stem_tc_fwd", ptr(xs), ptr(ws), ptr(bias), ptr(y), ptr(bn_sums), ci(B), ci(H), ci(W), ci(O), ci(K), ci(pad), _stream())
+    if act_slope is not None:
+        call("stem_tc_fwd_act", ptr(xs), ptr(ws), ptr(bias), ptr(y), float(act_slope), ci(B), ci(H), ci(W), ci(O), ci(K),
+             ci(pad), _stream())
+    else:
+        call("stem_tc_fwd", ptr(xs), ptr(ws), ptr(bias), ptr(y), ptr(bn_sums), ci(B), ci(H), ci(W), ci(O), ci(K), ci(pad),
+             _stream())
     _tc_account(B, H // 2, W // 2, O, 3, K, K)
     _count()
     return y

@@ -46,9 +46,9 @@ class BasicBlock(nn.Module):
     def run(self, ctx, x):
         idt = x
         if self.downsample is not None:
-            idt = E.bn_act(ctx, E.conv(ctx, x, self.downsample[0], bn=self.downsample[1]), self.downsample[1], slope=1.0)
-        y = E.bn_act(ctx, E.conv(ctx, x, self.conv1, bn=self.bn1), self.bn1, slope=0.0)
-        return E.bn_act(ctx, E.conv(ctx, y, self.conv2, bn=self.bn2), self.bn2, slope=0.0, residual=idt)
+            idt = E.conv_bn_act(ctx, x, self.downsample[0], self.downsample[1], slope=1.0)
+        y = E.conv_bn_act(ctx, x, self.conv1, self.bn1, slope=0.0)
+        return E.conv_bn_act(ctx, y, self.conv2, self.bn2, slope=0.0, residual=idt)
 
 
 class Bottleneck(nn.Module):
@@ -69,10 +69,10 @@ class Bottleneck(nn.Module):
     def run(self, ctx, x):
         idt = x
         if self.downsample is not None:
-            idt = E.bn_act(ctx, E.conv(ctx, x, self.downsample[0], bn=self.downsample[1]), self.downsample[1], slope=1.0)
-        y = E.bn_act(ctx, E.conv(ctx, x, self.conv1, bn=self.bn1), self.bn1, slope=0.0)
-        y = E.bn_act(ctx, E.conv(ctx, y, self.conv2, bn=self.bn2), self.bn2, slope=0.0)
-        return E.bn_act(ctx, E.conv(ctx, y, self.conv3, bn=self.bn3), self.bn3, slope=0.0, residual=idt)
+            idt = E.conv_bn_act(ctx, x, self.downsample[0], self.downsample[1], slope=1.0)
+        y = E.conv_bn_act(ctx, x, self.conv1, self.bn1, slope=0.0)
+        y = E.conv_bn_act(ctx, y, self.conv2, self.bn2, slope=0.0)
+        return E.conv_bn_act(ctx, y, self.conv3, self.bn3, slope=0.0, residual=idt)
 
 
 class ResNetEncoder(nn.Module):
@@ -99,7 +99,7 @@ class ResNetEncoder(nn.Module):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
 
     def run(self, ctx, x):
-        f1 = E.bn_act(ctx, E.conv(ctx, x, self.conv1, bn=self.bn1), self.bn1, slope=0.0)
+        f1 = E.conv_bn_act(ctx, x, self.conv1, self.bn1, slope=0.0)
         y = E.maxpool(ctx, f1)
         feats = [x, f1]
         for li in range(1, 5):
@@ -125,8 +125,8 @@ class DecoderBlock(nn.Module):
 
     def run(self, ctx, x, skip):
         y = E.upcat(ctx, x, skip)
-        y = E.bn_act(ctx, E.conv(ctx, y, self.conv1[0], bn=self.conv1[1]), self.conv1[1], slope=0.0)
-        return E.bn_act(ctx, E.conv(ctx, y, self.conv2[0], bn=self.conv2[1]), self.conv2[1], slope=0.0)
+        y = E.conv_bn_act(ctx, y, self.conv1[0], self.conv1[1], slope=0.0)
+        return E.conv_bn_act(ctx, y, self.conv2[0], self.conv2[1], slope=0.0)
 
 
 class UnetDecoder(nn.Module):
