@@ -206,7 +206,7 @@ def measure_workload(args, workload, env, full):
     world, rank, local, dev = env["world"], env["rank"], env["local"], env["dev"]
     torch.manual_seed(0)
     size, B = args.size, args.batch
-    adversarial, finetune = workload == "adversarial", workload == "finetune"
+    adversarial, finetune, grl = workload == "adversarial", workload == "finetune", workload == "adversarial_grl"
     if finetune and args.batch == 16:
         B = 4                                               # configs[3]: 32 images on 8 GPUs
     use_graph = not args.no_graph
@@ -214,6 +214,12 @@ def measure_workload(args, workload, env, full):
     nets = [model]
     crit = CrossEntropyLoss()
     opt = FusedAdam(model, lr=1e-3, capturable=use_graph and adversarial, max_grad_norm=1.0 if finetune else None)
+    if grl:   # output-space discriminator behind a gradient-reversal layer: ONE backward, ONE optimizer over both networks
+        from uda_aerial_semantic_segmentation_research_b200.discriminator import OutputSpaceAdversary
+        disc = DomainDiscriminator(CLASSES).to(dev).train()
+        nets.append(disc)
+        adversary, adv = OutputSpaceAdversary(disc, alpha=0.1), AdversarialLoss(0.001)
+        opt = FusedAdam([model, disc], lr=1e-3, capturable=use_graph)
     if adversarial:
         disc = DomainDiscriminator(3).to(dev).train()
         nets.append(disc)
@@ -237,11 +243,13 @@ def measure_workload(args, workload, env, full):
             dist.all_reduce(net._store.grad, op=dist.ReduceOp.AVG)
 
     # ---- inputs ------------------------------------------------------------------------------------------------
-    Bs = B // 2 if adversarial else B
+    Bs = B // 2 if (adversarial or grl) else B
     hx, ht = synthetic_batch(Bs, size, 1234 + rank, pinned=True)
     host = [hx, ht]
     if adversarial:
         host.append(synthetic_batch(Bs, size, 4321 + rank, pinned=True)[0])
+    if grl:       # source and target batch travel as one [2*Bs,...] tensor (one pass of the segmentation network)
+        host = [torch.cat([hx, synthetic_batch(Bs, size, 4321 + rank)[0]]).pin_memory(), ht]
     if finetune:   # second view = flipped + jittered copy (stand-in for the strong augmentation)
         gq = torch.Generator().manual_seed(77 + rank)
         hx2 = hx.flip(-1) + 0.1 * torch.randn(hx.shape, generator=gq)
@@ -271,16 +279,31 @@ def measure_workload(args, workload, env, full):
         return total.detach()
 
     class SplitViews(torch.autograd.Function):
-        """logits [2B,...] -> the two views; backward re-joins the two logit gradients with one copy (autograd's own
+        """logits [2n,...] -> the two halves; backward re-joins the two logit gradients with one copy (autograd's own
         slice backward would materialise two zero-padded full-size tensors and add them)."""
 
         @staticmethod
         def forward(ctx, p):
-            return p[:B], p[B:]
+            n = p.shape[0] // 2
+            return p[:n], p[n:]
 
         @staticmethod
         def backward(ctx, g1, g2):
+            g1 = torch.zeros_like(g2) if g1 is None else g1
+            g2 = torch.zeros_like(g1) if g2 is None else g2
             return torch.cat([g1, g2])
+
+    def grl_step(xcat, ts):              # north-star configs[2]: output-space discriminator + gradient reversal
+        opt.zero_grad()
+        logits = model(xcat)             # source images first, target images second
+        ls, _lt = SplitViews.apply(logits)
+        dom = adversary(logits)          # D(GRL(softmax(logits))): [2*Bs, 1]
+        total = crit(ls, ts) + adv.discriminator_loss(dom[:Bs], dom[Bs:])
+        total.backward()
+        flat_allreduce(model)
+        flat_allreduce(disc)
+        opt.step()
+        return total.detach()
 
     def ft_compute(*inp):                # src/models/unsupervised_trainer.py:99-150
         opt.zero_grad()
@@ -306,7 +329,7 @@ def measure_workload(args, workload, env, full):
         ft_finish()
         return out
 
-    eager = ft_step if finetune else adv_step if adversarial else sup_step
+    eager = ft_step if finetune else adv_step if adversarial else grl_step if grl else sup_step
     graphed, launch = None, "eager launches"
     nccl = "" if world == 1 else (" + one flat all-reduce after the replay" if args.nccl_outside_graph else
                                   "; bucketed NCCL all-reduce captured inside the graph on a side stream (overlaps backward)")
@@ -314,6 +337,9 @@ def measure_workload(args, workload, env, full):
         if finetune:
             graphed = GraphedPhases([(ft_compute, ft_finish)], devin, [model, disc])
             launch = "cuda-graph replay of fwd+loss+bwd, then clip + fused Adam" + nccl
+        elif grl:
+            graphed = GraphedFn(grl_step, devin, nets)
+            launch = "ONE cuda-graph replay of the whole step (fwd, CE + adversarial loss, bwd, fused Adam over both networks)" + nccl
         elif adversarial and not (world > 1 and args.nccl_outside_graph):
             graphed = GraphedFn(adv_step, devin, nets)
             launch = "ONE cuda-graph replay of the whole D step + G step (both fused Adam steps captured)" + nccl
@@ -395,13 +421,17 @@ def measure_workload(args, workload, env, full):
     e2e = {"value": imgs / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}
 
     wl = (f"supervised source-domain training, U-Net resnet34, batch {B}/GPU @{size}x{size}, {CLASSES} classes, "
-          "CE loss + Adam (BASELINE configs[1])") if not (adversarial or finetune) else \
+          "CE loss + Adam (BASELINE configs[1])") if not (adversarial or finetune or grl) else \
          (f"unsupervised target-domain fine-tuning (two views, FineTuningLoss consistency + domain confusion + entropy "
           f"minimisation, clip 1.0, Adam), U-Net resnet34, {B} images/GPU @{size}x{size} (BASELINE configs[3]); "
           + ("both views run as ONE pass of 2B images split at the loss (BatchNorm statistics pooled over the two views); "
              if args.ft_views == "pooled" else "two separate passes of B images; ")
           + "deviation from src/models/unsupervised_trainer.py:116-122: its third, unused segmentation forward of the "
             "un-augmented batch is not run, the critic is frozen") if finetune else \
+         (f"adversarial UDA with an OUTPUT-SPACE discriminator behind a gradient-reversal layer (north-star configs[2]): "
+          f"U-Net resnet34 on {Bs} source + {Bs} target images/GPU @{size}x{size} in one pass, CE(source) + "
+          f"BCE(D(GRL(softmax(logits)))), one backward, one fused Adam over both networks; beyond the reference, which "
+          f"defines the gradient-reversal layer and the discriminator but never wires them (SURVEY T3)") if grl else \
          (f"adversarial UDA step (D step + G step), U-Net resnet34 + image discriminator, {Bs}+{Bs} images/GPU "
           f"@{size}x{size} (BASELINE configs[2])")
     res = {"value": value, "ms_per_step": ms / args.steps, "e2e": e2e, "gpu_launches": launches,
@@ -418,10 +448,12 @@ def measure_workload(args, workload, env, full):
         _lib.PROFILE = {}
     sync()
     f0 = ops.TC_FLOPS
+    ws_saved, ops.WGRAD_STREAM = ops.WGRAD_STREAM, False   # one stream: event pairs then bracket ONE kernel family each
     for _ in range(prof_steps):                 # every rank runs them (they contain the gradient all-reduce)
         torch.cuda._sleep(int(60e-3 * 1.9e9))   # let the host run ahead: event pairs then bracket pure device time
         eager(*devin)
     torch.cuda.synchronize()
+    ops.WGRAD_STREAM = ws_saved
     if rank == 0:
         prof, _lib.PROFILE = _lib.PROFILE, None
         for name, evs in prof.items():
@@ -448,6 +480,8 @@ def measure_workload(args, workload, env, full):
                                     f"committed ncu launch list {tfile} (cold cache, same command); not re-measured in this run",
                     "peak_source": pk["which"] + " (sustained: kernels timed inside a long step)",
                     "gflop_per_step": tc_gflop, "ms_per_step": tc_ms, "launches_per_step": tc_n,
+                    "timing": "CUDA events around every entry point of eager single-stream replays of the step (the timed "
+                              "region itself is a graph replay with the wgrad launches on a second stream)",
                     "whole_step_frac": tc_gflop / (ms / args.steps) / pk["bf16_tflops_sustained"],
                     "top_entry_point_by_time": top}
     hbm_kernels = None
@@ -491,10 +525,12 @@ def run_ours(args):
     env = {"world": world, "rank": rank, "local": local, "dev": dev}
     size = args.size
     head = measure_workload(args, args.workload, env, full=True)
-    sub = None
+    subs = {}
     if args.workload == "supervised" and not args.no_sub:
-        # the north-star's scaling target is written for the adversarial UDA step: measure it in the same line
-        sub = measure_workload(args, "adversarial", env, full=False)
+        # the north-star's scaling target is written for the adversarial UDA step: measure it in the same line, both as
+        # the reference's D-step / G-step iteration and as the output-space + gradient-reversal variant
+        for name in ("adversarial", "adversarial_grl"):
+            subs[name] = measure_workload(args, name, env, full=False)
     if rank == 0:
         out = {
             "metric": "train_images_per_s", "value": head["value"], "unit": "images/s", "n_gpus": world, "steps": args.steps,
@@ -510,12 +546,13 @@ def run_ours(args):
             # every UDA_B200_* switch present in the environment of this run (none = the shipped defaults)
             "env": {k: v for k, v in sorted(os.environ.items()) if k.startswith("UDA_B200_")},
         }
-        if sub is not None:
-            out["adversarial"] = {"metric": "train_images_per_s", "value": sub["value"], "unit": "images/s",
-                                  "ms_per_step": sub["ms_per_step"], "e2e": sub["e2e"], "gpu_launches": sub["gpu_launches"],
-                                  "n_gpus": world, "scaling": "weak",
-                                  "config": {"workload": sub["workload"], "global_batch": sub["global_batch"],
-                                             "launch": sub["launch"]}}
+        for name, sub in subs.items():
+            if sub is not None:
+                out[name] = {"metric": "train_images_per_s", "value": sub["value"], "unit": "images/s",
+                             "ms_per_step": sub["ms_per_step"], "e2e": sub["e2e"], "gpu_launches": sub["gpu_launches"],
+                             "n_gpus": world, "scaling": "weak",
+                             "config": {"workload": sub["workload"], "global_batch": sub["global_batch"],
+                                        "launch": sub["launch"]}}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(size)
         print(json.dumps(out))
@@ -530,7 +567,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="supervised", choices=["supervised", "adversarial", "finetune"])
+    ap.add_argument("--workload", default="supervised", choices=["supervised", "adversarial", "adversarial_grl", "finetune"])
     ap.add_argument("--batch", type=int, default=16, help="images per GPU per step")
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--ref-batch", type=int, default=2, help="bounded sample batch of the reference arm")

@@ -141,6 +141,17 @@ int uda_conv2d_tc_fwd_fused(const void* x, const void* w, const float* bias, con
 int uda_bn_fold_conv(const float* w, const float* conv_bias, const float* gamma, const float* beta,
                      const float* running_mean, const float* running_var, float eps, void* w_folded, float* bias_folded,
                      int Cout, int per_out, void* stream);
+/* Output-space adversarial path (north-star config 3): softmax(logits) packed as the discriminator's channels-last bf16
+ * operand (channels >= C zero, Cpad in {8,16,32}); its backward with the gradient-reversal factor folded in
+ * (dlogits (+)= scale * p_c * (dp_c - sum_k p_k dp_k), scale = -alpha; reference GradientReverseFunction
+ * src/models/uda.py:103-112); y = scale * x (the stand-alone gradient-reversal backward); channel pad / un-pad glue for
+ * a first-layer weight whose input channel count is the class count. */
+int uda_softmax_nchw_to_nhwc(const float* logits, void* probs, int B, int C, int Cpad, long long HW, void* stream);
+int uda_softmax_bwd_grl(const void* probs, const void* dprobs, float* dlogits, float scale, int accumulate, int B, int C,
+                        int Cpad, long long HW, void* stream);
+int uda_scale(const void* x, void* y, int dtype, float scale, long long n, void* stream);
+int uda_pad_channels(const void* src, void* dst, long long rows, int c, int cpad, void* stream);
+int uda_unpad_channels_add(const float* src, float* dst, long long rows, int c, int cpad, void* stream);
 /* dgrad takes w_ft = uda_conv2d_weight_flip_transpose(w): [Cin][KH][KW][Cout] bf16 (the weights of the
  * equivalent forward convolution of dy); addend as in uda_conv2d_direct_dgrad. */
 int uda_conv2d_weight_flip_transpose(const void* w, void* w_ft, int Cout, int Cin, int KH, int KW, void* stream);
@@ -241,6 +252,22 @@ int uda_adam_step(float* p, const float* g, float* m, float* v, void* bf16_shado
                   const float* dev_clip_coef, int* dev_step, void* stream);
 int uda_grad_clip_coef(const float* g, long long n, float max_norm, float pre_scale, float* coef, float* norm_out,
                        void* workspace, void* stream);
+
+/* Metrics from the device-resident confusion matrix (one CTA, float64): out[0] in-tree mean IoU (nanmean(diag / (row + col
+ * - diag + 1e-7)), src/analysis/metrics.py:29-42), out[1] pixel accuracy, out[2] macro Jaccard with torchmetrics semantics
+ * (classes without support ignored, src/models/train.py:209-212,231), out[3] pixels counted, out[4..4+C) per-class in-tree
+ * IoU, out[4+C..4+2C) per-class binary Jaccard (0 for 0/0, train.py:236-241). */
+int uda_metrics_from_hist(const long long* hist, int C, double* out, void* stream);
+/* Sliding-window evaluation glue (BASELINE config 5; window = stride = win, row-major window grid): windows
+ * [first, first+count) of a [H,W,3] uint8 tile as normalised fp32 NCHW input ((u8/255 - mean) / std, the reference's
+ * ToTensor + Normalize, src/models/predict.py:93-97); the same windows of an int64 / uint8 [H,W] label tile as int64
+ * targets; uint8 window masks scattered back into the [H,W] tile mask.  mean3 / std3 are HOST arrays of three floats. */
+int uda_gather_windows_u8(const unsigned char* tile_hwc, float* out_nchw, int H, int W, int win, int first, int count,
+                          const float* mean3, const float* std3, void* stream);
+int uda_gather_label_windows(const void* tile, int dtype, long long* out, int H, int W, int win, int first, int count,
+                             void* stream);
+int uda_scatter_window_masks(const unsigned char* masks, unsigned char* tile_mask, int H, int W, int win, int first,
+                             int count, void* stream);
 
 #ifdef __cplusplus
 }

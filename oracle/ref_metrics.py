@@ -56,3 +56,22 @@ def f1_scores(pred, true, num_classes, ignore_index=None):
     fp = hist.sum(axis=0) - tp
     fn = hist.sum(axis=1) - tp
     return 2 * tp / (2 * tp + fp + fn + 1e-7)
+
+
+def trainer_metrics_from_hist(hist):
+    """The per-step metrics of ``SegmentationTrainer.calculate_metrics`` (``src/models/train.py:225-243``) restated on
+    the confusion matrix (rows = true, cols = pred).  ``iou``: ``torchmetrics.JaccardIndex(task='multiclass',
+    num_classes=C)`` — third-party, unpinned in requirements.txt and absent here (PARITY UNPINNED); its published
+    algorithm (torchmetrics >= 1.0, ``_jaccard_index_reduce`` with average='macro'): per-class diag / (row + col -
+    diag) with 0 for 0/0, averaged over the classes whose row + column is non-zero.  ``accuracy``: mean(pred == mask).
+    ``iou_class_c``: binary JaccardIndex of (pred == c, mask == c) = tp / (tp + fp + fn), 0 for 0/0."""
+    hist = np.asarray(hist, dtype=np.float64)
+    d = np.diag(hist)
+    row, col = hist.sum(axis=1), hist.sum(axis=0)
+    union = row + col - d
+    jac = np.where(union > 0, d / np.where(union > 0, union, 1.0), 0.0)
+    support = (row + col) > 0
+    return {"iou": float(jac[support].mean()) if support.any() else 0.0,
+            "accuracy": float(d.sum() / hist.sum()) if hist.sum() > 0 else 0.0,
+            "iou_per_class": jac,
+            "mean_iou": float(np.nanmean(d / (union + 1e-7))), "class_iou": d / (union + 1e-7)}

@@ -14,6 +14,9 @@ import torch.nn.functional as F
 
 LAUNCHES = 0
 USE_TC = False
+TC_PERSIST = False
+FOLD_BN_EVAL = False
+WGRAD_STREAM = False
 
 
 def dgrad_bnstats_supported(*a):

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN
+from conftest import GOLDEN, rel_err
 from oracle import ref_metrics as M
 
 pytestmark = pytest.mark.gpu
@@ -107,3 +107,81 @@ def test_full_tile_properties():
         row += torch.bincount(t.flatten(), minlength=C)
     assert hist_acc.sum().item() == 64 * 512 * 512
     assert torch.equal(hist_acc.sum(0), col) and torch.equal(hist_acc.sum(1), row)
+
+
+@pytest.mark.parametrize("C", [2, 24, 150])
+def test_device_metrics_from_resident_histogram(C):
+    """f2: IoU / accuracy / macro Jaccard derived on the device from the int64 [C,C] histogram (no host numpy) against
+    the numpy restatements (in-tree SegmentationMetrics formulas and the torchmetrics-semantics macro Jaccard)."""
+    metrics, predict, ops = _mods()
+    rng = np.random.default_rng(C)
+    h = rng.integers(0, 1000, size=(C, C)).astype(np.int64)
+    if C > 2:
+        h[3, :] = 0; h[:, 3] = 0                 # a class that occurs nowhere: ignored by the macro Jaccard
+        h[5, :] = 0                              # a class that is only predicted: union > 0, tp = 0
+    for hist in (h, np.zeros((C, C), np.int64)):
+        out = metrics.SegmentationMetrics.device_metrics(torch.from_numpy(hist).to("cuda:0"))
+        ref = M.trainer_metrics_from_hist(hist)
+        assert abs(float(out["iou"]) - ref["iou"]) < 1e-12
+        assert abs(float(out["accuracy"]) - ref["accuracy"]) < 1e-12
+        assert np.allclose(out["iou_per_class"].cpu().numpy(), ref["iou_per_class"], rtol=0, atol=1e-12)
+        assert np.allclose(out["class_iou"].cpu().numpy(), ref["class_iou"], rtol=0, atol=1e-12)
+        assert abs(float(out["mean_iou"]) - ref["mean_iou"]) < 1e-12
+        assert float(out["pixels"]) == float(hist.sum())
+    # and the in-tree host formulas on the same matrix
+    host = metrics.SegmentationMetrics.iou_from_hist(h)
+    assert abs(float(metrics.SegmentationMetrics.device_metrics(torch.from_numpy(h).to("cuda:0"))["mean_iou"]) - host["mean_iou"]) < 1e-12
+
+
+def test_u8_window_gather_normalise_and_mask_scatter():
+    """f3: raw uint8 tile -> normalised fp32 NCHW windows (ToTensor + Normalize, reference predict.py:93-97), int64
+    target windows, uint8 masks scattered back — against torch indexing; ragged last batch; bad windows rejected."""
+    metrics, predict, ops = _mods()
+    from uda_aerial_semantic_segmentation_research_b200 import _lib
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    H, W, win = 192, 320, 64
+    tile = torch.randint(0, 256, (H, W, 3), generator=g, dtype=torch.uint8)
+    target = torch.randint(0, 7, (H, W), generator=g)
+    mean, std = predict.IMAGENET_MEAN, predict.IMAGENET_STD
+    ref = ((tile.float() / 255 - torch.tensor(mean)) / torch.tensor(std)).permute(2, 0, 1)      # ToTensor + Normalize
+    ref_w = predict.tile_windows(ref, win)
+    ref_t = predict.tile_windows(target.reshape(1, H, W), win).reshape(-1, win, win)
+    n_win = (H // win) * (W // win)
+    tile_mask = torch.zeros((H, W), dtype=torch.uint8, device=dev)
+    fake = torch.randint(0, 7, (n_win, win, win), generator=g, dtype=torch.uint8)
+    for first in range(0, n_win, 4):
+        n = min(4, n_win - first)
+        x = ops.gather_windows_u8(tile.to(dev), win, first, n, mean, std)
+        assert rel_err(x.cpu(), ref_w[first:first + n]) < 1e-6
+        for tt in (target, target.to(torch.uint8)):
+            t = ops.gather_label_windows(tt.to(dev), win, first, n)
+            assert torch.equal(t.cpu(), ref_t[first:first + n])
+        ops.scatter_window_masks(fake[first:first + n].contiguous().to(dev), tile_mask, win, first)
+    back = predict.tile_windows(tile_mask.cpu().reshape(1, H, W), win).reshape(-1, win, win)
+    assert torch.equal(back, fake)
+    with pytest.raises(_lib.UdaError):
+        ops.gather_windows_u8(tile.to(dev), win, n_win - 1, 2, mean, std)
+
+
+def test_sliding_window_from_raw_tile_is_bit_exact():
+    """Config 5 from the raw uint8 tile: masks and confusion matrix equal torch.argmax + bincount on the same logits."""
+    metrics, predict, ops = _mods()
+    import uda_aerial_semantic_segmentation_research_b200 as U
+    dev = torch.device("cuda:0")
+    torch.manual_seed(2)
+    model = U.Unet("resnet18", classes=9).to(dev).eval()
+    g = torch.Generator().manual_seed(6)
+    H, W, win = 128, 192, 64
+    tile = torch.randint(0, 256, (H, W, 3), generator=g, dtype=torch.uint8).to(dev)
+    target = torch.randint(0, 9, (H, W), generator=g, dtype=torch.uint8).to(dev)
+    out = predict.sliding_window_evaluate_u8(model, tile, target, 9, window=win, batch=4, return_mask=True)
+    n_win = (H // win) * (W // win)
+    with torch.no_grad():
+        x = ops.gather_windows_u8(tile, win, 0, n_win, predict.IMAGENET_MEAN, predict.IMAGENET_STD)
+        full = torch.cat([model(x[i:i + 4]) for i in range(0, n_win, 4)]).argmax(1)
+    full = full.reshape(H // win, W // win, win, win).permute(0, 2, 1, 3).reshape(H, W)
+    assert torch.equal(out["mask"].long(), full)
+    assert np.array_equal(out["hist"].cpu().numpy(), M.fast_hist(full.cpu().numpy(), target.cpu().numpy(), 9))
+    ref = M.trainer_metrics_from_hist(out["hist"].cpu().numpy())
+    assert abs(float(out["metrics"]["iou"]) - ref["iou"]) < 1e-12 and abs(float(out["metrics"]["accuracy"]) - ref["accuracy"]) < 1e-12

@@ -230,3 +230,21 @@ def test_reference_domain_model_wraps_uda_b200_networks(monkeypatch):
     assert len(ours.parameters()) == len(ref.parameters())
     ours.train()
     assert seg.training and disc.training
+
+
+def test_trainer_metrics_known_answers():
+    """oracle.ref_metrics.trainer_metrics_from_hist (restated torchmetrics macro Jaccard / binary Jaccard / accuracy of
+    src/models/train.py:225-243) on hand-computed confusion matrices."""
+    r = M.trainer_metrics_from_hist(np.array([[2, 1], [0, 3]]))
+    assert abs(r["iou"] - (2 / 3 + 3 / 4) / 2) < 1e-12 and abs(r["accuracy"] - 5 / 6) < 1e-12
+    assert np.allclose(r["iou_per_class"], [2 / 3, 3 / 4])
+    # class 2 occurs nowhere: ignored by the macro average; class 1 only predicted: counts with IoU 0
+    r = M.trainer_metrics_from_hist(np.array([[4, 2, 0], [0, 0, 0], [0, 0, 0]]))
+    assert np.allclose(r["iou_per_class"], [4 / 6, 0.0, 0.0]) and abs(r["iou"] - (4 / 6 + 0.0) / 2) < 1e-12
+    assert M.trainer_metrics_from_hist(np.zeros((3, 3)))["iou"] == 0.0
+    # consistency with the in-tree metric on the same pixels
+    rng = np.random.default_rng(0)
+    p, t = rng.integers(0, 5, 1000), rng.integers(0, 5, 1000)
+    h = M.fast_hist(p, t, 5)
+    assert abs(M.trainer_metrics_from_hist(h)["mean_iou"] - M.batch_iou(p, t, 5)["mean_iou"]) < 1e-12
+    assert abs(M.trainer_metrics_from_hist(h)["accuracy"] - float((p == t).mean())) < 1e-12

@@ -232,3 +232,156 @@ extern "C" int uda_confmat(const void* pred, int pred_dtype, const long long* ta
   UDA_LAUNCH_OK("confmat_kernel");
   return UDA_OK;
 }
+
+// ================================================================================================================
+// Metrics from the device-resident confusion matrix (the reference derives 26 scalars per step
+// with one `.item()` each, src/models/train.py:225-243; here they are derived on the device and read once per epoch).
+//   out[0]          mean IoU of the in-tree metric: nanmean(diag / (row + col - diag + 1e-7))   (src/analysis/metrics.py:29-42)
+//   out[1]          pixel accuracy: sum(diag) / sum(hist)   (0 when the matrix is empty)         (train.py:232)
+//   out[2]          macro Jaccard with torchmetrics semantics (train.py:209-212,231): mean over the classes that occur
+//                   in the target or the prediction of diag / (row + col - diag); 0 when no class occurs
+//   out[3]          number of pixels counted
+//   out[4 .. 4+C)   per-class IoU of the in-tree metric
+//   out[4+C .. 4+2C) per-class binary Jaccard (train.py:236-241): tp / (tp + fp + fn), 0 for 0/0
+// One CTA; float64 like the numpy formulas.
+// ================================================================================================================
+namespace uda {
+namespace {
+__global__ void __launch_bounds__(256) metrics_from_hist_kernel(const long long* __restrict__ hist, int C, double* __restrict__ out) {
+  extern __shared__ double sm[];      // row[C], col[C], diag[C]
+  double* row = sm; double* col = sm + C; double* dg = sm + 2 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    long long r = 0, k = 0;
+    for (int j = 0; j < C; ++j) { r += hist[(long long)c * C + j]; k += hist[(long long)j * C + c]; }
+    row[c] = (double)r; col[c] = (double)k; dg[c] = (double)hist[(long long)c * C + c];
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double uni = row[c] + col[c] - dg[c];
+    out[4 + c] = dg[c] / (uni + 1e-7);
+    out[4 + C + c] = uni > 0.0 ? dg[c] / uni : 0.0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s_iou = 0.0, s_jac = 0.0, correct = 0.0, total = 0.0;
+    int n_iou = 0, n_jac = 0;
+    for (int c = 0; c < C; ++c) {
+      const double v = out[4 + c];
+      if (v == v) { s_iou += v; ++n_iou; }                          // nanmean (the 1e-7 keeps every term finite)
+      if (row[c] + col[c] > 0.0) { s_jac += out[4 + C + c]; ++n_jac; }
+      correct += dg[c]; total += row[c];
+    }
+    out[0] = n_iou ? s_iou / n_iou : 0.0;
+    out[1] = total > 0.0 ? correct / total : 0.0;
+    out[2] = n_jac ? s_jac / n_jac : 0.0;
+    out[3] = total;
+  }
+}
+
+// ---- sliding-window evaluation glue (BASELINE config 5; reference preprocessing src/models/predict.py:93-97:
+//      ToTensor (u8 HWC -> float CHW / 255) + Normalize(mean, std)) ------------------------------------------------
+// windows [first, first + count) of a [H, W, 3] uint8 tile (row-major window grid, window = stride = win) as normalised
+// fp32 NCHW network input
+__global__ void __launch_bounds__(256)
+gather_windows_u8_kernel(const unsigned char* __restrict__ tile, float* __restrict__ out, int H, int W, int win, int first,
+                         int count, float m0, float m1, float m2, float i0, float i1, float i2) {
+  const long long n = (long long)count * win * win;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int wpr = W / win;
+  const int k = (int)(i / ((long long)win * win));
+  const int r = (int)(i - (long long)k * win * win);
+  const int y = r / win, x = r - y * win;
+  const int wi = first + k, wy = wi / wpr, wx = wi - wy * wpr;
+  const unsigned char* p = tile + ((long long)(wy * win + y) * W + (wx * win + x)) * 3;
+  float* o = out + (long long)k * 3 * win * win + r;
+  const long long plane = (long long)win * win;
+  o[0] = ((float)p[0] * (1.f / 255.f) - m0) * i0;
+  o[plane] = ((float)p[1] * (1.f / 255.f) - m1) * i1;
+  o[2 * plane] = ((float)p[2] * (1.f / 255.f) - m2) * i2;
+}
+// the same windows of an int64 / uint8 [H, W] label tile as int64 [count, win, win] (confusion-matrix targets)
+template <typename T>
+__global__ void __launch_bounds__(256)
+gather_label_windows_kernel(const T* __restrict__ tile, long long* __restrict__ out, int W, int win, int first, int count) {
+  const long long n = (long long)count * win * win;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int wpr = W / win;
+  const int k = (int)(i / ((long long)win * win));
+  const int r = (int)(i - (long long)k * win * win);
+  const int y = r / win, x = r - y * win;
+  const int wi = first + k, wy = wi / wpr, wx = wi - wy * wpr;
+  out[i] = (long long)tile[(long long)(wy * win + y) * W + (wx * win + x)];
+}
+// uint8 window masks [count, win, win] back into the [H, W] uint8 tile mask
+__global__ void __launch_bounds__(256)
+scatter_window_masks_kernel(const unsigned char* __restrict__ masks, unsigned char* __restrict__ tile, int W, int win,
+                            int first, int count) {
+  const long long n = (long long)count * win * win / 4;     // 4 pixels per thread (win % 4 == 0)
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int wpr = W / win;
+  const long long e = i * 4;
+  const int k = (int)(e / ((long long)win * win));
+  const int r = (int)(e - (long long)k * win * win);
+  const int y = r / win, x = r - y * win;
+  const int wi = first + k, wy = wi / wpr, wx = wi - wy * wpr;
+  *reinterpret_cast<uchar4*>(tile + (long long)(wy * win + y) * W + (wx * win + x)) =
+      *reinterpret_cast<const uchar4*>(masks + e);
+}
+}  // namespace
+}  // namespace uda
+
+extern "C" int uda_metrics_from_hist(const long long* hist, int C, double* out, void* stream) {
+  UDA_REQUIRE(hist && out && C > 0 && C <= 1024, UDA_ERR_BAD_ARG, "metrics_from_hist: bad argument");
+  uda::metrics_from_hist_kernel<<<1, 256, 3 * C * sizeof(double), (cudaStream_t)stream>>>(hist, C, out);
+  UDA_LAUNCH_OK("metrics_from_hist_kernel");
+  return UDA_OK;
+}
+
+static int check_windows(int H, int W, int win, int first, int count, const char* who) {
+  UDA_REQUIRE(H > 0 && W > 0 && win > 0 && H % win == 0 && W % win == 0, UDA_ERR_BAD_ARG,
+              "%s: tile %dx%d is not a multiple of the window %d", who, H, W, win);
+  UDA_REQUIRE(first >= 0 && count > 0 && first + count <= (H / win) * (W / win), UDA_ERR_BAD_ARG,
+              "%s: windows [%d, %d) outside the %d windows of the tile", who, first, first + count, (H / win) * (W / win));
+  return UDA_OK;
+}
+
+extern "C" int uda_gather_windows_u8(const unsigned char* tile_hwc, float* out_nchw, int H, int W, int win, int first,
+                                     int count, const float* mean3, const float* std3, void* stream) {
+  UDA_REQUIRE(tile_hwc && out_nchw && mean3 && std3, UDA_ERR_BAD_ARG, "gather_windows_u8: null pointer");
+  if (int rc = check_windows(H, W, win, first, count, "gather_windows_u8")) return rc;
+  const long long n = (long long)count * win * win;
+  uda::gather_windows_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      tile_hwc, out_nchw, H, W, win, first, count, mean3[0], mean3[1], mean3[2], 1.f / std3[0], 1.f / std3[1], 1.f / std3[2]);
+  UDA_LAUNCH_OK("gather_windows_u8_kernel");
+  return UDA_OK;
+}
+
+extern "C" int uda_gather_label_windows(const void* tile, int dtype, long long* out, int H, int W, int win, int first,
+                                        int count, void* stream) {
+  UDA_REQUIRE(tile && out, UDA_ERR_BAD_ARG, "gather_label_windows: null pointer");
+  UDA_REQUIRE(dtype == UDA_I64 || dtype == UDA_U8, UDA_ERR_BAD_ARG, "gather_label_windows: dtype must be UDA_I64 or UDA_U8");
+  if (int rc = check_windows(H, W, win, first, count, "gather_label_windows")) return rc;
+  const long long n = (long long)count * win * win;
+  const unsigned grid = (unsigned)((n + 255) / 256);
+  if (dtype == UDA_I64)
+    uda::gather_label_windows_kernel<long long><<<grid, 256, 0, (cudaStream_t)stream>>>((const long long*)tile, out, W, win, first, count);
+  else
+    uda::gather_label_windows_kernel<unsigned char><<<grid, 256, 0, (cudaStream_t)stream>>>((const unsigned char*)tile, out, W, win, first, count);
+  UDA_LAUNCH_OK("gather_label_windows_kernel");
+  return UDA_OK;
+}
+
+extern "C" int uda_scatter_window_masks(const unsigned char* masks, unsigned char* tile_mask, int H, int W, int win,
+                                        int first, int count, void* stream) {
+  UDA_REQUIRE(masks && tile_mask, UDA_ERR_BAD_ARG, "scatter_window_masks: null pointer");
+  UDA_REQUIRE(win % 4 == 0 && W % 4 == 0 && uda::aligned<unsigned char>(masks, 4) && uda::aligned<unsigned char>(tile_mask, 4),
+              UDA_ERR_UNSUPPORTED, "scatter_window_masks: window / tile width must be multiples of 4, buffers 4-byte aligned");
+  if (int rc = check_windows(H, W, win, first, count, "scatter_window_masks")) return rc;
+  const long long n = (long long)count * win * win / 4;
+  uda::scatter_window_masks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(masks, tile_mask, W, win, first, count);
+  UDA_LAUNCH_OK("scatter_window_masks_kernel");
+  return UDA_OK;
+}

@@ -26,6 +26,7 @@ class GradSync:
         self._plans = {}
         self._state = {}
         self._comm_stream = None
+        self.producer_stream = None   # extra stream whose work (side-stream wgrads) a bucket must also wait for
         for net in self.networks:
             net._grad_sync = self
         if broadcast_parameters:
@@ -93,6 +94,8 @@ class GradSync:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream())
             self._comm_stream.wait_event(ev)
+            if self.producer_stream is not None:
+                self._comm_stream.wait_stream(self.producer_stream)
             with torch.cuda.stream(self._comm_stream):
                 work = dist.all_reduce(view, op=dist.ReduceOp.AVG, group=self.group, async_op=True)
             view.record_stream(self._comm_stream)

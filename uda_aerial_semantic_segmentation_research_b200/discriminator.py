@@ -77,14 +77,22 @@ class DomainDiscriminator(nn.Module):
         self._store = _DiscStore(self)
         self._grad_sync = None
 
-    def _run(self, x, record):
+    def _run(self, x, record, xin=None):
+        """``xin``: an already prepared channels-last input Var (output-space use: softmax probabilities, channel
+        dimension possibly zero-padded to a tensor-core atom) instead of the NCHW image ``x``."""
         dtype = self.compute_dtype
         tape = Tape() if record else None
         ctx = Ctx(self._store, dtype, self.training, tape)
         ctx.sync = self._grad_sync
-        xin = E.input_var(x, dtype, self.features[0], record and x.requires_grad)
         f = self.features
-        y = E.bias_act(ctx, E.conv(ctx, xin, f[0]), 0.2)
+        if xin is None:
+            xin = E.input_var(x, dtype, f[0], record and x.requires_grad)
+            z0 = E.conv(ctx, xin, f[0])
+        elif xin.t.shape[-1] != f[0].in_channels:
+            z0 = E.conv_padded_cin(ctx, xin, f[0])
+        else:
+            z0 = E.conv(ctx, xin, f[0])
+        y = E.bias_act(ctx, z0, 0.2)
         for ci, bi in ((2, 3), (5, 6), (8, 9)):
             y = E.conv_bn_act(ctx, y, f[ci], f[bi], slope=0.2)
         ctx.finish_forward()
@@ -103,6 +111,80 @@ class DomainDiscriminator(nn.Module):
         self._prepare(x.device)
         record = torch.is_grad_enabled() and (any(p.requires_grad for p in self._store.params) or x.requires_grad)
         return _DiscFn.apply(self, record, x, *self._store.params)
+
+
+class _OutputSpaceFn(torch.autograd.Function):
+    """logits -> D(GRL(softmax(logits))) as one autograd node.  Forward: fused softmax + NCHW->NHWC bf16 pack, then the
+    discriminator's layers.  Backward: the discriminator's tape, then ONE pass that applies the softmax Jacobian and
+    the gradient-reversal factor -alpha (reference ``GradientReverseFunction``, src/models/uda.py:103-112) and writes
+    the fp32 NCHW logit gradient."""
+
+    @staticmethod
+    def forward(ctx, net, record, alpha, logits, *params):
+        z = logits.contiguous().float()
+        C = z.shape[1]
+        cpad = 8 if C <= 8 else (16 if C <= 16 else 32)
+        probs = ops.softmax_nhwc(z, cpad)
+        xin = Var(probs)
+        y, tape, xin, state = net._run(None, record, xin=xin)
+        ctx.net, ctx.tape, ctx.xin, ctx.state = net, tape, xin, state
+        ctx.alpha, ctx.C = float(alpha), C
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        net, tape, st = ctx.net, ctx.tape, ctx.net._store
+        if tape is None:
+            raise RuntimeError("OutputSpaceAdversary: backward called on a graph recorded without gradients")
+        st.new_grad()
+        if net._grad_sync is not None:
+            net._grad_sync.begin(st)
+        need_x = ctx.needs_input_grad[3]
+        if not need_x:
+            ctx.xin.g = False
+        feat, y, pooled = ctx.state
+        lin = net.classifier[2]
+        feat.g = ops.gap_linear_sigmoid_bwd(gy.contiguous().float(), y, pooled, st.w2d(lin.weight), st.g(lin.weight),
+                                            st.g(lin.bias), feat.t.shape, feat.t.dtype)
+        if net._grad_sync is not None:
+            net._grad_sync.param_done(st, lin.weight)
+            net._grad_sync.param_done(st, lin.bias)
+        tape.backward()
+        if net._grad_sync is not None:
+            net._grad_sync.end(st)
+        gz = None
+        if need_x and isinstance(ctx.xin.g, torch.Tensor):
+            gz = ops.softmax_bwd_grl(ctx.xin.t, ctx.xin.g, -ctx.alpha, ctx.C)
+        ctx.tape = ctx.xin = ctx.state = None
+        return (None, None, None, gz) + tuple(st.grad_views())
+
+
+class OutputSpaceAdversary(nn.Module):
+    """Output-space domain adversary behind a gradient-reversal layer — the north-star's adversarial variant
+    (BASELINE configs[2]: "output-space discriminator, gradient reversal"), i.e. the composition
+
+        DomainDiscriminator(num_classes)(gradient_reverse_layer(softmax(logits, dim=1), alpha))
+
+    of the reference's own building blocks (``src/models/uda.py:99-112``, ``src/models/discriminator.py:4-55``; the
+    reference defines both and never wires them together).  One backward pass trains the discriminator
+    to tell the domains apart and hands the segmentation network the REVERSED gradient, scaled by ``alpha``."""
+
+    def __init__(self, discriminator, alpha=1.0):
+        super().__init__()
+        if discriminator.compute_dtype != torch.bfloat16:
+            raise NotImplementedError("OutputSpaceAdversary runs on the bf16 tensor-core path")
+        self.discriminator = discriminator
+        self.alpha = alpha
+
+    def forward(self, logits):
+        d = self.discriminator
+        if not logits.is_cuda:
+            raise RuntimeError("OutputSpaceAdversary runs on CUDA (sm_100a) only — no CPU fallback")
+        if logits.shape[1] != d.features[0].in_channels:
+            raise ValueError(f"discriminator expects {d.features[0].in_channels} classes, logits have {logits.shape[1]}")
+        d._prepare(logits.device)
+        record = torch.is_grad_enabled() and (any(p.requires_grad for p in d._store.params) or logits.requires_grad)
+        return _OutputSpaceFn.apply(d, record, self.alpha, logits, *d._store.params)
 
 
 class _DiscStore(ParamStore):

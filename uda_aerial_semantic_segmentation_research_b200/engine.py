@@ -236,12 +236,28 @@ class ParamStore:
         return [self._view_like(self.grad, p) for p in self.params]
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    """One persistent side stream per device (persistent so that CUDA-graph captures see a stable stream)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    s = _SIDE_STREAMS.get(key)
+    if s is None:
+        s = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+    return s
+
+
 class Ctx:
     """Per-forward execution context."""
 
     def __init__(self, store, dtype, training, tape):
         self.store, self.dtype, self.training, self.tape = store, dtype, training, tape
         self.sync = None  # optional gradient-sync object (ddp.GradSync): param_done(store, param)
+        self.side = None          # second stream carrying the wgrad launches of this backward (ops.WGRAD_STREAM)
+        self._keep = []           # tensors the side stream still reads: freed only after the join
+        if tape is not None:
+            tape.push(self._join_side)      # first pushed = last executed in backward
         self.fold_key = None                    # eval mode: freshness key of the folded weights, taken once per forward
         self._pool, self._pool_used = None, 0   # zero-filled float64 scratch for the fused BatchNorm statistics
         self._trackers = []                     # num_batches_tracked buffers to bump at the end of the forward
@@ -264,8 +280,25 @@ class Ctx:
             self._trackers = []
             self.store.stats_epoch += 1
 
+    def wgrad_stream(self, *tensors):
+        """Context manager: run the enclosed wgrad launches on the side stream, after everything issued so far."""
+        dev = tensors[0].device
+        if self.side is None:
+            self.side = _side_stream(dev)
+        self.side.wait_stream(torch.cuda.current_stream(dev))
+        self._keep.extend(tensors)
+        return torch.cuda.stream(self.side)
+
+    def _join_side(self):
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
+            self.side = None
+        self._keep = []
+
     def done(self, *params):
         """Tell the data-parallel layer that the gradients of ``params`` are final for this backward."""
+        if self.sync is not None and self.side is not None:
+            self.sync.producer_stream = self.side       # the bucket's all-reduce must also wait for the wgrad stream
         if self.sync is not None:
             for p in params:
                 if p is not None:
@@ -324,9 +357,15 @@ def conv(ctx, xin, cp, nchw_out=False, bn=None):
             xin.uses -= 1
             if dy is None:
                 return
-            if cp.bias is not None:
-                ops.colsum(dy, st.g(cp.bias))
-            ops.conv_wgrad(dy, xin.t, st.g(cp.weight), cp.stride, cp.padding)
+            if ops.WGRAD_STREAM and dy.is_cuda:
+                with ctx.wgrad_stream(dy, xin.t):
+                    if cp.bias is not None:
+                        ops.colsum(dy, st.g(cp.bias))
+                    ops.conv_wgrad(dy, xin.t, st.g(cp.weight), cp.stride, cp.padding)
+            else:
+                if cp.bias is not None:
+                    ops.colsum(dy, st.g(cp.bias))
+                ops.conv_wgrad(dy, xin.t, st.g(cp.weight), cp.stride, cp.padding)
             if xin.g is not False:  # False marks "no gradient needed" (network input)
                 wft = st.w_ft(cp.weight) if (ctx.dtype == torch.bfloat16 and ops.USE_TC) else None
                 stats = None
@@ -337,6 +376,37 @@ def conv(ctx, xin, cp, nchw_out=False, bn=None):
                     xin.bwd_sums = ctx.stats_slot(2 * xin.t.shape[-1], xin.t.device)
                     stats = (xin.t, z, slope, xin.bwd_sums)
                 xin.g = ops.conv_dgrad(dy, w, xin.t.shape, cp.stride, cp.padding, addend=xin.g, w_ft=wft, bn_stats=stats)
+            ctx.done(cp.weight, cp.bias)
+        ctx.tape.push(bwd)
+    return out
+
+
+def conv_padded_cin(ctx, xin, cp):
+    """y = conv(x) + bias for an input tensor whose channel dimension is zero-padded beyond ``cp.in_channels`` (the
+    24-class probability map padded to 32 channels: a tensor-core channel atom).  The weights are padded on the fly
+    (a few thousand elements), the weight gradient is un-padded into the flat gradient buffer."""
+    st = ctx.store
+    cpad = xin.t.shape[-1]
+    w = st.w(cp.weight, ctx.dtype)
+    wp = ops.pad_channels(w, cpad)
+    y = ops.conv_fwd(xin.t, wp, cp.bias, cp.stride, cp.padding)
+    out = Var(y)
+    if ctx.tape is not None:
+        xin.uses += 1
+
+        def bwd():
+            dy = out.g
+            out.g = None
+            xin.uses -= 1
+            if dy is None:
+                return
+            if cp.bias is not None:
+                ops.colsum(dy, st.g(cp.bias))
+            dwp = torch.zeros(wp.shape, dtype=torch.float32, device=wp.device)
+            ops.conv_wgrad(dy, xin.t, dwp, cp.stride, cp.padding)
+            ops.unpad_channels_add(dwp, st.g(cp.weight))
+            if xin.g is not False:
+                xin.g = ops.conv_dgrad(dy, wp, xin.t.shape, cp.stride, cp.padding, addend=xin.g)
             ctx.done(cp.weight, cp.bias)
         ctx.tape.push(bwd)
     return out

@@ -303,17 +303,22 @@ class FineTuningLoss(nn.Module):
 
 
 class GradientReverseFunction(torch.autograd.Function):
-    """Reference ``GradientReverseFunction`` (``src/models/uda.py:103-112``): identity forward,
-    ``-alpha * grad`` backward.  (Defined but never called by the reference's trainers — SURVEY T3.)"""
+    """Gradient-reversal layer with the reference's interface (``src/models/uda.py:103-112``; defined but never called
+    by the reference's trainers): the forward is the identity, the backward multiplies the incoming
+    gradient by ``-alpha`` in ONE kernel pass (``uda_scale``).  When the layer sits between softmax(logits) and the
+    discriminator, ``discriminator.OutputSpaceAdversary`` folds the factor into the softmax-backward pass instead."""
 
     @staticmethod
     def forward(ctx, x, alpha):
-        ctx.alpha = alpha
+        ctx.alpha = float(alpha)
         return x.view_as(x)
 
     @staticmethod
     def backward(ctx, grad_output):
-        return grad_output.neg() * ctx.alpha, None
+        g = grad_output
+        if g.is_cuda and g.dtype in (torch.float32, torch.bfloat16):
+            return ops.scale(g.contiguous(), -ctx.alpha), None
+        raise RuntimeError("gradient_reverse_layer: CUDA float32 / bfloat16 gradients only (no CPU fallback)")
 
 
 def gradient_reverse_layer(x, alpha):

@@ -53,6 +53,20 @@ class SegmentationMetrics:
         return self.iou_from_hist(self._fast_hist(predictions.flatten(), targets.flatten()))
 
     @staticmethod
+    def device_metrics(hist: torch.Tensor) -> dict:
+        """Per-step metrics of ``SegmentationTrainer.calculate_metrics`` (``src/models/train.py:225-243``: macro
+        Jaccard, accuracy, per-class binary Jaccard — 26 ``.item()`` synchronisations per step in the reference) derived
+        ON THE DEVICE from the resident int64 [C,C] confusion matrix: one tiny launch, no host synchronisation; read the
+        returned tensors once per epoch.  ``mean_iou`` / ``class_iou`` follow the in-tree metric
+        (``src/analysis/metrics.py:29-42``); ``iou`` follows ``torchmetrics.JaccardIndex(task='multiclass')`` (macro
+        average over the classes that occur in the target or the prediction; third-party, absent here: restated from
+        its published algorithm, torchmetrics >= 1.0 — parity unpinned, checked against oracle.ref_metrics)."""
+        out = ops.metrics_from_hist(hist)
+        C = hist.shape[0]
+        return {"mean_iou": out[0], "accuracy": out[1], "iou": out[2], "pixels": out[3],
+                "class_iou": out[4:4 + C], "iou_per_class": out[4 + C:4 + 2 * C]}
+
+    @staticmethod
     def iou_from_hist(hist: np.ndarray) -> dict:
         iu = np.diag(hist) / (hist.sum(axis=1) + hist.sum(axis=0) - np.diag(hist) + 1e-7)
         return {"mean_iou": np.nanmean(iu), "class_iou": {i: iou for i, iou in enumerate(iu)}}

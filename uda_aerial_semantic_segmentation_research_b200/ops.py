@@ -13,6 +13,7 @@ import torch
 from . import _lib
 from ._lib import call, ptr, ll, ci, F32, BF16, I64, U8
 
+I64_T = torch.int64
 _WS = {}
 #: set to "0" to force the FP32-pipe direct convolution everywhere (debug / A-B comparison)
 USE_TC = os.environ.get("UDA_B200_USE_TC", "1") != "0"
@@ -27,6 +28,10 @@ TC_PERSIST = os.environ.get("UDA_B200_TC_PERSIST", "1") != "0"
 #: eval mode: fold BatchNorm into the convolution weights and run conv + BN (+ residual) + activation as one launch
 #: (set "0" to run the separate normalise pass, e.g. to A/B the two inference paths)
 FOLD_BN_EVAL = os.environ.get("UDA_B200_FOLD_BN_EVAL", "1") != "0"
+#: backward: launch the weight-gradient kernels on a second stream (they are off the dgrad -> BatchNorm-backward critical
+#: path, so their CTAs fill the SMs that the tails / prologues of the chain leave idle); joined at the end of backward
+#: (measured at B=16, 512x512: 8.99 -> 8.73 ms per supervised step; UDA_B200_WGRAD_STREAM=0 keeps everything on one stream)
+WGRAD_STREAM = os.environ.get("UDA_B200_WGRAD_STREAM", "1") != "0"
 #: counts launches issued through this module (bench.py reports it as gpu_launches)
 LAUNCHES = 0
 #: algorithmic FLOPs (2*M*N*K) and call count of the convolutions routed to the tcgen05 kernels
@@ -353,6 +358,67 @@ def conv_wgrad(dy, x, dw, stride=1, pad=1, force_direct=False):
              ci(KH), ci(KW), ci(stride), ci(pad), _stream())
     _count()
     return dw
+
+
+# ------------------------------------------------------------------------------------------------
+# output-space adversarial path (softmax -> discriminator behind a gradient-reversal layer)
+# ------------------------------------------------------------------------------------------------
+def softmax_nhwc(logits, cpad):
+    """fp32 NCHW logits [B,C,H,W] -> channels-last bf16 probabilities [B,H,W,cpad] (channels >= C are zero)."""
+    _chk(logits, "softmax_nhwc.logits", torch.float32)
+    B, C, H, W = logits.shape
+    out = torch.empty((B, H, W, cpad), dtype=torch.bfloat16, device=logits.device)
+    call("softmax_nchw_to_nhwc", ptr(logits), ptr(out), ci(B), ci(C), ci(cpad), ll(H * W), _stream())
+    _count()
+    return out
+
+
+def softmax_bwd_grl(probs, dprobs, scale, C, out=None):
+    """dlogits (fp32 NCHW) = scale * softmax_backward(probs, dprobs); accumulated into ``out`` when given.
+    ``scale`` = -alpha folds the gradient-reversal layer (reference src/models/uda.py:103-112) into this pass."""
+    _chk(probs, "softmax_bwd_grl.probs", torch.bfloat16); _chk(dprobs, "softmax_bwd_grl.dprobs", torch.bfloat16)
+    B, H, W, cpad = probs.shape
+    if tuple(dprobs.shape) != tuple(probs.shape):
+        raise _lib.UdaError("softmax_bwd_grl: probs / dprobs shape mismatch")
+    acc = out is not None
+    if acc:
+        _chk(out, "softmax_bwd_grl.out", torch.float32)
+        if tuple(out.shape) != (B, C, H, W):
+            raise _lib.UdaError("softmax_bwd_grl: out must be fp32 [B,C,H,W]")
+    else:
+        out = torch.empty((B, C, H, W), dtype=torch.float32, device=probs.device)
+    call("softmax_bwd_grl", ptr(probs), ptr(dprobs), ptr(out), float(scale), ci(1 if acc else 0), ci(B), ci(C), ci(cpad),
+         ll(H * W), _stream())
+    _count()
+    return out
+
+
+def scale(x, s):
+    """y = s * x in one pass (fp32 / bf16)."""
+    _chk(x, "scale.x")
+    y = torch.empty_like(x)
+    call("scale", ptr(x), ptr(y), ci(dt(x)), float(s), ll(x.numel()), _stream())
+    _count()
+    return y
+
+
+def pad_channels(w, cpad):
+    """bf16 [..., c] -> [..., cpad] zero-padded copy (weights whose input channel count is not a tensor-core atom)."""
+    _chk(w, "pad_channels.w", torch.bfloat16)
+    c = w.shape[-1]
+    out = torch.empty(tuple(w.shape[:-1]) + (cpad,), dtype=torch.bfloat16, device=w.device)
+    call("pad_channels", ptr(w), ptr(out), ll(w.numel() // c), ci(c), ci(cpad), _stream())
+    _count()
+    return out
+
+
+def unpad_channels_add(src, dst):
+    """dst[..., c] (fp32) += src[..., :c]."""
+    _chk(src, "unpad_channels_add.src", torch.float32); _chk(dst, "unpad_channels_add.dst", torch.float32)
+    c, cpad = dst.shape[-1], src.shape[-1]
+    call("unpad_channels_add", ptr(src), ptr(dst), ll(dst.numel() // c), ci(c), ci(cpad), _stream())
+    _count()
+    return dst
 
 
 # ------------------------------------------------------------------------------------------------
@@ -686,3 +752,62 @@ def confmat(pred, target, num_classes, ignore_index=None, hist=None):
          ll(ignore_index if ignore_index is not None else 0), ci(0 if ignore_index is None else 1), ci(zero), _stream())
     _count()
     return hist, bad
+
+
+def metrics_from_hist(hist):
+    """Device-side metrics of an int64 [C,C] confusion matrix -> float64 [4 + 2C] device tensor (no host sync):
+    [0] in-tree mean IoU, [1] pixel accuracy, [2] torchmetrics-style macro Jaccard, [3] pixels, [4:4+C] class IoU,
+    [4+C:4+2C] per-class binary Jaccard (see ``uda_metrics_from_hist``)."""
+    _chk(hist, "metrics_from_hist.hist", I64_T)
+    C = hist.shape[0]
+    if tuple(hist.shape) != (C, C):
+        raise _lib.UdaError("metrics_from_hist: hist must be [C,C]")
+    out = torch.empty(4 + 2 * C, dtype=torch.float64, device=hist.device)
+    call("metrics_from_hist", ptr(hist), ci(C), ptr(out), _stream())
+    _count()
+    return out
+
+
+def _f3(v):
+    import ctypes
+    return (ctypes.c_float * 3)(*[float(x) for x in v])
+
+
+def gather_windows_u8(tile_hwc, win, first, count, mean, std, out=None):
+    """Windows [first, first+count) of a uint8 [H,W,3] tile as normalised fp32 NCHW [count,3,win,win]."""
+    _chk(tile_hwc, "gather_windows_u8.tile", torch.uint8)
+    H, W, Cc = tile_hwc.shape
+    if Cc != 3:
+        raise _lib.UdaError("gather_windows_u8: tile must be [H,W,3] uint8")
+    if out is None:
+        out = torch.empty((count, 3, win, win), dtype=torch.float32, device=tile_hwc.device)
+    call("gather_windows_u8", ptr(tile_hwc), ptr(out), ci(H), ci(W), ci(win), ci(first), ci(count), _f3(mean), _f3(std),
+         _stream())
+    _count()
+    return out
+
+
+def gather_label_windows(tile, win, first, count, out=None):
+    """The same windows of an int64 / uint8 [H,W] label tile as int64 [count,win,win]."""
+    _chk(tile, "gather_label_windows.tile")
+    if tile.dtype == torch.int64:
+        d = I64
+    elif tile.dtype == torch.uint8:
+        d = U8
+    else:
+        raise TypeError("gather_label_windows: tile must be int64 or uint8")
+    H, W = tile.shape
+    if out is None:
+        out = torch.empty((count, win, win), dtype=torch.int64, device=tile.device)
+    call("gather_label_windows", ptr(tile), ci(d), ptr(out), ci(H), ci(W), ci(win), ci(first), ci(count), _stream())
+    _count()
+    return out
+
+
+def scatter_window_masks(masks, tile_mask, win, first):
+    """uint8 [count,win,win] window masks -> their place in the uint8 [H,W] tile mask."""
+    _chk(masks, "scatter_window_masks.masks", torch.uint8); _chk(tile_mask, "scatter_window_masks.tile_mask", torch.uint8)
+    H, W = tile_mask.shape
+    call("scatter_window_masks", ptr(masks), ptr(tile_mask), ci(H), ci(W), ci(win), ci(first), ci(masks.shape[0]), _stream())
+    _count()
+    return tile_mask

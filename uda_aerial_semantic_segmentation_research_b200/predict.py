@@ -42,6 +42,44 @@ def tile_windows(tile, window=512, stride=None):
     return t.reshape(-1, C, window, window)
 
 
+#: ImageNet statistics — the usual ``Config.NORMALIZE_MEAN / NORMALIZE_STD`` (the reference's config module is missing)
+IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
+
+
+@torch.no_grad()
+def sliding_window_evaluate_u8(model, tile_u8, target, num_classes, window=512, batch=16, ignore_index=None,
+                               mean=IMAGENET_MEAN, std=IMAGENET_STD, return_mask=False):
+    """Config 5 from the RAW tile: ``tile_u8`` is the uint8 [H,W,3] image as it comes from disk, ``target`` an int64 or
+    uint8 [H,W] label map.  Per batch of windows: one gather + ToTensor + Normalize kernel (reference
+    ``src/models/predict.py:93-97``), the conv-only eval forward, one fused argmax + confusion-matrix kernel (uint8
+    masks scattered back into the tile mask).  The metrics are derived on the device from the resident histogram
+    (``SegmentationMetrics.device_metrics``); nothing synchronises with the host.
+    Returns ``{'hist', 'metrics' (device tensors)[, 'mask': uint8 [H,W]]}``."""
+    model.eval()
+    if not (tile_u8.is_cuda and tile_u8.dtype == torch.uint8 and tile_u8.dim() == 3 and tile_u8.shape[2] == 3):
+        raise ValueError("sliding_window_evaluate_u8: tile must be a CUDA uint8 [H,W,3] tensor")
+    H, W = tile_u8.shape[:2]
+    if H % window or W % window:
+        raise ValueError("tile size must be a multiple of the window")
+    n_win = (H // window) * (W // window)
+    hist = torch.zeros((num_classes, num_classes), dtype=torch.int64, device=tile_u8.device)
+    tile_mask = torch.empty((H, W), dtype=torch.uint8, device=tile_u8.device) if return_mask else None
+    target = target.contiguous()
+    for first in range(0, n_win, batch):
+        n = min(batch, n_win - first)
+        x = ops.gather_windows_u8(tile_u8, window, first, n, mean, std)
+        t = ops.gather_label_windows(target, window, first, n)
+        logits = model(x)
+        m, _ = ops.argmax_confmat(logits.contiguous(), t, num_classes=num_classes, ignore_index=ignore_index,
+                                  want_mask=return_mask, mask_dtype=torch.uint8, hist=hist)
+        if return_mask:
+            ops.scatter_window_masks(m, tile_mask, window, first)
+    out = {"hist": hist, "metrics": SegmentationMetrics.device_metrics(hist)}
+    if return_mask:
+        out["mask"] = tile_mask
+    return out
+
+
 @torch.no_grad()
 def sliding_window_evaluate(model, tile, target, num_classes, window=512, batch=16, ignore_index=None,
                             return_mask=False):
