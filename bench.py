@@ -234,7 +234,11 @@ def measure_workload(args, workload, env, full):
     if world > 1:
         from uda_aerial_semantic_segmentation_research_b200.ddp import GradSync
         GradSync(nets)                                      # bucketed all-reduce, overlapped with backward
-        if use_graph and args.nccl_outside_graph:           # A/B switch: one flat all-reduce after the replay
+        # Captured steps: by default ONE flat all-reduce of the gradient buffer right after the backward kernels.
+        # --nccl-in-graph captures the bucketed, backward-overlapped all-reduces instead; measured slower on 2 and 8
+        # B200s (8.91 vs 8.71 ms/step at N=8, profiles/r02_bench_*_8gpu.json): the NCCL CTAs hold SMs for the duration of
+        # every bucket and break the one-CTA-per-SM assumption of the persistent convolution kernels.
+        if use_graph and not args.nccl_in_graph:
             for n in nets:
                 n._grad_sync = None
 
@@ -331,8 +335,8 @@ def measure_workload(args, workload, env, full):
 
     eager = ft_step if finetune else adv_step if adversarial else grl_step if grl else sup_step
     graphed, launch = None, "eager launches"
-    nccl = "" if world == 1 else (" + one flat all-reduce after the replay" if args.nccl_outside_graph else
-                                  "; bucketed NCCL all-reduce captured inside the graph on a side stream (overlaps backward)")
+    nccl = "" if world == 1 else ("; bucketed NCCL all-reduce captured inside the graph on a side stream (overlaps backward)"
+                                  if args.nccl_in_graph else "; one flat NCCL all-reduce of the gradient buffer after backward")
     if use_graph:
         if finetune:
             graphed = GraphedPhases([(ft_compute, ft_finish)], devin, [model, disc])
@@ -340,7 +344,7 @@ def measure_workload(args, workload, env, full):
         elif grl:
             graphed = GraphedFn(grl_step, devin, nets)
             launch = "ONE cuda-graph replay of the whole step (fwd, CE + adversarial loss, bwd, fused Adam over both networks)" + nccl
-        elif adversarial and not (world > 1 and args.nccl_outside_graph):
+        elif adversarial and (world == 1 or args.nccl_in_graph):
             graphed = GraphedFn(adv_step, devin, nets)
             launch = "ONE cuda-graph replay of the whole D step + G step (both fused Adam steps captured)" + nccl
         elif adversarial:
@@ -574,8 +578,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every launch from Python instead of replaying a CUDA graph")
     ap.add_argument("--no-sub", action="store_true", help="skip the adversarial sub-record of the supervised line")
-    ap.add_argument("--nccl-outside-graph", action="store_true",
-                    help="A/B switch (N>1): one flat all-reduce after the graph replay instead of the captured, overlapped buckets")
+    ap.add_argument("--nccl-in-graph", action="store_true",
+                    help="A/B switch (N>1): capture the bucketed, backward-overlapped all-reduces inside the step graph "
+                         "instead of one flat all-reduce after the backward kernels")
     ap.add_argument("--ft-views", default="pooled", choices=["pooled", "separate"],
                     help="finetune workload: both views as one 2B pass (default) or two B passes")
     args = ap.parse_args()

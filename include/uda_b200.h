@@ -269,6 +269,12 @@ int uda_gather_label_windows(const void* tile, int dtype, long long* out, int H,
 int uda_scatter_window_masks(const unsigned char* masks, unsigned char* tile_mask, int H, int W, int win, int first,
                              int count, void* stream);
 
+/* Device-side strong augmentation of a batch (unsupervised fine-tuning; reference: host-side albumentations pipeline,
+ * src/models/unsupervised_trainer.py:99-114, src/models/augmentation.py:40-80): one gather pass per view.  table = device
+ * array of B rows x 12 floats {m00,m01,m02, m10,m11,m12 (output pixel -> source coordinates, bilinear, BORDER_REFLECT_101),
+ * alpha, beta (value * alpha + beta), sigma (additive Gaussian noise), seed, 0, 0}.  images / out: fp32 NCHW, distinct. */
+int uda_strong_augment(const float* images, float* out, const float* table, int B, int C, int H, int W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -254,3 +254,38 @@ def test_adam_and_clip():
     R.adam_step(p, g, m, v, None, 1e-3, 0.9, 0.999, 1e-8, 0.01, 3, 1.0, cr)
     assert rel_err(pg.cpu(), p) < 1e-6 and rel_err(mg.cpu(), m) < 1e-6 and rel_err(vg.cpu(), v) < 2e-5
     assert torch.equal(sh.cpu(), p.bfloat16()) or rel_err(sh.float().cpu(), p) < 4e-3
+
+
+def test_strong_augmentation_kernel():
+    """f4: device-side strong augmentation (one gather pass per view) against the numpy restatement on the same
+    parameter table; the D4 members reproduce numpy's rot90 / flip / transpose EXACTLY; the noise term statistically."""
+    import numpy as np
+    from uda_aerial_semantic_segmentation_research_b200 import ops
+    from uda_aerial_semantic_segmentation_research_b200.augment import StrongAugmentation, build_table
+    from oracle import ref_augment as RA
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(6, 3, 64, 64, generator=g)
+    params = [{"k": 1}, {"hflip": True}, {"vflip": True, "transpose": True}, {"k": 3, "hflip": True},
+              {"angle": 30.0, "scale": 1.2, "dx": 0.05, "dy": -0.08, "alpha": 1.1, "beta": -0.05},
+              {"k": 2, "angle": -55.0, "scale": 0.75, "transpose": True, "alpha": 0.8, "beta": 0.1}]
+    table = build_table(params, 64, 64)
+    y = ops.strong_augment(x.to(DEV), torch.from_numpy(table).to(DEV)).cpu().numpy()
+    xn = x.numpy()
+    assert np.array_equal(y[0], np.rot90(xn[0], 1, (1, 2)))
+    assert np.array_equal(y[1], xn[1][:, :, ::-1])
+    assert np.array_equal(y[2], xn[2][:, ::-1].transpose(0, 2, 1))
+    assert np.array_equal(y[3], np.rot90(xn[3], 3, (1, 2))[:, :, ::-1])
+    ref = RA.strong_augment(xn, table)
+    assert np.abs(y - ref).max() < 2e-4          # fp32 coordinate arithmetic + bilinear weights vs float64
+    # noise: zero mean, requested sigma, different streams per image / seed, deterministic per seed
+    z = torch.zeros(2, 3, 128, 128, device=DEV)
+    t = build_table([{"sigma": 0.1, "seed": 5}, {"sigma": 0.25, "seed": 6}], 128, 128)
+    n1 = ops.strong_augment(z, torch.from_numpy(t).to(DEV))
+    n2 = ops.strong_augment(z, torch.from_numpy(t).to(DEV))
+    assert torch.equal(n1, n2)
+    assert abs(float(n1[0].std()) - 0.1) < 5e-3 and abs(float(n1[1].std()) - 0.25) < 1e-2 and abs(float(n1.mean())) < 5e-3
+    assert abs(float(torch.corrcoef(torch.stack([n1[0, 0].flatten(), n1[0, 1].flatten()]))[0, 1])) < 0.05
+    # the sampler draws the pipeline's decisions; the call runs end to end
+    aug = StrongAugmentation(seed=1)
+    v1, v2 = aug(x.to(DEV)), aug(x.to(DEV))
+    assert v1.shape == x.shape and torch.isfinite(v1).all() and not torch.equal(v1, v2)

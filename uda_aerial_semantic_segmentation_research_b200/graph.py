@@ -25,7 +25,8 @@ import torch.distributed as dist
 def _capture_kwargs(with_nccl):
     """NCCL's watchdog thread may touch the CUDA API while a capture is open: relax the capture error mode to the
     capturing thread when collectives are captured."""
-    return {"capture_error_mode": "thread_local"} if with_nccl else {}
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    return {"capture_error_mode": "thread_local"} if (with_nccl or multi) else {}
 
 
 class _Staging:

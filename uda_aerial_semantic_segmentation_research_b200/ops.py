@@ -811,3 +811,15 @@ def scatter_window_masks(masks, tile_mask, win, first):
     call("scatter_window_masks", ptr(masks), ptr(tile_mask), ci(H), ci(W), ci(win), ci(first), ci(masks.shape[0]), _stream())
     _count()
     return tile_mask
+
+
+def strong_augment(images, table):
+    """One augmented view of an fp32 NCHW batch from a [B,12] device parameter table (see ``augment.build_table``)."""
+    _chk(images, "strong_augment.images", torch.float32); _chk(table, "strong_augment.table", torch.float32)
+    B, C, H, W = images.shape
+    if tuple(table.shape) != (B, 12):
+        raise _lib.UdaError("strong_augment: table must be [B,12] float32")
+    out = torch.empty_like(images)
+    call("strong_augment", ptr(images), ptr(out), ptr(table), ci(B), ci(C), ci(H), ci(W), _stream())
+    _count()
+    return out
