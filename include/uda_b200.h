@@ -152,6 +152,22 @@ int uda_softmax_bwd_grl(const void* probs, const void* dprobs, float* dlogits, f
 int uda_scale(const void* x, void* y, int dtype, float scale, long long n, void* stream);
 int uda_pad_channels(const void* src, void* dst, long long rows, int c, int cpad, void* stream);
 int uda_unpad_channels_add(const float* src, float* dst, long long rows, int c, int cpad, void* stream);
+/* Decoder conv1 of the U-Net WITHOUT the upsampled / concatenated tensor (reference: smp's DecoderBlock
+ * F.interpolate(x, 2, 'nearest') -> torch.cat([x, skip], 1) -> conv3x3, created at src/models/train.py:572-577):
+ *   conv3x3(cat(up2(x), skip), W) = conv_transpose4x4_s2_p1(x, W4) + conv3x3(skip, Ws)
+ * uda_upconv_split_weights: w bf16 [O][3][3][C1+C2] -> wx_ft bf16 [O][4][4][C1] (tap groups summed) and ws bf16 [O][3][3][C2];
+ * uda_upconv_tc_fwd: y[B,H,W,O] = act(conv_transpose(x[B,H/2,W/2,C1], wx_ft) + bias (+ addend)) (+ BatchNorm statistics);
+ * uda_conv2d_tc_fwd_add: y = conv(x, w) + addend with the BatchNorm statistics of the sum (the skip half);
+ * uda_upconv_merge_wgrad: dW fp32 [O][3][3][C1+C2] += un-grouped dW4 fp32 [C1][4][4][O] (x channels), dWs (skip channels).
+ * Backward of the x half = the forward / wgrad entry points of the 4x4 stride-2 convolution with W4 =
+ * uda_conv2d_weight_flip_transpose(wx_ft). */
+int uda_upconv_split_weights(const void* w, void* wx_ft, void* ws, void* w4, void* ws_ft, int Cout, int C1, int C2,
+                             void* stream);   /* w4 / ws_ft (nullable): the flipped-transposed copies for the backward */
+int uda_upconv_tc_fwd(const void* x, const void* wx_ft, const float* bias, const void* addend, float act_slope, void* y,
+                      double* bn_sums, int B, int H, int W, int C1, int Cout, void* stream);
+int uda_conv2d_tc_fwd_add(const void* x, const void* w, const void* addend, void* y_nhwc, double* bn_sums, int B, int H,
+                          int W, int Cin, int Cout, int KH, int KW, int stride, int pad, void* stream);
+int uda_upconv_merge_wgrad(const float* dw4, const float* dws, float* dw, int Cout, int C1, int C2, void* stream);
 /* dgrad takes w_ft = uda_conv2d_weight_flip_transpose(w): [Cin][KH][KW][Cout] bf16 (the weights of the
  * equivalent forward convolution of dy); addend as in uda_conv2d_direct_dgrad. */
 int uda_conv2d_weight_flip_transpose(const void* w, void* w_ft, int Cout, int Cin, int KH, int KW, void* stream);

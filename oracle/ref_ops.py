@@ -17,6 +17,7 @@ USE_TC = False
 TC_PERSIST = False
 FOLD_BN_EVAL = False
 WGRAD_STREAM = False
+FUSE_UPCAT = False
 
 
 def dgrad_bnstats_supported(*a):

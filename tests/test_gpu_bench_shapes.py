@@ -102,3 +102,59 @@ def test_stem_at_benchmark_shape():
     ops.stem_wgrad(dy, xs, dw, S, S, 7, 3)
     dwr = R.conv_wgrad(dy.float(), x_nhwc, torch.zeros(64, 7, 7, 3, device=DEV), 2, 3)
     assert rel_err(dw, dwr) < 2e-3
+
+
+DEC_BLOCKS = [  # name, low-res H(=W) of x, C1 (upsampled channels), C2 (skip channels), Cout
+    ("dec0.c1", s32, 512, 256, 256), ("dec1.c1", s16, 256, 128, 128), ("dec2.c1", s8, 128, 64, 64),
+    ("dec3.c1", s4, 64, 64, 32), ("dec4.c1", s2, 32, 0, 16),
+]
+
+
+@pytest.mark.parametrize("blk", DEC_BLOCKS, ids=[b[0] for b in DEC_BLOCKS])
+def test_decoder_conv1_without_materialised_concat(blk):
+    """conv3x3(cat(upsample2x(x), skip), W) as conv_transpose4x4_s2(x, W4) + conv3x3(skip, Ws) at the benchmarked shape:
+    forward (with the BatchNorm statistics of the sum), dx at low resolution, dskip and the merged weight gradient against
+    the fp32 oracle ops (nearest upsample + concat + conv / torch.nn.grad on the device) on the same bf16 inputs."""
+    from uda_aerial_semantic_segmentation_research_b200 import ops
+    name, h, C1, C2, O = blk
+    H = 2 * h
+    x = _rand((B, h, h, C1), 21)
+    skip = _rand((B, H, H, C2), 22) if C2 else None
+    w = _rand((O, 3, 3, C1 + C2), 23, (9 * (C1 + C2)) ** -0.5)
+    cat = R.upcat_fwd(x.float(), skip.float() if C2 else None)
+    zr = R.conv_fwd(cat, w.float(), None, 1, 1)
+    wx, ws, w4, ws_ft = ops.upconv_split_weights(w, C1, backward=True)
+    assert torch.equal(w4, ops.weight_flip_transpose(wx)) and (not C2 or torch.equal(ws_ft, ops.weight_flip_transpose(ws)))
+    sums = torch.zeros(2 * O, dtype=torch.float64, device=DEV)
+    if C2:
+        z = ops.conv_fwd_add(skip, ws, ops.upconv_fwd(x, wx), bn_sums=sums)
+    else:
+        z = ops.upconv_fwd(x, wx, bn_sums=sums)
+    assert rel_err(z.float(), zr) < 1e-2, name
+    zf = z.double().reshape(-1, O)
+    assert rel_err(sums[O:], (zf * zf).sum(0)) < 1e-4
+    assert float((sums[:O] - zf.sum(0)).abs().max()) < 1e-3 * float(zf.abs().sum(0).max())
+    del zf, z
+    dz = _rand(tuple(zr.shape), 24)
+    del zr
+    dcat = R.conv_dgrad(dz.float(), w.float(), cat.shape, 1, 1)
+    dxr, dskipr = R.upcat_bwd(dcat, C1, C2)
+    del dcat
+    dx = ops.conv_fwd(dz, w4, None, 2, 1)
+    assert rel_err(dx.float(), dxr) < 1e-2, name
+    if C2:
+        dskip = ops.conv_dgrad(dz, ws, skip.shape, 1, 1, w_ft=ws_ft)
+        assert rel_err(dskip.float(), dskipr) < 1e-2, name
+        del dskip
+    del dx, dxr, dskipr
+    dwr = R.conv_wgrad(dz.float(), cat, torch.zeros(O, 3, 3, C1 + C2, device=DEV), 1, 1)
+    del cat
+    dw4 = torch.zeros((C1, 4, 4, O), device=DEV)
+    ops.conv_wgrad(x, dz, dw4, 2, 1)
+    dws = None
+    if C2:
+        dws = torch.zeros((O, 3, 3, C2), device=DEV)
+        ops.conv_wgrad(dz, skip, dws, 1, 1)
+    dw = torch.zeros((O, 3, 3, C1 + C2), device=DEV)
+    ops.upconv_merge_wgrad(dw4, dws, dw, C1)
+    assert rel_err(dw, dwr) < 2e-3, name

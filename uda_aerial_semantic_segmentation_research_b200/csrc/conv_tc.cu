@@ -417,7 +417,8 @@ bool dgrad_shape_ok(int B, int H, int W, int Cin, int Cout, int KH, int KW, int 
 // produced by exactly one launch; parities without any tap are zero).
 int run_dgrad(const void* dy, const void* w_ft, const void* addend, void* dx, int B, int H, int W, int Cin, int Cout,
               int KH, int KW, int stride, int pad, cudaStream_t st, const void* st_a = nullptr,
-              const void* st_z = nullptr, float st_slope = 0.f, double* st_sums = nullptr) {
+              const void* st_z = nullptr, float st_slope = 0.f, double* st_sums = nullptr, const float* bias = nullptr,
+              double* bn_sums = nullptr, int act = 0, float act_slope = 0.f) {
   UDA_REQUIRE(dgrad_shape_ok(B, H, W, Cin, Cout, KH, KW, stride, pad), UDA_ERR_UNSUPPORTED,
               "conv_tc_dgrad: shape not covered (B=%d H=%d W=%d Cin=%d Cout=%d k=%d s=%d p=%d)", B, H, W, Cin, Cout,
               KH, stride, pad);
@@ -428,7 +429,8 @@ int run_dgrad(const void* dy, const void* w_ft, const void* addend, void* dx, in
   g.st_a = st_a; g.st_z = st_z; g.st_slope = st_slope; g.st_sums = st_sums;
   g.src = dy; g.B = B; g.Cred = Cout; g.src_s2 = 0;
   g.wmat = w_ft; g.Cout = Cin; g.wtaps = KH * KW;
-  g.OH = H; g.OW = W; g.bias = nullptr; g.addend = addend; g.out = dx; g.out_nchw = nullptr;
+  g.OH = H; g.OW = W; g.bias = bias; g.addend = addend; g.out = dx; g.out_nchw = nullptr;
+  g.bn_sums = bn_sums; g.act = act; g.act_slope = act_slope;
   if (stride == 1) {
     g.SH = H; g.SW = W; g.os = 1; g.ncls = 1;
     TapClass& c = g.cls[0];
@@ -957,6 +959,17 @@ extern "C" int uda_conv2d_tc_fwd_fused(const void* x, const void* w, const float
                  (cudaStream_t)stream, act_slope != 1.f ? 1 : 0, act_slope);
 }
 
+// training form of the skip-channel half of the decoder convolution: y = conv(x, w) + addend with the BatchNorm
+// statistics of the SUM accumulated in the epilogue
+extern "C" int uda_conv2d_tc_fwd_add(const void* x, const void* w, const void* addend, void* y_nhwc, double* bn_sums, int B,
+                                     int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad, void* stream) {
+  UDA_REQUIRE(x && w && y_nhwc && addend, UDA_ERR_BAD_ARG, "conv_tc_fwd_add: null pointer");
+  UDA_REQUIRE(use_persistent(), UDA_ERR_UNSUPPORTED, "conv_tc_fwd_add: needs the persistent kernels");
+  UDA_REQUIRE(aligned<bf16>(addend, 16), UDA_ERR_BAD_ARG, "conv_tc_fwd_add: addend must be 16-byte aligned");
+  return run_fwd(x, w, nullptr, addend, y_nhwc, nullptr, bn_sums, B, H, W, Cin, Cout, KH, KW, stride, pad,
+                 (cudaStream_t)stream);
+}
+
 // w_ft: weights from uda_conv2d_weight_flip_transpose ([Cin][KH][KW][Cout] bf16)
 extern "C" int uda_conv2d_tc_dgrad(const void* dy, const void* w_ft, const void* addend, void* dx, int B, int H, int W,
                                    int Cin, int Cout, int KH, int KW, int stride, int pad, void* stream) {
@@ -972,6 +985,94 @@ extern "C" int uda_conv2d_tc_dgrad_bnstats(const void* dy, const void* w_ft, con
   UDA_REQUIRE(aligned<bf16>(a, 16) && (!z || aligned<bf16>(z, 16)), UDA_ERR_BAD_ARG,
               "conv_tc_dgrad_bnstats: a / z must be 16-byte aligned");
   return run_dgrad(dy, w_ft, addend, dx, B, H, W, Cin, Cout, KH, KW, stride, pad, (cudaStream_t)stream, a, z, slope, sums);
+}
+
+// ---- decoder conv1 without the upsampled / concatenated tensor -------------------------------------------------------
+// conv3x3(cat(upsample2x(x), skip), W)  =  conv_transpose4x4_s2_p1(x, W4)  +  conv3x3(skip, Ws):
+// on the nearest-upsampled image the nine taps of an output pixel of parity (a, c) fall on only 2 x 2 source pixels of
+// x, so the 3x3 kernel collapses per parity into a 2x2 kernel — together exactly a 4x4 stride-2 transposed
+// convolution, i.e. the DGRAD of a 4x4 stride-2 pad-1 convolution, which the tensor-core path already has (4 output
+// parity classes x 4 taps in one launch, 16/36 of the FLOPs).  Row / column groups of the flipped-transposed weights:
+// r = 0 <- {kh 0}, 1 <- {0, 1}, 2 <- {1, 2}, 3 <- {2}.
+//   w     : bf16 [O][3][3][C1 + C2]   (x channels first, as torch.cat([up(x), skip], 1) orders them)
+//   wx_ft : bf16 [O][4][4][C1] = sum over the tap group (fp32 sum, one rounding) — the `w_ft` of run_dgrad
+//   ws    : bf16 [O][3][3][C2] contiguous copy of the skip channels
+// w4 (optional): bf16 [C1][4][4][O] = weight_flip_transpose(wx_ft) — the weights of the 4x4 stride-2 convolution whose
+// forward is dx; ws_ft (optional): bf16 [C2][3][3][O] = weight_flip_transpose(ws) for the skip dgrad.  One launch
+// prepares everything a decoder block needs for a training step.
+__global__ void __launch_bounds__(256)
+upconv_split_weights_kernel(const bf16* __restrict__ w, bf16* __restrict__ wx_ft, bf16* __restrict__ ws,
+                            bf16* __restrict__ w4, bf16* __restrict__ ws_ft, int O, int C1, int C2) {
+  const int C = C1 + C2;
+  const long long nx = (long long)O * 16 * C1, ns = (long long)O * 9 * C2;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nx) {
+    const int c = (int)(i % C1);
+    const int rs = (int)((i / C1) % 16), o = (int)(i / ((long long)C1 * 16));
+    const int r = rs >> 2, q = rs & 3;
+    const int kh0 = r == 0 ? 0 : r - 1, kh1 = r == 3 ? 2 : (r == 0 ? 0 : r);      // rows of group r: [kh0, kh1]
+    const int kw0 = q == 0 ? 0 : q - 1, kw1 = q == 3 ? 2 : (q == 0 ? 0 : q);
+    float acc = 0.f;
+    for (int kh = kh0; kh <= kh1; ++kh)
+      for (int kw = kw0; kw <= kw1; ++kw) acc += __bfloat162float(w[((long long)o * 9 + kh * 3 + kw) * C + c]);
+    const bf16 v = __float2bfloat16_rn(acc);
+    wx_ft[i] = v;
+    if (w4) w4[(((long long)c * 4 + (3 - r)) * 4 + (3 - q)) * O + o] = v;
+  } else if (i < nx + ns) {
+    const long long j = i - nx;
+    const int c = (int)(j % C2);
+    const long long ot = j / C2;      // o * 9 + tap
+    const bf16 v = w[ot * C + C1 + c];
+    ws[j] = v;
+    if (ws_ft) {
+      const int o = (int)(ot / 9), tap = (int)(ot % 9);
+      ws_ft[((long long)c * 9 + (8 - tap)) * O + o] = v;
+    }
+  }
+}
+// backward of the split: dW[o][kh][kw][c] += sum over the groups (r, q) that contain (kh, kw) of dW4[c][3-r][3-q][o]
+// (dW4 = fp32 wgrad of the 4x4 stride-2 convolution, [C1][4][4][O]) for the x channels; += dWs for the skip channels
+__global__ void __launch_bounds__(256)
+upconv_merge_wgrad_kernel(const float* __restrict__ dw4, const float* __restrict__ dws, float* __restrict__ dw, int O,
+                          int C1, int C2) {
+  const int C = C1 + C2;
+  const long long n = (long long)O * 9 * C;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (int)(i % C);
+  const int tap = (int)((i / C) % 9), o = (int)(i / ((long long)C * 9));
+  if (c >= C1) { dw[i] += dws[((long long)o * 9 + tap) * C2 + (c - C1)]; return; }
+  const int kh = tap / 3, kw = tap % 3;
+  float acc = 0.f;
+  for (int r = kh; r <= kh + 1; ++r)          // kh belongs to groups r = kh and r = kh + 1
+    for (int q = kw; q <= kw + 1; ++q)
+      acc += dw4[(((long long)c * 4 + (3 - r)) * 4 + (3 - q)) * O + o];
+  dw[i] += acc;
+}
+extern "C" int uda_upconv_split_weights(const void* w, void* wx_ft, void* ws, void* w4, void* ws_ft, int Cout, int C1,
+                                        int C2, void* stream) {
+  UDA_REQUIRE(w && wx_ft && (ws || C2 == 0) && Cout > 0 && C1 > 0 && C2 >= 0, UDA_ERR_BAD_ARG, "upconv_split_weights: bad argument");
+  const long long n = (long long)Cout * (16 * C1 + 9 * C2);
+  upconv_split_weights_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const bf16*)w, (bf16*)wx_ft, (bf16*)ws, (bf16*)w4, (bf16*)ws_ft, Cout, C1, C2);
+  UDA_LAUNCH_OK("upconv_split_weights_kernel");
+  return UDA_OK;
+}
+extern "C" int uda_upconv_merge_wgrad(const float* dw4, const float* dws, float* dw, int Cout, int C1, int C2, void* stream) {
+  UDA_REQUIRE(dw4 && dw && (dws || C2 == 0) && Cout > 0 && C1 > 0 && C2 >= 0, UDA_ERR_BAD_ARG, "upconv_merge_wgrad: bad argument");
+  const long long n = (long long)Cout * 9 * (C1 + C2);
+  upconv_merge_wgrad_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(dw4, dws, dw, Cout, C1, C2);
+  UDA_LAUNCH_OK("upconv_merge_wgrad_kernel");
+  return UDA_OK;
+}
+// y[B,H,W,Cout] = act(conv_transpose4x4_s2_p1(x[B,H/2,W/2,C1], wx_ft) + bias (+ addend)), optional BatchNorm statistics:
+// the x-channel half of the decoder convolution (see above).  H, W are the OUTPUT (full-resolution) sizes.
+extern "C" int uda_upconv_tc_fwd(const void* x, const void* wx_ft, const float* bias, const void* addend, float act_slope,
+                                 void* y, double* bn_sums, int B, int H, int W, int C1, int Cout, void* stream) {
+  UDA_REQUIRE(x && wx_ft && y, UDA_ERR_BAD_ARG, "upconv_tc_fwd: null pointer");
+  UDA_REQUIRE(use_persistent(), UDA_ERR_UNSUPPORTED, "upconv_tc_fwd: needs the persistent kernels");
+  return run_dgrad(x, wx_ft, addend, y, B, H, W, Cout, C1, 4, 4, 2, 1, (cudaStream_t)stream, nullptr, nullptr, 0.f, nullptr,
+                   bias, bn_sums, act_slope != 1.f ? 1 : 0, act_slope);
 }
 
 // ---- eval-mode BatchNorm folding:  w'[o] = w[o] * gamma[o] / sqrt(var[o] + eps),  b' = beta - mean * gamma / sqrt(...) (+ b * ...)

@@ -412,6 +412,103 @@ def conv_padded_cin(ctx, xin, cp):
     return out
 
 
+def _upconv_ok(ctx, xin, skip, cp):
+    if not (ctx.dtype == torch.bfloat16 and ops.USE_TC and ops.TC_PERSIST and ops.FUSE_UPCAT and xin.t is not None
+            and cp.kernel_size == 3 and cp.stride == 1 and cp.padding == 1 and cp.bias is None):
+        return False
+    B, h, w, C1 = xin.t.shape
+    H, W, O = 2 * h, 2 * w, cp.out_channels
+    # measured per block at B=16, 512x512 (tools/upconv_bench.py, profiles/r02_upconv_bench.txt): the split form wins
+    # from decoder block 1 on (-10 % .. -36 % forward + backward); on block 0 (512 upsampled channels on 16x16 pixels:
+    # four parity classes of 256-pixel work each) the dgrad / wgrad launches of the two halves cost more than the copy
+    if C1 > 256:
+        return False
+    ok = all(ops.tc_supported(op, B, H, W, O, C1, 4, 4, 2, 1) for op in (0, 1, 2))      # the 4x4 stride-2 convolution
+    if skip is not None:
+        C2 = skip.t.shape[-1]
+        ok = ok and all(ops.tc_supported(op, B, H, W, C2, O, 3, 3, 1, 1) for op in (0, 1, 2))
+    return ok
+
+
+def upconv_bn_act(ctx, xin, skip, cp, bn, slope=0.0):
+    """Decoder conv1: a = act(BN(conv3x3(cat(upsample2x(x), skip)))) WITHOUT the upsampled / concatenated tensor:
+
+        conv3x3(cat(up2(x), skip), W) = conv_transpose4x4_s2_p1(x, W4) + conv3x3(skip, Ws)
+
+    (on the nearest-upsampled image the nine taps of an output pixel fall on 2 x 2 pixels of x: per output parity the
+    3x3 kernel collapses to 2x2, together a 4x4 stride-2 transposed convolution = the dgrad launch of the tensor-core
+    path; 16/36 of the FLOPs of the x channels).  The skip half accumulates onto it and emits the BatchNorm statistics
+    of the sum.  Backward: dx = conv4x4_s2(dz, W4) at LOW resolution (no 2x2 gradient-sum pass), dskip = dgrad3x3(dz,
+    Ws), weight gradients of both halves merged into the [O,3,3,C1+C2] parameter gradient.  Falls back to the
+    materialising ``upcat`` + ``conv_bn_act`` when a shape is not on the tensor-core path."""
+    if not _upconv_ok(ctx, xin, skip, cp):
+        return conv_bn_act(ctx, upcat(ctx, xin, skip), cp, bn, slope=slope)
+    st = ctx.store
+    C1 = xin.t.shape[-1]
+    fold = not ctx.training and ctx.tape is None and ops.FOLD_BN_EVAL
+    if fold:    # inference: BatchNorm folded into the weights, bias + activation in the epilogue of the last half
+        if ctx.fold_key is None:
+            ctx.fold_key = st.fold_key()
+        w, b = st.folded(ctx.fold_key, cp, bn)
+        wx, ws = ops.upconv_split_weights(w, C1)
+        if skip is None:
+            return Var(ops.upconv_fwd(xin.t, wx, bias=b, act_slope=slope))
+        zx = ops.upconv_fwd(xin.t, wx)
+        return Var(ops.conv_fwd_fused(skip.t, ws, b, slope, addend=zx))
+    w = st.w(cp.weight, ctx.dtype)
+    if ctx.tape is not None:
+        wx, ws, w4, ws_ft = ops.upconv_split_weights(w, C1, backward=True)
+    else:
+        wx, ws = ops.upconv_split_weights(w, C1)
+    sums = ctx.stats_slot(2 * cp.out_channels, w.device) if (ctx.training and ops.FUSE_BN_STATS) else None
+    if skip is None:
+        z = ops.upconv_fwd(xin.t, wx, bn_sums=sums)
+    else:
+        z = ops.conv_fwd_add(skip.t, ws, ops.upconv_fwd(xin.t, wx), bn_sums=sums)
+    zv = Var(z)
+    zv.sums = sums
+    if ctx.tape is not None:
+        xin.uses += 1
+        if skip is not None:
+            skip.uses += 1
+
+        def bwd():
+            dz = zv.g
+            zv.g = None
+            xin.uses -= 1
+            if skip is not None:
+                skip.uses -= 1
+            if dz is None:
+                return
+            O = cp.out_channels
+
+            def wgrads():
+                C2 = skip.t.shape[-1] if skip is not None else 0
+                buf = torch.zeros(O * (16 * C1 + 9 * C2), dtype=torch.float32, device=dz.device)     # one memset
+                dw4 = buf[:O * 16 * C1].view(C1, 4, 4, O)
+                ops.conv_wgrad(xin.t, dz, dw4, 2, 1)            # roles: "dy" = x (low resolution), "x" = dz
+                dws = None
+                if skip is not None:
+                    dws = buf[O * 16 * C1:].view(O, 3, 3, C2)
+                    ops.conv_wgrad(dz, skip.t, dws, 1, 1)
+                ops.upconv_merge_wgrad(dw4, dws, st.g(cp.weight), C1)
+
+            if ops.WGRAD_STREAM:
+                with ctx.wgrad_stream(dz, xin.t, *([skip.t] if skip is not None else [])):
+                    wgrads()
+            else:
+                wgrads()
+            if isinstance(xin.g, torch.Tensor):
+                raise RuntimeError("upconv: the low-resolution input is expected to have no earlier gradient on the tape")
+            if xin.g is not False:
+                xin.g = ops.conv_fwd(dz, w4, None, 2, 1)     # dx at low resolution
+            if skip is not None and skip.g is not False:
+                skip.g = ops.conv_dgrad(dz, ws, skip.t.shape, 1, 1, addend=skip.g, w_ft=ws_ft)
+            ctx.done(cp.weight)
+        ctx.tape.push(bwd)
+    return bn_act(ctx, zv, bn, slope=slope)
+
+
 def conv_bn_act(ctx, xin, cp, bn, slope=0.0, residual=None):
     """a = act(BN(conv(x)) (+ residual)).  Training: convolution with the BatchNorm statistics in its epilogue, then the
     normalise + activation pass.  Eval mode on the tensor cores (inference, ``src/models/predict.py:113-130``): the

@@ -32,6 +32,9 @@ FOLD_BN_EVAL = os.environ.get("UDA_B200_FOLD_BN_EVAL", "1") != "0"
 #: path, so their CTAs fill the SMs that the tails / prologues of the chain leave idle); joined at the end of backward
 #: (measured at B=16, 512x512: 8.99 -> 8.73 ms per supervised step; UDA_B200_WGRAD_STREAM=0 keeps everything on one stream)
 WGRAD_STREAM = os.environ.get("UDA_B200_WGRAD_STREAM", "1") != "0"
+#: decoder conv1 as conv_transpose4x4(x) + conv3x3(skip): the upsampled / concatenated tensor is never materialised
+#: (UDA_B200_FUSE_UPCAT=0 runs the upsample+concat copy kernel and one 3x3 convolution over the concatenation)
+FUSE_UPCAT = os.environ.get("UDA_B200_FUSE_UPCAT", "1") != "0"
 #: counts launches issued through this module (bench.py reports it as gpu_launches)
 LAUNCHES = 0
 #: algorithmic FLOPs (2*M*N*K) and call count of the convolutions routed to the tcgen05 kernels
@@ -212,6 +215,63 @@ def bn_fold_conv(w_f32, conv_bias, gamma, beta, running_mean, running_var, eps=1
          float(eps), ptr(w_out), ptr(b_out), ci(O), ci(w_f32.numel() // O), _stream())
     _count()
     return w_out, b_out
+
+
+# ---- decoder conv1 without the upsampled / concatenated tensor (see uda_upconv_* in include/uda_b200.h) ----------
+def upconv_split_weights(w, C1, backward=False):
+    """OHWI bf16 [O,3,3,C1+C2] -> (wx_ft bf16 [O,4,4,C1] tap groups summed, ws bf16 [O,3,3,C2] or None); with
+    ``backward`` also (w4 bf16 [C1,4,4,O] = flip-transpose(wx_ft), ws_ft bf16 [C2,3,3,O] or None) — one launch."""
+    _chk(w, "upconv_split_weights.w", torch.bfloat16)
+    O, KH, KW, C = w.shape
+    if KH != 3 or KW != 3 or C1 <= 0 or C1 > C:
+        raise _lib.UdaError("upconv_split_weights: expects a 3x3 weight and 0 < C1 <= Cin")
+    C2 = C - C1
+    wx = torch.empty((O, 4, 4, C1), dtype=torch.bfloat16, device=w.device)
+    ws = torch.empty((O, 3, 3, C2), dtype=torch.bfloat16, device=w.device) if C2 else None
+    w4 = torch.empty((C1, 4, 4, O), dtype=torch.bfloat16, device=w.device) if backward else None
+    wsf = torch.empty((C2, 3, 3, O), dtype=torch.bfloat16, device=w.device) if (backward and C2) else None
+    call("upconv_split_weights", ptr(w), ptr(wx), ptr(ws), ptr(w4), ptr(wsf), ci(O), ci(C1), ci(C2), _stream())
+    _count()
+    return (wx, ws, w4, wsf) if backward else (wx, ws)
+
+
+def upconv_fwd(x, wx_ft, bias=None, addend=None, act_slope=1.0, bn_sums=None):
+    """y[B,2H,2W,O] = act(conv_transpose4x4_s2_p1(x, wx_ft) + bias (+ addend)) == conv3x3(upsample2x(x), Wx) (...)."""
+    _chk(x, "upconv_fwd.x", torch.bfloat16); _chk(wx_ft, "upconv_fwd.wx_ft", torch.bfloat16)
+    B, h, w_, C1 = x.shape
+    O = wx_ft.shape[0]
+    y = torch.empty((B, 2 * h, 2 * w_, O), dtype=torch.bfloat16, device=x.device)
+    if addend is not None:
+        _chk(addend, "upconv_fwd.addend", torch.bfloat16)
+    call("upconv_tc_fwd", ptr(x), ptr(wx_ft), ptr(bias), ptr(addend), float(act_slope), ptr(y), ptr(bn_sums), ci(B),
+         ci(2 * h), ci(2 * w_), ci(C1), ci(O), _stream())
+    _tc_account(B, h, w_, O, C1, 4, 4)
+    _count()
+    return y
+
+
+def conv_fwd_add(x, w, addend, bn_sums=None, stride=1, pad=1):
+    """y = conv(x, w) + addend, BatchNorm statistics of the sum in the epilogue (tensor-core path)."""
+    _chk(x, "conv_fwd_add.x", torch.bfloat16); _chk(w, "conv_fwd_add.w", torch.bfloat16)
+    _chk(addend, "conv_fwd_add.addend", torch.bfloat16)
+    B, H, W, Cin, Cout, KH, KW, Ho, Wo = _geom(x.shape, w.shape, stride, pad)
+    if tuple(addend.shape) != (B, Ho, Wo, Cout):
+        raise _lib.UdaError("conv_fwd_add: addend must have the output's shape")
+    y = torch.empty((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
+    call("conv2d_tc_fwd_add", ptr(x), ptr(w), ptr(addend), ptr(y), ptr(bn_sums), ci(B), ci(H), ci(W), ci(Cin), ci(Cout),
+         ci(KH), ci(KW), ci(stride), ci(pad), _stream())
+    _tc_account(B, Ho, Wo, Cout, Cin, KH, KW)
+    _count()
+    return y
+
+
+def upconv_merge_wgrad(dw4, dws, dw, C1):
+    """dw (fp32 OHWI [O,3,3,C1+C2]) += un-grouped dw4 (fp32 [C1,4,4,O]) on the x channels, dws on the skip channels."""
+    _chk(dw4, "upconv_merge_wgrad.dw4", torch.float32); _chk(dw, "upconv_merge_wgrad.dw", torch.float32)
+    O, _, _, C = dw.shape
+    call("upconv_merge_wgrad", ptr(dw4), ptr(dws), ptr(dw), ci(O), ci(C1), ci(C - C1), _stream())
+    _count()
+    return dw
 
 
 def weight_flip_transpose(w, out=None):

@@ -42,18 +42,52 @@ def tile_windows(tile, window=512, stride=None):
     return t.reshape(-1, C, window, window)
 
 
+class GraphedForward:
+    """Eval-mode forward of a uda_b200 network captured in a CUDA graph (inference is ~70 launches of 10-40 us each:
+    issued one by one from Python the host, not the B200, bounds the window rate).  ``fwd = GraphedForward(model,
+    example); logits = fwd(x)`` — ``x`` must have the example's shape; the returned logits buffer is reused by the next
+    call.  The folded BatchNorm weights are baked in: build a new object after the model's weights change."""
+
+    def __init__(self, model, example, warmup=2):
+        if not example.is_cuda:
+            raise RuntimeError("GraphedForward needs a CUDA example input")
+        model.eval()
+        self.model = model
+        self.x = example.clone()
+        s = torch.cuda.Stream(device=example.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s), torch.no_grad():
+            for _ in range(warmup):          # fills the folded-weight cache, sizes the workspaces
+                model(self.x)
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        self._keep = dict(model._store._fold_cache)     # the captured launches read these tensors
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.y = model(self.x)
+
+    def __call__(self, x=None):
+        """``x`` None: the caller has already written the input into ``self.x`` (e.g. a gather kernel's output)."""
+        if x is not None:
+            self.x.copy_(x, non_blocking=True)
+        self.graph.replay()
+        return self.y
+
+
 #: ImageNet statistics — the usual ``Config.NORMALIZE_MEAN / NORMALIZE_STD`` (the reference's config module is missing)
 IMAGENET_MEAN, IMAGENET_STD = (0.485, 0.456, 0.406), (0.229, 0.224, 0.225)
 
 
 @torch.no_grad()
 def sliding_window_evaluate_u8(model, tile_u8, target, num_classes, window=512, batch=16, ignore_index=None,
-                               mean=IMAGENET_MEAN, std=IMAGENET_STD, return_mask=False):
+                               mean=IMAGENET_MEAN, std=IMAGENET_STD, return_mask=False, graphed=None):
     """Config 5 from the RAW tile: ``tile_u8`` is the uint8 [H,W,3] image as it comes from disk, ``target`` an int64 or
     uint8 [H,W] label map.  Per batch of windows: one gather + ToTensor + Normalize kernel (reference
     ``src/models/predict.py:93-97``), the conv-only eval forward, one fused argmax + confusion-matrix kernel (uint8
     masks scattered back into the tile mask).  The metrics are derived on the device from the resident histogram
-    (``SegmentationMetrics.device_metrics``); nothing synchronises with the host.
+    (``SegmentationMetrics.device_metrics``); nothing synchronises with the host.  ``graphed``: a ``GraphedForward`` of
+    ``model`` for ``[batch,3,window,window]`` inputs — the windows are then gathered straight into its input buffer and
+    the forward is one graph replay.
     Returns ``{'hist', 'metrics' (device tensors)[, 'mask': uint8 [H,W]]}``."""
     model.eval()
     if not (tile_u8.is_cuda and tile_u8.dtype == torch.uint8 and tile_u8.dim() == 3 and tile_u8.shape[2] == 3):
@@ -67,9 +101,12 @@ def sliding_window_evaluate_u8(model, tile_u8, target, num_classes, window=512, 
     target = target.contiguous()
     for first in range(0, n_win, batch):
         n = min(batch, n_win - first)
-        x = ops.gather_windows_u8(tile_u8, window, first, n, mean, std)
         t = ops.gather_label_windows(target, window, first, n)
-        logits = model(x)
+        if graphed is not None and n == graphed.x.shape[0]:
+            ops.gather_windows_u8(tile_u8, window, first, n, mean, std, out=graphed.x)
+            logits = graphed()
+        else:
+            logits = model(ops.gather_windows_u8(tile_u8, window, first, n, mean, std))
         m, _ = ops.argmax_confmat(logits.contiguous(), t, num_classes=num_classes, ignore_index=ignore_index,
                                   want_mask=return_mask, mask_dtype=torch.uint8, hist=hist)
         if return_mask:

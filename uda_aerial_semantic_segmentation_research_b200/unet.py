@@ -124,8 +124,7 @@ class DecoderBlock(nn.Module):
         self.conv2 = _Seq(ConvParams(cout, cout, 3, 1, 1), BNParams(cout), nn.Identity())
 
     def run(self, ctx, x, skip):
-        y = E.upcat(ctx, x, skip)
-        y = E.conv_bn_act(ctx, y, self.conv1[0], self.conv1[1], slope=0.0)
+        y = E.upconv_bn_act(ctx, x, skip, self.conv1[0], self.conv1[1], slope=0.0)
         return E.conv_bn_act(ctx, y, self.conv2[0], self.conv2[1], slope=0.0)
 
 
