@@ -91,6 +91,7 @@ def test_conv_direct(dtype, cfg):
 @pytest.mark.parametrize("slope", [0.0, 0.2, 1.0])
 def test_batchnorm(dtype, shape, slope):
     ops = _ops()
+    torch.manual_seed(1234)          # gamma / beta / running statistics below come from the global generator
     C = shape[-1]
     x = _rand(shape, dtype, 8, 2.0) + 0.5
     res = _rand(shape, dtype, 9)
@@ -126,7 +127,12 @@ def test_batchnorm(dtype, shape, slope):
             dx2 = ops.bn_bwd(dy.to(DEV), x.to(DEV), None, gamma.to(DEV), mean, rstd, slope, dg2, db2, scale=scale, shift=shift)
             dgr2, dbr2 = torch.zeros(C), torch.zeros(C)
             dxr2 = R.bn_bwd(dy, x, None, gamma, mr, rr, slope, dgr2, dbr2, scale=sr, shift=fr)
-            assert rel_err(dx2.float().cpu(), dxr2.float()) < tol
+            # the activation mask is the SIGN of x*scale+shift: where that is within round-off of zero, an FMA and a
+            # separate multiply-add may legitimately disagree (one flipped element = a max-norm error of O(1))
+            pre = x.float() * sr + fr
+            sure = (pre.abs() > 1e-5 * (pre.abs().max() + 1.0)).float()
+            assert rel_err(dx2.float().cpu() * sure, dxr2.float() * sure) < tol
+            assert float(1.0 - sure.mean()) < 1e-3
             assert rel_err(dg2.cpu(), dgr2) < 1e-4 and rel_err(db2.cpu(), dbr2) < 1e-4
     sc, sf = ops.bn_eval_coeffs(gamma.to(DEV), beta.to(DEV), rm_g, rv_g)
     scr, sfr = R.bn_eval_coeffs(gamma, beta, rm_r, rv_r)

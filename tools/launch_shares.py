@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """Summarise an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv` launch list:
-per kernel launches, total time, share of the window, DRAM bytes and DRAM GB/s.  Usage: launch_shares.py launches.csv [out.csv]
+per kernel launches, total time, share of the window, DRAM bytes and DRAM GB/s.
+Usage: launch_shares.py launches.csv [out.csv] [--step]   (--step: only the last complete training step of the list)
 (per-launch times are cold-cache and serialised: compare SHARES, not absolutes)."""
 import collections
 import csv
@@ -25,6 +26,13 @@ def main():
             per.setdefault((int(r[idi]), r[ki]), {})[r[mi]] = (float(r[vi].replace(",", "")), r[ui])
     scale_t = {"ns": 1e-3, "nsecond": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3}
     scale_b = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    # --step: keep only the LAST complete training step = the launches between the last two optimizer launches
+    if "--step" in sys.argv:
+        keys = list(per.keys())
+        adam = [i for i, k in enumerate(keys) if "adam_kernel" in k[1]]
+        if len(adam) >= 2:
+            keep = set(k for k in keys[adam[-2] + 1:adam[-1] + 1] if "spin_kernel" not in k[1])   # torch.cuda._sleep
+            per = collections.OrderedDict((k, v) for k, v in per.items() if k in keep)
     agg, tot = collections.OrderedDict(), 0.0
     for (_, name), m in per.items():
         t, u = m["gpu__time_duration.sum"]
@@ -42,8 +50,9 @@ def main():
     lines.append(f"TOTAL,{len(per)},{tot:.1f},100.00,,,")
     text = "\n".join(lines)
     print(text)
-    if len(sys.argv) > 2:
-        open(sys.argv[2], "w").write(text + "\n")
+    outs = [a for a in sys.argv[2:] if not a.startswith("--")]
+    if outs:
+        open(outs[0], "w").write(text + "\n")
 
 
 if __name__ == "__main__":

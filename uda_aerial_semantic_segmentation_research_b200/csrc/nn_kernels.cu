@@ -605,6 +605,65 @@ maxpool_bwd_kernel(const T* __restrict__ dy, const unsigned char* __restrict__ i
   }
 }
 
+// Even H, W: one thread per 2x2 INPUT block (and 8 channels).  The four pixels of a block can only have won in the four
+// windows (i,j), (i,j+1), (i+1,j), (i+1,j+1) — the even/even pixel only as the centre tap of window (i,j) — so every
+// thread does the same work (no parity divergence), with four dy / winner-tap loads and four dx stores in flight
+// (the per-pixel gather above spends its time in divergent parity tests).
+template <typename T, typename IT>
+__global__ void __launch_bounds__(kThreads)
+maxpool_bwd_block_kernel(const T* __restrict__ dy, const unsigned char* __restrict__ idx, const T* addend, T* dx, int B,
+                         int H, int W, int C, int Ho, int Wo) {
+  constexpr int VEC = 8;
+  const int cv = C / VEC;
+  const IT total = (IT)B * Ho * Wo * cv;
+  for (IT i = (IT)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (IT)gridDim.x * blockDim.x) {
+    const int v = (int)(i % cv);
+    IT p = i / cv;
+    const int wo = (int)(p % Wo); p /= Wo;
+    const int ho = (int)(p % Ho);
+    const int b = (int)(p / Ho);
+    float g[4][VEC];
+    uint2 win[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int oh = ho + (q >> 1), ow = wo + (q & 1);
+      if (oh < Ho && ow < Wo) {
+        const long long o = (((long long)b * Ho + oh) * Wo + ow) * C + v * VEC;
+        ld_vec<VEC>(dy + o, g[q]);
+        win[q] = *reinterpret_cast<const uint2*>(idx + o);
+      } else {
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) g[q][j] = 0.f;
+        win[q] = make_uint2(0xffffffffu, 0xffffffffu);
+      }
+    }
+    // window q = (i + qh, j + qw) covers input rows 2(i+qh)-1 .. 2(i+qh)+1: block row dh is its tap kh = dh + 1 - 2 qh
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh) {
+#pragma unroll
+      for (int dw = 0; dw < 2; ++dw) {
+        const long long o = (((long long)b * H + 2 * ho + dh) * W + 2 * wo + dw) * C + v * VEC;
+        float acc[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) acc[j] = 0.f;
+        if (addend) ld_vec<VEC>(addend + o, acc);     // may alias dx (same elements, same thread)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int kh = dh + 1 - 2 * (q >> 1), kw = dw + 1 - 2 * (q & 1);
+          if (kh < 0 || kw < 0) continue;             // compile-time: this window does not reach the pixel
+          const unsigned int tap = (unsigned int)(kh * 3 + kw);
+#pragma unroll
+          for (int j = 0; j < VEC; ++j) {
+            const unsigned int wj = ((j < 4 ? win[q].x : win[q].y) >> (8 * (j & 3))) & 0xffu;
+            if (wj == tap) acc[j] += g[q][j];
+          }
+        }
+        st_vec<VEC>(dx + o, acc);
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Decoder operand: out[b,h,w,:] = concat(x[b,h/2,w/2,:C1], skip[b,h,w,:C2])  (nearest x2)
 // ---------------------------------------------------------------------------------------------
@@ -1182,6 +1241,14 @@ extern "C" int uda_maxpool3x3s2_bwd(const void* dy, const unsigned char* idx, co
   UDA_REQUIRE(dy && idx && dx && B > 0 && H > 0 && W > 0 && C > 0, UDA_ERR_BAD_ARG, "maxpool_bwd: bad argument");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   int vec = vec_for(dtype, C, dy, dx, addend);
+  if (vec == 8 && H % 2 == 0 && W % 2 == 0 && aligned<unsigned char>(idx, 8)) {   // 2x2-block form (no divergence)
+    const long long items = (long long)B * Ho * Wo * (C / 8);
+#define KB(T, ...) do { if (items * 32 < (1LL << 31)) maxpool_bwd_block_kernel<T, int><<<grid_for(items), kThreads, 0, st>>>((const T*)dy, idx, (const T*)addend, (T*)dx, B, H, W, C, Ho, Wo); else maxpool_bwd_block_kernel<T, long long><<<grid_for(items), kThreads, 0, st>>>((const T*)dy, idx, (const T*)addend, (T*)dx, B, H, W, C, Ho, Wo); } while (0)
+    UDA_DT(dtype, KB, 0);
+#undef KB
+    UDA_LAUNCH_OK("maxpool_bwd_block_kernel");
+    return UDA_OK;
+  }
   const long long total = (long long)B * H * W * (C / vec);
 #define K(T, V) do { if (total * 8 < (1LL << 31)) maxpool_bwd_kernel<T, V, int><<<grid_for(total), kThreads, 0, st>>>((const T*)dy, idx, (const T*)addend, (T*)dx, B, H, W, C, Ho, Wo); else maxpool_bwd_kernel<T, V, long long><<<grid_for(total), kThreads, 0, st>>>((const T*)dy, idx, (const T*)addend, (T*)dx, B, H, W, C, Ho, Wo); } while (0)
 #define KV(T, ...) do { if (vec == 8) K(T, 8); else if (vec == 4) K(T, 4); else if (vec == 2) K(T, 2); else K(T, 1); } while (0)
