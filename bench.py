@@ -344,25 +344,11 @@ def measure_workload(args, workload, env, full):
         elif grl:
             graphed = GraphedFn(grl_step, devin, nets)
             launch = "ONE cuda-graph replay of the whole step (fwd, CE + adversarial loss, bwd, fused Adam over both networks)" + nccl
-        elif adversarial and (world == 1 or args.nccl_in_graph):
+        elif adversarial:
+            # one graph for every world size: the two flat all-reduces (or, with --nccl-in-graph, the bucketed ones) are
+            # captured in-stream between the backward kernels and the captured fused-Adam launches
             graphed = GraphedFn(adv_step, devin, nets)
             launch = "ONE cuda-graph replay of the whole D step + G step (both fused Adam steps captured)" + nccl
-        elif adversarial:
-            def d_compute(xs, ts, xtg):
-                dopt.zero_grad()
-                d_loss = adv.discriminator_loss(disc(xs), disc(xtg))
-                d_loss.backward()
-                return d_loss.detach()
-
-            def g_compute(xs, ts, xtg):
-                opt.zero_grad()
-                total = crit(model(xs), ts) + adv.generator_loss(disc(xtg))
-                total.backward()
-                return total.detach()
-
-            graphed = GraphedPhases([(d_compute, lambda: (flat_allreduce(disc), dopt.step())),
-                                     (g_compute, lambda: (flat_allreduce(model), opt.step()))], devin, nets)
-            launch = "cuda-graph replay of the D-step and G-step compute phases, all-reduce + fused Adam after each"
         else:
             graphed = GraphedStep(model, crit, opt, devin[0], devin[1])
             launch = "cuda-graph replay of fwd+loss+bwd, then fused Adam" + nccl
