@@ -454,7 +454,9 @@ def measure_workload(args, workload, env, full):
                 last = [round(a.elapsed_time(b) * 1e3, 1) for a, b in evs[-per:]]
                 print(f"[profile] {name}: {last}", file=sys.stderr)
         pk = peaks()
-        tc_keys = ("conv2d_tc_fwd", "conv2d_tc_dgrad", "conv2d_tc_wgrad", "stem_tc_fwd", "stem_tc_wgrad")
+        # every entry point whose FLOPs ops._tc_account() counts (the two halves of the split decoder conv1 included)
+        tc_keys = ("conv2d_tc_fwd", "conv2d_tc_fwd_add", "conv2d_tc_fwd_fused", "upconv_tc_fwd", "conv2d_tc_dgrad",
+                   "conv2d_tc_dgrad_bnstats", "conv2d_tc_wgrad", "stem_tc_fwd", "stem_tc_fwd_act", "stem_tc_wgrad")
         tc_ms = sum(breakdown.get(k, {}).get("ms_per_step", 0.0) for k in tc_keys)
         tc_n = sum(breakdown.get(k, {}).get("launches_per_step", 0.0) for k in tc_keys)
         tc_gflop = (ops.TC_FLOPS - f0) / prof_steps / 1e9

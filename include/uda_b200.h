@@ -168,6 +168,20 @@ int uda_upconv_tc_fwd(const void* x, const void* wx_ft, const float* bias, const
 int uda_conv2d_tc_fwd_add(const void* x, const void* w, const void* addend, void* y_nhwc, double* bn_sums, int B, int H,
                           int W, int Cin, int Cout, int KH, int KW, int stride, int pad, void* stream);
 int uda_upconv_merge_wgrad(const float* dw4, const float* dws, float* dw, int Cout, int C1, int C2, void* stream);
+/* Training-mode conv + BatchNorm2d + activation (+ residual add) as ONE launch (replaces aten::cudnn_convolution ->
+ * aten::batch_norm -> aten::add_ -> aten::relu_ of a torchvision BasicBlock / smp Conv2dReLU under the model created at
+ * src/models/train.py:572-577): z = conv(x, w) (+ addend), batch statistics of the bf16-rounded z, grid-wide barrier
+ * with the accumulators held in TMEM, a = act(z*scale + shift (+ residual)); z and a are both written (z is saved for
+ * the backward), mean / rstd / scale / shift and the running statistics as uda_bn_apply_fused.  bn_sums (double[2*Cout])
+ * and counter (one uint32) must be zero on entry.  Returns UDA_ERR_UNSUPPORTED before launching anything when the
+ * layer's output tiles do not fit the tensor memory of one wave of CTAs (callers fall back to uda_conv2d_tc_fwd +
+ * uda_bn_apply_fused).  All CTAs of the launch spin on the barrier: do not run two such launches concurrently on
+ * different streams of one device. */
+int uda_conv2d_tc_fwd_bn_act(const void* x, const void* w, const void* addend, const void* residual, void* z, void* a,
+                             double* bn_sums, unsigned int* counter, const float* gamma, const float* beta,
+                             float* running_mean, float* running_var, float* mean, float* rstd, float* scale,
+                             float* shift, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
+                             float eps, float momentum, float slope, void* stream);
 /* dgrad takes w_ft = uda_conv2d_weight_flip_transpose(w): [Cin][KH][KW][Cout] bf16 (the weights of the
  * equivalent forward convolution of dy); addend as in uda_conv2d_direct_dgrad. */
 int uda_conv2d_weight_flip_transpose(const void* w, void* w_ft, int Cout, int Cin, int KH, int KW, void* stream);

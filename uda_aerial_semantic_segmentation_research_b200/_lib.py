@@ -53,8 +53,9 @@ def _conv(a):
 PROFILE = None
 
 
-def call(name, *args):
-    """Call ``uda_<name>``; raise with the library's thread-local message on a negative return code."""
+def call(name, *args, unsupported_ok=False):
+    """Call ``uda_<name>``; raise with the library's thread-local message on a negative return code.  With
+    ``unsupported_ok`` a return code of UDA_ERR_UNSUPPORTED (-2: nothing was launched) returns False instead."""
     fn = getattr(lib(), "uda_" + name)
     if PROFILE is not None:
         import torch
@@ -65,9 +66,14 @@ def call(name, *args):
         PROFILE.setdefault(name, []).append((e0, e1))
     else:
         rc = fn(*[_conv(a) for a in args])
+    if rc == -2 and unsupported_ok:
+        if PROFILE is not None:
+            PROFILE[name].pop()
+        return False
     if rc != 0:
         msg = lib().uda_last_error()
         raise UdaError(f"uda_{name} failed ({rc}): {msg.decode() if msg else '?'}")
+    return True
 
 
 def ptr(t):

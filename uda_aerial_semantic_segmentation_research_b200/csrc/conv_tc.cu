@@ -356,6 +356,7 @@ int run_gemm_conv(const GemmConv& g, cudaStream_t st) {
     }
     return run_gemm_conv_persistent(g, st);
   }
+  if (g.fuse) return UDA_ERR_UNSUPPORTED;
   for (int ci = 0; ci < g.ncls; ++ci)
     if (int rc = run_gemm_conv_class(g, ci, st)) return rc;
   return UDA_OK;
@@ -376,7 +377,7 @@ bool fwd_shape_ok(int B, int H, int W, int Cin, int Cout, int KH, int KW, int st
 // x: [B,H,W,Cin] bf16; w: [Cout][KH*KW][Cin] bf16; "same" (stride 1) or halving (stride 2) forward convolution
 int run_fwd(const void* x, const void* w, const float* bias, const void* addend, void* y, float* y_nchw,
             double* bn_sums, int B, int H, int W, int Cin, int Cout, int KH, int KW, int stride, int pad,
-            cudaStream_t st, int act = 0, float act_slope = 0.f) {
+            cudaStream_t st, int act = 0, float act_slope = 0.f, const BnFuse* fuse = nullptr) {
   UDA_REQUIRE(fwd_shape_ok(B, H, W, Cin, Cout, KH, KW, stride, pad), UDA_ERR_UNSUPPORTED,
               "conv_tc: shape not covered by the tensor-core kernel (B=%d H=%d W=%d Cin=%d Cout=%d k=%d s=%d p=%d)",
               B, H, W, Cin, Cout, KH, stride, pad);
@@ -399,6 +400,7 @@ int run_fwd(const void* x, const void* w, const float* bias, const void* addend,
   g.OH = stride == 1 ? H : H / 2; g.OW = stride == 1 ? W : W / 2; g.os = 1;
   g.bias = bias; g.addend = addend; g.out = y; g.out_nchw = y_nchw; g.bn_sums = bn_sums;
   g.act = act; g.act_slope = act_slope;
+  g.fuse = fuse;
   return run_gemm_conv(g, st);
 }
 
@@ -871,9 +873,18 @@ using namespace uda;
 
 // ---- Cin = 3 stem entry points (xs: packed input of uda_stem_pack_input; ws: uda_stem_pack_weight) ----
 #ifdef UDA_B200_EXPERIMENTS
-namespace uda { namespace tcconv { long long* g_trace_buf = nullptr; } }
+namespace uda { namespace tcconv { long long* g_trace_buf = nullptr; int g_trace_series_left = 0; } }
 // experiment builds only: device buffer of 16 int64 per CTA (see conv_tc_internal.cuh), or null to switch tracing off
-extern "C" int uda_exp_set_trace(void* buf) { uda::tcconv::g_trace_buf = (long long*)buf; return 0; }
+extern "C" int uda_exp_set_trace(void* buf) {
+  uda::tcconv::g_trace_buf = (long long*)buf; uda::tcconv::g_trace_series_left = 0; return 0;
+}
+// ... or `n` slices of 148 x 16 int64: every traced launch takes the next one (returns the slices still unused when
+// called with buf == null)
+extern "C" int uda_exp_set_trace_series(void* buf, int n) {
+  const int left = uda::tcconv::g_trace_series_left;
+  uda::tcconv::g_trace_buf = (long long*)buf; uda::tcconv::g_trace_series_left = buf ? n : 0;
+  return left;
+}
 #endif
 
 extern "C" int uda_stem_tc_supported(int B, int H, int W, int Cin, int Cout, int K, int stride, int pad) {
@@ -968,6 +979,29 @@ extern "C" int uda_conv2d_tc_fwd_add(const void* x, const void* w, const void* a
   UDA_REQUIRE(aligned<bf16>(addend, 16), UDA_ERR_BAD_ARG, "conv_tc_fwd_add: addend must be 16-byte aligned");
   return run_fwd(x, w, nullptr, addend, y_nhwc, nullptr, bn_sums, B, H, W, Cin, Cout, KH, KW, stride, pad,
                  (cudaStream_t)stream);
+}
+
+// Training form of conv + BatchNorm + activation (+ residual) as ONE launch (BnFuse, conv_tc_internal.cuh): returns
+// UDA_ERR_UNSUPPORTED — before anything is launched and without an error message the caller would surface — when the
+// layer's output tiles do not fit the TMEM of one wave (the caller then runs uda_conv2d_tc_fwd + uda_bn_apply_fused).
+extern "C" int uda_conv2d_tc_fwd_bn_act(const void* x, const void* w, const void* addend, const void* residual, void* z,
+                                        void* a, double* bn_sums, unsigned int* counter, const float* gamma,
+                                        const float* beta, float* running_mean, float* running_var, float* mean,
+                                        float* rstd, float* scale, float* shift, int B, int H, int W, int Cin, int Cout,
+                                        int KH, int KW, int stride, int pad, float eps, float momentum, float slope,
+                                        void* stream) {
+  UDA_REQUIRE(x && w && z && a && bn_sums && counter && mean && rstd && scale && shift, UDA_ERR_BAD_ARG,
+              "conv_tc_fwd_bn_act: null pointer");
+  if (!use_persistent() || !fwd_shape_ok(B, H, W, Cin, Cout, KH, KW, stride, pad)) return UDA_ERR_UNSUPPORTED;
+  UDA_REQUIRE(aligned<bf16>(a, 16) && (!addend || aligned<bf16>(addend, 16)) && (!residual || aligned<bf16>(residual, 16)),
+              UDA_ERR_BAD_ARG, "conv_tc_fwd_bn_act: pointers must be 16-byte aligned");
+  const int Ho = stride == 1 ? H : H / 2, Wo = stride == 1 ? W : W / 2;
+  BnFuse f{};
+  f.a_out = a; f.residual = residual; f.gamma = gamma; f.beta = beta; f.running_mean = running_mean;
+  f.running_var = running_var; f.mean = mean; f.rstd = rstd; f.scale = scale; f.shift = shift;
+  f.M = (long long)B * Ho * Wo; f.eps = eps; f.momentum = momentum; f.slope = slope; f.counter = counter;
+  return run_fwd(x, w, nullptr, addend, z, nullptr, bn_sums, B, H, W, Cin, Cout, KH, KW, stride, pad,
+                 (cudaStream_t)stream, 0, 0.f, &f);
 }
 
 // w_ft: weights from uda_conv2d_weight_flip_transpose ([Cin][KH][KW][Cout] bf16)

@@ -62,7 +62,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_per_img = p.tiles_w * p.tiles_h;
 
-  UDA_TR(const long long tr0 = clock64(); long long* const trp = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;)
+  UDA_TR(const long long tr0 = clock64(); const long long tr_g0 = trace_globaltimer();
+         long long* const trp = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;)
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
   if (warp == 1) {
@@ -81,7 +82,8 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible from here on
-  UDA_TR(if (trp && threadIdx.x == 0) { trp[0] = tr0; trp[1] = clock64() - tr0; })
+  UDA_TR(if (trp && threadIdx.x == 0) { trp[0] = tr0; trp[1] = clock64() - tr0; trp[14] = tr_g0;
+                                        trp[15] = 2LL | ((long long)p.Cout << 8) | ((long long)p.Cred << 24) | ((long long)p.total_tiles << 40); })
 
   if (warp == 0) {
     // ===================== TMA producer: weights once, then one halo box per (tile, channel chunk) ==========
@@ -304,6 +306,7 @@ int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, HParams& p, cudaSt
 // Returns UDA_ERR_UNSUPPORTED (without setting an error message the caller would surface) when the shape is
 // not a 3x3 stride-1 "same" convolution on a 128-multiple-wide image with resident weights.
 int run_gemm_conv_halo(const GemmConv& g, cudaStream_t st) {
+  if (g.fuse) return UDA_ERR_UNSUPPORTED;   // wide images: the tile set does not fit TMEM, BatchNorm stays a separate pass
   if (g.ncls != 1 || g.src_s2 || g.a_map || g.os != 1 || g.wtaps != 9 || g.cls[0].ntaps != 9) return UDA_ERR_UNSUPPORTED;
   const TapClass& c = g.cls[0];
   if (c.oh != 0 || c.ow != 0) return UDA_ERR_UNSUPPORTED;
@@ -333,7 +336,7 @@ int run_gemm_conv_halo(const GemmConv& g, cudaStream_t st) {
   p.act = g.act; p.act_slope = g.act_slope;
   p.st_a = (const bf16*)g.st_a; p.st_z = (const bf16*)g.st_z; p.st_slope = g.st_slope; p.st_sums = g.st_sums;
   if (g.st_sums && (!g.st_a || !g.out || g.bn_sums)) return UDA_ERR_UNSUPPORTED;
-  UDA_TR(p.trace = g_trace_buf;)
+  UDA_TR(p.trace = take_trace_slice();)
   CUtensorMap ma, mb;
   {
     const uint64_t C = (uint64_t)g.Cred;

@@ -1,6 +1,7 @@
 // Internal interface between the tensor-core convolution translation units.
 #pragma once
 #include "tc_common.cuh"
+#include "bn_common.cuh"
 
 namespace uda {
 namespace tcconv {
@@ -34,6 +35,23 @@ struct TapClass {
   int oh, ow;
 };
 
+// Training-mode BatchNorm + activation (+ residual) of the convolution's output applied in the SAME launch (north-star
+// "BatchNorm+ReLU fused in the epilogue").  Batch statistics couple every output pixel, so the launch must hold ALL its
+// accumulators in TMEM across a grid-wide barrier: pass 1 of the epilogue reduces sum / sum of squares of the
+// bf16-rounded outputs (GemmConv::bn_sums), every CTA arrives on `counter` and spins until the whole grid has (the grid
+// is <= one CTA per SM, all co-resident), then pass 2 re-reads TMEM, stores z (saved for the backward) and
+// a = act(z*scale + shift (+ residual)).  Replaces the bn_apply launch (one kernel boundary, one read of z) for every
+// layer whose output tile set fits the TMEM of one wave: layer2-4 and decoder blocks 0-1 at B=16, 512x512.
+struct BnFuse {
+  void* a_out;              // bf16, shape of `out`; nullptr = not fused
+  const void* residual;     // optional bf16, shape of `out`
+  const float* gamma; const float* beta; float* running_mean; float* running_var;
+  float* mean; float* rstd; float* scale; float* shift;     // per-channel outputs (saved for the backward)
+  long long M;              // pixels per channel (B*OH*OW)
+  float eps, momentum, slope;
+  unsigned int* counter;    // zero on entry; arrival counter of the grid barrier
+};
+
 // out[b, i*os+oh, j*os+ow, :] = sum_taps src[b, (i,j)+tap, :] * wmat[:, wtap, :]   (+bias, +addend)
 //   src  : [B,SH,SW,Cred] bf16 read through a stride-1 4-D map (src_s2 = 0; M-grid = SHxSW) or the stride-2
 //          space-to-depth 5-D map (src_s2 = 1; M-grid = SH/2 x SW/2);   wmat : [Cout][wtaps][Cred] bf16
@@ -57,6 +75,7 @@ struct GemmConv {
   // optional: caller-built A-operand tensor map (rank-5 coordinate form {c, w, ph, h, b}) over an M-grid of
   // MH x MW pixels — used by the Cin=3 stem, whose A operand is a padded 4-channel row view of the image
   const CUtensorMap* a_map; int a_MH, a_MW, a_kc;
+  const BnFuse* fuse;   // optional (needs bn_sums and out): see BnFuse; UDA_ERR_UNSUPPORTED when the tiles are not TMEM-resident
 };
 
 inline int pick_kc(int c) {
@@ -74,8 +93,27 @@ inline int pick_bn(int cout) { return cout > 64 ? 128 : (cout > 32 ? 64 : 32); }
 //   4 MMA thread: clocks waiting for operands (full barriers)  5 MMA thread: clocks waiting for a drained accumulator
 //   6 first MMA issued  7 last commit issued  8 epilogue warp 2: clocks waiting for accumulators  9 epilogue: busy clocks
 //   10 epilogue done  11 CTA exit  12 tiles of this CTA     (all times relative to 0)
+//   14 %globaltimer (ns) at entry  15 kernel kind | Cout << 8 | Cred << 24 | tiles << 40   (kind: 1 persist, 2 halo, 3 phalo, 4 wgrad_big)
+// With uda_exp_set_trace_series(buf, n) every traced launch takes the NEXT slice of 148 x 16 int64 (n slices), so the
+// launches of a whole captured training step can be laid on one time axis (tools/trace_step.py).
 #ifdef UDA_B200_EXPERIMENTS
 extern long long* g_trace_buf;
+extern int g_trace_series_left;
+inline long long* take_trace_slice() {
+  long long* b = g_trace_buf;
+  if (b && g_trace_series_left > 0) {
+    g_trace_buf += 148 * 16;
+    if (--g_trace_series_left == 0) g_trace_buf = nullptr;
+  }
+  return b;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ long long trace_globaltimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#endif
 #define UDA_TR(...) __VA_ARGS__
 #define UDA_TR_WAIT(acc, ...) { const long long _t0 = clock64(); __VA_ARGS__; acc += clock64() - _t0; }
 #else
@@ -84,6 +122,54 @@ extern long long* g_trace_buf;
 #endif
 
 #ifdef __CUDACC__
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// Grid-wide barrier for the `nthreads` epilogue threads of every CTA (named barrier `id`); `leader` = one of them.
+// Everything the calling threads wrote (the statistics atomics) is visible to every thread of the grid afterwards.
+// All CTAs of the grid must be co-resident (grid <= SMs at one CTA per SM).  A protocol bug traps instead of hanging.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int expected, int id, int nthreads,
+                                             bool leader) {
+  __threadfence();
+  bar_sync(id, nthreads);
+  if (leader) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+    long long t0 = 0;
+    for (unsigned int spin = 0;; ++spin) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+      if (v >= expected) break;
+      __nanosleep(32);
+      if ((spin & 0x3ff) == 0x3ff) {
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000LL) {
+          printf("uda_b200: grid barrier timed out (block %d: %u of %u arrived)\n", blockIdx.x, v, expected);
+          __trap();
+        }
+      }
+    }
+    __threadfence();
+  }
+  bar_sync(id, nthreads);
+}
+// per-channel scale / shift of a fused BatchNorm from the completed statistics (same arithmetic as bn_apply_stream_kernel)
+__device__ __forceinline__ void bn_fuse_coeffs(const BnFuse& f, const double* sums, int C, int ch, float& sc, float& sf) {
+  const double s1 = __ldcg(sums + ch), s2 = __ldcg(sums + C + ch);
+  const double inv_m = 1.0 / (double)f.M;
+  const double mean = s1 * inv_m;
+  const float var = fmaxf((float)(s2 * inv_m - mean * mean), 0.f);
+  const float rstd = rsqrtf(var + f.eps);
+  const float g = f.gamma ? f.gamma[ch] : 1.f, b = f.beta ? f.beta[ch] : 0.f;
+  sc = g * rstd;
+  sf = b - (float)mean * g * rstd;
+}
+// the ONE thread that owns channel `ch` publishes mean / rstd / scale / shift and updates the running statistics
+__device__ __forceinline__ void bn_fuse_publish(const BnFuse& f, const double* sums, int C, int ch) {
+  const bn::BnFwdFinal fin{f.gamma, f.beta, f.running_mean, f.running_var, f.mean, f.rstd, f.scale, f.shift,
+                           f.M, f.eps, f.momentum, nullptr};
+  bn::bn_fwd_finalize_channel(fin, __ldcg(sums + ch), __ldcg(sums + C + ch), ch);
+}
 // Column sums over the 32 rows a warp holds (one row per lane, 32 values per lane): recursive halving,
 // 31 shuffles; afterwards lane L holds the sum of column L in v[0].
 __device__ __forceinline__ float warp_column_sums(float (&v)[32], int lane) {

@@ -44,6 +44,7 @@ struct PParams {
   double* bn_sums;
   int act; float act_slope;            // GemmConv::act
   const bf16* st_a; const bf16* st_z; float st_slope; double* st_sums;   // GemmConv::st_*
+  BnFuse fuse;        // fuse.a_out != nullptr: BatchNorm + activation in this launch (FUSE instances: every CTA's tiles stay in TMEM)
   long long* trace;   // experiment builds only: per-CTA trace records (conv_tc_internal.cuh)
   int debug;   // experiment builds only (UDA_B200_TC_DEBUG bit mask): 1 = no epilogue stores, 2 = no MMAs, 4 = no TMA loads
 };
@@ -53,7 +54,7 @@ struct PParams {
 #define UDA_TC_DBG(p, bit) false
 #endif
 
-template <int KC, int BN, int MT>
+template <int KC, int BN, int MT, bool FUSE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                        const PParams p) {
@@ -84,7 +85,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const int total_tiles = p.ncls * tiles_per_cls;
   const int tiles_per_group = p.tiles_w * p.tiles_h;
 
-  UDA_TR(const long long tr0 = clock64(); long long* const trp = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;)
+  UDA_TR(const long long tr0 = clock64(); const long long tr_g0 = trace_globaltimer();
+         long long* const trp = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;)
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
   if (warp == 1) {
@@ -103,7 +105,8 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible from here on
-  UDA_TR(if (trp && threadIdx.x == 0) { trp[0] = tr0; trp[1] = clock64() - tr0; })
+  UDA_TR(if (trp && threadIdx.x == 0) { trp[0] = tr0; trp[1] = clock64() - tr0; trp[14] = tr_g0;
+                                        trp[15] = 1LL | ((long long)p.Cout << 8) | ((long long)p.Cred << 24) | ((long long)total_tiles << 40); })
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -210,6 +213,124 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     double* const sums_out = p.bn_sums ? p.bn_sums : p.st_sums;   // forward statistics or BN-backward statistics
     const float inv_slope = p.st_slope != 0.f ? 1.f / p.st_slope : 0.f;
     int j = 0;
+    if constexpr (FUSE) {
+      // ---- conv + BatchNorm + activation in one launch (BnFuse): this CTA's (<= kSets) tiles stay in TMEM across
+      // the grid barrier; one tap class, BN >= 64 ----
+      float* const s_tab = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);   // [kSets][2][BN] scale | shift
+      const int et = threadIdx.x - 64;   // 0..127 among the epilogue threads
+      // pass 1: statistics of the bf16-rounded outputs; the accumulator sets are NOT released
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+        const int mt = t % p.m_tiles, n0 = (t / p.m_tiles) * BN;
+        const int grp = mt / tiles_per_group, tin = mt % tiles_per_group;
+        const int b0 = grp * p.NB, h0 = (tin / p.tiles_w) * p.TH, w0 = (tin % p.tiles_w) * p.TW;
+        if (n0 != bn_n0) {
+          if (bn_n0 >= 0) {
+#pragma unroll
+            for (int cc = 0; cc < kChunks; ++cc) {
+              const int col = bn_n0 + cc * 32 + lane;
+              atomicAdd(p.bn_sums + col, (double)bn_s[cc]); atomicAdd(p.bn_sums + p.Cout + col, (double)bn_q[cc]);
+              bn_s[cc] = 0.f; bn_q[cc] = 0.f;
+            }
+          }
+          bn_n0 = n0;
+        }
+        UDA_TR_WAIT(tr_wt, mbar_wait(tfull_bar(j), 0))
+        tc_fence_after();
+#pragma unroll 1
+        for (int sub = 0; sub < MT; ++sub) {
+          const int r = sub * 128 + qw * 32 + lane;
+          const int nb = r / (p.TH * p.TW);
+          const int th = (r / p.TW) % p.TH, tw = r % p.TW;
+          const long long pix = ((long long)(b0 + nb) * p.OH + (h0 + th)) * p.OW + (w0 + tw);
+          const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)j * kAccCols + (uint32_t)sub * BN;
+#pragma unroll
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tbase + (uint32_t)c0, v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) f[k] = __uint_as_float(v[k]);
+            if (p.addend) {
+              const bf16* add = p.addend + pix * p.Cout + n0 + c0;
+#pragma unroll
+              for (int k = 0; k < 32; k += 8) {
+                float a8[8];
+                ld_vec<8>(add + k, a8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[k + e] += a8[e];
+              }
+            }
+            bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);
+          }
+        }
+      }
+      if (bn_n0 >= 0) {
+#pragma unroll
+        for (int cc = 0; cc < kChunks; ++cc) {
+          const int col = bn_n0 + cc * 32 + lane;
+          atomicAdd(p.bn_sums + col, (double)bn_s[cc]); atomicAdd(p.bn_sums + p.Cout + col, (double)bn_q[cc]);
+        }
+      }
+      grid_barrier(p.fuse.counter, gridDim.x, 2, 128, et == 0);
+      j = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+        const int mt = t % p.m_tiles, n0 = (t / p.m_tiles) * BN;
+        float* const sc = s_tab + j * 2 * BN;
+        for (int ch = et; ch < BN; ch += 128) {
+          bn_fuse_coeffs(p.fuse, p.bn_sums, p.Cout, n0 + ch, sc[ch], sc[BN + ch]);
+          if (mt == 0) bn_fuse_publish(p.fuse, p.bn_sums, p.Cout, n0 + ch);
+        }
+      }
+      bar_sync(2, 128);
+      // pass 2: z (saved for the backward) and a = act(z*scale + shift (+ residual))
+      const bf16* const res = (const bf16*)p.fuse.residual;
+      bf16* const aout = (bf16*)p.fuse.a_out;
+      const float slope = p.fuse.slope;
+      j = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
+        const int mt = t % p.m_tiles, n0 = (t / p.m_tiles) * BN;
+        const int grp = mt / tiles_per_group, tin = mt % tiles_per_group;
+        const int b0 = grp * p.NB, h0 = (tin / p.tiles_w) * p.TH, w0 = (tin % p.tiles_w) * p.TW;
+        const float* const sc = s_tab + j * 2 * BN;
+#pragma unroll 1
+        for (int sub = 0; sub < MT; ++sub) {
+          const int r = sub * 128 + qw * 32 + lane;
+          const int nb = r / (p.TH * p.TW);
+          const int th = (r / p.TW) % p.TH, tw = r % p.TW;
+          const long long pix = ((long long)(b0 + nb) * p.OH + (h0 + th)) * p.OW + (w0 + tw);
+          const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)j * kAccCols + (uint32_t)sub * BN;
+#pragma unroll
+          for (int c0 = 0; c0 < BN; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(tbase + (uint32_t)c0, v);
+            tmem_ld_wait();
+            const long long off = pix * p.Cout + n0 + c0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              float z8[8], a8[8], r8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) z8[e] = __uint_as_float(v[k + e]);
+              if (p.addend) {
+                ld_vec<8>(p.addend + off + k, a8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) z8[e] += a8[e];
+              }
+              st_vec<8>(p.out + off + k, z8);
+              if (res) ld_vec<8>(res + off + k, r8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float zr = __bfloat162float(__float2bfloat16_rn(z8[e]));
+                float y = zr * sc[c0 + k + e] + sc[BN + c0 + k + e];
+                if (res) y += r8[e];
+                a8[e] = y > 0.f ? y : y * slope;
+              }
+              st_vec<8>(aout + off + k, a8);
+            }
+          }
+        }
+      }
+    } else {
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
       const int ci = t / tiles_per_cls, rem = t % tiles_per_cls;
       const int mt = rem % p.m_tiles, n0 = (rem / p.m_tiles) * BN;
@@ -335,6 +456,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         if (col < p.Cout) { atomicAdd(sums_out + col, (double)bn_s[cc]); atomicAdd(sums_out + p.Cout + col, (double)bn_q[cc]); }
       }
     }
+    }   // !FUSE
   }
   tc_fence_before();
   __syncthreads();
@@ -345,9 +467,10 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   }
 }
 
-template <int KC, int BN, int MT>
+template <int KC, int BN, int MT, bool FUSE = false>
 int launch_persist(const CUtensorMap& ma, const CUtensorMap& mb, PParams& p, int total_tiles, cudaStream_t st) {
   constexpr int kABytes = MT * 128 * KC * 2, kBBytes = BN * KC * 2;
+  constexpr int kSetsH = 2 * MT * BN <= 512 ? 2 : 1;
   const int budget = 200 * 1024;
   const int ws_bytes = p.wtaps * p.kchunks * kBBytes;
   p.ws = (p.n_tiles == 1 && ws_bytes <= 96 * 1024) ? 1 : 0;
@@ -356,15 +479,17 @@ int launch_persist(const CUtensorMap& ma, const CUtensorMap& mb, PParams& p, int
   if (S > kMaxStages) S = kMaxStages;
   UDA_REQUIRE(S >= 2, UDA_ERR_UNSUPPORTED, "conv_tc_persist: not enough shared memory for a 2-stage ring");
   p.stages = S;
-  const int smem = (p.ws ? ws_bytes : 0) + S * stage_bytes + 1024 + 512;
+  const int smem = (p.ws ? ws_bytes : 0) + S * stage_bytes + 1024 + 512 + (FUSE ? kSetsH * 2 * BN * 4 : 0);
   static int configured = 0;
   if (configured < smem) {
-    UDA_CUDA_OK(cudaFuncSetAttribute(conv_tc_persist_kernel<KC, BN, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    UDA_CUDA_OK(cudaFuncSetAttribute(conv_tc_persist_kernel<KC, BN, MT, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      227 * 1024));
     configured = 227 * 1024;
   }
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  UDA_CUDA_OK(launch_pdl(conv_tc_persist_kernel<KC, BN, MT>, dim3(grid), dim3(kThreads), smem, st, ma, mb, p));
+  // fused BatchNorm: all tiles of a CTA must still be in TMEM at the grid barrier
+  if (FUSE && (total_tiles + grid - 1) / grid > kSetsH) return UDA_ERR_UNSUPPORTED;
+  UDA_CUDA_OK(launch_pdl(conv_tc_persist_kernel<KC, BN, MT, FUSE>, dim3(grid), dim3(kThreads), smem, st, ma, mb, p));
   UDA_LAUNCH_OK("conv_tc_persist_kernel");
   return UDA_OK;
 }
@@ -433,8 +558,28 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
       }
     }
     MT = best_mt; BN = best_bn;
+    if (g.fuse) {
+      // fused BatchNorm: every tile of the launch must still sit in TMEM at the grid barrier (<= kSets tiles per CTA);
+      // keep the cost model's shape when it is resident, else the first resident one
+      auto resident = [&](int mt, int bn) {
+        if ((mt == 2 && !can256) || g.Cout % bn || pixels % (128 * mt)) return false;
+        const long long tiles = (pixels / (128 * mt)) * (g.Cout / bn);
+        const long long grid = tiles < num_sms() ? tiles : num_sms();
+        const int sets = 2 * mt * bn <= 512 ? 2 : 1;
+        return (tiles + grid - 1) / grid <= sets;
+      };
+      if (!resident(MT, BN)) {
+        const int cand[4][2] = {{2, 128}, {1, 256}, {1, 128}, {2, 256}};
+        bool found = false;
+        for (int i = 0; i < 4 && !found; ++i)
+          if (resident(cand[i][0], cand[i][1])) { MT = cand[i][0]; BN = cand[i][1]; found = true; }
+        if (!found) return UDA_ERR_UNSUPPORTED;
+      }
+    }
     n_tiles = g.Cout / BN;
     tp = plan_tiles(g.B, MH, MW, 128 * MT);
+  } else if (g.fuse) {
+    return UDA_ERR_UNSUPPORTED;   // fused BatchNorm: 64-channel chunks and 128-multiple output channels only
   }
   UDA_REQUIRE(tp.ok, UDA_ERR_UNSUPPORTED, "conv_tc_persist: pixel grid %dx%dx%d cannot be tiled", g.B, MH, MW);
   UDA_REQUIRE(aligned<bf16>(g.src, 16) && aligned<bf16>(g.wmat, 16) && (!g.out || aligned<bf16>(g.out, 16)) &&
@@ -462,7 +607,7 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
   p.act = g.act; p.act_slope = g.act_slope;
   p.debug = 0;
   p.trace = nullptr;
-  UDA_TR(p.trace = g_trace_buf;)
+  UDA_TR(p.trace = take_trace_slice();)
 #ifdef UDA_B200_EXPERIMENTS
   {   // timing experiments that SKIP WORK: compiled only into experiment builds (make EXPERIMENTS=1)
     const char* e = getenv("UDA_B200_TC_DEBUG");
@@ -501,6 +646,16 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
     if (int rc = make_tmap_bf16(&mb, g.wmat, 2, dims, str, box, KC * 2)) return rc;
   }
   const int total_tiles = p.ncls * p.m_tiles * p.n_tiles;
+  if (g.fuse) {
+    if (!g.bn_sums || !g.out || g.out_nchw || g.bias || g.act || g.st_sums || g.ncls != 1 || g.os != 1 || KC != 64)
+      return UDA_ERR_UNSUPPORTED;
+    p.fuse = *g.fuse;
+    if (BN == 128) return MT == 2 ? launch_persist<64, 128, 2, true>(ma, mb, p, total_tiles, st)
+                                  : launch_persist<64, 128, 1, true>(ma, mb, p, total_tiles, st);
+    if (BN == 256) return MT == 2 ? launch_persist<64, 256, 2, true>(ma, mb, p, total_tiles, st)
+                                  : launch_persist<64, 256, 1, true>(ma, mb, p, total_tiles, st);
+    return UDA_ERR_UNSUPPORTED;
+  }
 #define UDA_P(KCv, BNv)                                                                            \
   if (KC == KCv && BN == BNv)                                                                      \
     return MT == 2 ? launch_persist<KCv, BNv, 2>(ma, mb, p, total_tiles, st)                       \

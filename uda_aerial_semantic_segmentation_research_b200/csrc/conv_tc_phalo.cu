@@ -35,10 +35,11 @@ struct PHParams {
   int HR, halo_bytes, halo_stride, b_stages;
   bf16* out; const bf16* addend; double* bn_sums;
   const float* bias; int act; float act_slope;   // GemmConv::bias / act
+  BnFuse fuse;        // fuse.a_out != nullptr: BatchNorm + activation in this launch (FUSE instances, one tile per CTA)
   long long* trace;   // experiment builds only: per-CTA trace records (conv_tc_internal.cuh)
 };
 
-template <int KC, int BN, int NBLK>
+template <int KC, int BN, int NBLK, bool FUSE>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                      const PHParams p) {
@@ -67,7 +68,8 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
-  UDA_TR(const long long tr0 = clock64(); long long* const trp = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;)
+  UDA_TR(const long long tr0 = clock64(); const long long tr_g0 = trace_globaltimer();
+         long long* const trp = p.trace ? p.trace + (size_t)blockIdx.x * 16 : nullptr;)
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_a); tma_prefetch_desc(&map_b); }
   if (warp == 1) {
@@ -86,7 +88,8 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible from here on
-  UDA_TR(if (trp && threadIdx.x == 0) { trp[0] = tr0; trp[1] = clock64() - tr0; })
+  UDA_TR(if (trp && threadIdx.x == 0) { trp[0] = tr0; trp[1] = clock64() - tr0; trp[14] = tr_g0;
+                                        trp[15] = 3LL | ((long long)p.Cout << 8) | ((long long)p.Cred << 24) | ((long long)total_tiles << 40); })
 
   if (warp == 0) {
     // ===================== TMA producer: per channel chunk one halo box per block, then nine weight tiles =====
@@ -187,6 +190,107 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     float bn_s[kChunks], bn_q[kChunks];
 #pragma unroll
     for (int cc = 0; cc < kChunks; ++cc) { bn_s[cc] = 0.f; bn_q[cc] = 0.f; }
+    if constexpr (FUSE) {
+      // ---- conv + BatchNorm + activation in one launch (BnFuse): exactly one tile per CTA, accumulators stay in
+      // TMEM across the grid barrier ----
+      const int t = blockIdx.x;
+      const int mt = t % p.m_tiles, n0 = (t / p.m_tiles) * BN;
+      const int gb0 = mt * NBLK;
+      const int nblk = min(NBLK, p.total_blocks - gb0);
+      float* const s_sc = reinterpret_cast<float*>(bars + 26);
+      float* const s_sf = s_sc + BN;
+      const int et = threadIdx.x - 64;   // 0..127 among the epilogue threads
+      UDA_TR_WAIT(tr_wt, mbar_wait(tfull(0), 0))
+      UDA_TR(const long long tr_b0 = clock64();)
+      tc_fence_after();
+      // pass 1: statistics of the bf16-rounded outputs (junk rows contribute zeros)
+#pragma unroll 1
+      for (int i = 0; i < nblk; ++i) {
+        const int gb = gb0 + i, b = gb / p.nb_img;
+        const int m = (gb % p.nb_img) * 128 + qw * 32 + lane;
+        const int r = m / p.P, c = m - r * p.P;
+        const bool valid = c < p.W && r < p.H;
+        const long long pix = ((long long)b * p.H + r) * p.W + c;
+        const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)i * BN;
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tbase + (uint32_t)c0, v);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int k = 0; k < 32; ++k) f[k] = valid ? __uint_as_float(v[k]) : 0.f;
+          if (p.addend && valid) {
+            const bf16* add = p.addend + pix * p.Cout + n0 + c0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              float a8[8];
+              ld_vec<8>(add + k, a8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) f[k + e] += a8[e];
+            }
+          }
+          bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);
+        }
+      }
+#pragma unroll
+      for (int cc = 0; cc < kChunks; ++cc) {
+        const int col = n0 + cc * 32 + lane;
+        atomicAdd(p.bn_sums + col, (double)bn_s[cc]);
+        atomicAdd(p.bn_sums + p.Cout + col, (double)bn_q[cc]);
+      }
+      grid_barrier(p.fuse.counter, gridDim.x, 2, 128, et == 0);
+      for (int ch = et; ch < BN; ch += 128) {
+        bn_fuse_coeffs(p.fuse, p.bn_sums, p.Cout, n0 + ch, s_sc[ch], s_sf[ch]);
+        if (mt == 0) bn_fuse_publish(p.fuse, p.bn_sums, p.Cout, n0 + ch);
+      }
+      bar_sync(2, 128);
+      // pass 2: z (saved for the backward) and a = act(z*scale + shift (+ residual))
+      const bf16* const res = (const bf16*)p.fuse.residual;
+      bf16* const aout = (bf16*)p.fuse.a_out;
+      const float slope = p.fuse.slope;
+#pragma unroll 1
+      for (int i = 0; i < nblk; ++i) {
+        const int gb = gb0 + i, b = gb / p.nb_img;
+        const int m = (gb % p.nb_img) * 128 + qw * 32 + lane;
+        const int r = m / p.P, c = m - r * p.P;
+        const bool valid = c < p.W && r < p.H;
+        const long long pix = ((long long)b * p.H + r) * p.W + c;
+        const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)i * BN;
+#pragma unroll
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tbase + (uint32_t)c0, v);
+          tmem_ld_wait();
+          if (valid) {
+            const long long off = pix * p.Cout + n0 + c0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 8) {
+              float z8[8], a8[8], r8[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) z8[e] = __uint_as_float(v[k + e]);
+              if (p.addend) {
+                ld_vec<8>(p.addend + off + k, a8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) z8[e] += a8[e];
+              }
+              st_vec<8>(p.out + off + k, z8);
+              if (res) ld_vec<8>(res + off + k, r8);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const float zr = __bfloat162float(__float2bfloat16_rn(z8[e]));
+                float y = zr * s_sc[c0 + k + e] + s_sf[c0 + k + e];
+                if (res) y += r8[e];
+                a8[e] = y > 0.f ? y : y * slope;
+              }
+              st_vec<8>(aout + off + k, a8);
+            }
+          }
+        }
+      }
+      UDA_TR(tr_busy += clock64() - tr_b0;)
+      UDA_TR(if (trp && warp == 2 && lane == 0) { trp[8] = tr_wt; trp[9] = tr_busy; trp[10] = clock64() - tr0; })
+    } else {
     int bn_n0 = -1;
     int j = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
@@ -275,6 +379,7 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         if (col < p.Cout) { atomicAdd(p.bn_sums + col, (double)bn_s[cc]); atomicAdd(p.bn_sums + p.Cout + col, (double)bn_q[cc]); }
       }
     }
+    }   // !FUSE
   }
   tc_fence_before();
   __syncthreads();
@@ -291,7 +396,7 @@ int phalo_mode() {
   return e ? atoi(e) : 1;
 }
 
-template <int KC, int BN, int NBLK>
+template <int KC, int BN, int NBLK, bool FUSE>
 int launch_phalo(const CUtensorMap& ma, const CUtensorMap& mb, PHParams& p, cudaStream_t st) {
   constexpr int kBBytes = BN * KC * 2;
   p.halo_bytes = p.HR * p.P * KC * 2;
@@ -302,16 +407,18 @@ int launch_phalo(const CUtensorMap& ma, const CUtensorMap& mb, PHParams& p, cuda
   if (SB < 3) return UDA_ERR_UNSUPPORTED;   // caller falls back
   p.b_stages = SB;
   p.m_tiles = (p.total_blocks + NBLK - 1) / NBLK;
-  const int smem = a_bytes + SB * kBBytes + 1024 + 256;
+  const int smem = a_bytes + SB * kBBytes + 1024 + 256 + (FUSE ? 2 * BN * 4 : 0);   // + scale / shift tables
   static bool configured = false;
   if (!configured) {
-    UDA_CUDA_OK(cudaFuncSetAttribute(conv_tc_phalo_kernel<KC, BN, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    UDA_CUDA_OK(cudaFuncSetAttribute(conv_tc_phalo_kernel<KC, BN, NBLK, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      227 * 1024));
     configured = true;
   }
   const int total_tiles = p.m_tiles * p.n_tiles;
+  // fused BatchNorm: every tile must be resident in TMEM at the grid barrier -> one tile per CTA, one CTA per SM
+  if (FUSE && total_tiles > num_sms()) return UDA_ERR_UNSUPPORTED;
   const int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  UDA_CUDA_OK(launch_pdl(conv_tc_phalo_kernel<KC, BN, NBLK>, dim3(grid), dim3(kThreads), smem, st, ma, mb, p));
+  UDA_CUDA_OK(launch_pdl(conv_tc_phalo_kernel<KC, BN, NBLK, FUSE>, dim3(grid), dim3(kThreads), smem, st, ma, mb, p));
   UDA_LAUNCH_OK("conv_tc_phalo_kernel");
   return UDA_OK;
 }
@@ -349,7 +456,7 @@ int run_gemm_conv_phalo(const GemmConv& g, cudaStream_t st) {
   p.HR = (128 + p.P - 1) / p.P + 3;
   p.out = (bf16*)g.out; p.addend = (const bf16*)g.addend; p.bn_sums = g.bn_sums;
   p.bias = g.bias; p.act = g.act; p.act_slope = g.act_slope;
-  UDA_TR(p.trace = g_trace_buf;)
+  UDA_TR(p.trace = take_trace_slice();)
   // enough work for a full wave, else the persistent kernel's smaller tiles are the better fit
   const int nblk = 2;
   if (mode != 2 && (long long)((p.total_blocks + nblk - 1) / nblk) * p.n_tiles < num_sms() / 2) return UDA_ERR_UNSUPPORTED;
@@ -368,8 +475,14 @@ int run_gemm_conv_phalo(const GemmConv& g, cudaStream_t st) {
     uint32_t box[2] = {(uint32_t)KC, (uint32_t)BN};
     if (int rc = make_tmap_bf16(&mb, g.wmat, 2, dims, str, box, KC * 2)) return rc;
   }
-  if (BN == 128) return launch_phalo<64, 128, 2>(ma, mb, p, st);
-  return launch_phalo<64, 64, 2>(ma, mb, p, st);
+  if (g.fuse) {
+    if (!g.bn_sums || g.bias || g.act) return UDA_ERR_UNSUPPORTED;
+    p.fuse = *g.fuse;
+    if (BN == 128) return launch_phalo<64, 128, 2, true>(ma, mb, p, st);
+    return launch_phalo<64, 64, 2, true>(ma, mb, p, st);
+  }
+  if (BN == 128) return launch_phalo<64, 128, 2, false>(ma, mb, p, st);
+  return launch_phalo<64, 64, 2, false>(ma, mb, p, st);
 }
 
 }  // namespace tcconv

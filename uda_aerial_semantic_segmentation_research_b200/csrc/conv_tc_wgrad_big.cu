@@ -77,7 +77,8 @@ conv_tc_wgrad_big_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
   const int n_iters = st_end - st_begin;   // >= 1 by construction of the grid
   const int tiles_per_group = p.tiles_w * p.tiles_h;
 
-  UDA_TR(const long long tr0 = clock64(); const int tr_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+  UDA_TR(const long long tr0 = clock64(); const long long tr_g0 = trace_globaltimer();
+         const int tr_cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
          long long* const trp = (p.trace && tr_cta < 148) ? p.trace + (size_t)tr_cta * 16 : nullptr;)
   pdl_launch_dependents();
   if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_dy); }
@@ -96,7 +97,8 @@ conv_tc_wgrad_big_kernel(const __grid_constant__ CUtensorMap map_x, const __grid
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible from here on
-  UDA_TR(if (trp && threadIdx.x == 0) { trp[0] = tr0; trp[1] = clock64() - tr0; trp[12] = n_iters; })
+  UDA_TR(if (trp && threadIdx.x == 0) { trp[0] = tr0; trp[1] = clock64() - tr0; trp[12] = n_iters; trp[14] = tr_g0;
+                                        trp[15] = 4LL | ((long long)gridDim.x * gridDim.y * gridDim.z << 40); })
 
   if (warp == 0) {
     if (elect_one()) {
@@ -290,7 +292,7 @@ int run_wgrad_big(const void* dy, const void* x, float* dw, int B, int H, int W,
     }
   p.n_steps = (B / tp.NB) * p.tiles_w * p.tiles_h;
   p.dw_out = dw;
-  UDA_TR(p.trace = g_trace_buf;)
+  UDA_TR(p.trace = take_trace_slice();)
   // at most one wave: groups x n_tiles x splits <= SMs
   int splits = num_sms() / (groups * n_tiles);
   if (splits < 1) splits = 1;

@@ -9,6 +9,8 @@ the backward replays the tape in reverse.  One ``torch.autograd.Function`` per n
 Gradient accumulation for tensors with several consumers (residual identity, encoder skips) is
 folded into the consumer kernels through their ``addend`` argument instead of separate add passes.
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -158,6 +160,7 @@ class ParamStore:
         self.shadow_version = None
         self.shadow_ft_version = None
         self._ft_table = None
+        self._ft_event = None
 
     def param_version(self):
         """Freshness key of the bf16 shadow copies.  The parameters are re-pointed into the flat buffer with
@@ -183,15 +186,36 @@ class ParamStore:
         all copies are refreshed together, lazily, the first time a backward needs them after an update."""
         ver = self.param_version()
         if self.shadow_ft_version != ver or self.shadow_ft_version is None:
-            if self._ft_table is None:
-                rows = [[self.offsets[id(q)]] + [q.shape[0], q.shape[1], q.shape[2], q.shape[3]]
-                        for q in self.params if q.dim() == 4]
-                self._ft_table = torch.tensor(rows, dtype=torch.int32, device=self.flat.device).contiguous()
-            ops.weight_flip_transpose_batch(self.shadow, self.shadow_ft, self._ft_table)
+            self._flip_transpose_all()
             self.shadow_ft_version = ver
+            self._ft_event = None
+        elif self._ft_event is not None:     # refreshed on the side stream during the forward (prefetch_w_ft)
+            torch.cuda.current_stream().wait_event(self._ft_event)
+            self._ft_event = None
         off = self.offsets[id(p)]
         O, I, KH, KW = p.shape
         return self.shadow_ft[off:off + p.numel()].view(I, KH, KW, O)
+
+    def _flip_transpose_all(self):
+        if self._ft_table is None:
+            rows = [[self.offsets[id(q)]] + [q.shape[0], q.shape[1], q.shape[2], q.shape[3]]
+                    for q in self.params if q.dim() == 4]
+            self._ft_table = torch.tensor(rows, dtype=torch.int32, device=self.flat.device).contiguous()
+        ops.weight_flip_transpose_batch(self.shadow, self.shadow_ft, self._ft_table)
+
+    def prefetch_w_ft(self, side):
+        """Refresh the dgrad weight copies on ``side`` while the forward runs (they are first needed in the backward and
+        depend only on the bf16 shadow): ~80 us off the step's critical chain.  ``w_ft`` waits for the event."""
+        ver = self.param_version()
+        if self.shadow_ft_version == ver:
+            return False
+        side.wait_stream(torch.cuda.current_stream(self.flat.device))      # after the shadow refresh / earlier dgrads
+        with torch.cuda.stream(side):
+            self._flip_transpose_all()
+            self._ft_event = torch.cuda.Event()
+            self._ft_event.record(side)
+        self.shadow_ft_version = ver
+        return True
 
     def w(self, p, dtype):
         """OHWI kernel view of conv weight ``p`` in ``dtype`` (bf16 -> shadow copy)."""
@@ -244,7 +268,9 @@ def _side_stream(device):
     key = device.index if device.index is not None else torch.cuda.current_device()
     s = _SIDE_STREAMS.get(key)
     if s is None:
-        s = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+        # UDA_B200_WGRAD_PRIORITY=1: high-priority side stream (A/B switch)
+        prio = -1 if os.environ.get("UDA_B200_WGRAD_PRIORITY", "0") == "1" else 0
+        s = _SIDE_STREAMS[key] = torch.cuda.Stream(device=device, priority=prio)
     return s
 
 
@@ -261,6 +287,11 @@ class Ctx:
         self.fold_key = None                    # eval mode: freshness key of the folded weights, taken once per forward
         self._pool, self._pool_used = None, 0   # zero-filled float64 scratch for the fused BatchNorm statistics
         self._trackers = []                     # num_batches_tracked buffers to bump at the end of the forward
+        if (tape is not None and dtype == torch.bfloat16 and ops.USE_TC and ops.WGRAD_STREAM and ops.PREFETCH_WFT
+                and store.flat is not None and store.flat.is_cuda):
+            side = _side_stream(store.flat.device)
+            if store.prefetch_w_ft(side):
+                self.side = side                # joined at the end of the backward (_join_side)
 
     def stats_slot(self, n, device):
         """``n`` zeroed float64 values for a conv epilogue's BatchNorm sums: slices of ONE zero-filled pool per
@@ -318,14 +349,15 @@ def _fused_stats_ok(ctx, xin, cp):
     return ops.tc_supported(0, B, H, W, Cin, cp.out_channels, cp.kernel_size, cp.kernel_size, cp.stride, cp.padding)
 
 
-def conv(ctx, xin, cp, nchw_out=False, bn=None):
+def conv(ctx, xin, cp, nchw_out=False, bn=None, _pre=None):
     """y = conv(x) (+bias).  Returns Var (NHWC) or, with nchw_out, a raw fp32 NCHW tensor + grad hook.
     ``bn``: the BatchNorm that consumes the output — its batch statistics are then accumulated by the conv
-    epilogue (``out.sums``) instead of a separate pass over the output."""
+    epilogue (``out.sums``) instead of a separate pass over the output.  ``_pre``: the output was already computed
+    by a fused launch (``_conv_bn_act_fused``); only the backward is recorded."""
     st = ctx.store
     w = st.w(cp.weight, ctx.dtype)
     sums = None
-    if bn is not None and _fused_stats_ok(ctx, xin, cp):
+    if _pre is None and bn is not None and _fused_stats_ok(ctx, xin, cp):
         sums = ctx.stats_slot(2 * cp.out_channels, w.device)
     if xin.t is None:   # Cin = 3 stem on the tensor cores (see ops.stem_*)
         H, W = xin.nchw.shape[2:]
@@ -345,7 +377,8 @@ def conv(ctx, xin, cp, nchw_out=False, bn=None):
                 ctx.done(cp.weight, cp.bias)
             ctx.tape.push(bwd_stem)
         return out
-    y = ops.conv_fwd(xin.t, w, cp.bias, cp.stride, cp.padding, nchw_out=nchw_out, bn_sums=sums)
+    y = _pre if _pre is not None else ops.conv_fwd(xin.t, w, cp.bias, cp.stride, cp.padding, nchw_out=nchw_out,
+                                                   bn_sums=sums)
     out = Var(y)
     out.sums = sums
     if ctx.tape is not None:
@@ -460,11 +493,20 @@ def upconv_bn_act(ctx, xin, skip, cp, bn, slope=0.0):
         wx, ws, w4, ws_ft = ops.upconv_split_weights(w, C1, backward=True)
     else:
         wx, ws = ops.upconv_split_weights(w, C1)
-    sums = ctx.stats_slot(2 * cp.out_channels, w.device) if (ctx.training and ops.FUSE_BN_STATS) else None
-    if skip is None:
-        z = ops.upconv_fwd(xin.t, wx, bn_sums=sums)
-    else:
-        z = ops.conv_fwd_add(skip.t, ws, ops.upconv_fwd(xin.t, wx), bn_sums=sums)
+    sums, pre = None, None
+    zx = ops.upconv_fwd(xin.t, wx) if skip is not None else None
+    if skip is not None and _bn_fuse_ok(ctx, skip, cp):
+        # skip half + BatchNorm + activation as ONE launch (the x half is its addend) when the tiles fit one wave's TMEM
+        r = ops.conv_bn_act_fused(skip.t, ws, ctx.stats_slot(2 * cp.out_channels + 1, w.device), bn.weight, bn.bias,
+                                  bn.running_mean, bn.running_var, bn.eps, bn.momentum, slope, 1, 1, addend=zx)
+        if r is not None:
+            z, pre = r[0], r[1:]
+    if pre is None:
+        sums = ctx.stats_slot(2 * cp.out_channels, w.device) if (ctx.training and ops.FUSE_BN_STATS) else None
+        if skip is None:
+            z = ops.upconv_fwd(xin.t, wx, bn_sums=sums)
+        else:
+            z = ops.conv_fwd_add(skip.t, ws, zx, bn_sums=sums)
     zv = Var(z)
     zv.sums = sums
     if ctx.tape is not None:
@@ -506,7 +548,7 @@ def upconv_bn_act(ctx, xin, skip, cp, bn, slope=0.0):
                 skip.g = ops.conv_dgrad(dz, ws, skip.t.shape, 1, 1, addend=skip.g, w_ft=ws_ft)
             ctx.done(cp.weight)
         ctx.tape.push(bwd)
-    return bn_act(ctx, zv, bn, slope=slope)
+    return bn_act(ctx, zv, bn, slope=slope, _pre=pre)
 
 
 def conv_bn_act(ctx, xin, cp, bn, slope=0.0, residual=None):
@@ -529,14 +571,31 @@ def conv_bn_act(ctx, xin, cp, bn, slope=0.0, residual=None):
             w, b = st.folded(ctx.fold_key, cp, bn)
             return Var(ops.conv_fwd_fused(xin.t, w, b, slope, addend=residual.t if residual is not None else None,
                                           stride=cp.stride, pad=cp.padding))
+    if _bn_fuse_ok(ctx, xin, cp):
+        r = ops.conv_bn_act_fused(xin.t, ctx.store.w(cp.weight, ctx.dtype), ctx.stats_slot(2 * cp.out_channels + 1, xin.t.device),
+                                  bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps, bn.momentum, slope,
+                                  cp.stride, cp.padding, residual=residual.t if residual is not None else None)
+        if r is not None:   # ONE launch: conv, batch statistics, grid barrier, normalise (+ residual) + activation
+            return bn_act(ctx, conv(ctx, xin, cp, _pre=r[0]), bn, slope=slope, residual=residual, _pre=r[1:])
     return bn_act(ctx, conv(ctx, xin, cp, bn=bn), bn, slope=slope, residual=residual)
 
 
-def bn_act(ctx, zin, bn, slope=0.0, residual=None):
-    """a = act(BN(z) (+ residual)); train mode uses batch statistics and updates the running ones."""
+def _bn_fuse_ok(ctx, xin, cp):
+    """Training-mode conv + BatchNorm + activation as one launch (``ops.conv_bn_act_fused``): tensor-core path, no conv
+    bias; whether the layer's tiles fit the tensor memory of one wave is decided by the launch itself."""
+    return (ctx.training and ctx.dtype == torch.bfloat16 and ops.USE_TC and ops.TC_PERSIST and ops.FUSE_BN_STATS
+            and ops.FUSE_BN_APPLY and xin.t is not None and cp.bias is None and xin.t.is_cuda)
+
+
+def bn_act(ctx, zin, bn, slope=0.0, residual=None, _pre=None):
+    """a = act(BN(z) (+ residual)); train mode uses batch statistics and updates the running ones.  ``_pre``: (a, mean,
+    rstd, scale, shift) already computed by a fused conv + BatchNorm launch; only the backward is recorded."""
     st = ctx.store
     res_t = residual.t if residual is not None else None
-    if ctx.training and zin.sums is not None:
+    if _pre is not None:
+        a, mean, rstd, scale, shift = _pre
+        ctx._trackers.append(bn.num_batches_tracked)
+    elif ctx.training and zin.sums is not None:
         a, mean, rstd, scale, shift = ops.bn_apply_fused(zin.t, zin.sums, bn.weight, bn.bias, bn.running_mean,
                                                          bn.running_var, bn.eps, bn.momentum, res_t, slope)
         ctx._trackers.append(bn.num_batches_tracked)

@@ -23,8 +23,10 @@ import torch.distributed as dist
 
 
 def _capture_kwargs(with_nccl):
-    """NCCL's watchdog thread may touch the CUDA API while a capture is open: relax the capture error mode to the
-    capturing thread when collectives are captured."""
+    """Arguments of ``torch.cuda.graph``.  NCCL's watchdog thread may touch the CUDA API while a capture is open: relax
+    the capture error mode to the capturing thread when collectives are captured.  (Capturing the step on a
+    high-priority stream, so that the dgrad -> BatchNorm-backward chain wins SMs over the side-stream weight-gradient
+    kernels, was measured SLOWER: 8.81 vs 8.50 ms/step — the weight gradients then all run after the chain.)"""
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
     return {"capture_error_mode": "thread_local"} if (with_nccl or multi) else {}
 

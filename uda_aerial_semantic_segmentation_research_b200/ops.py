@@ -32,6 +32,14 @@ FOLD_BN_EVAL = os.environ.get("UDA_B200_FOLD_BN_EVAL", "1") != "0"
 #: path, so their CTAs fill the SMs that the tails / prologues of the chain leave idle); joined at the end of backward
 #: (measured at B=16, 512x512: 8.99 -> 8.73 ms per supervised step; UDA_B200_WGRAD_STREAM=0 keeps everything on one stream)
 WGRAD_STREAM = os.environ.get("UDA_B200_WGRAD_STREAM", "1") != "0"
+#: refresh the flipped / transposed dgrad weight copies on the side stream during the forward
+PREFETCH_WFT = os.environ.get("UDA_B200_PREFETCH_WFT", "1") != "0"
+#: training: conv + BatchNorm + activation (+ residual) as ONE launch for the layers whose output tiles fit the tensor
+#: memory of one wave of CTAs (grid barrier between the statistics and the normalise pass; uda_conv2d_tc_fwd_bn_act).
+#: Opt-in (UDA_B200_FUSE_BN_APPLY=1): parity-tested (tests/test_gpu_bnfuse.py) but measured SLOWER at B=16, 512x512 —
+#: 8.81 vs 8.58 ms per step: with programmatic dependent launch the separate normalise pass of these L2-resident
+#: tensors costs ~4 us on 148 x 16 streaming warps, the in-kernel pass 2 + barrier ~10 us on 4 epilogue warps per SM
+FUSE_BN_APPLY = os.environ.get("UDA_B200_FUSE_BN_APPLY", "0") == "1"
 #: decoder conv1 as conv_transpose4x4(x) + conv3x3(skip): the upsampled / concatenated tensor is never materialised
 #: (UDA_B200_FUSE_UPCAT=0 runs the upsample+concat copy kernel and one 3x3 convolution over the concatenation)
 FUSE_UPCAT = os.environ.get("UDA_B200_FUSE_UPCAT", "1") != "0"
@@ -263,6 +271,42 @@ def conv_fwd_add(x, w, addend, bn_sums=None, stride=1, pad=1):
     _tc_account(B, Ho, Wo, Cout, Cin, KH, KW)
     _count()
     return y
+
+
+_FUSED_BN_SHAPES = {}   # (B,H,W,Cin,Cout,k,stride,pad) -> did the fused conv + BatchNorm launch accept the shape?
+
+
+def conv_bn_act_fused(x, w, slot, gamma, beta, running_mean, running_var, eps, momentum, slope, stride=1, pad=1,
+                      addend=None, residual=None):
+    """Training-mode a = act(BN(conv(x, w) (+ addend)) (+ residual)) as ONE launch (``uda_conv2d_tc_fwd_bn_act``).
+    ``slot``: zeroed float64[2*Cout + 1] (statistics + the grid barrier's arrival counter).  Returns
+    (z, a, mean, rstd, scale, shift), or None when the layer's output tiles do not fit one wave's tensor memory
+    (nothing was launched: the caller runs the two-launch form)."""
+    _chk(x, "conv_bn_act_fused.x", torch.bfloat16); _chk(w, "conv_bn_act_fused.w", torch.bfloat16)
+    B, H, W, Cin, Cout, KH, KW, Ho, Wo = _geom(x.shape, w.shape, stride, pad)
+    key = (B, H, W, Cin, Cout, KH, stride, pad)
+    if _FUSED_BN_SHAPES.get(key) is False:
+        return None
+    for t, nm in ((addend, "addend"), (residual, "residual")):
+        if t is not None:
+            _chk(t, "conv_bn_act_fused." + nm, torch.bfloat16)
+            if tuple(t.shape) != (B, Ho, Wo, Cout):
+                raise _lib.UdaError(f"conv_bn_act_fused: {nm} must have the output's shape")
+    if slot.dtype != torch.float64 or slot.numel() < 2 * Cout + 1 or not slot.is_contiguous():
+        raise _lib.UdaError("conv_bn_act_fused: slot must be a contiguous float64[2*Cout+1]")
+    z = torch.empty((B, Ho, Wo, Cout), dtype=torch.bfloat16, device=x.device)
+    a = torch.empty_like(z)
+    st = torch.empty((4, Cout), dtype=torch.float32, device=x.device)
+    ok = call("conv2d_tc_fwd_bn_act", ptr(x), ptr(w), ptr(addend), ptr(residual), ptr(z), ptr(a), ptr(slot),
+              ptr(slot[2 * Cout:]), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var), ptr(st[0]), ptr(st[1]),
+              ptr(st[2]), ptr(st[3]), ci(B), ci(H), ci(W), ci(Cin), ci(Cout), ci(KH), ci(KW), ci(stride), ci(pad),
+              float(eps), float(momentum), float(slope), _stream(), unsupported_ok=True)
+    _FUSED_BN_SHAPES[key] = ok
+    if not ok:
+        return None
+    _tc_account(B, Ho, Wo, Cout, Cin, KH, KW)
+    _count()
+    return z, a, st[0], st[1], st[2], st[3]
 
 
 def upconv_merge_wgrad(dw4, dws, dw, C1):
