@@ -50,7 +50,7 @@ torch.cuda.synchronize()
 tr = buf.view(NS, 148, 16)[:used].cpu()
 live = [i for i in range(used) if int((tr[i, :, 11] > 0).sum()) > 0]
 print(f"traced launches issued {used}, in the captured graph {len(live)}; B={B} S={S}, clk = {GHZ} GHz")
-KIND = {1: "persist", 2: "halo", 3: "phalo", 4: "wgrad_big"}
+KIND = {1: "persist", 2: "halo", 3: "phalo", 4: "wgrad_big", 17: "persist+bn", 19: "phalo+bn"}
 rows = []
 for i in live:
     r = tr[i]
@@ -64,7 +64,8 @@ for i in live:
                      entry0=float(g0.min()), entry1=float(g0.max()), go=float(ns(1).max()), mma0=float(ns(6).mean()),
                      mmaN=float(ns(7).max()), epi=float(ns(10).max()), exit=float(ns(11).max()),
                      w_ops=float(r[:, 4].mean()), w_epi=float(r[:, 5].mean()), w_prod=float(r[:, 2].mean()),
-                     epi_busy=float(r[:, 9].mean()), in_kernel=float((r[:, 11] - r[:, 1]).max())))
+                     epi_busy=float(r[:, 9].mean()), in_kernel=float((r[:, 11] - r[:, 1]).max()),
+                     p1=float(ns(5).max()), bar=float(ns(13).max()), raw=r[0].tolist()))
 rows.sort(key=lambda d: d["entry0"])
 t_base = rows[0]["entry0"]
 print("  #   t_us kind      Cred Cout tiles ctas | rel. to prev traced exit (us): entry0 entryN    go  mma0  mmaN   epi  exit |"
@@ -77,7 +78,12 @@ for d in rows:
     print(f"{d['i']:4d} {(d['entry0'] - t_base) / 1e3:7.1f} {d['kind']:9s} {d['cred']:4d} {d['cout']:4d} {d['tiles']:5d} {d['ctas']:4d} | "
           f"{f(d['entry0'])} {f(d['entry1'])} {f(d['go'])} {f(d['mma0'])} {f(d['mmaN'])} {f(d['epi'])} {f(d['exit'])} | "
           f"{(d['exit'] - d['go']) / 1e3:6.1f} | {d['w_ops'] / 1e3:6.1f} {d['w_epi'] / 1e3:6.1f} {d['w_prod'] / 1e3:6.1f} {d['epi_busy'] / 1e3:6.1f}")
+    if d["kind"].endswith("+bn"):     # fused conv + BatchNorm: pass 1 done / barrier passed / pass 2 done, relative to go (us)
+        print(f"       fused epilogue: pass1 done {(d['p1'] - d['go']) / 1e3:5.1f}  barrier passed {(d['bar'] - d['go']) / 1e3:5.1f}  "
+              f"pass2 done {(d['epi'] - d['go']) / 1e3:5.1f}  (last MMA {(d['mmaN'] - d['go']) / 1e3:5.1f})")
     prev_exit[stream] = d["exit"]
+mid = rows[len(rows) // 4]
+print("raw record of CTA 0 of launch", mid["i"], mid["kind"], [int(v) for v in mid["raw"]])
 # summary per kind: time from go to exit (in-kernel useful window) vs first-mma delay and tail
 import collections
 agg = collections.defaultdict(lambda: [0, 0.0, 0.0, 0.0, 0.0])

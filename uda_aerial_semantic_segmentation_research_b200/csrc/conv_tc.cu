@@ -999,7 +999,7 @@ extern "C" int uda_conv2d_tc_fwd_bn_act(const void* x, const void* w, const void
   BnFuse f{};
   f.a_out = a; f.residual = residual; f.gamma = gamma; f.beta = beta; f.running_mean = running_mean;
   f.running_var = running_var; f.mean = mean; f.rstd = rstd; f.scale = scale; f.shift = shift;
-  f.M = (long long)B * Ho * Wo; f.eps = eps; f.momentum = momentum; f.slope = slope; f.counter = counter;
+  f.M = (long long)B * Ho * Wo; f.inv_m = 1.0 / (double)f.M; f.eps = eps; f.momentum = momentum; f.slope = slope; f.counter = counter;
   return run_fwd(x, w, nullptr, addend, z, nullptr, bn_sums, B, H, W, Cin, Cout, KH, KW, stride, pad,
                  (cudaStream_t)stream, 0, 0.f, &f);
 }

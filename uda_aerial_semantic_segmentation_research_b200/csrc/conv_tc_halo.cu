@@ -17,7 +17,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 192;
+constexpr int kThreads = kConvThreads;
 constexpr int kHaloW = 130;   // 128 pixels + one halo pixel on each side
 constexpr int kSmemBudget = 222 * 1024;
 
@@ -69,7 +69,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-      for (int q = 0; q < 2; ++q) { mbar_init(tfull_bar(q), 1); mbar_init(tempty_bar(q), 4); }
+      for (int q = 0; q < 2; ++q) { mbar_init(tfull_bar(q), 1); mbar_init(tempty_bar(q), kEpiWarps); }
       mbar_init(ws_bar, 1);
       fence_barrier_init();
     }
@@ -146,10 +146,12 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       UDA_TR(if (trp) { trp[4] = tr_wf; trp[5] = tr_we; trp[6] = tr_first; trp[7] = clock64() - tr0; trp[12] = j; })
     }
   } else {
-    // ===================== epilogue (4 warps): one image row of 128 pixels per sub-tile =====================
+    // ===================== epilogue (kEpiWarps warps): one image row of 128 pixels per sub-tile ===============
     UDA_TR(long long tr_wt = 0, tr_busy = 0;)
     const int qw = warp & 3;
+    const int eh = (warp - 2) >> 2;          // which of the kEpiSplit warps of this lane quadrant
     constexpr int kChunks = (BN + 31) / 32;
+    constexpr bool kSplitCols = (kChunks % kEpiSplit) == 0;   // else the quadrant's warps take alternate rows
     float bn_s[kChunks], bn_q[kChunks];
 #pragma unroll
     for (int cc = 0; cc < kChunks; ++cc) { bn_s[cc] = 0.f; bn_q[cc] = 0.f; }
@@ -172,12 +174,14 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int w = w0 + qw * 32 + lane;
 #pragma unroll 1
       for (int sub = 0; sub < R; ++sub) {
+        if (!kSplitCols && (sub % kEpiSplit) != eh) continue;
         const int h = h0 + sub;
         const long long pix = ((long long)b * p.H + h) * p.W + w;
         const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)q * kAccCols + (uint32_t)sub * BN;
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
           if (c0 >= p.Cout) break;
+          if (kSplitCols && ((c0 / 32) % kEpiSplit) != eh) continue;
           uint32_t v[32];
           tmem_ld_32x32(tbase + (uint32_t)c0, v);
           tmem_ld_wait();
@@ -216,7 +220,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             } else {
               bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);
             }
-          } else if (p.st_sums) {
+          } else if (!kLate && p.st_sums) {   // (the BN = 32 instances do not carry the BatchNorm-backward statistics)
             float g[32], gv[32];
             const long long off = pix * p.Cout + c0;
             bn_bwd_chunk_terms(f, p.st_a + off, p.st_z ? p.st_z + off : nullptr, p.st_slope, inv_slope, p.Cout - c0, g, gv);
@@ -335,7 +339,7 @@ int run_gemm_conv_halo(const GemmConv& g, cudaStream_t st) {
   p.bn_sums = g.bn_sums;
   p.act = g.act; p.act_slope = g.act_slope;
   p.st_a = (const bf16*)g.st_a; p.st_z = (const bf16*)g.st_z; p.st_slope = g.st_slope; p.st_sums = g.st_sums;
-  if (g.st_sums && (!g.st_a || !g.out || g.bn_sums)) return UDA_ERR_UNSUPPORTED;
+  if (g.st_sums && (!g.st_a || !g.out || g.bn_sums || BN < 64)) return UDA_ERR_UNSUPPORTED;
   UDA_TR(p.trace = take_trace_slice();)
   CUtensorMap ma, mb;
   {

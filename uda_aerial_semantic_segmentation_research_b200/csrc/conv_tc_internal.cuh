@@ -9,6 +9,21 @@ namespace tcconv {
 constexpr int kMaxTaps = 16;
 constexpr int kMaxClasses = 4;
 
+// Warp roles of the persistent / halo / pitched-halo kernels: warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+// then kEpiWarps epilogue warps.  A warp can only read the TMEM lane quadrant (warp % 4), so kEpiSplit = kEpiWarps / 4
+// warps share a quadrant and split its work items — (sub-tile, 32-column chunk) pairs — between them.  In-graph role
+// traces (tools/trace_step.py, profiles/r02_trace_step.txt) showed the 4-warp epilogue as the exposed tail of every
+// single-tile launch (~8 us of a 21 us layer3 convolution) and as what the MMA thread waits for in the few-channel
+// high-resolution layers (decoder blocks 3-4, head: more than half of the kernel).  -DUDA_EPI_WARPS=4 restores it.
+#ifndef UDA_EPI_WARPS
+#define UDA_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = UDA_EPI_WARPS;
+constexpr int kEpiSplit = kEpiWarps / 4;
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kConvThreads = 64 + kEpiThreads;
+static_assert(kEpiWarps == 4 || kEpiWarps == 8, "epilogue warps: one or two per TMEM lane quadrant");
+
 struct TilePlan { int TW, TH, NB; bool ok; };
 
 // Tile of `target` (128 or 256) pixels = NB images x TH rows x TW columns of a [B, MH, MW] pixel grid.
@@ -48,6 +63,7 @@ struct BnFuse {
   const float* gamma; const float* beta; float* running_mean; float* running_var;
   float* mean; float* rstd; float* scale; float* shift;     // per-channel outputs (saved for the backward)
   long long M;              // pixels per channel (B*OH*OW)
+  double inv_m;             // 1.0 / M computed on the host (a DP divide on the device is a long software sequence)
   float eps, momentum, slope;
   unsigned int* counter;    // zero on entry; arrival counter of the grid barrier
 };
@@ -130,9 +146,9 @@ __device__ __forceinline__ void bar_sync(int id, int nthreads) {
 // All CTAs of the grid must be co-resident (grid <= SMs at one CTA per SM).  A protocol bug traps instead of hanging.
 __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int expected, int id, int nthreads,
                                              bool leader) {
-  __threadfence();
-  bar_sync(id, nthreads);
+  bar_sync(id, nthreads);      // CTA-scope: the other threads' global atomics happen-before the leader's release
   if (leader) {
+    __threadfence();
     asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
     long long t0 = 0;
     for (unsigned int spin = 0;; ++spin) {
@@ -156,7 +172,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 // per-channel scale / shift of a fused BatchNorm from the completed statistics (same arithmetic as bn_apply_stream_kernel)
 __device__ __forceinline__ void bn_fuse_coeffs(const BnFuse& f, const double* sums, int C, int ch, float& sc, float& sf) {
   const double s1 = __ldcg(sums + ch), s2 = __ldcg(sums + C + ch);
-  const double inv_m = 1.0 / (double)f.M;
+  const double inv_m = f.inv_m;
   const double mean = s1 * inv_m;
   const float var = fmaxf((float)(s2 * inv_m - mean * mean), 0.f);
   const float rstd = rsqrtf(var + f.eps);
@@ -196,6 +212,14 @@ __device__ __forceinline__ void bn_chunk_stats(const float (&f)[32], int lane, f
   for (int k = 0; k < 32; ++k) u[k] = t[k] * t[k];
   s += warp_column_sums(t, lane);
   q += warp_column_sums(u, lane);
+}
+// the same when `f` is dead afterwards (called after the stores): rounds in place, 64 live values instead of 96
+__device__ __forceinline__ void bn_chunk_stats_clobber(float (&f)[32], int lane, float& s, float& q) {
+  float u[32];
+#pragma unroll
+  for (int k = 0; k < 32; ++k) { f[k] = __bfloat162float(__float2bfloat16_rn(f[k])); u[k] = f[k] * f[k]; }
+  q += warp_column_sums(u, lane);
+  s += warp_column_sums(f, lane);
 }
 // BatchNorm-backward partial sums of one 32-column chunk (GemmConv::st_*): o = the final output values of this
 // thread's row (after the addend), a_row / z_row = the row's 32 channels of a / z (z_row may be null).

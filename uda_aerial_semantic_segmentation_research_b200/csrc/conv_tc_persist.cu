@@ -15,6 +15,7 @@
 //     high-resolution layers (decoder blocks 2-4, head, layer1) are HBM/issue bound, not FLOP bound;
 //   * stride-2 dgrad: the four output-parity classes are tiles of ONE launch.
 #include "conv_tc_internal.cuh"
+#include "stream_common.cuh"
 #include <stdlib.h>
 
 namespace uda {
@@ -23,7 +24,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 192;
+constexpr int kThreads = kConvThreads;
 constexpr int kMaxStages = 12;
 
 struct PClass {
@@ -92,7 +93,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-      for (int q = 0; q < 2; ++q) { mbar_init(tfull_bar(q), 1); mbar_init(tempty_bar(q), 4); }
+      for (int q = 0; q < 2; ++q) { mbar_init(tfull_bar(q), 1); mbar_init(tempty_bar(q), kEpiWarps); }
       mbar_init(ws_bar, 1);
       fence_barrier_init();
     }
@@ -106,7 +107,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible from here on
   UDA_TR(if (trp && threadIdx.x == 0) { trp[0] = tr0; trp[1] = clock64() - tr0; trp[14] = tr_g0;
-                                        trp[15] = 1LL | ((long long)p.Cout << 8) | ((long long)p.Cred << 24) | ((long long)total_tiles << 40); })
+                                        trp[15] = (FUSE ? 17LL : 1LL) | ((long long)p.Cout << 8) | ((long long)p.Cred << 24) | ((long long)total_tiles << 40); })
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -196,10 +197,12 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       UDA_TR(if (trp) { trp[4] = tr_wf; trp[5] = tr_we; trp[6] = tr_first; trp[7] = clock64() - tr0; trp[12] = j; })
     }
   } else {
-    // ===================== epilogue (4 warps) =====================
+    // ===================== epilogue (kEpiWarps warps) =====================
     UDA_TR(long long tr_wt = 0, tr_busy = 0;)
     const int qw = warp & 3;
+    const int eh = (warp - 2) >> 2;          // which of the kEpiSplit warps of this lane quadrant
     constexpr int kChunks = (BN + 31) / 32;
+    constexpr bool kSplitCols = (kChunks % kEpiSplit) == 0;   // else (BN = 32) the quadrant's warps take alternate sub-tiles
     float bn_s[kChunks], bn_q[kChunks];
 #pragma unroll
     for (int cc = 0; cc < kChunks; ++cc) { bn_s[cc] = 0.f; bn_q[cc] = 0.f; }
@@ -217,7 +220,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       // ---- conv + BatchNorm + activation in one launch (BnFuse): this CTA's (<= kSets) tiles stay in TMEM across
       // the grid barrier; one tap class, BN >= 64 ----
       float* const s_tab = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);   // [kSets][2][BN] scale | shift
-      const int et = threadIdx.x - 64;   // 0..127 among the epilogue threads
+      const int et = threadIdx.x - 64;   // index among the epilogue threads
       // pass 1: statistics of the bf16-rounded outputs; the accumulator sets are NOT released
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
         const int mt = t % p.m_tiles, n0 = (t / p.m_tiles) * BN;
@@ -227,6 +230,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
           if (bn_n0 >= 0) {
 #pragma unroll
             for (int cc = 0; cc < kChunks; ++cc) {
+              if ((cc % kEpiSplit) != eh) continue;
               const int col = bn_n0 + cc * 32 + lane;
               atomicAdd(p.bn_sums + col, (double)bn_s[cc]); atomicAdd(p.bn_sums + p.Cout + col, (double)bn_q[cc]);
               bn_s[cc] = 0.f; bn_q[cc] = 0.f;
@@ -245,6 +249,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
           const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)j * kAccCols + (uint32_t)sub * BN;
 #pragma unroll
           for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (((c0 / 32) % kEpiSplit) != eh) continue;
             uint32_t v[32];
             tmem_ld_32x32(tbase + (uint32_t)c0, v);
             tmem_ld_wait();
@@ -262,28 +267,41 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
               }
             }
             bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);
+            {   // z is saved for the backward: stored here, under the remaining main loops of the grid
+              bf16* dst = p.out + pix * p.Cout + n0 + c0;
+#pragma unroll
+              for (int k = 0; k < 32; k += 8) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = f[k + e];
+                st_vec<8>(dst + k, o);
+              }
+            }
           }
         }
       }
       if (bn_n0 >= 0) {
 #pragma unroll
         for (int cc = 0; cc < kChunks; ++cc) {
+          if ((cc % kEpiSplit) != eh) continue;
           const int col = bn_n0 + cc * 32 + lane;
           atomicAdd(p.bn_sums + col, (double)bn_s[cc]); atomicAdd(p.bn_sums + p.Cout + col, (double)bn_q[cc]);
         }
       }
-      grid_barrier(p.fuse.counter, gridDim.x, 2, 128, et == 0);
+      UDA_TR(if (trp && warp == 2 && lane == 0) trp[5] = clock64() - tr0;)      // pass 1 done
+      grid_barrier(p.fuse.counter, gridDim.x, 2, kEpiThreads, et == 0);
       j = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
         const int mt = t % p.m_tiles, n0 = (t / p.m_tiles) * BN;
         float* const sc = s_tab + j * 2 * BN;
-        for (int ch = et; ch < BN; ch += 128) {
+        for (int ch = et; ch < BN; ch += kEpiThreads) {
           bn_fuse_coeffs(p.fuse, p.bn_sums, p.Cout, n0 + ch, sc[ch], sc[BN + ch]);
           if (mt == 0) bn_fuse_publish(p.fuse, p.bn_sums, p.Cout, n0 + ch);
         }
       }
-      bar_sync(2, 128);
-      // pass 2: z (saved for the backward) and a = act(z*scale + shift (+ residual))
+      bar_sync(2, kEpiThreads);
+      UDA_TR(if (trp && warp == 2 && lane == 0) trp[13] = clock64() - tr0;)     // barrier passed, coefficients ready
+      // pass 2: a = act(z*scale + shift (+ residual)) from the accumulators still in TMEM
       const bf16* const res = (const bf16*)p.fuse.residual;
       bf16* const aout = (bf16*)p.fuse.a_out;
       const float slope = p.fuse.slope;
@@ -302,6 +320,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
           const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)j * kAccCols + (uint32_t)sub * BN;
 #pragma unroll
           for (int c0 = 0; c0 < BN; c0 += 32) {
+            if (((c0 / 32) % kEpiSplit) != eh) continue;
             uint32_t v[32];
             tmem_ld_32x32(tbase + (uint32_t)c0, v);
             tmem_ld_wait();
@@ -316,7 +335,6 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 #pragma unroll
                 for (int e = 0; e < 8; ++e) z8[e] += a8[e];
               }
-              st_vec<8>(p.out + off + k, z8);
               if (res) ld_vec<8>(res + off + k, r8);
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
@@ -330,6 +348,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
           }
         }
       }
+      UDA_TR(if (trp && warp == 2 && lane == 0) { trp[8] = tr_wt; trp[10] = clock64() - tr0; })
     } else {
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
       const int ci = t / tiles_per_cls, rem = t % tiles_per_cls;
@@ -354,6 +373,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       tc_fence_after();
 #pragma unroll 1
       for (int sub = 0; sub < MT; ++sub) {
+        if (!kSplitCols && (sub % kEpiSplit) != eh) continue;
         const int r = sub * 128 + qw * 32 + lane;
         const int nb = r / (p.TH * p.TW);
         const int th = (r / p.TW) % p.TH, tw = r % p.TW;
@@ -364,6 +384,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         for (int c0 = 0; c0 < BN; c0 += 32) {
           const int nbase = n0 + c0;
           if (nbase >= p.Cout) break;   // warp-uniform
+          if (kSplitCols && ((c0 / 32) % kEpiSplit) != eh) continue;
           uint32_t v[32];
           tmem_ld_32x32(tbase + (uint32_t)c0, v);
           tmem_ld_wait();
@@ -402,7 +423,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             } else {
               bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);
             }
-          } else if (p.st_sums) {
+          } else if (!kLate && p.st_sums) {   // (the BN = 32 instances do not carry the BatchNorm-backward statistics)
             float g[32], gv[32];
             const long long off = pix * p.Cout + nbase;
             bn_bwd_chunk_terms(f, p.st_a + off, p.st_z ? p.st_z + off : nullptr, p.st_slope, inv_slope,
@@ -622,6 +643,7 @@ int run_gemm_conv_persistent(const GemmConv& g, cudaStream_t st) {
   p.st_a = (const bf16*)g.st_a; p.st_z = (const bf16*)g.st_z; p.st_slope = g.st_slope; p.st_sums = g.st_sums;
   UDA_REQUIRE(!(g.bn_sums && g.st_sums), UDA_ERR_BAD_ARG, "conv_tc_persist: forward and backward statistics are exclusive");
   UDA_REQUIRE(!g.st_sums || (g.st_a && g.out), UDA_ERR_BAD_ARG, "conv_tc_persist: backward statistics need `a` and an NHWC output");
+  UDA_REQUIRE(!g.st_sums || BN >= 64, UDA_ERR_UNSUPPORTED, "conv_tc_persist: backward statistics need more than 32 output channels");
 
   CUtensorMap ma, mb;
   const uint64_t C = (uint64_t)g.Cred, H = (uint64_t)g.SH, W = (uint64_t)g.SW;

@@ -15,6 +15,7 @@
 // A CTA tile is NBLK consecutive blocks (of the whole batch: blocks never straddle images, tiles may) x BN
 // output channels; TMEM is double-buffered when 2*NBLK*BN <= 512 columns.
 #include "conv_tc_internal.cuh"
+#include "stream_common.cuh"
 #include <stdlib.h>
 
 namespace uda {
@@ -23,7 +24,7 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 192;
+constexpr int kThreads = kConvThreads;
 constexpr int kSmemBudget = 218 * 1024;
 constexpr int kAStages = 2;
 constexpr int kMaxBStages = 8;
@@ -76,7 +77,8 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (lane == 0) {
       for (int s = 0; s < kAStages; ++s) { mbar_init(afull(s), 1); mbar_init(aempty(s), 1); }
       for (int s = 0; s < SB; ++s) { mbar_init(bfull(s), 1); mbar_init(bempty(s), 1); }
-      for (int q = 0; q < 2; ++q) { mbar_init(tfull(q), 1); mbar_init(tempty(q), 4); }
+      for (int q = 0; q < 2; ++q) { mbar_init(tfull(q), 1); mbar_init(tempty(q), kEpiWarps); }
+      if (FUSE) mbar_init(bar_base + 8u * 25, 1);     // residual rows landed (fused BatchNorm epilogue)
       fence_barrier_init();
     }
     __syncwarp();
@@ -89,7 +91,7 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are visible from here on
   UDA_TR(if (trp && threadIdx.x == 0) { trp[0] = tr0; trp[1] = clock64() - tr0; trp[14] = tr_g0;
-                                        trp[15] = 3LL | ((long long)p.Cout << 8) | ((long long)p.Cred << 24) | ((long long)total_tiles << 40); })
+                                        trp[15] = (FUSE ? 19LL : 3LL) | ((long long)p.Cout << 8) | ((long long)p.Cred << 24) | ((long long)total_tiles << 40); })
 
   if (warp == 0) {
     // ===================== TMA producer: per channel chunk one halo box per block, then nine weight tiles =====
@@ -186,42 +188,77 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     // ===================== epilogue (4 warps): 128 pitched positions per block, junk columns skipped ==========
     UDA_TR(long long tr_wt = 0, tr_busy = 0;)
     const int qw = warp & 3;
+    const int eh = (warp - 2) >> 2;          // which of the kEpiSplit warps of this lane quadrant: alternate column chunks
     constexpr int kChunks = (BN + 31) / 32;
+    static_assert(kChunks % kEpiSplit == 0, "BN >= 64");
     float bn_s[kChunks], bn_q[kChunks];
 #pragma unroll
     for (int cc = 0; cc < kChunks; ++cc) { bn_s[cc] = 0.f; bn_q[cc] = 0.f; }
     if constexpr (FUSE) {
-      // ---- conv + BatchNorm + activation in one launch (BnFuse): exactly one tile per CTA, accumulators stay in
-      // TMEM across the grid barrier ----
+      // ---- conv + BatchNorm + activation in one launch (BnFuse): exactly one tile per CTA.  When the epilogue starts
+      // every MMA of the CTA has completed, so the operand rings are free: the bf16 z tile is STAGED there (rows of
+      // kPitch bytes: conflict-free 16-byte accesses), leaves through one bulk copy per row (full lines instead of the
+      // 32 row-strided 16-byte pieces of a register-file store), survives the grid barrier, and pass 2 turns it into
+      // a = act(z*scale + shift (+ residual)) IN PLACE with all epilogue threads on consecutive vectors (no TMEM lane
+      // constraint).  The residual rows arrive through bulk copies issued before pass 1. ----
+      using stream::bulk_load; using stream::bulk_store; using stream::bulk_commit; using stream::fence_async_smem;
+      constexpr int kPitch = BN * 2 + 16;
+      constexpr int kVecs = BN / 8;                       // 16-byte vectors per row
       const int t = blockIdx.x;
       const int mt = t % p.m_tiles, n0 = (t / p.m_tiles) * BN;
       const int gb0 = mt * NBLK;
       const int nblk = min(NBLK, p.total_blocks - gb0);
       float* const s_sc = reinterpret_cast<float*>(bars + 26);
       float* const s_sf = s_sc + BN;
-      const int et = threadIdx.x - 64;   // 0..127 among the epilogue threads
+      float* const s_red = s_sf + BN;                     // [2][BN] CTA-level partial statistics
+      uint8_t* const st_out = smem;                       // [NBLK*128][kPitch] z
+      uint8_t* const st_res = smem + NBLK * 128 * kPitch; // [NBLK*128][kPitch] residual rows
+      uint8_t* const st_a = st_res + NBLK * 128 * kPitch; // [NBLK*128][kPitch] a (the z rows may still be leaving)
+      const uint32_t rbar = bar_base + 8u * 25;
+      const int et = threadIdx.x - 64;   // index among the epilogue threads
+      const bf16* const res = (const bf16*)p.fuse.residual;
+      bf16* const aout = (bf16*)p.fuse.a_out;
+      for (int ch = et; ch < 2 * BN; ch += kEpiThreads) s_red[ch] = 0.f;
+      bar_sync(2, kEpiThreads);
       UDA_TR_WAIT(tr_wt, mbar_wait(tfull(0), 0))
       UDA_TR(const long long tr_b0 = clock64();)
       tc_fence_after();
-      // pass 1: statistics of the bf16-rounded outputs (junk rows contribute zeros)
-#pragma unroll 1
-      for (int i = 0; i < nblk; ++i) {
+      // this thread's row of each block (two warps share a row: alternate 32-column chunks)
+      long long pix[NBLK]; bool valid[NBLK];
+#pragma unroll
+      for (int i = 0; i < NBLK; ++i) {
         const int gb = gb0 + i, b = gb / p.nb_img;
         const int m = (gb % p.nb_img) * 128 + qw * 32 + lane;
         const int r = m / p.P, c = m - r * p.P;
-        const bool valid = c < p.W && r < p.H;
-        const long long pix = ((long long)b * p.H + r) * p.W + c;
+        valid[i] = i < nblk && c < p.W && r < p.H;
+        pix[i] = valid[i] ? ((long long)b * p.H + r) * p.W + c : (long long)b * p.H * p.W;   // junk rows: any valid pixel
+      }
+      if (res) {   // residual rows -> shared memory, under pass 1
+        if (et == 0) mbar_expect_tx(rbar, (uint32_t)nblk * 128u * (uint32_t)(BN * 2));
+        if (eh == 0) {
+#pragma unroll
+          for (int i = 0; i < NBLK; ++i)
+            if (i < nblk)
+              bulk_load(smem_u32(st_res + (i * 128 + qw * 32 + lane) * kPitch), res + pix[i] * p.Cout + n0, BN * 2, rbar);
+        }
+      }
+      // pass 1: statistics of the bf16-rounded outputs (junk rows contribute zeros); z staged for its bulk store
+#pragma unroll
+      for (int i = 0; i < NBLK; ++i) {
+        if (i >= nblk) break;
         const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)i * BN;
+        uint8_t* const srow = st_out + (i * 128 + qw * 32 + lane) * kPitch;
 #pragma unroll
         for (int c0 = 0; c0 < BN; c0 += 32) {
+          if (((c0 / 32) % kEpiSplit) != eh) continue;
           uint32_t v[32];
           tmem_ld_32x32(tbase + (uint32_t)c0, v);
           tmem_ld_wait();
           float f[32];
 #pragma unroll
-          for (int k = 0; k < 32; ++k) f[k] = valid ? __uint_as_float(v[k]) : 0.f;
-          if (p.addend && valid) {
-            const bf16* add = p.addend + pix * p.Cout + n0 + c0;
+          for (int k = 0; k < 32; ++k) f[k] = valid[i] ? __uint_as_float(v[k]) : 0.f;
+          if (p.addend && valid[i]) {
+            const bf16* add = p.addend + pix[i] * p.Cout + n0 + c0;
 #pragma unroll
             for (int k = 0; k < 32; k += 8) {
               float a8[8];
@@ -230,63 +267,78 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
               for (int e = 0; e < 8; ++e) f[k + e] += a8[e];
             }
           }
-          bn_chunk_stats(f, lane, bn_s[c0 / 32], bn_q[c0 / 32]);
+#pragma unroll
+          for (int k = 0; k < 32; k += 8)
+            *reinterpret_cast<uint4*>(srow + (c0 + k) * 2) =
+                make_uint4(pack_bf16x2(f[k], f[k + 1]), pack_bf16x2(f[k + 2], f[k + 3]),
+                           pack_bf16x2(f[k + 4], f[k + 5]), pack_bf16x2(f[k + 6], f[k + 7]));
         }
       }
-#pragma unroll
-      for (int cc = 0; cc < kChunks; ++cc) {
-        const int col = n0 + cc * 32 + lane;
-        atomicAdd(p.bn_sums + col, (double)bn_s[cc]);
-        atomicAdd(p.bn_sums + p.Cout + col, (double)bn_q[cc]);
+      fence_async_smem();
+      bar_sync(2, kEpiThreads);
+      // statistics of the staged (bf16) tile: a thread owns one channel pair over a slice of the rows — consecutive
+      // lanes read consecutive 4-byte words (no bank conflicts), ~3x fewer instructions than the per-warp shuffle trees
+      {
+        constexpr int kPairs = BN / 2, kSlices = kEpiThreads / kPairs;
+        const int cp = et % kPairs, sl = et / kPairs;
+        const int rows = nblk * 128;
+        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+        for (int row = sl; row < rows; row += kSlices) {
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(st_out + row * kPitch + cp * 4);
+          const float x0 = __uint_as_float(w << 16), x1 = __uint_as_float(w & 0xffff0000u);
+          s0 += x0; s1 += x1; q0 = fmaf(x0, x0, q0); q1 = fmaf(x1, x1, q1);
+        }
+        atomicAdd(s_red + 2 * cp, s0); atomicAdd(s_red + 2 * cp + 1, s1);
+        atomicAdd(s_red + BN + 2 * cp, q0); atomicAdd(s_red + BN + 2 * cp + 1, q1);
       }
-      grid_barrier(p.fuse.counter, gridDim.x, 2, 128, et == 0);
-      for (int ch = et; ch < BN; ch += 128) {
+      bar_sync(2, kEpiThreads);
+      if (et < 2 * BN)    // one fp64 atomic per channel and CTA
+        atomicAdd(p.bn_sums + (et < BN ? n0 + et : p.Cout + n0 + et - BN), (double)s_red[et]);
+      if (eh == 0) {      // z leaves: one bulk copy per valid row
+#pragma unroll
+        for (int i = 0; i < NBLK; ++i)
+          if (valid[i])
+            bulk_store(p.out + pix[i] * p.Cout + n0, smem_u32(st_out + (i * 128 + qw * 32 + lane) * kPitch), BN * 2);
+        bulk_commit();
+      }
+      UDA_TR(if (trp && warp == 2 && lane == 0) trp[5] = clock64() - tr0;)      // pass 1 done
+      grid_barrier(p.fuse.counter, gridDim.x, 2, kEpiThreads, et == 0);
+      for (int ch = et; ch < BN; ch += kEpiThreads) {
         bn_fuse_coeffs(p.fuse, p.bn_sums, p.Cout, n0 + ch, s_sc[ch], s_sf[ch]);
         if (mt == 0) bn_fuse_publish(p.fuse, p.bn_sums, p.Cout, n0 + ch);
       }
-      bar_sync(2, 128);
-      // pass 2: z (saved for the backward) and a = act(z*scale + shift (+ residual))
-      const bf16* const res = (const bf16*)p.fuse.residual;
-      bf16* const aout = (bf16*)p.fuse.a_out;
+      bar_sync(2, kEpiThreads);
+      UDA_TR(if (trp && warp == 2 && lane == 0) trp[13] = clock64() - tr0;)     // barrier passed, coefficients ready
+      // pass 2: a = act(z*scale + shift (+ residual)), consecutive threads on consecutive 16-byte vectors
+      if (res) mbar_wait(rbar, 0);
       const float slope = p.fuse.slope;
-#pragma unroll 1
-      for (int i = 0; i < nblk; ++i) {
-        const int gb = gb0 + i, b = gb / p.nb_img;
-        const int m = (gb % p.nb_img) * 128 + qw * 32 + lane;
-        const int r = m / p.P, c = m - r * p.P;
-        const bool valid = c < p.W && r < p.H;
-        const long long pix = ((long long)b * p.H + r) * p.W + c;
-        const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)i * BN;
+      for (int vi = et; vi < nblk * 128 * kVecs; vi += kEpiThreads) {
+        const int row = vi / kVecs, pc = vi - row * kVecs;
+        uint8_t* const zp = st_out + row * kPitch + pc * 16;
+        float z8[8], r8[8];
+        stream::lds8(zp, z8);
+        if (res) stream::lds8(st_res + row * kPitch + pc * 16, r8);
+        const float4 sa = *reinterpret_cast<const float4*>(s_sc + pc * 8), sb = *reinterpret_cast<const float4*>(s_sc + pc * 8 + 4);
+        const float4 fa = *reinterpret_cast<const float4*>(s_sf + pc * 8), fb = *reinterpret_cast<const float4*>(s_sf + pc * 8 + 4);
+        const float sc8[8] = {sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w};
+        const float sf8[8] = {fa.x, fa.y, fa.z, fa.w, fb.x, fb.y, fb.z, fb.w};
 #pragma unroll
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          uint32_t v[32];
-          tmem_ld_32x32(tbase + (uint32_t)c0, v);
-          tmem_ld_wait();
-          if (valid) {
-            const long long off = pix * p.Cout + n0 + c0;
-#pragma unroll
-            for (int k = 0; k < 32; k += 8) {
-              float z8[8], a8[8], r8[8];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) z8[e] = __uint_as_float(v[k + e]);
-              if (p.addend) {
-                ld_vec<8>(p.addend + off + k, a8);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) z8[e] += a8[e];
-              }
-              st_vec<8>(p.out + off + k, z8);
-              if (res) ld_vec<8>(res + off + k, r8);
-#pragma unroll
-              for (int e = 0; e < 8; ++e) {
-                const float zr = __bfloat162float(__float2bfloat16_rn(z8[e]));
-                float y = zr * s_sc[c0 + k + e] + s_sf[c0 + k + e];
-                if (res) y += r8[e];
-                a8[e] = y > 0.f ? y : y * slope;
-              }
-              st_vec<8>(aout + off + k, a8);
-            }
-          }
+        for (int e = 0; e < 8; ++e) {
+          float y = z8[e] * sc8[e] + sf8[e];
+          if (res) y += r8[e];
+          z8[e] = y > 0.f ? y : y * slope;
         }
+        stream::sts8(st_a + row * kPitch + pc * 16, z8);
+      }
+      fence_async_smem();
+      bar_sync(2, kEpiThreads);
+      if (eh == 0) {
+#pragma unroll
+        for (int i = 0; i < NBLK; ++i)
+          if (valid[i])
+            bulk_store(aout + pix[i] * p.Cout + n0, smem_u32(st_a + (i * 128 + qw * 32 + lane) * kPitch), BN * 2);
+        bulk_commit();
+        stream::bulk_wait_read<0>();     // shared memory must outlive the copies' reads
       }
       UDA_TR(tr_busy += clock64() - tr_b0;)
       UDA_TR(if (trp && warp == 2 && lane == 0) { trp[8] = tr_wt; trp[9] = tr_busy; trp[10] = clock64() - tr0; })
@@ -324,6 +376,7 @@ conv_tc_phalo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         for (int c0 = 0; c0 < BN; c0 += 32) {
           const int nbase = n0 + c0;
           if (nbase >= p.Cout) break;   // warp-uniform
+          if (((c0 / 32) % kEpiSplit) != eh) continue;
           uint32_t v[32];
           tmem_ld_32x32(tbase + (uint32_t)c0, v);
           tmem_ld_wait();
@@ -407,7 +460,8 @@ int launch_phalo(const CUtensorMap& ma, const CUtensorMap& mb, PHParams& p, cuda
   if (SB < 3) return UDA_ERR_UNSUPPORTED;   // caller falls back
   p.b_stages = SB;
   p.m_tiles = (p.total_blocks + NBLK - 1) / NBLK;
-  const int smem = a_bytes + SB * kBBytes + 1024 + 256 + (FUSE ? 2 * BN * 4 : 0);   // + scale / shift tables
+  const int smem = a_bytes + SB * kBBytes + 1024 + 256 + (FUSE ? 4 * BN * 4 : 0);   // + scale / shift / statistics tables
+  if (FUSE && a_bytes + SB * kBBytes < 3 * NBLK * 128 * (BN * 2 + 16)) return UDA_ERR_UNSUPPORTED;   // z / residual / a staging
   static bool configured = false;
   if (!configured) {
     UDA_CUDA_OK(cudaFuncSetAttribute(conv_tc_phalo_kernel<KC, BN, NBLK, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,

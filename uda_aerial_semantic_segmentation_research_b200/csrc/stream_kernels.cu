@@ -3,6 +3,7 @@
 // dispatches here when the fast-path conditions hold.
 #include "stream_common.cuh"
 #include "bn_common.cuh"
+#include <stdlib.h>
 
 namespace uda {
 namespace {
@@ -335,6 +336,170 @@ __global__ void __launch_bounds__(kCta, 1) bn_bwd_apply_stream_kernel(const BwdA
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// backward reduce + apply as ONE launch for tensors that fit the shared memory of one wave of CTAs (layer3 / layer4 /
+// decoder block 0 at B=16, 512x512: <= 8 MB per tensor).  In-graph traces (profiles/r02_trace_step.txt) show the
+// two-launch form costing ~25 us per layer on these L2-resident tensors — launch boundaries, prologues and a second
+// read, not bandwidth.  Here every CTA loads its tiles ONCE (they stay in shared memory), reduces, meets the other
+// CTAs at a grid-wide barrier (grid <= one CTA per SM, all co-resident), finalizes the per-channel coefficients from
+// the completed sums and applies them in place; outputs leave through bulk stores.
+// ------------------------------------------------------------------------------------------------
+struct MergedParams {
+  StreamIO io;   // in: dy, x (, a) (, dres when accumulating)   out: dx (, dres);  io.stages >= tiles per CTA
+  const float* gamma; const float* mean; const float* rstd; const float* scale; const float* shift;
+  double* sums;            // [2*C], zero on entry, zero again on exit
+  unsigned int* counters;  // [0] grid-barrier arrivals, [1] CTAs that have read the sums; zero on entry / exit
+  float* dgamma; float* dbeta; int accumulate;
+  long long M; int C; float slope; int has_a, res_in;
+};
+
+__global__ void __launch_bounds__(kCta, 1) bn_bwd_merged_stream_kernel(const MergedParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.io.stages * p.io.nin * kTile);
+  float* red = reinterpret_cast<float*>(bars + 2 * kMaxStages);   // [kCompute][16] partial sums, then [3][C] coefficients
+  __shared__ bool is_last;
+  Pipe pipe(p.io, smem, bars);
+  const int C = p.C;
+  const int c = (threadIdx.x * 8) % C;
+  const bool zmask = !p.has_a && p.scale != nullptr;
+  float sc[8], sf[8];
+  if (pipe.is_io()) {
+    const int lane = threadIdx.x - kCompute;
+    for (int k = 0; k < pipe.n_my; ++k) pipe.load(k, lane);      // every tile of this CTA: they stay resident
+  } else {
+    float nmr[8], rs[8], s1[8], s2[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      rs[j] = p.rstd[c + j]; nmr[j] = -p.mean[c + j] * rs[j];
+      sc[j] = zmask ? p.scale[c + j] : 0.f; sf[j] = zmask ? p.shift[c + j] : 0.f;
+      s1[j] = 0.f; s2[j] = 0.f;
+    }
+    for (int k = 0; k < pipe.n_my; ++k) {
+      pipe.wait(k);
+      const uint32_t nb = pipe.bytes_of(pipe.tile_of(k));
+      const uint8_t* dyin = pipe.tile(k, 0);
+      const uint8_t* xin = pipe.tile(k, 1);
+      const uint8_t* ain = pipe.tile(k, 2);
+#pragma unroll
+      for (int u = 0; u < kVecs; ++u) {
+        const uint32_t off = (threadIdx.x + u * kCompute) * 16;
+        if (off < nb) {
+          float d[8], x[8], a[8];
+          lds8(dyin + off, d);
+          lds8(xin + off, x);
+          if (p.has_a) lds8(ain + off, a);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float g = d[j];
+            if (p.has_a) g *= (a[j] > 0.f) ? 1.f : p.slope;
+            else if (zmask) g *= (x[j] * sc[j] + sf[j] > 0.f) ? 1.f : p.slope;
+            s1[j] += g;
+            s2[j] = fmaf(g, fmaf(x[j], rs[j], nmr[j]), s2[j]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s1[j]; red[threadIdx.x * 16 + 8 + j] = s2[j]; }
+  }
+  __syncthreads();
+  const int cv = C / 8;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    const int ch = i % C, k = i / C;
+    float acc = 0.f;
+    for (int t = ch / 8; t < kCompute; t += cv) acc += red[t * 16 + k * 8 + (ch & 7)];
+    atomicAdd(p.sums + k * C + ch, (double)acc);
+  }
+  // ---- grid-wide barrier (all CTAs co-resident: grid <= SMs, one CTA per SM) ----
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(p.counters) : "memory");
+    long long t0 = 0;
+    for (unsigned int spin = 0;; ++spin) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p.counters) : "memory");
+      if (v >= gridDim.x) break;
+      __nanosleep(32);
+      if ((spin & 0x3ff) == 0x3ff) {
+        const long long now = clock64();
+        if (t0 == 0) t0 = now;
+        else if (now - t0 > 4000000000LL) { printf("uda_b200: bn_bwd grid barrier timed out (block %d)\n", blockIdx.x); __trap(); }
+      }
+    }
+    __threadfence();
+  }
+  __syncthreads();
+  // ---- per-channel coefficients  dx = kA*g + kB*x + kC  (bn_bwd_finalize_channel's arithmetic) ----
+  {
+    const float inv_m = 1.f / (float)p.M;
+    for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+      const float s1 = (float)__ldcg(p.sums + ch), s2 = (float)__ldcg(p.sums + C + ch);
+      const float g = p.gamma ? p.gamma[ch] : 1.f;
+      const float r = p.rstd[ch], mu = p.mean[ch];
+      const float k0 = g * r;
+      const float k1 = k0 * s1 * inv_m, k2 = k0 * s2 * inv_m;
+      red[ch] = k0; red[C + ch] = -k2 * r; red[2 * C + ch] = -k1 + k2 * r * mu;
+      if (blockIdx.x == 0) {
+        if (p.dgamma) p.dgamma[ch] = (p.accumulate ? p.dgamma[ch] : 0.f) + s2;
+        if (p.dbeta) p.dbeta[ch] = (p.accumulate ? p.dbeta[ch] : 0.f) + s1;
+      }
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicAdd(p.counters + 1, 1u) == gridDim.x - 1;   // every CTA has read the sums
+  if (pipe.is_io()) {
+    const int lane = threadIdx.x - kCompute;
+    for (int k = 0; k < pipe.n_my; ++k) {
+      mbar_wait(pipe.done_base + 8u * (k % p.io.stages), 0u);
+      const long long t = pipe.tile_of(k);
+      if (lane < p.io.nout) bulk_store(p.io.out[lane] + t * kTile, smem_u32(pipe.tile(k, p.io.out_slot[lane])), pipe.bytes_of(t));
+      bulk_commit();
+    }
+    bulk_wait_all<0>();
+  } else {
+    float kA[8], kB[8], kC[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { kA[j] = red[c + j]; kB[j] = red[C + c + j]; kC[j] = red[2 * C + c + j]; }
+    const bool wres = p.io.nout > 1;
+    for (int k = 0; k < pipe.n_my; ++k) {
+      const uint32_t nb = pipe.bytes_of(pipe.tile_of(k));
+      uint8_t* dyin = pipe.tile(k, 0);     // dx overwrites dy in place
+      uint8_t* xin = pipe.tile(k, 1);      // dres overwrites x in place
+      const uint8_t* ain = pipe.tile(k, 2);
+      const uint8_t* rin = pipe.tile(k, p.res_in >= 0 ? p.res_in : 0);
+#pragma unroll
+      for (int u = 0; u < kVecs; ++u) {
+        const uint32_t off = (threadIdx.x + u * kCompute) * 16;
+        if (off < nb) {
+          float d[8], x[8], a[8], r[8], o[8];
+          lds8(dyin + off, d);
+          lds8(xin + off, x);
+          if (p.has_a) lds8(ain + off, a);
+          if (p.res_in >= 0) lds8(rin + off, r);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float g = d[j];
+            if (p.has_a) g *= (a[j] > 0.f) ? 1.f : p.slope;
+            else if (zmask) g *= (x[j] * sc[j] + sf[j] > 0.f) ? 1.f : p.slope;
+            o[j] = kA[j] * g + kB[j] * x[j] + kC[j];
+            d[j] = p.res_in >= 0 ? r[j] + g : g;
+          }
+          sts8(dyin + off, o);
+          if (wres) sts8(xin + off, d);
+        }
+      }
+      pipe.release(k);
+    }
+  }
+  __syncthreads();
+  if (is_last) {   // leave the workspace zeroed for the next launch
+    for (int ch = threadIdx.x; ch < 2 * C; ch += blockDim.x) p.sums[ch] = 0.0;
+    if (threadIdx.x == 0) { p.counters[0] = 0u; p.counters[1] = 0u; }
+  }
+}
+
 // one CTA per SM; as many stages (<= 4) as fit beside `extra_smem`; small tensors get >= 2 tiles per CTA
 int stream_launch_geometry(StreamIO& io, size_t extra_smem, int* grid, size_t* smem) {
 #ifdef UDA_B200_EXPERIMENTS
@@ -395,6 +560,39 @@ int bn_bwd_stream(const void* dy, const void* x, const void* a, const float* mea
                   const float* scale, const float* shift, void* dx, void* dres, int dres_accumulate, double* sums,
                   float* coef, const bn::BnBwdFinal& fin, long long M, int C, float slope, cudaStream_t st) {
   const long long nbytes = M * (long long)C * 2;
+  {   // one launch when every CTA's tiles fit its shared memory.  Opt-in (UDA_B200_BN_BWD_MERGED=1): parity-tested, but in
+      // the captured step it measured no faster than the two launches (8.426 vs 8.422 ms; the backward is bound by the
+      // sum of kernel work — the side-stream weight-gradient kernels fill every gap — not by launch boundaries)
+    const char* const env_merged = getenv("UDA_B200_BN_BWD_MERGED");     // read on every call: the tests switch it
+    const bool merged_on = env_merged && env_merged[0] == '1';
+    const int nin = 2 + (a ? 1 : 0) + ((dres && dres_accumulate) ? 1 : 0);
+    const long long total_tiles = (nbytes + kTile - 1) / kTile;
+    const long long grid = total_tiles < num_sms() ? total_tiles : num_sms();
+    const long long per_cta = (total_tiles + grid - 1) / grid;
+    const size_t extra = kCompute * 16 * sizeof(float) > 3 * (size_t)C * sizeof(float) ? kCompute * 16 * sizeof(float)
+                                                                                         : 3 * (size_t)C * sizeof(float);
+    const size_t need = (size_t)per_cta * nin * kTile + 128 + 64 + extra;
+    if (merged_on && per_cta <= kMaxStages && need <= 224 * 1024 && fin.counter) {
+      MergedParams p{};
+      int n = 0;
+      p.io.in[n++] = (const uint8_t*)dy; p.io.in[n++] = (const uint8_t*)x;
+      if (a) { p.io.in[2] = (const uint8_t*)a; n = 3; }
+      p.res_in = -1;
+      if (dres && dres_accumulate) { p.res_in = a ? 3 : 2; p.io.in[p.res_in] = (const uint8_t*)dres; n = p.res_in + 1; }
+      p.io.nin = n;
+      p.io.out[0] = (uint8_t*)dx; p.io.out[1] = (uint8_t*)dres; p.io.nout = dres ? 2 : 1;
+      p.io.out_slot[0] = 0; p.io.out_slot[1] = 1;   // dx over the dy tile, dres over the x tile
+      p.io.nbytes = nbytes; p.io.stages = (int)per_cta;
+      p.gamma = fin.gamma; p.mean = mean; p.rstd = rstd; p.scale = scale; p.shift = shift;
+      p.sums = sums; p.counters = fin.counter; p.dgamma = fin.dgamma; p.dbeta = fin.dbeta; p.accumulate = fin.accumulate;
+      p.M = M; p.C = C; p.slope = slope; p.has_a = a ? 1 : 0;
+      static bool cfg = false;
+      if (!cfg) { if (int rc = set_smem_attr(bn_bwd_merged_stream_kernel)) return rc; cfg = true; }
+      UDA_CUDA_OK(launch_pdl(bn_bwd_merged_stream_kernel, dim3((unsigned)grid), dim3(kCta), need, st, p));
+      UDA_LAUNCH_OK("bn_bwd_merged_stream_kernel");
+      return UDA_OK;
+    }
+  }
   {
     ReduceParams p{};
     p.io.in[0] = (const uint8_t*)dy; p.io.in[1] = (const uint8_t*)x; p.io.in[2] = (const uint8_t*)a;

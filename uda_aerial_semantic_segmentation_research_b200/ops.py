@@ -35,11 +35,10 @@ WGRAD_STREAM = os.environ.get("UDA_B200_WGRAD_STREAM", "1") != "0"
 #: refresh the flipped / transposed dgrad weight copies on the side stream during the forward
 PREFETCH_WFT = os.environ.get("UDA_B200_PREFETCH_WFT", "1") != "0"
 #: training: conv + BatchNorm + activation (+ residual) as ONE launch for the layers whose output tiles fit the tensor
-#: memory of one wave of CTAs (grid barrier between the statistics and the normalise pass; uda_conv2d_tc_fwd_bn_act).
-#: Opt-in (UDA_B200_FUSE_BN_APPLY=1): parity-tested (tests/test_gpu_bnfuse.py) but measured SLOWER at B=16, 512x512 —
-#: 8.81 vs 8.58 ms per step: with programmatic dependent launch the separate normalise pass of these L2-resident
-#: tensors costs ~4 us on 148 x 16 streaming warps, the in-kernel pass 2 + barrier ~10 us on 4 epilogue warps per SM
-FUSE_BN_APPLY = os.environ.get("UDA_B200_FUSE_BN_APPLY", "0") == "1"
+#: memory of one wave of CTAs (grid barrier between the statistics and the normalise pass; uda_conv2d_tc_fwd_bn_act):
+#: layer2-4 and decoder blocks 0-1 at B=16, 512x512 (33 of the 46 BatchNorm layers).  Measured 8.37-8.43 vs 8.53 ms per
+#: step; UDA_B200_FUSE_BN_APPLY=0 runs the separate normalise pass everywhere
+FUSE_BN_APPLY = os.environ.get("UDA_B200_FUSE_BN_APPLY", "1") != "0"
 #: decoder conv1 as conv_transpose4x4(x) + conv3x3(skip): the upsampled / concatenated tensor is never materialised
 #: (UDA_B200_FUSE_UPCAT=0 runs the upsample+concat copy kernel and one 3x3 convolution over the concatenation)
 FUSE_UPCAT = os.environ.get("UDA_B200_FUSE_UPCAT", "1") != "0"
@@ -397,7 +396,7 @@ def weight_flip_transpose_batch(base, out, table):
 def dgrad_bnstats_supported(x_shape, w_shape, stride, pad, dtype):
     """Can the tensor-core dgrad of this convolution also emit the BatchNorm-backward statistics of its output?"""
     B, H, W, Cin, Cout, KH, KW, Ho, Wo = _geom(x_shape, w_shape, stride, pad)
-    if not (USE_TC and TC_PERSIST and FUSE_BN_BWD and dtype == torch.bfloat16) or (stride == 2 and KH < 2):
+    if not (USE_TC and TC_PERSIST and FUSE_BN_BWD and dtype == torch.bfloat16) or (stride == 2 and KH < 2) or Cin <= 32:
         return False
     return bool(tc_supported(1, B, H, W, Cin, Cout, KH, KW, stride, pad)
                 and _lib.lib().uda_bn_bwd_fused_supported(ci(BF16), ll(B * H * W), ci(Cin)))
