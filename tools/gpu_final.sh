@@ -4,12 +4,16 @@
 R=${R:-r02}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
-for f in losses eval layers conv_tc bench_shapes stages unet adversary; do
+for f in losses eval layers conv_tc bench_shapes bnfuse stages unet adversary; do
   timeout 900 python -m pytest tests/test_gpu_$f.py -q -m gpu --tb=short -p no:cacheprovider > gpurun_out/test_$f.log 2>&1
   echo "== test_gpu_$f exit $? =="; grep -v "^E    +" gpurun_out/test_$f.log | tail -n 3
 done
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "== smoke exit $? =="; tail -n 2 gpurun_out/smoke.log
 timeout 120 tools/exp/umma_rate > gpurun_out/${R}_umma_rate.txt 2>&1; echo "== umma_rate exit $? =="
+timeout 120 tools/exp/tmem_ld_rate > gpurun_out/${R}_tmem_ld_rate.txt 2>&1; echo "== tmem_ld_rate exit $? =="
+timeout 600 python tools/timeline.py --dump --out gpurun_out/${R}_timeline.txt > gpurun_out/timeline.log 2>&1; echo "== timeline exit $? =="; head -n 5 gpurun_out/${R}_timeline.txt
+timeout 600 python tools/trace_step.py > gpurun_out/${R}_trace_step.txt 2> gpurun_out/trace_step.err; echo "== trace_step exit $? =="; tail -n 9 gpurun_out/${R}_trace_step.txt
+timeout 600 env UDA_B200_FUSE_BN_APPLY=0 python tools/trace_step.py > gpurun_out/${R}_trace_step_unfused.txt 2> gpurun_out/trace_step.err; echo "== trace_step (separate BatchNorm passes) exit $? =="; tail -n 7 gpurun_out/${R}_trace_step_unfused.txt
 timeout 300 python tools/trace_conv.py layer1 layer2 layer3 layer4 l3.0 dec0.c1 dec2.c1 dec3.c1 > gpurun_out/${R}_trace_conv.txt 2>&1; echo "== trace exit $? =="
 timeout 600 python tools/conv_bench.py > gpurun_out/${R}_conv_bench.txt 2>&1; echo "== conv_bench exit $? =="; tail -n 1 gpurun_out/${R}_conv_bench.txt
 timeout 600 python tools/hbm_bench.py > gpurun_out/${R}_hbm_bench.txt 2>&1; echo "== hbm_bench exit $? =="

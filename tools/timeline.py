@@ -92,7 +92,8 @@ def main():
     # per name
     agg = collections.defaultdict(lambda: [0, 0.0])
     for e in last:
-        n = e["name"].split("<")[0].split("(")[0].replace("void ", "").replace("uda::", "")
+        n = e["name"].replace("void ", "").replace("(anonymous namespace)::", "").replace("uda::", "").replace("tcconv::", "")
+        n = n.split("<")[0].split("(")[0]
         agg[n][0] += 1
         agg[n][1] += e["dur"]
     tot = sum(v[1] for v in agg.values())
