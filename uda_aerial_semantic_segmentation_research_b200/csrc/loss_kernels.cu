@@ -363,7 +363,7 @@ template <> __device__ __forceinline__ void st_one<__nv_bfloat16>(uint8_t* r, in
 // shared-memory access at the target's row instead of a compare-select per class.
 template <typename T, int CPAD, int PPT, int PASS, bool FULL>
 __global__ void __launch_bounds__(pxstream::px_threads<PPT>(), 1)
-seg_loss_stream_kernel(const SegLossParams p, const pxstream::PxIO io) {
+seg_loss_stream_kernel(const SegLossParams p, const pxstream::PxIO io, const __grid_constant__ pxstream::PxMaps maps) {
   using namespace pxstream;
   constexpr int NT = px_compute_threads<PPT>();
   extern __shared__ __align__(128) uint8_t smem_raw[];
@@ -373,15 +373,17 @@ seg_loss_stream_kernel(const SegLossParams p, const pxstream::PxIO io) {
   float* coefA = reinterpret_cast<float*>(tail + 64);   // [CPAD]
   float* coefB = coefA + CPAD;                           // [CPAD]
   float* wsm = coefB + CPAD;                             // [CPAD]
-  float* inter_s = wsm + CPAD;                           // [CPAD] Dice intersection of the current image
-  float* tsum_s = inter_s + CPAD;                        // [CPAD] target pixel counts of the current image
-  float* red = tsum_s + CPAD;                            // reduction scratch
+  // Dice intersection / target pixel counts of the current image, PRIVATE PER WARP ([nw][CPAD] each): with one copy per
+  // CTA the two shared-memory atomics per pixel of up to 512 pixels land on <= 24 addresses and serialise (~20-way) —
+  // that, not the loads, bounded pass 1 of CE + Dice (2.9 TB/s)
+  constexpr int kNw = NT / 32;
+  float* inter_s = wsm + CPAD;                           // [kNw][CPAD]
+  float* tsum_s = inter_s + kNw * CPAD;                  // [kNw][CPAD]
+  float* red = tsum_s + kNw * CPAD;                      // reduction scratch
   const int C = p.C;
-  if (threadIdx.x < CPAD) {
-    wsm[threadIdx.x] = (threadIdx.x < C && p.class_w) ? p.class_w[threadIdx.x] : 1.f;
-    inter_s[threadIdx.x] = 0.f; tsum_s[threadIdx.x] = 0.f;
-  }
-  PixelPipe<PPT, NT> pipe(io, smem, bars);    // (its constructor synchronises the CTA)
+  if (threadIdx.x < CPAD) wsm[threadIdx.x] = (threadIdx.x < C && p.class_w) ? p.class_w[threadIdx.x] : 1.f;
+  for (int i = threadIdx.x; i < kNw * CPAD; i += blockDim.x) { inter_s[i] = 0.f; tsum_s[i] = 0.f; }
+  PixelPipe<PPT, NT> pipe(io, smem, bars, &maps);    // (its constructor synchronises the CTA)
   const float ce_scale = (PASS == 2) ? (p.has_ce ? *p.dev_scale : 0.f) : p.ce_grad_scale;
   const bool dice = (PASS == 2) && p.has_dice;
   const bool sums = (PASS == 1) && p.has_dice;
@@ -403,13 +405,16 @@ seg_loss_stream_kernel(const SegLossParams p, const pxstream::PxIO io) {
       }
       named_sync(1, NT);   // also orders every thread's shared-memory atomics of this image
       for (int c = threadIdx.x; c < C; c += NT) {
-        float sp = 0.f;
-        for (int w = 0; w < nw; ++w) sp += red[c * nw + w];
+        float sp = 0.f, si = 0.f, stt = 0.f;
+        for (int w = 0; w < nw; ++w) {
+          sp += red[c * nw + w];
+          si += inter_s[w * CPAD + c]; stt += tsum_s[w * CPAD + c];
+          inter_s[w * CPAD + c] = 0.f; tsum_s[w * CPAD + c] = 0.f;
+        }
         double* dst = p.dice_sums + ((long long)b * C + c) * 3;
-        atomicAdd(dst + 0, (double)inter_s[c]);
+        atomicAdd(dst + 0, (double)si);
         atomicAdd(dst + 1, (double)sp);
-        atomicAdd(dst + 2, (double)tsum_s[c]);
-        inter_s[c] = 0.f; tsum_s[c] = 0.f;
+        atomicAdd(dst + 2, (double)stt);
       }
       named_sync(1, NT);
     }
@@ -513,8 +518,8 @@ seg_loss_stream_kernel(const SegLossParams p, const pxstream::PxIO io) {
 #pragma unroll
             for (int j = 0; j < PPT; ++j) {
               if (y[j] >= 0) {
-                atomicAdd(inter_s + y[j], ey[j] * inv[j]);
-                atomicAdd(tsum_s + y[j], 1.f);
+                atomicAdd(inter_s + (threadIdx.x >> 5) * CPAD + y[j], ey[j] * inv[j]);
+                atomicAdd(tsum_s + (threadIdx.x >> 5) * CPAD + y[j], 1.f);
               }
             }
           }
@@ -597,8 +602,9 @@ inline bool loss_stream_enabled() {
 }
 
 template <typename T, int CPAD, int PPT, int PASS, bool FULL>
-int launch_seg_stream_t(const SegLossParams& p, const pxstream::PxIO& io, cudaStream_t st) {
-  const size_t smem = 128 + (size_t)io.stages * io.stage_bytes + 64 + 5 * CPAD * 4 +
+int launch_seg_stream_t(const SegLossParams& p, const pxstream::PxIO& io, const pxstream::PxMaps& maps, cudaStream_t st) {
+  constexpr int kNw = pxstream::px_compute_threads<PPT>() / 32;
+  const size_t smem = 128 + (size_t)io.stages * io.stage_bytes + 64 + (3 + 2 * kNw) * CPAD * 4 +
                       (CPAD * 17 + 64) * 4;
   auto kfn = seg_loss_stream_kernel<T, CPAD, PPT, PASS, FULL>;
   static bool attr = false;
@@ -606,7 +612,7 @@ int launch_seg_stream_t(const SegLossParams& p, const pxstream::PxIO& io, cudaSt
     UDA_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  kfn<<<pxstream::px_grid(io), pxstream::px_threads<PPT>(), smem, st>>>(p, io);
+  kfn<<<pxstream::px_grid(io), pxstream::px_threads<PPT>(), smem, st>>>(p, io, maps);
   UDA_LAUNCH_OK("seg_loss_stream_kernel");
   return UDA_OK;
 }
@@ -622,13 +628,15 @@ int try_seg_stream(const SegLossParams& p, cudaStream_t st) {
   io.nten = 1; io.nout = (PASS == 1) ? 0 : 1;
   io.B = p.B; io.C = p.C; io.HW = p.HW; io.esize = (int)sizeof(T);
   int ppt = 0;
-  if (!pxstream::plan_px(io, ppt, 0)) return 0;
+  // CE + Dice (two passes): 16 compute warps with one pixel each measured faster than 8 with a pixel pair (280 vs 310 us)
+  pxstream::PxMaps maps;
+  if (!pxstream::plan_px(io, ppt, 0, &maps, pxstream::kPxTile, p.has_dice ? 1 : pxstream::kDefaultPpt)) return 0;
   int rc;
 #define UDA_SEG_STREAM(CP)                                                                         \
-  rc = (p.C == CP) ? ((ppt == 2) ? launch_seg_stream_t<T, CP, 2, PASS, true>(p, io, st)            \
-                                 : launch_seg_stream_t<T, CP, 1, PASS, true>(p, io, st))           \
-                   : ((ppt == 2) ? launch_seg_stream_t<T, CP, 2, PASS, false>(p, io, st)           \
-                                 : launch_seg_stream_t<T, CP, 1, PASS, false>(p, io, st))
+  rc = (p.C == CP) ? ((ppt == 2) ? launch_seg_stream_t<T, CP, 2, PASS, true>(p, io, maps, st)            \
+                                 : launch_seg_stream_t<T, CP, 1, PASS, true>(p, io, maps, st))           \
+                   : ((ppt == 2) ? launch_seg_stream_t<T, CP, 2, PASS, false>(p, io, maps, st)           \
+                                 : launch_seg_stream_t<T, CP, 1, PASS, false>(p, io, maps, st))
   if (p.C <= 8) UDA_SEG_STREAM(8);
   else if (p.C <= 24) UDA_SEG_STREAM(24);
   else UDA_SEG_STREAM(32);
@@ -824,16 +832,19 @@ __global__ void bce_logits_kernel(const float* __restrict__ x, float* __restrict
 // seg_loss_stream_kernel's (one FMNMX, one FFMA + MUFU.EX2 and a handful of FADD/FFMA per logit) ----
 constexpr float kLn2 = 0.6931471805599453f;
 
-template <typename T, int CPAD, int PPT>
-__global__ void __launch_bounds__(pxstream::px_threads<PPT>(), 1)
-consistency_stream_kernel(const pxstream::PxIO io, double* __restrict__ acc, float inv_T, float scale) {
+// (TP = 256-pixel tiles: two logit tensors in, two gradients out — 512-pixel tiles leave room for only TWO stages of
+// 98 KB and the kernel sat at 3.2 TB/s whatever the warp count; four 49 KB stages keep loads, compute and stores apart)
+template <typename T, int CPAD, int PPT, int TP>
+__global__ void __launch_bounds__(pxstream::px_threads<PPT, TP>(), 1)
+consistency_stream_kernel(const pxstream::PxIO io, const __grid_constant__ pxstream::PxMaps maps, double* __restrict__ acc,
+                          float inv_T, float scale) {
   using namespace pxstream;
-  constexpr int NT = px_compute_threads<PPT>();
-  constexpr int RS = kPxTile * (int)sizeof(T);
+  constexpr int NT = px_compute_threads<PPT, TP>();
+  constexpr int RS = TP * (int)sizeof(T);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* tail = smem + (size_t)io.stages * io.stage_bytes;
-  PixelPipe<PPT, NT> pipe(io, smem, reinterpret_cast<uint64_t*>(tail));
+  PixelPipe<PPT, NT> pipe(io, smem, reinterpret_cast<uint64_t*>(tail), &maps);
   float* red = reinterpret_cast<float*>(tail + 64);
   const int C = io.C;
   const float k2 = inv_T * kLog2e;        // logits -> log2 units of the tempered softmax
@@ -918,14 +929,15 @@ consistency_stream_kernel(const pxstream::PxIO io, double* __restrict__ acc, flo
 
 template <typename T, int CPAD, int PPT>
 __global__ void __launch_bounds__(pxstream::px_threads<PPT>(), 1)
-entropy_stream_kernel(const pxstream::PxIO io, double* __restrict__ acc, float scale) {
+entropy_stream_kernel(const pxstream::PxIO io, const __grid_constant__ pxstream::PxMaps maps, double* __restrict__ acc,
+                      float scale) {
   using namespace pxstream;
   constexpr int NT = px_compute_threads<PPT>();
   constexpr int RS = kPxTile * (int)sizeof(T);
   extern __shared__ __align__(128) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   uint8_t* tail = smem + (size_t)io.stages * io.stage_bytes;
-  PixelPipe<PPT, NT> pipe(io, smem, reinterpret_cast<uint64_t*>(tail));
+  PixelPipe<PPT, NT> pipe(io, smem, reinterpret_cast<uint64_t*>(tail), &maps);
   float* red = reinterpret_cast<float*>(tail + 64);
   const int C = io.C;
   float lsum = 0.f;
@@ -991,11 +1003,12 @@ entropy_stream_kernel(const pxstream::PxIO io, double* __restrict__ acc, float s
   if (threadIdx.x == 0 && o[0] != 0.f) atomicAdd(acc, (double)o[0] * (double)scale);
 }
 
-template <int PPT, typename K, typename... Args>
-int launch_px_stream(K kfn, const pxstream::PxIO& io, cudaStream_t st, const char* what, Args... args) {
+template <int PPT, int TP = pxstream::kPxTile, typename K, typename... Args>
+int launch_px_stream(K kfn, const pxstream::PxIO& io, const pxstream::PxMaps& maps, cudaStream_t st, const char* what,
+                     Args... args) {
   const size_t smem = 128 + (size_t)io.stages * io.stage_bytes + 64 + 64 * 4;
   UDA_CUDA_OK(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-  kfn<<<pxstream::px_grid(io), pxstream::px_threads<PPT>(), smem, st>>>(io, args...);
+  kfn<<<pxstream::px_grid(io), pxstream::px_threads<PPT, TP>(), smem, st>>>(io, maps, args...);
   UDA_LAUNCH_OK(what);
   return UDA_OK;
 }
@@ -1003,23 +1016,32 @@ int launch_px_stream(K kfn, const pxstream::PxIO& io, cudaStream_t st, const cha
 #define UDA_PX_DISPATCH(KERN, T, ...)                                                               \
   do {                                                                                              \
     if (ppt == 2) {                                                                                 \
-      if (io.C <= 8) return launch_px_stream<2>(KERN<T, 8, 2>, io, st, #KERN, __VA_ARGS__);            \
-      if (io.C <= 16) return launch_px_stream<2>(KERN<T, 16, 2>, io, st, #KERN, __VA_ARGS__);          \
-      if (io.C <= 24) return launch_px_stream<2>(KERN<T, 24, 2>, io, st, #KERN, __VA_ARGS__);          \
-      return launch_px_stream<2>(KERN<T, 32, 2>, io, st, #KERN, __VA_ARGS__);                          \
+      if (io.C <= 8) return launch_px_stream<2>(KERN<T, 8, 2>, io, maps, st, #KERN, __VA_ARGS__);            \
+      if (io.C <= 16) return launch_px_stream<2>(KERN<T, 16, 2>, io, maps, st, #KERN, __VA_ARGS__);          \
+      if (io.C <= 24) return launch_px_stream<2>(KERN<T, 24, 2>, io, maps, st, #KERN, __VA_ARGS__);          \
+      return launch_px_stream<2>(KERN<T, 32, 2>, io, maps, st, #KERN, __VA_ARGS__);                          \
     }                                                                                               \
-    if (io.C <= 8) return launch_px_stream<1>(KERN<T, 8, 1>, io, st, #KERN, __VA_ARGS__);              \
-    if (io.C <= 16) return launch_px_stream<1>(KERN<T, 16, 1>, io, st, #KERN, __VA_ARGS__);            \
-    if (io.C <= 24) return launch_px_stream<1>(KERN<T, 24, 1>, io, st, #KERN, __VA_ARGS__);            \
-    return launch_px_stream<1>(KERN<T, 32, 1>, io, st, #KERN, __VA_ARGS__);                            \
+    if (io.C <= 8) return launch_px_stream<1>(KERN<T, 8, 1>, io, maps, st, #KERN, __VA_ARGS__);              \
+    if (io.C <= 16) return launch_px_stream<1>(KERN<T, 16, 1>, io, maps, st, #KERN, __VA_ARGS__);            \
+    if (io.C <= 24) return launch_px_stream<1>(KERN<T, 24, 1>, io, maps, st, #KERN, __VA_ARGS__);            \
+    return launch_px_stream<1>(KERN<T, 32, 1>, io, maps, st, #KERN, __VA_ARGS__);                            \
   } while (0)
 
 template <typename T>
-int consistency_stream(const pxstream::PxIO& io, int ppt, double* acc, float inv_T, float scale, cudaStream_t st) {
-  UDA_PX_DISPATCH(consistency_stream_kernel, T, acc, inv_T, scale);
+int consistency_stream(const pxstream::PxIO& io, const pxstream::PxMaps& maps, int ppt, double* acc, float inv_T, float scale,
+                       cudaStream_t st) {
+  constexpr int TP = pxstream::kPxTile / 2;
+#define UDA_CS(CP)                                                                                                  \
+  return ppt == 2 ? launch_px_stream<2, TP>(consistency_stream_kernel<T, CP, 2, TP>, io, maps, st, "consistency_stream_kernel", acc, inv_T, scale) \
+                  : launch_px_stream<1, TP>(consistency_stream_kernel<T, CP, 1, TP>, io, maps, st, "consistency_stream_kernel", acc, inv_T, scale)
+  if (io.C <= 8) UDA_CS(8);
+  if (io.C <= 16) UDA_CS(16);
+  if (io.C <= 24) UDA_CS(24);
+  UDA_CS(32);
+#undef UDA_CS
 }
 template <typename T>
-int entropy_stream(const pxstream::PxIO& io, int ppt, double* acc, float scale, cudaStream_t st) {
+int entropy_stream(const pxstream::PxIO& io, const pxstream::PxMaps& maps, int ppt, double* acc, float scale, cudaStream_t st) {
   UDA_PX_DISPATCH(entropy_stream_kernel, T, acc, scale);
 }
 
@@ -1076,7 +1098,8 @@ int consistency_dispatch(const void* z1, const void* z2, void* g1, void* g2, dou
     io.out[0] = (uint8_t*)g1; io.out[1] = (uint8_t*)g2;
     io.nten = 2; io.nout = 2; io.B = B; io.C = C; io.HW = HW; io.esize = (int)sizeof(T);
     int ppt = 0;
-    if (pxstream::plan_px(io, ppt, 0)) return consistency_stream<T>(io, ppt, acc, inv_T, scale, st);
+    pxstream::PxMaps maps;
+    if (pxstream::plan_px(io, ppt, 0, &maps, pxstream::kPxTile / 2, 1)) return consistency_stream<T>(io, maps, ppt, acc, inv_T, scale, st);
   }
   bool v2 = (HW % 2 == 0) && aligned<T>(z1, 2 * sizeof(T)) && aligned<T>(z2, 2 * sizeof(T)) &&
             aligned<T>(g1, 2 * sizeof(T)) && aligned<T>(g2, 2 * sizeof(T));
@@ -1090,7 +1113,8 @@ int entropy_dispatch(const void* z, void* g, double* acc, int B, int C, long lon
     io.in[0] = (const uint8_t*)z; io.out[0] = (uint8_t*)g;
     io.nten = 1; io.nout = 1; io.B = B; io.C = C; io.HW = HW; io.esize = (int)sizeof(T);
     int ppt = 0;
-    if (pxstream::plan_px(io, ppt, 0)) return entropy_stream<T>(io, ppt, acc, scale, st);
+    pxstream::PxMaps maps;
+    if (pxstream::plan_px(io, ppt, 0, &maps)) return entropy_stream<T>(io, maps, ppt, acc, scale, st);
   }
   bool v2 = (HW % 2 == 0) && aligned<T>(z, 2 * sizeof(T)) && aligned<T>(g, 2 * sizeof(T));
   UDA_DISPATCH_CV(launch_entropy, T, C, v2, z, g, acc, B, C, HW, scale, st);

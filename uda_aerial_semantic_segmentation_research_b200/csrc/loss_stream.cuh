@@ -8,6 +8,7 @@
 // stores.  Up to four stages (~200 KB per SM) are in flight, independent of the register file.
 #pragma once
 #include "stream_common.cuh"
+#include <stdlib.h>
 
 namespace uda {
 namespace pxstream {
@@ -17,14 +18,21 @@ using namespace stream;
 constexpr size_t kSmemBudget = 220 * 1024;   // stages; coefficient / reduction scratch lives above it
 constexpr int kDefaultPpt = 2;
 constexpr int kPxTile = 512;                 // pixels per tile = compute threads x pixels per thread
-template <int PPT> constexpr int px_compute_threads() { return kPxTile / PPT; }
-template <int PPT> constexpr int px_threads() { return kPxTile / PPT + 32; }   // + the IO warp
+template <int PPT, int TP = kPxTile> constexpr int px_compute_threads() { return TP / PPT; }
+template <int PPT, int TP = kPxTile> constexpr int px_threads() { return TP / PPT + 32; }   // + the IO warp
+
+// One tensor map per logit / gradient tensor: [B*C][HW] seen as {256 pixels, HW/256, B*C}, box {256, TP/256, C} — the
+// whole [C][TP] tile of a stage is ONE cp.async.bulk.tensor instruction.  With one bulk copy per class row the kernels
+// were bound by the per-copy cost (~100 clocks per copy and SM: 96 copies per tile of the consistency kernel, 505 us
+// for fp32 and bf16 alike), not by HBM.
+struct alignas(64) PxMaps { CUtensorMap in[2]; CUtensorMap out[2]; };
 
 struct PxIO {
   const uint8_t* in[2];       // nten tensors [B,C,HW]
   uint8_t* out[2];            // nout in {0, nten}: gradients, written from the same shared-memory rows
   const long long* target;    // [B,HW] or null
   int nten, nout, B, C, esize, stages, tiles_per_img, tiles_per_cta;
+  int use_maps;               // tiles travel through the tensor maps (HW % 256 == 0), else one bulk copy per class row
   long long HW, total_tiles;
   uint32_t stage_bytes;
 };
@@ -38,14 +46,16 @@ __device__ __forceinline__ void named_sync(int id, int nthreads) {
 // stage freed LAG tiles earlier, so neither the store drain nor the copy-issue latency sits on the compute path.
 template <int PPT, int NT>
 struct PixelPipe {
-  static constexpr int TP = NT * PPT;
-  static_assert(TP == kPxTile, "tile size");
+  static constexpr int TP = NT * PPT;     // pixels per tile: 512, or 256 for the two-tensor kernels (four stages)
+  static_assert(TP == kPxTile || TP == kPxTile / 2, "tile size");
   const PxIO& io;
+  const PxMaps* maps;
   uint8_t* smem;
   uint32_t full_base, done_base;
   long long t_begin;
   int n_my;
-  __device__ PixelPipe(const PxIO& io_, uint8_t* smem_, uint64_t* bars) : io(io_), smem(smem_) {
+  __device__ PixelPipe(const PxIO& io_, uint8_t* smem_, uint64_t* bars, const PxMaps* maps_ = nullptr)
+      : io(io_), maps(maps_), smem(smem_) {
     full_base = smem_u32(bars);
     done_base = full_base + 8u * 4;
     t_begin = (long long)blockIdx.x * io.tiles_per_cta;
@@ -88,6 +98,14 @@ struct PixelPipe {
     const long long p0 = pixel0_of(k);
     const uint32_t bar = full_base + 8u * (k % io.stages);
     const uint32_t rb = (uint32_t)np * io.esize;
+    if (io.use_maps) {     // the whole [C][TP] tile of each tensor in one instruction (out-of-range pixels read as zero)
+      if (lane == 0) mbar_expect_tx(bar, (uint32_t)(TP * io.esize) * io.nten * io.C + (io.target ? (uint32_t)np * 8u : 0u));
+      __syncwarp();
+      if (lane < io.nten) tc::tma_load_3d(smem_u32(row(k, lane, 0)), &maps->in[lane], bar, 0, (int)(p0 / 256), b * io.C);
+      if (io.target && lane == 31)
+        bulk_load(smem_u32(target_row(k)), io.target + (long long)b * io.HW + p0, (uint32_t)np * 8u, bar);
+      return;
+    }
     if (lane == 0) mbar_expect_tx(bar, rb * io.nten * io.C + (io.target ? (uint32_t)np * 8u : 0u));
     __syncwarp();
     for (int r = lane; r < io.nten * io.C; r += 32) {
@@ -108,10 +126,14 @@ struct PixelPipe {
         const int b = image_of(k);
         const long long p0 = pixel0_of(k);
         const uint32_t rb = (uint32_t)npix_of(k) * io.esize;
-        for (int r = lane; r < io.nout * io.C; r += 32) {
-          const int i = r >= io.C ? 1 : 0, c = r - i * io.C;
-          bulk_store((i ? io.out[1] : io.out[0]) + (((long long)b * io.C + c) * io.HW + p0) * io.esize,
-                     smem_u32(row(k, i, c)), rb);
+        if (io.use_maps) {
+          if (lane < io.nout) tc::tma_store_3d(&maps->out[lane], smem_u32(row(k, lane, 0)), 0, (int)(p0 / 256), b * io.C);
+        } else {
+          for (int r = lane; r < io.nout * io.C; r += 32) {
+            const int i = r >= io.C ? 1 : 0, c = r - i * io.C;
+            bulk_store((i ? io.out[1] : io.out[0]) + (((long long)b * io.C + c) * io.HW + p0) * io.esize,
+                       smem_u32(row(k, i, c)), rb);
+          }
         }
         bulk_commit();   // bulk groups are per thread: every lane tracks the rows it stored
         // the stage of tile k-lag is free once ITS stores have read shared memory: refill it
@@ -160,7 +182,8 @@ template <> __device__ __forceinline__ void st_px<__nv_bfloat16, 2>(uint8_t* r, 
 
 // Host: choose pixels-per-thread and stage count for nten tensors of C classes; false when the streaming path
 // does not apply (alignment, too many classes for the shared-memory budget, tiny tensors).
-inline bool plan_px(PxIO& io, int& ppt, size_t extra_smem) {
+inline bool plan_px(PxIO& io, int& ppt, size_t extra_smem, PxMaps* maps = nullptr, int tile_px = kPxTile,
+                    int prefer_ppt = kDefaultPpt) {
   if (io.C > 32 || io.HW <= 0) return false;
   if ((io.HW * io.esize) % 16 != 0 || (io.target && (io.HW * 8) % 16 != 0)) return false;
   for (int i = 0; i < io.nten; ++i)
@@ -170,8 +193,8 @@ inline bool plan_px(PxIO& io, int& ppt, size_t extra_smem) {
   (void)extra_smem;
   // pixel pairs per thread (8 compute warps) or single pixels (16 compute warps); UDA_B200_LOSS_PPT overrides
   static const int forced = [] { const char* e = getenv("UDA_B200_LOSS_PPT"); return e ? atoi(e) : 0; }();
-  ppt = forced == 1 ? 1 : (forced == 2 ? 2 : kDefaultPpt);
-  const size_t tp = kPxTile;
+  ppt = forced == 1 ? 1 : (forced == 2 ? 2 : prefer_ppt);
+  const size_t tp = (size_t)tile_px;
   const size_t sb = (size_t)io.nten * io.C * tp * io.esize + (io.target ? tp * 8 : 0);
   const int st = (int)(kSmemBudget / sb);
   if (st < 2) return false;
@@ -183,6 +206,17 @@ inline bool plan_px(PxIO& io, int& ppt, size_t extra_smem) {
   if (((io.HW % tp) * io.esize) % 16 != 0) return false;
   const long long grid = io.total_tiles < num_sms() ? io.total_tiles : num_sms();
   io.tiles_per_cta = (int)((io.total_tiles + grid - 1) / grid);
+  io.use_maps = 0;
+  static const bool maps_on = [] { const char* e = getenv("UDA_B200_LOSS_TMA"); return !(e && e[0] == '0'); }();
+  if (maps && maps_on && io.HW % 256 == 0 && tp % 256 == 0 && io.C <= 256) {
+    const uint64_t dims[3] = {256, (uint64_t)(io.HW / 256), (uint64_t)io.B * io.C};
+    const uint64_t str[2] = {256ull * io.esize, (uint64_t)io.HW * io.esize};
+    const uint32_t box[3] = {256, (uint32_t)(tp / 256), (uint32_t)io.C};
+    bool ok = true;
+    for (int i = 0; i < io.nten && ok; ++i) ok = tc::make_tmap_plain(&maps->in[i], io.esize, io.in[i], 3, dims, str, box);
+    for (int i = 0; i < io.nout && ok; ++i) ok = tc::make_tmap_plain(&maps->out[i], io.esize, io.out[i], 3, dims, str, box);
+    io.use_maps = ok ? 1 : 0;
+  }
   return true;
 }
 inline unsigned px_grid(const PxIO& io) { return (unsigned)((io.total_tiles + io.tiles_per_cta - 1) / io.tiles_per_cta); }
