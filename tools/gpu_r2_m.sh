@@ -1,9 +1,8 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_gpu_bnfuse.py -q -m gpu --tb=short -p no:cacheprovider 2>&1 | grep -v "^E    +" | tail -12
-timeout 600 env UDA_B200_FUSE_BN_APPLY=1 python tools/trace_step.py > gpurun_out/r02_trace_step_epi8_bnfuse.txt 2> gpurun_out/trace_step.err; echo "== trace_step fused exit $? =="; tail -3 gpurun_out/trace_step.err; grep -A1 "phalo+bn" gpurun_out/r02_trace_step_epi8_bnfuse.txt | head -6;  grep -A1 "persist+bn" gpurun_out/r02_trace_step_epi8_bnfuse.txt | head -24
-for name in bnfuse base bnfuse2; do
-  if [[ $name == bnfuse* ]]; then export UDA_B200_FUSE_BN_APPLY=1; else export UDA_B200_FUSE_BN_APPLY=0; fi
+timeout 300 python -m pytest tests/test_gpu_bnfuse.py -q -m gpu --tb=short -p no:cacheprovider 2>&1 | grep -v "^E    +" | tail -6
+timeout 600 python tools/trace_step.py > gpurun_out/r02_trace_step.txt 2> gpurun_out/trace_step.err; echo "== trace_step fused exit $? =="; tail -3 gpurun_out/trace_step.err; grep -A1 "persist+bn" gpurun_out/r02_trace_step.txt | head -30 | cut -c1-200
+for name in a b; do
   timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu-baseline --no-sub > gpurun_out/bench_$name.log 2> gpurun_out/bench_$name.err; echo "== bench $name exit $? =="
   python - "$name" <<'PY'
 import json, sys

@@ -95,6 +95,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
       for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
       for (int q = 0; q < 2; ++q) { mbar_init(tfull_bar(q), 1); mbar_init(tempty_bar(q), kEpiWarps); }
       mbar_init(ws_bar, 1);
+      if (FUSE) mbar_init(bar_base + 8u * (2 * kMaxStages + 6), 1);   // residual rows landed (fused BatchNorm pass 2)
       fence_barrier_init();
     }
     __syncwarp();
@@ -219,7 +220,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if constexpr (FUSE) {
       // ---- conv + BatchNorm + activation in one launch (BnFuse): this CTA's (<= kSets) tiles stay in TMEM across
       // the grid barrier; one tap class, BN >= 64 ----
-      float* const s_tab = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);   // [kSets][2][BN] scale | shift
+      float* const s_tab = reinterpret_cast<float*>(bars + 2 * kMaxStages + 8);   // [2][BN] scale | shift of the current tile
       const int et = threadIdx.x - 64;   // index among the epilogue threads
       // pass 1: statistics of the bf16-rounded outputs; the accumulator sets are NOT released
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
@@ -289,34 +290,51 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         }
       }
       UDA_TR(if (trp && warp == 2 && lane == 0) trp[5] = clock64() - tr0;)      // pass 1 done
+      // Every MMA of this CTA has completed (the loop above waited for its last accumulator): the operand ring is free.
+      // The residual rows of a tile arrive there through bulk copies (the first tile's are issued BEFORE the barrier),
+      // pass 2 reads them conflict-free (row pitch + 16 bytes) and stages a = act(z*scale + shift (+ residual)) for one
+      // bulk store per row — the register-file version of this pass (row-strided 16-byte global loads and stores from
+      // 8 warps) took 8 us per launch without and 14-20 us with a residual (profiles/r02_trace_step.txt).
+      using stream::bulk_load; using stream::bulk_store; using stream::bulk_commit; using stream::fence_async_smem;
+      constexpr int kRowB = BN * 2, kPitch = kRowB + 16, kRows = MT * 128;
+      static_assert(kRows <= kEpiThreads, "one epilogue thread per tile row");
+      uint8_t* const st_r = smem + ws_bytes;               // [kRows][kPitch] residual rows of the current tile
+      uint8_t* const st_a = st_r + kRows * kPitch;         // [kRows][kPitch] a of the current tile
+      const uint32_t rbar = bar_base + 8u * (2 * kMaxStages + 6);
+      const bf16* const res = (const bf16*)p.fuse.residual;
+      bf16* const aout = (bf16*)p.fuse.a_out;
+      const float slope = p.fuse.slope;
+      const int n_mine = j;
+      auto tile_pix0 = [&](int t) {          // a tile's 128*MT pixels are contiguous (plan_tiles)
+        const int mt = t % p.m_tiles;
+        const int grp = mt / tiles_per_group, tin = mt % tiles_per_group;
+        const int b0 = grp * p.NB, h0 = (tin / p.tiles_w) * p.TH, w0 = (tin % p.tiles_w) * p.TW;
+        return ((long long)b0 * p.OH + h0) * p.OW + w0;
+      };
+      auto load_res = [&](int t) {
+        if (!res) return;
+        if (et == 0) mbar_expect_tx(rbar, (uint32_t)kRows * kRowB);
+        if (et < kRows)
+          bulk_load(smem_u32(st_r + et * kPitch), res + (tile_pix0(t) + et) * p.Cout + (t / p.m_tiles) * BN, kRowB, rbar);
+      };
+      if (n_mine > 0) load_res(blockIdx.x);
       grid_barrier(p.fuse.counter, gridDim.x, 2, kEpiThreads, et == 0);
+      UDA_TR(if (trp && warp == 2 && lane == 0) trp[13] = clock64() - tr0;)     // barrier passed
       j = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
         const int mt = t % p.m_tiles, n0 = (t / p.m_tiles) * BN;
-        float* const sc = s_tab + j * 2 * BN;
+        const long long pix0 = tile_pix0(t);
+        float* const sc = s_tab;
         for (int ch = et; ch < BN; ch += kEpiThreads) {
           bn_fuse_coeffs(p.fuse, p.bn_sums, p.Cout, n0 + ch, sc[ch], sc[BN + ch]);
           if (mt == 0) bn_fuse_publish(p.fuse, p.bn_sums, p.Cout, n0 + ch);
         }
-      }
-      bar_sync(2, kEpiThreads);
-      UDA_TR(if (trp && warp == 2 && lane == 0) trp[13] = clock64() - tr0;)     // barrier passed, coefficients ready
-      // pass 2: a = act(z*scale + shift (+ residual)) from the accumulators still in TMEM
-      const bf16* const res = (const bf16*)p.fuse.residual;
-      bf16* const aout = (bf16*)p.fuse.a_out;
-      const float slope = p.fuse.slope;
-      j = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
-        const int mt = t % p.m_tiles, n0 = (t / p.m_tiles) * BN;
-        const int grp = mt / tiles_per_group, tin = mt % tiles_per_group;
-        const int b0 = grp * p.NB, h0 = (tin / p.tiles_w) * p.TH, w0 = (tin % p.tiles_w) * p.TW;
-        const float* const sc = s_tab + j * 2 * BN;
+        if (j > 0 && et < kRows) stream::bulk_wait_read<0>();      // the previous tile's a rows have left st_a
+        bar_sync(2, kEpiThreads);
+        if (res) mbar_wait(rbar, (uint32_t)(j & 1));
 #pragma unroll 1
         for (int sub = 0; sub < MT; ++sub) {
           const int r = sub * 128 + qw * 32 + lane;
-          const int nb = r / (p.TH * p.TW);
-          const int th = (r / p.TW) % p.TH, tw = r % p.TW;
-          const long long pix = ((long long)(b0 + nb) * p.OH + (h0 + th)) * p.OW + (w0 + tw);
           const uint32_t tbase = tmem_base + ((uint32_t)(qw * 32) << 16) + (uint32_t)j * kAccCols + (uint32_t)sub * BN;
 #pragma unroll
           for (int c0 = 0; c0 < BN; c0 += 32) {
@@ -324,7 +342,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             uint32_t v[32];
             tmem_ld_32x32(tbase + (uint32_t)c0, v);
             tmem_ld_wait();
-            const long long off = pix * p.Cout + n0 + c0;
+            const long long off = (pix0 + r) * p.Cout + n0 + c0;
 #pragma unroll
             for (int k = 0; k < 32; k += 8) {
               float z8[8], a8[8], r8[8];
@@ -335,7 +353,7 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 #pragma unroll
                 for (int e = 0; e < 8; ++e) z8[e] += a8[e];
               }
-              if (res) ld_vec<8>(res + off + k, r8);
+              if (res) stream::lds8(st_r + r * kPitch + (c0 + k) * 2, r8);
 #pragma unroll
               for (int e = 0; e < 8; ++e) {
                 const float zr = __bfloat162float(__float2bfloat16_rn(z8[e]));
@@ -343,11 +361,19 @@ conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 if (res) y += r8[e];
                 a8[e] = y > 0.f ? y : y * slope;
               }
-              st_vec<8>(aout + off + k, a8);
+              stream::sts8(st_a + r * kPitch + (c0 + k) * 2, a8);
             }
           }
         }
+        fence_async_smem();
+        bar_sync(2, kEpiThreads);                 // a staged, residual rows and coefficient table consumed
+        if (t + (int)gridDim.x < total_tiles) load_res(t + gridDim.x);
+        if (et < kRows) {
+          bulk_store(aout + (pix0 + et) * p.Cout + n0, smem_u32(st_a + et * kPitch), kRowB);
+          bulk_commit();
+        }
       }
+      if (et < kRows) stream::bulk_wait_read<0>();   // shared memory must outlive the copies' reads
       UDA_TR(if (trp && warp == 2 && lane == 0) { trp[8] = tr_wt; trp[10] = clock64() - tr0; })
     } else {
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++j) {
@@ -500,7 +526,7 @@ int launch_persist(const CUtensorMap& ma, const CUtensorMap& mb, PParams& p, int
   if (S > kMaxStages) S = kMaxStages;
   UDA_REQUIRE(S >= 2, UDA_ERR_UNSUPPORTED, "conv_tc_persist: not enough shared memory for a 2-stage ring");
   p.stages = S;
-  const int smem = (p.ws ? ws_bytes : 0) + S * stage_bytes + 1024 + 512 + (FUSE ? kSetsH * 2 * BN * 4 : 0);
+  const int smem = (p.ws ? ws_bytes : 0) + S * stage_bytes + 1024 + 512 + (FUSE ? 2 * BN * 4 + 64 : 0);
   static int configured = 0;
   if (configured < smem) {
     UDA_CUDA_OK(cudaFuncSetAttribute(conv_tc_persist_kernel<KC, BN, MT, FUSE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -508,8 +534,10 @@ int launch_persist(const CUtensorMap& ma, const CUtensorMap& mb, PParams& p, int
     configured = 227 * 1024;
   }
   int grid = total_tiles < num_sms() ? total_tiles : num_sms();
-  // fused BatchNorm: all tiles of a CTA must still be in TMEM at the grid barrier
-  if (FUSE && (total_tiles + grid - 1) / grid > kSetsH) return UDA_ERR_UNSUPPORTED;
+  // fused BatchNorm: all tiles of a CTA must still be in TMEM at the grid barrier, and pass 2 stages one tile's residual
+  // and output rows in the (then idle) operand ring
+  if (FUSE && ((total_tiles + grid - 1) / grid > kSetsH || S * stage_bytes < 2 * MT * 128 * (BN * 2 + 16)))
+    return UDA_ERR_UNSUPPORTED;
   UDA_CUDA_OK(launch_pdl(conv_tc_persist_kernel<KC, BN, MT, FUSE>, dim3(grid), dim3(kThreads), smem, st, ma, mb, p));
   UDA_LAUNCH_OK("conv_tc_persist_kernel");
   return UDA_OK;
