@@ -10,6 +10,7 @@
 // Each image row of 128 pixels is one M=128 accumulator; all weights stay resident in shared memory;
 // two accumulator sets in TMEM overlap the epilogue of tile j with the MMAs of tile j+1.
 #include "conv_tc_internal.cuh"
+#include <stdlib.h>
 
 namespace uda {
 namespace tcconv {
@@ -31,7 +32,13 @@ struct HParams {
   int act; float act_slope;            // GemmConv::act
   const bf16* st_a; const bf16* st_z; float st_slope; double* st_sums;   // GemmConv::st_*
   long long* trace;   // experiment builds only: per-CTA trace records (conv_tc_internal.cuh)
+  int debug;          // experiment builds only (UDA_B200_TC_DEBUG bit mask): 1 = no epilogue stores, 8 = no statistics
 };
+#ifdef UDA_B200_EXPERIMENTS
+#define UDA_H_DBG(p, bit) ((p).debug & (bit))
+#else
+#define UDA_H_DBG(p, bit) false
+#endif
 
 template <int KC, int BN, int R>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -209,7 +216,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
             for (int k = 0; k < 32; ++k) f[k] = f[k] > 0.f ? f[k] : f[k] * p.act_slope;
           }
-          if (p.bn_sums) {
+          if (p.bn_sums && !UDA_H_DBG(p, 8)) {
             if constexpr (kLate) {
 #pragma unroll
               for (int k = 0; k < 32; ++k) {
@@ -232,7 +239,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               bn_q[c0 / 32] += warp_column_sums(gv, lane);
             }
           }
-          if (p.out) {
+          if (p.out && !UDA_H_DBG(p, 1)) {
             bf16* dst = p.out + pix * p.Cout + c0;
 #pragma unroll
             for (int k = 0; k < 32; k += 8) {
@@ -244,7 +251,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               }
             }
           }
-          if (p.out_nchw) {
+          if (p.out_nchw && !UDA_H_DBG(p, 1)) {
             const long long hw = (long long)p.H * p.W;
             float* dst = p.out_nchw + ((long long)b * p.Cout + c0) * hw + (long long)h * p.W + w;
 #pragma unroll
@@ -341,6 +348,9 @@ int run_gemm_conv_halo(const GemmConv& g, cudaStream_t st) {
   p.st_a = (const bf16*)g.st_a; p.st_z = (const bf16*)g.st_z; p.st_slope = g.st_slope; p.st_sums = g.st_sums;
   if (g.st_sums && (!g.st_a || !g.out || g.bn_sums || BN < 64)) return UDA_ERR_UNSUPPORTED;
   UDA_TR(p.trace = take_trace_slice();)
+#ifdef UDA_B200_EXPERIMENTS
+  { const char* e = getenv("UDA_B200_TC_DEBUG"); p.debug = e ? atoi(e) : 0; }   // timing experiments that SKIP WORK
+#endif
   CUtensorMap ma, mb;
   {
     const uint64_t C = (uint64_t)g.Cred;
