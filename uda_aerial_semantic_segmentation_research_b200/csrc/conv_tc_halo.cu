@@ -40,7 +40,15 @@ struct HParams {
 #define UDA_H_DBG(p, bit) false
 #endif
 
-template <int KC, int BN, int R>
+// NP ("N-packed", BN = 32 instances): at N <= 64 a tcgen05.mma holds the issue slot for a flat ~55 clocks whatever N is,
+// and the 16- / 32-channel layers were bound by exactly that — 72 instructions per 1024-pixel tile (experiment build:
+// dec4.c2 still takes 110k clocks per CTA with the stores AND the statistics switched off = 2016 instructions x 55).
+// With NP the N dimension also carries the kernel row: for ONE halo row rx of X and one kw, the weight rows of
+// kh = 2, 1, 0 are three N atoms (three consecutive 32-row weight boxes in shared memory) that accumulate into the
+// three consecutive output rows rx-2, rx-1, rx of the TMEM accumulator — (R+2) x 3 instructions per channel chunk and
+// tile instead of R x 9 (dec4.c2: 40 instead of 72).  Output row rx is written for the first time by halo row rx, so
+// that instruction is issued apart from the two rows that already hold data.
+template <int KC, int BN, int R, bool NP>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                     const HParams p) {
@@ -97,9 +105,17 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     if (elect_one()) {
       UDA_TR(long long tr_w = 0;)
       mbar_expect_tx(ws_bar, ws_bytes);
-      for (int t = 0; t < 9; ++t)
-        for (int kc = 0; kc < p.kchunks; ++kc)
-          tma_load_2d(ws_base + (t * p.kchunks + kc) * kBBytes, &map_b, ws_bar, t * p.Cred + kc * KC, 0);
+      if constexpr (NP) {      // [kw][channel chunk][kh = 2, 1, 0]: the three kernel rows of a (kw, chunk) are adjacent N atoms
+        for (int kw = 0; kw < 3; ++kw)
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            for (int jj = 0; jj < 3; ++jj)
+              tma_load_2d(ws_base + ((kw * p.kchunks + kc) * 3 + jj) * kBBytes, &map_b, ws_bar,
+                          ((2 - jj) * 3 + kw) * p.Cred + kc * KC, 0);
+      } else {
+        for (int t = 0; t < 9; ++t)
+          for (int kc = 0; kc < p.kchunks; ++kc)
+            tma_load_2d(ws_base + (t * p.kchunks + kc) * kBBytes, &map_b, ws_bar, t * p.Cred + kc * KC, 0);
+      }
       int it = 0;
       for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
         const int b = t / tiles_per_img, tin = t % tiles_per_img;
@@ -132,6 +148,33 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           UDA_TR(if (!tr_first) tr_first = clock64() - tr0;)
           tc_fence_after();
           const uint32_t halo = ring_base + s * kHaloStride;
+          if constexpr (NP) {
+            constexpr uint32_t id1 = make_idesc_bf16(128, BN), id2 = make_idesc_bf16(128, 2 * BN), id3 = make_idesc_bf16(128, 3 * BN);
+#pragma unroll 1
+            for (int rx = 0; rx < R + 2; ++rx) {
+              // N atom j <-> output row rx-2+j (kh = 2-j); only rows inside the tile
+              const int j_lo = rx < 2 ? 2 - rx : 0, j_hi = (R + 1 - rx) < 2 ? (R + 1 - rx) : 2;
+              const bool fresh = kc == 0 && rx < R;        // output row rx has not been written in this tile yet
+              const uint32_t d0 = acc + (uint32_t)(rx - 2 + j_lo) * BN;
+              const int n = j_hi - j_lo + 1;
+              const uint32_t idn = n == 3 ? id3 : (n == 2 ? id2 : id1);
+#pragma unroll
+              for (int kw = 0; kw < 3; ++kw) {
+                const uint64_t adesc = make_kmajor_desc(halo + (rx * kHaloW + kw) * kRowB, kRowB);
+                const uint32_t wrow = ws_base + ((kw * p.kchunks + kc) * 3) * kBBytes;
+                const uint64_t bdesc = make_kmajor_desc(wrow + j_lo * kBBytes, kRowB);
+#pragma unroll
+                for (int k = 0; k < KC / 16; ++k) {
+                  if (fresh && kw == 0 && k == 0) {
+                    if (j_lo < 2) umma_bf16(d0, adesc, bdesc, j_lo == 0 ? id2 : id1, 1u);              // rows rx-2 / rx-1
+                    umma_bf16(acc + (uint32_t)rx * BN, adesc, make_kmajor_desc(wrow + 2 * kBBytes, kRowB), id1, 0u);   // row rx
+                  } else {
+                    umma_bf16(d0, adesc + 2ull * k, bdesc + 2ull * k, idn, 1u);
+                  }
+                }
+              }
+            }
+          } else {
 #pragma unroll 1
           for (int sub = 0; sub < R; ++sub) {
 #pragma unroll
@@ -146,6 +189,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                           (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
             }
           }
+          }   // !NP
           umma_commit(empty_bar(s));
         }
         umma_commit(tfull_bar(q));
@@ -290,7 +334,7 @@ conv_tc_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   }
 }
 
-template <int KC, int BN, int R>
+template <int KC, int BN, int R, bool NP = false>
 int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, HParams& p, cudaStream_t st) {
   constexpr int kHaloBytes = (R + 2) * kHaloW * KC * 2;
   constexpr int kHaloStride = (kHaloBytes + 1023) / 1024 * 1024;
@@ -302,12 +346,12 @@ int launch_halo(const CUtensorMap& ma, const CUtensorMap& mb, HParams& p, cudaSt
   const int smem = ws_bytes + S * kHaloStride + 1024 + 256;
   static bool configured = false;
   if (!configured) {
-    UDA_CUDA_OK(cudaFuncSetAttribute(conv_tc_halo_kernel<KC, BN, R>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    UDA_CUDA_OK(cudaFuncSetAttribute(conv_tc_halo_kernel<KC, BN, R, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      227 * 1024));
     configured = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  UDA_CUDA_OK(launch_pdl(conv_tc_halo_kernel<KC, BN, R>, dim3(grid), dim3(kThreads), smem, st, ma, mb, p));
+  UDA_CUDA_OK(launch_pdl(conv_tc_halo_kernel<KC, BN, R, NP>, dim3(grid), dim3(kThreads), smem, st, ma, mb, p));
   UDA_LAUNCH_OK("conv_tc_halo_kernel");
   return UDA_OK;
 }
@@ -366,8 +410,14 @@ int run_gemm_conv_halo(const GemmConv& g, cudaStream_t st) {
     uint32_t box[2] = {(uint32_t)KC, (uint32_t)BN};
     if (int rc = make_tmap_bf16(&mb, g.wmat, 2, dims, str, box, KC * 2)) return rc;
   }
-#define UDA_H(KCv, BNv, Rv) \
-  if (KC == KCv && BN == BNv && R == Rv) return launch_halo<KCv, BNv, Rv>(ma, mb, p, st);
+  // UDA_B200_HALO_NPACK=0 keeps one instruction group per tap for the BN = 32 instances (read on every call: A/B, tests)
+  const char* const env_np = getenv("UDA_B200_HALO_NPACK");
+  const bool npack = BN == 32 && !(env_np && env_np[0] == '0');
+#define UDA_H(KCv, BNv, Rv)                                                                  \
+  if (KC == KCv && BN == BNv && R == Rv) {                                                   \
+    if constexpr (BNv == 32) { if (npack) return launch_halo<KCv, BNv, Rv, true>(ma, mb, p, st); } \
+    return launch_halo<KCv, BNv, Rv>(ma, mb, p, st);                                         \
+  }
 #define UDA_HK(KCv) \
   UDA_H(KCv, 32, 8) UDA_H(KCv, 32, 4) UDA_H(KCv, 32, 2) UDA_H(KCv, 64, 4) UDA_H(KCv, 64, 2) UDA_H(KCv, 128, 2)
   UDA_HK(16) UDA_HK(32) UDA_HK(64)
