@@ -99,10 +99,12 @@ def test_closed_form_kats():
     assert torch.allclose(g.grad, torch.full((5,), -0.3, device=dev))
 
 
-# the last two shapes are large enough (>= 1 MiB of logits) for the bulk-copy streaming kernels, with CTAs that
-# cross image boundaries; (2, 19, ...) exercises the padded-class instance
+# the last shapes are large enough (>= 1 MiB of logits) for the streaming kernels, with CTAs that cross image
+# boundaries; (2, 19, ...) exercises the padded-class instance; 144 x 112 = 63 x 256 pixels per image: the tensor-map
+# path with a PARTIAL last 512-pixel tile (out-of-range half zero-filled on load, clipped on store); 136 x 120 is not a
+# multiple of 256 pixels: the row-copy path
 @pytest.mark.parametrize("shape", [(2, 24, 64, 64), (1, 23, 37, 53), (3, 5, 8, 8), (2, 33, 16, 16),
-                                   (3, 24, 128, 128), (2, 19, 128, 96)])
+                                   (3, 24, 128, 128), (2, 19, 128, 96), (2, 24, 144, 112), (2, 24, 136, 120)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_against_oracle(shape, dtype):
     """Odd class counts / ragged sizes (scalar path), C > 32 (64-wide instance), bf16 logits."""
