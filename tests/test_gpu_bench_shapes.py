@@ -158,3 +158,34 @@ def test_decoder_conv1_without_materialised_concat(blk):
     dw = torch.zeros((O, 3, 3, C1 + C2), device=DEV)
     ops.upconv_merge_wgrad(dw4, dws, dw, C1)
     assert rel_err(dw, dwr) < 2e-3, name
+
+
+@pytest.mark.parametrize("shape", [(16, 256, 32, 16, True), (16, 128, 64, 32, False), (2, 4, 32, 8, True),
+                                   (3, 6, 96, 24, True)],
+                         ids=["dec4", "dec3", "tiny", "c96_o24"])
+def test_transposed_conv_halo_kernel_matches_persistent_path_and_oracle(shape, monkeypatch):
+    """``uda_upconv_tc_fwd`` on wide images with <= 32 output channels runs ``conv_tc_uphalo_kernel`` (x halo loaded once,
+    all four output parities in one accumulator set, N-packed instructions): same result as the four-tap-class launch of
+    the persistent kernel (UDA_B200_UPHALO=0) up to accumulation order, and both against the fp32 oracle
+    conv3x3(upsample2x(x)) on the device; BatchNorm statistics of the bf16-rounded output."""
+    from uda_aerial_semantic_segmentation_research_b200 import ops
+    Bn, h, C1, O, with_sums = shape
+    w_lo = 128 if h < 64 else h          # the kernel needs w % 128 == 0
+    x = _rand((Bn, h, w_lo, C1), 31)
+    w = _rand((O, 3, 3, C1), 32, (9 * C1) ** -0.5)
+    wx, _ = ops.upconv_split_weights(w, C1)
+    yr = R.conv_fwd(R.upcat_fwd(x.float(), None), w.float(), None, 1, 1)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("UDA_B200_UPHALO", mode)
+        sums = torch.zeros(2 * O, dtype=torch.float64, device=DEV) if with_sums else None
+        y = ops.upconv_fwd(x, wx, bn_sums=sums)
+        torch.cuda.synchronize()
+        assert rel_err(y.float(), yr) < 1e-2, (shape, mode)
+        if with_sums:
+            yf = y.double().reshape(-1, O)
+            assert rel_err(sums[O:], (yf * yf).sum(0)) < 1e-4, (shape, mode)
+            assert float((sums[:O] - yf.sum(0)).abs().max()) < 1e-3 * float(yf.abs().sum(0).max()), (shape, mode)
+        res[mode] = y
+    assert rel_err(res["1"].float(), res["0"].float()) < 1e-2
+    assert float((res["1"].float() - res["0"].float()).abs().mean()) < 2e-3 * float(res["0"].float().abs().mean())

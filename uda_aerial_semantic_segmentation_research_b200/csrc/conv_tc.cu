@@ -1105,6 +1105,10 @@ extern "C" int uda_upconv_tc_fwd(const void* x, const void* wx_ft, const float* 
                                  void* y, double* bn_sums, int B, int H, int W, int C1, int Cout, void* stream) {
   UDA_REQUIRE(x && wx_ft && y, UDA_ERR_BAD_ARG, "upconv_tc_fwd: null pointer");
   UDA_REQUIRE(use_persistent(), UDA_ERR_UNSUPPORTED, "upconv_tc_fwd: needs the persistent kernels");
+  if (!bias && !addend && act_slope == 1.f && H % 2 == 0 && W % 2 == 0) {   // wide, few-channel blocks: halo kernel
+    const int rc = run_upconv_halo(x, wx_ft, y, bn_sums, B, H / 2, W / 2, C1, Cout, (cudaStream_t)stream);
+    if (rc != UDA_ERR_UNSUPPORTED) return rc;
+  }
   return run_dgrad(x, wx_ft, addend, y, B, H, W, Cout, C1, 4, 4, 2, 1, (cudaStream_t)stream, nullptr, nullptr, 0.f, nullptr,
                    bias, bn_sums, act_slope != 1.f ? 1 : 0, act_slope);
 }

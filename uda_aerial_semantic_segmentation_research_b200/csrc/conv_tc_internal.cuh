@@ -257,6 +257,10 @@ int run_gemm_conv_halo(const GemmConv& g, cudaStream_t st);
 // conv_tc_phalo.cu: pitched-halo kernel for 3x3 stride-1 convolutions on narrow images (W = 32 / 64) with 64-multiple
 // channel counts; UDA_ERR_UNSUPPORTED (no message) otherwise
 int run_gemm_conv_phalo(const GemmConv& g, cudaStream_t st);
+// conv_tc_uphalo.cu: conv_transpose4x4_s2_p1 on wide images with <= 32 output channels (decoder conv1, x half);
+// UDA_ERR_UNSUPPORTED (no message) otherwise
+int run_upconv_halo(const void* x, const void* wx_ft, void* y, double* bn_sums, int B, int h, int w, int C1, int O,
+                    cudaStream_t st);
 // conv_tc_wgrad_halo.cu: halo-tile wgrad (3x3 stride 1 pad 1, W % 128 == 0); UDA_ERR_UNSUPPORTED otherwise
 int run_wgrad_halo(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, cudaStream_t st);
 // conv_tc_wgrad_big.cu: multi-accumulator wgrad sharing one dY tile (Cin, Cout multiples of 64); UDA_ERR_UNSUPPORTED otherwise
