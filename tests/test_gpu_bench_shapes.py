@@ -189,3 +189,25 @@ def test_transposed_conv_halo_kernel_matches_persistent_path_and_oracle(shape, m
         res[mode] = y
     assert rel_err(res["1"].float(), res["0"].float()) < 1e-2
     assert float((res["1"].float() - res["0"].float()).abs().mean()) < 2e-3 * float(res["0"].float().abs().mean())
+
+
+@pytest.mark.parametrize("shape", [(16, 512, 32), (2, 256, 16), (3, 8, 24)], ids=["dec4_dx", "b2_c16", "r2_c24"])
+def test_stride2_4x4_halo_kernel_matches_persistent_path_and_oracle(shape, monkeypatch):
+    """``uda_conv2d_tc_fwd`` for a 4x4 stride-2 pad-1 convolution of a wide 16-channel tensor (dx of the transposed half of
+    decoder conv1, block 4) runs ``conv_tc_downhalo_kernel`` (space-to-depth halo loaded once, sixteen shifted
+    descriptors): same result as the persistent kernel's sixteen TMA boxes (UDA_B200_DOWNHALO=0) up to accumulation
+    order, and both against F.conv2d in fp32 on the device."""
+    from uda_aerial_semantic_segmentation_research_b200 import ops
+    Bn, H, Co = shape
+    W = max(H, 256)                      # the kernel needs (W/2) % 128 == 0
+    x = _rand((Bn, H, W, 16), 41)
+    w = _rand((Co, 4, 4, 16), 42, (16 * 16) ** -0.5)
+    yr = R.conv_fwd(x.float(), w.float(), None, 2, 1)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("UDA_B200_DOWNHALO", mode)
+        y = ops.conv_fwd(x, w, None, 2, 1)
+        torch.cuda.synchronize()
+        assert rel_err(y.float(), yr) < 1e-2, (shape, mode)
+        res[mode] = y
+    assert float((res["1"].float() - res["0"].float()).abs().mean()) < 2e-3 * float(res["0"].float().abs().mean())

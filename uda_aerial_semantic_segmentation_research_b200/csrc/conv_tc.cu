@@ -953,6 +953,10 @@ extern "C" int uda_conv2d_tc_fwd(const void* x, const void* w, const float* bias
   UDA_REQUIRE(x && w && (y_nhwc || y_nchw_f32), UDA_ERR_BAD_ARG, "conv_tc_fwd: null pointer");
   UDA_REQUIRE(bn_sums == nullptr || use_persistent(), UDA_ERR_UNSUPPORTED,
               "conv_tc_fwd: fused BN statistics need the persistent kernels");
+  if (KH == 4 && KW == 4 && stride == 2 && pad == 1 && !bias && !bn_sums && y_nhwc && !y_nchw_f32 && use_persistent()) {
+    const int rc = run_downconv_halo(x, w, y_nhwc, B, H, W, Cin, Cout, (cudaStream_t)stream);   // wide 16-channel inputs
+    if (rc != UDA_ERR_UNSUPPORTED) return rc;
+  }
   return run_fwd(x, w, bias, nullptr, y_nhwc, y_nchw_f32, bn_sums, B, H, W, Cin, Cout, KH, KW, stride, pad,
                  (cudaStream_t)stream);
 }
