@@ -211,3 +211,25 @@ def test_stride2_4x4_halo_kernel_matches_persistent_path_and_oracle(shape, monke
         assert rel_err(y.float(), yr) < 1e-2, (shape, mode)
         res[mode] = y
     assert float((res["1"].float() - res["0"].float()).abs().mean()) < 2e-3 * float(res["0"].float().abs().mean())
+
+
+@pytest.mark.parametrize("shape", [(16, 512, 32), (2, 256, 16), (3, 8, 24)], ids=["dec4_dw4", "b2_c16", "r2_c24"])
+def test_stride2_4x4_halo_wgrad_matches_generic_path_and_oracle(shape, monkeypatch):
+    """Weight gradient of the 4x4 stride-2 pad-1 convolution of a wide 16-channel tensor (dW4 of the transposed half of
+    decoder conv1, block 4): ``conv_tc_wgrad_downhalo_kernel`` vs the generic tap-by-tap kernel (UDA_B200_DOWNHALO=0) and
+    vs torch.nn.grad.conv2d_weight in fp32 on the device (2e-3, as every wgrad test)."""
+    from uda_aerial_semantic_segmentation_research_b200 import ops
+    Bn, H, Co = shape
+    W = max(H, 256)
+    x = _rand((Bn, H, W, 16), 51)
+    dy = _rand((Bn, H // 2, W // 2, Co), 52)
+    dwr = R.conv_wgrad(dy.float(), x.float(), torch.zeros(Co, 4, 4, 16, device=DEV), 2, 1)
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("UDA_B200_DOWNHALO", mode)
+        dw = torch.full((Co, 4, 4, 16), 0.25, device=DEV)        # the kernels ACCUMULATE
+        ops.conv_wgrad(dy, x, dw, 2, 1)
+        torch.cuda.synchronize()
+        assert rel_err(dw - 0.25, dwr) < 2e-3, (shape, mode)
+        res[mode] = dw
+    assert rel_err(res["1"], res["0"]) < 1e-3

@@ -693,6 +693,10 @@ int run_wgrad(const void* dy, const void* x, float* dw, int B, int H, int W, int
     const int rc = run_wgrad_halo(dy, x, dw, B, H, W, Cin, Cout, st);
     if (rc != UDA_ERR_UNSUPPORTED) return rc;
   }
+  if (KH == 4 && KW == 4 && stride == 2 && pad == 1 && use_persistent() && use_halo()) {   // wide 16-channel inputs
+    const int rc = run_wgrad_downhalo(dy, x, dw, B, H, W, Cin, Cout, st);
+    if (rc != UDA_ERR_UNSUPPORTED) return rc;
+  }
   if (use_persistent()) {
     const int rc = run_wgrad_big(dy, x, dw, B, H, W, Cin, Cout, KH, KW, stride, pad, st);
     if (rc != UDA_ERR_UNSUPPORTED) return rc;

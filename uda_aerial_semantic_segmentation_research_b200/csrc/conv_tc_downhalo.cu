@@ -194,6 +194,144 @@ int launch_downhalo(const CUtensorMap& ma, const CUtensorMap& mb, DHParams& p, c
   return UDA_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Weight gradient of the same convolution:  dW[co][kh][kw][c] += sum_pixels dy[i][j][co] * x[2i+kh-1][2j+kw-1][c]
+// (x = the wide 16-channel tensor, dy = the low-resolution tensor; decoder block 4: dW4 of the transposed half).
+// The generic wgrad kernel loads one 32-byte-row TMA box per tap and pixel tile (148 us).  Here the space-to-depth halo
+// of x is loaded once per tile and is an MN-major operand as it stands: a 64-byte row is 32 M rows (dj, c), four pixel
+// shifts (LBO = one pixel) make the 128 rows of one MMA = (column shift cj, dj, c), of which (0,1), (1,0), (1,1), (2,0)
+// are the taps kw = 0..3; the four kernel rows kh are four accumulators (row shift, di).  N = the dy channels.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mn_desc64(uint32_t addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((8u * 64u) >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= 4ull << 61;            // SWIZZLE_64B
+  return d;
+}
+
+struct DWParams {
+  int h, w, B, tiles_w, tiles_h, total_tiles, tiles_per_cta;
+  int Cout, stages;
+  float* dw_out;   // [Cout][16][16] fp32
+};
+
+template <int R>
+__global__ void __launch_bounds__(192, 1)
+conv_tc_wgrad_downhalo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_dy,
+                              const DWParams p) {
+  constexpr int kRow = 64;                                     // bytes per row of either operand
+  constexpr int kHaloBytes = (R + 2) * 2 * kHaloW * kRow;
+  constexpr int kHaloStride = (kHaloBytes + 8 * kRow + 1023) / 1024 * 1024;   // slack: the junk shift over-reads
+  constexpr int kDyBytes = R * 128 * kRow;
+  constexpr int kStageBytes = kHaloStride + kDyBytes;
+  constexpr uint32_t kTmemCols = 128;                          // four accumulators (kh) of 32 columns
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * kStageBytes);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);   // full[4], empty[4], done
+  const uint32_t ring_base = smem_u32(smem);
+  const uint32_t bar_base = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (4 + s); };
+  const uint32_t done_bar = bar_base + 8u * 8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_per_img = p.tiles_w * p.tiles_h;
+  const int t_begin = blockIdx.x * p.tiles_per_cta;
+  int t_end = t_begin + p.tiles_per_cta;
+  if (t_end > p.total_tiles) t_end = p.total_tiles;
+
+  pdl_launch_dependents();
+  if (warp == 0 && lane == 0) { tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_dy); }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < S; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      mbar_init(done_bar, 1);
+      fence_barrier_init();
+    }
+    __syncwarp();
+    tmem_alloc(smem_u32(tmem_slot), kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int it = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int b = t / tiles_per_img, tin = t % tiles_per_img;
+        const int i0 = (tin / p.tiles_w) * R, j0 = (tin % p.tiles_w) * 128;
+        const int s = it % S;
+        mbar_wait(empty_bar(s), ((it / S) & 1) ^ 1);
+        const uint32_t st = ring_base + s * kStageBytes;
+        mbar_expect_tx(full_bar(s), kHaloBytes + kDyBytes);
+        tma_load_5d(st, &map_x, full_bar(s), 0, j0 - 1, 0, i0 - 1, b);
+        tma_load_4d(st + kHaloStride, &map_dy, full_bar(s), 0, j0, i0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 32) | (1u << 15) | (1u << 16);   // both operands MN-major
+      int it = 0;
+      for (int t = t_begin; t < t_end; ++t, ++it) {
+        const int s = it % S;
+        mbar_wait(full_bar(s), (it / S) & 1);
+        tc_fence_after();
+        const uint32_t st = ring_base + s * kStageBytes;
+#pragma unroll 1
+        for (int sub = 0; sub < R; ++sub) {
+#pragma unroll
+          for (int kh = 0; kh < 4; ++kh) {
+            const int ri = sub + 1 + (kh == 0 ? -1 : (kh == 3 ? 1 : 0)), di = (kh == 0 || kh == 2) ? 1 : 0;
+            const uint32_t a0 = st + (uint32_t)((ri * 2 + di) * kHaloW) * kRow;
+            const uint32_t b0 = st + kHaloStride + (uint32_t)(sub * 128) * kRow;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)     // 16 pixels per MMA
+              umma_bf16(tmem_base + (uint32_t)kh * 32, mn_desc64(a0 + k * 16 * kRow, kRow), mn_desc64(b0 + k * 16 * kRow, kRow),
+                        idesc, (it > 0 || sub > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(empty_bar(s));
+      }
+      umma_commit(done_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int cj = r >> 5, dj = (r >> 4) & 1, c = r & 15;
+    const int kw = cj == 0 ? (dj ? 0 : -1) : (cj == 1 ? 1 + dj : (cj == 2 ? (dj ? -1 : 3) : -1));
+    mbar_wait(done_bar, 0);
+    tc_fence_after();
+    if (t_end > t_begin) {
+#pragma unroll 1
+      for (int kh = 0; kh < 4; ++kh) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)kh * 32, v);
+        tmem_ld_wait();
+        if (kw >= 0) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k)
+            if (k < p.Cout) atomicAdd(p.dw_out + ((long long)k * 16 + kh * 4 + kw) * kO + c, __uint_as_float(v[k]));
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
 }  // namespace
 
 // out[B, H/2, W/2, Cout] = conv4x4_s2_p1(x[B, H, W, 16], wmat[Cout][4][4][16]), Cout <= 32, (W/2) % 128 == 0.
@@ -226,6 +364,60 @@ int run_downconv_halo(const void* x, const void* wmat, void* y, int B, int H, in
   }
   if (R == 4) return launch_downhalo<4>(ma, mb, p, st);
   return launch_downhalo<2>(ma, mb, p, st);
+}
+
+}  // namespace tcconv
+}  // namespace uda
+
+namespace uda {
+namespace tcconv {
+
+// dw[Cout][4][4][16] += wgrad of conv4x4_s2_p1(x[B, H, W, 16]) with dy[B, H/2, W/2, Cout], Cout <= 32, (W/2) % 128 == 0.
+// UDA_ERR_UNSUPPORTED (no message) otherwise; UDA_B200_DOWNHALO=0 switches the path off.
+int run_wgrad_downhalo(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, cudaStream_t st) {
+  const char* e = getenv("UDA_B200_DOWNHALO");
+  if (e && e[0] == '0') return UDA_ERR_UNSUPPORTED;
+  if (Cin != kO || Cout > kBN || Cout % 8 || Cout < 8 || H % 2 || W % 2) return UDA_ERR_UNSUPPORTED;
+  const int h = H / 2, w = W / 2;
+  constexpr int R = 2;
+  if (w % 128 || h % R) return UDA_ERR_UNSUPPORTED;
+  if (!(aligned<bf16>(x, 16) && aligned<bf16>(dy, 16))) return UDA_ERR_UNSUPPORTED;
+  constexpr int kHaloBytes = (R + 2) * 2 * kHaloW * 64;
+  constexpr int kHaloStride = (kHaloBytes + 8 * 64 + 1023) / 1024 * 1024;
+  constexpr int kStageBytes = kHaloStride + R * 128 * 64;
+  int S = kSmemBudget / kStageBytes;
+  if (S > 4) S = 4;
+  if (S < 2) return UDA_ERR_UNSUPPORTED;
+  DWParams p{};
+  p.h = h; p.w = w; p.B = B; p.tiles_w = w / 128; p.tiles_h = h / R; p.total_tiles = B * p.tiles_w * p.tiles_h;
+  p.Cout = Cout; p.stages = S; p.dw_out = dw;
+  int ctas = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+  p.tiles_per_cta = (p.total_tiles + ctas - 1) / ctas;
+  ctas = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  CUtensorMap mx, mdy;
+  {
+    const uint64_t C = (uint64_t)Cin;
+    uint64_t dims[5] = {2 * C, (uint64_t)w, 2, (uint64_t)h, (uint64_t)B};
+    uint64_t str[4] = {2 * C * 2, (uint64_t)W * C * 2, 2 * (uint64_t)W * C * 2, (uint64_t)H * W * C * 2};
+    uint32_t box[5] = {(uint32_t)(2 * Cin), (uint32_t)kHaloW, 2, (uint32_t)(R + 2), 1};
+    if (int rc = make_tmap_bf16(&mx, x, 5, dims, str, box, 64)) return rc;
+  }
+  {
+    const uint64_t Co = (uint64_t)Cout;     // may be smaller than the 32-channel box: the rest reads as zero
+    uint64_t dims[4] = {Co, (uint64_t)w, (uint64_t)h, (uint64_t)B};
+    uint64_t str[3] = {Co * 2, (uint64_t)w * Co * 2, (uint64_t)h * w * Co * 2};
+    uint32_t box[4] = {32, 128, (uint32_t)R, 1};
+    if (int rc = make_tmap_bf16(&mdy, dy, 4, dims, str, box, 64)) return rc;
+  }
+  const int smem = S * kStageBytes + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    UDA_CUDA_OK(cudaFuncSetAttribute(conv_tc_wgrad_downhalo_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  UDA_CUDA_OK(launch_pdl(conv_tc_wgrad_downhalo_kernel<R>, dim3(ctas), dim3(192), smem, st, mx, mdy, p));
+  UDA_LAUNCH_OK("conv_tc_wgrad_downhalo_kernel");
+  return UDA_OK;
 }
 
 }  // namespace tcconv

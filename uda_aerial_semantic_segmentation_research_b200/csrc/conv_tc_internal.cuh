@@ -264,6 +264,7 @@ int run_upconv_halo(const void* x, const void* wx_ft, void* y, double* bn_sums, 
 // conv_tc_downhalo.cu: 4x4 stride-2 pad-1 convolution of a wide 16-channel tensor into <= 32 channels (dx of the transposed
 // half of decoder conv1 in block 4); UDA_ERR_UNSUPPORTED (no message) otherwise
 int run_downconv_halo(const void* x, const void* wmat, void* y, int B, int H, int W, int Cin, int Cout, cudaStream_t st);
+int run_wgrad_downhalo(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, cudaStream_t st);
 // conv_tc_wgrad_halo.cu: halo-tile wgrad (3x3 stride 1 pad 1, W % 128 == 0); UDA_ERR_UNSUPPORTED otherwise
 int run_wgrad_halo(const void* dy, const void* x, float* dw, int B, int H, int W, int Cin, int Cout, cudaStream_t st);
 // conv_tc_wgrad_big.cu: multi-accumulator wgrad sharing one dY tile (Cin, Cout multiples of 64); UDA_ERR_UNSUPPORTED otherwise
