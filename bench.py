@@ -455,8 +455,11 @@ def measure_workload(args, workload, env, full):
                 print(f"[profile] {name}: {last}", file=sys.stderr)
         pk = peaks()
         # every entry point whose FLOPs ops._tc_account() counts (the two halves of the split decoder conv1 included)
-        tc_keys = ("conv2d_tc_fwd", "conv2d_tc_fwd_add", "conv2d_tc_fwd_fused", "upconv_tc_fwd", "conv2d_tc_dgrad",
-                   "conv2d_tc_dgrad_bnstats", "conv2d_tc_wgrad", "stem_tc_fwd", "stem_tc_fwd_act", "stem_tc_wgrad")
+        # conv2d_tc_fwd_bn_act = convolution + BatchNorm + activation in one launch: its WHOLE time is charged to the
+        # convolutions (the launch contains the grid barrier and the normalisation pass) - conservative, not flattering
+        tc_keys = ("conv2d_tc_fwd", "conv2d_tc_fwd_add", "conv2d_tc_fwd_fused", "conv2d_tc_fwd_bn_act", "upconv_tc_fwd",
+                   "conv2d_tc_dgrad", "conv2d_tc_dgrad_bnstats", "conv2d_tc_wgrad", "stem_tc_fwd", "stem_tc_fwd_act",
+                   "stem_tc_wgrad")
         tc_ms = sum(breakdown.get(k, {}).get("ms_per_step", 0.0) for k in tc_keys)
         tc_n = sum(breakdown.get(k, {}).get("launches_per_step", 0.0) for k in tc_keys)
         tc_gflop = (ops.TC_FLOPS - f0) / prof_steps / 1e9
@@ -472,6 +475,7 @@ def measure_workload(args, workload, env, full):
                                     f"committed ncu launch list {tfile} (cold cache, same command); not re-measured in this run",
                     "peak_source": pk["which"] + " (sustained: kernels timed inside a long step)",
                     "gflop_per_step": tc_gflop, "ms_per_step": tc_ms, "launches_per_step": tc_n,
+                    "fused_bn_launches_ms_per_step": breakdown.get("conv2d_tc_fwd_bn_act", {}).get("ms_per_step", 0.0),
                     "timing": "CUDA events around every entry point of eager single-stream replays of the step (the timed "
                               "region itself is a graph replay with the wgrad launches on a second stream)",
                     "whole_step_frac": tc_gflop / (ms / args.steps) / pk["bf16_tflops_sustained"],

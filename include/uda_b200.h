@@ -230,6 +230,14 @@ int uda_bn_apply_fused(const void* x, const void* residual, void* y, int dtype, 
                        const float* beta, float* running_mean, float* running_var, float* mean, float* rstd,
                        float* scale, float* shift, long long M, int C, float eps, float momentum, float slope,
                        void* stream);
+/* The ResNet stem tail bn1 -> relu -> maxpool (torchvision encoder inside smp.Unet, src/models/train.py:572-577) as ONE
+ * pass over x: a = act(BN(x)) exactly as uda_bn_apply_fused (a is kept: it is the first skip connection) and
+ * (y, idx) = uda_maxpool3x3s2_fwd(a), taken from the rows while they are in shared memory.  bf16 NHWC only, H and W
+ * even, C a power of two in [8, 2048], W*C*2 <= ~50 KB; returns UDA_ERR_UNSUPPORTED (nothing launched) otherwise. */
+int uda_bn_apply_maxpool_fused(const void* x, void* a, void* y, unsigned char* idx, int dtype, const double* sums,
+                               const float* gamma, const float* beta, float* running_mean, float* running_var,
+                               float* mean, float* rstd, float* scale, float* shift, int B, int H, int W, int C,
+                               float eps, float momentum, float slope, void* stream);
 /* a == NULL with scale/shift given: the activation mask is recomputed from x*scale+shift (non-residual layers),
  * which saves reading the saved output in both backward passes. */
 int uda_bn_bwd(const void* dy, const void* x, const void* a, int dtype, const float* gamma, const float* mean,

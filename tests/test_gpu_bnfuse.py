@@ -188,3 +188,61 @@ def test_bn_backward_single_launch_matches_oracle(case, monkeypatch):
         assert rel_err(dg, dgr) < 1e-3 and rel_err(db, dbr) < 1e-3, (name, rep)
         if residual:
             assert rel_err(dres.float(), dresr.float()) < 1e-2, (name, rep)
+
+
+POOL_CASES = [
+    # B, H, W, C, slope   (the stem at the benchmarked shape first; strips crossing image boundaries, fewer pooled rows
+    # than SMs, one-row images, leaky slope, NaN propagation)
+    (16, 256, 256, 64, 0.0),
+    (3, 38, 52, 64, 0.0),
+    (5, 2, 4, 8, 0.0),
+    (2, 64, 96, 128, 0.2),
+    (1, 300, 16, 16, 0.0),
+    (7, 6, 64, 256, 0.0),
+]
+
+
+@pytest.mark.parametrize("case", POOL_CASES, ids=["x".join(map(str, c[:4])) for c in POOL_CASES])
+def test_bn_apply_maxpool_fused_matches_two_launch_form_and_torch(case):
+    """Stem tail bn1 -> relu -> maxpool as ONE pass (``uda_bn_apply_maxpool_fused``): a / mean / rstd / scale / shift /
+    running statistics bit-identical with ``uda_bn_apply_fused``, pooled values and winning taps bit-identical with
+    ``uda_maxpool3x3s2_fwd`` of that a, pooled values equal to ``F.max_pool2d`` (``torchvision`` ResNet stem under the
+    model of ``/root/reference/src/models/train.py:572-577``)."""
+    from uda_aerial_semantic_segmentation_research_b200 import ops
+    Bn, H, W, C, slope = case
+    z = _rand((Bn, H, W, C), 11, 1.5)
+    if (Bn, H) == (3, 38):
+        z[1, 5, 7, 3] = float("nan")
+        z[2, 37, 51, 9] = float("nan")
+    zf = z.double()
+    sums = torch.cat([torch.nan_to_num(zf).sum((0, 1, 2)), (torch.nan_to_num(zf) ** 2).sum((0, 1, 2))]).contiguous()
+    gamma, beta, rm0, rv0 = _bn_params(C)
+    rm1, rv1 = rm0.clone(), rv0.clone()
+    a1, mean1, rstd1, sc1, sf1 = ops.bn_apply_fused(z, sums, gamma, beta, rm1, rv1, 1e-5, 0.1, None, slope)
+    y1, i1 = ops.maxpool_fwd(a1)
+    rm2, rv2 = rm0.clone(), rv0.clone()
+    r = ops.bn_apply_maxpool_fused(z, sums, gamma, beta, rm2, rv2, 1e-5, 0.1, slope)
+    assert r is not None, "fused stem tail declined a supported shape"
+    a2, mean2, rstd2, sc2, sf2, y2, i2 = r
+    torch.cuda.synchronize()
+    for u, v in ((sc1, sc2), (sf1, sf2)):   # what the normalisation uses: bit-identical
+        assert torch.equal(u, v)
+    for u, v in ((mean1, mean2), (rstd1, rstd2), (rm1, rm2), (rv1, rv2)):   # published statistics: the small shapes run
+        torch.testing.assert_close(u, v, rtol=1e-6, atol=1e-7)              # another kernel's copy of the same fp32 lines
+    assert torch.equal(a1.view(torch.int16), a2.view(torch.int16))
+    assert torch.equal(y1.view(torch.int16), y2.view(torch.int16))
+    assert torch.equal(i1, i2)
+    ref = torch.nn.functional.max_pool2d(a2.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(torch.nan_to_num(ref, nan=-7.0), torch.nan_to_num(y2.float(), nan=-7.0))
+
+
+def test_bn_apply_maxpool_fused_declines_odd_sizes_and_wide_rows():
+    from uda_aerial_semantic_segmentation_research_b200 import ops
+    for shape in ((2, 9, 8, 16), (2, 8, 10, 4096), (1, 4, 1024, 64)):
+        z = _rand(shape, 5)
+        C = shape[-1]
+        sums = torch.zeros(2 * C, dtype=torch.float64, device=DEV)
+        gamma, beta, rm, rv = _bn_params(C)
+        rm0 = rm.clone()
+        assert ops.bn_apply_maxpool_fused(z, sums, gamma, beta, rm, rv) is None
+        assert torch.equal(rm, rm0)

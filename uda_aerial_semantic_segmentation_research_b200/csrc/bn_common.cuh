@@ -79,6 +79,8 @@ __device__ __forceinline__ void bn_bwd_finalize_channel(const BnBwdFinal& f, dou
 bool bn_stream_ok(int dtype, long long M, int C);
 int bn_apply_stream(const void* x, const void* residual, void* y, const float* scale, const float* shift,
                     const double* sums, const bn::BnFwdFinal& fin, long long M, int C, float slope, cudaStream_t st);
+int bn_apply_maxpool_stream(const void* x, void* a, void* y, unsigned char* idx, const double* sums,
+                            const bn::BnFwdFinal& fin, int B, int H, int W, int C, float slope, cudaStream_t st);
 int bn_bwd_stream(const void* dy, const void* x, const void* a, const float* mean, const float* rstd,
                   const float* scale, const float* shift, void* dx, void* dres, int dres_accumulate, double* sums,
                   float* coef, const bn::BnBwdFinal& fin, long long M, int C, float slope, cudaStream_t st);

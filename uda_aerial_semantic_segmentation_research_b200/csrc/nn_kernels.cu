@@ -1071,6 +1071,24 @@ extern "C" int uda_bn_apply(const void* x, const void* residual, void* y, int dt
   return UDA_OK;
 }
 
+// The ResNet stem tail as one pass: uda_bn_apply_fused followed by uda_maxpool3x3s2_fwd of its output, without reading
+// the normalised tensor back (stream_kernels.cu: bn_apply_maxpool_stream_kernel).  Declines (nothing launched) unless
+// bf16, H and W even, C a power of two in [8, 2048] and four rows of x fit the shared-memory ring.
+extern "C" int uda_bn_apply_maxpool_fused(const void* x, void* a, void* y, unsigned char* idx, int dtype,
+                                          const double* sums, const float* gamma, const float* beta,
+                                          float* running_mean, float* running_var, float* mean, float* rstd,
+                                          float* scale, float* shift, int B, int H, int W, int C, float eps,
+                                          float momentum, float slope, void* stream) {
+  UDA_REQUIRE(x && a && y && idx && sums && mean && rstd && scale && shift && B > 0 && H > 0 && W > 0 && C > 0,
+              UDA_ERR_BAD_ARG, "bn_apply_maxpool_fused: bad argument");
+  if (dtype != UDA_BF16 || !use_stream() || ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(a) |
+                                              reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(idx)) & 15))
+    return UDA_ERR_UNSUPPORTED;
+  const long long M = (long long)B * H * W;
+  BnFwdFinal fin{gamma, beta, running_mean, running_var, mean, rstd, scale, shift, M, eps, momentum, nullptr};
+  return bn_apply_maxpool_stream(x, a, y, idx, sums, fin, B, H, W, C, slope, (cudaStream_t)stream);
+}
+
 // BatchNorm apply with the statistics taken from the producing convolution's epilogue (sums = [sum | sum of squares],
 // double[2*C]); scale/shift (float[C], scratch outputs kept for API symmetry) may be NULL.
 extern "C" int uda_bn_apply_fused(const void* x, const void* residual, void* y, int dtype, const double* sums,

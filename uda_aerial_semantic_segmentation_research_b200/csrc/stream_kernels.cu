@@ -657,4 +657,182 @@ int bn_bwd_apply_fused_stream(const void* dy, const void* x, const void* a, cons
   return UDA_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// a = act(x*scale + shift) AND (y, idx) = maxpool3x3 s2 p1 of a, ONE pass over x (the ResNet stem tail bn1 -> relu ->
+// maxpool).  Separate launches read `a` back for the pooling (x 1 + a 2 + y 0.25 tensor sizes of traffic); here every
+// CTA owns a strip of pooled rows and streams the 2*rows (+1 halo) input rows it needs through a shared-memory ring,
+// one cp.async.bulk per row: the compute warps normalise a row in place, the IO thread stores it as `a`, and when the
+// bottom row of a pooling window has been normalised the window's three rows are still in the ring and the pooled row
+// is taken from shared memory (x 1 + a 1 + y 0.25).  Values and indices are those of bn_apply_stream_kernel followed by
+// maxpool_fwd_kernel (first maximum in scan order, NaN propagating), bit for bit.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPoolMaxStages = 8;
+struct PoolParams {
+  const uint8_t* x; uint8_t* a; uint8_t* y; unsigned char* idx;
+  const double* sums; bn::BnFwdFinal fin;
+  int B, H, W, C, stages;
+  uint32_t row_bytes;
+  float slope;
+};
+
+namespace {
+
+__global__ void __launch_bounds__(kCta, 1) bn_apply_maxpool_stream_kernel(const PoolParams p) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  const int S = p.stages, C = p.C;
+  const uint32_t RB = p.row_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)S * RB);
+  const uint32_t full_base = smem_u32(bars);                       // row landed (bulk load)
+  const uint32_t norm_base = full_base + 8u * kPoolMaxStages;      // row normalised in place by every compute thread
+  const uint32_t done_base = norm_base + 8u * kPoolMaxStages;      // row no longer needed by the pooling
+  float* s_sc = reinterpret_cast<float*>(bars + 3 * kPoolMaxStages);
+  float* s_sf = s_sc + C;
+  const int Ho = p.H >> 1, Wo = p.W >> 1;
+  // pooled rows r = b*Ho + ho need input rows 2r, 2r+1 (and 2r-1 inside an image): a strip is a contiguous row range
+  const long long NR = (long long)p.B * Ho;
+  const long long r0 = NR * blockIdx.x / gridDim.x, r1 = NR * (blockIdx.x + 1) / gridDim.x;
+  const int halo = (r0 % Ho) > 0 ? 1 : 0;
+  const long long z0 = 2 * r0 - halo;                  // first input row (b*H + h) of the strip
+  const int n = (int)(2 * (r1 - r0)) + halo;           // rows streamed (host: grid <= NR, so n >= 2)
+  pdl_launch_dependents();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(full_base + 8u * s, 1); mbar_init(norm_base + 8u * s, kCompute); mbar_init(done_base + 8u * s, kCompute);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  pdl_wait();
+  if (threadIdx.x >= kCompute) {
+    if (threadIdx.x != kCompute) return;
+    auto load = [&](int k) {
+      const uint32_t bar = full_base + 8u * (k % S);
+      mbar_expect_tx(bar, RB);
+      bulk_load(smem_u32(smem + (size_t)(k % S) * RB), p.x + (z0 + k) * (long long)RB, RB, bar);
+    };
+    for (int k = 0; k < S && k < n; ++k) load(k);
+    int jr = 0;   // next row whose slot is refilled (with row jr + S)
+    for (int k = 0; k < n; ++k) {
+      mbar_wait(norm_base + 8u * (k % S), (uint32_t)((k / S) & 1));
+      if (k >= halo) bulk_store(p.a + (z0 + k) * (long long)RB, smem_u32(smem + (size_t)(k % S) * RB), RB);
+      bulk_commit();   // one group per row (empty for the halo row, which the strip above stores)
+      // rows <= k-2 are released by the pooling step that row k completes at the latest; their stores are among all
+      // but the two newest groups
+      while (jr + S < n && jr <= k - 2) {
+        mbar_wait(done_base + 8u * (jr % S), (uint32_t)((jr / S) & 1));
+        bulk_wait_read<2>();
+        load(jr + S);
+        ++jr;
+      }
+    }
+    bulk_wait_all<0>();
+    return;
+  }
+  // ---- compute warps ----
+  {
+    const double inv_m = 1.0 / (double)p.fin.M;     // same arithmetic as bn_apply_stream_kernel
+    for (int ch = threadIdx.x; ch < C; ch += kCompute) {
+      const double s1 = p.sums[ch], s2 = p.sums[C + ch];
+      const double mean = s1 * inv_m;
+      const float var = fmaxf((float)(s2 * inv_m - mean * mean), 0.f);
+      const float rstd = rsqrtf(var + p.fin.eps);
+      const float g = p.fin.gamma ? p.fin.gamma[ch] : 1.f, b = p.fin.beta ? p.fin.beta[ch] : 0.f;
+      s_sc[ch] = g * rstd;
+      s_sf[ch] = b - (float)mean * g * rstd;
+      if (blockIdx.x == 0) bn_fwd_finalize_channel(p.fin, s1, s2, ch);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kCompute) : "memory");
+  }
+  const int c = (threadIdx.x * 8) % C;   // (kCompute*8) % C == 0: fixed channels per thread
+  float sc[8], sf[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sc[j] = s_sc[c + j]; sf[j] = s_sf[c + j]; }
+  const int row_vecs = (int)(RB >> 4);
+  const int cv = C >> 3, items = Wo * cv;
+  for (int k = 0; k < n; ++k) {
+    mbar_wait(full_base + 8u * (k % S), (uint32_t)((k / S) & 1));
+    uint8_t* row = smem + (size_t)(k % S) * RB;
+    for (int v = threadIdx.x; v < row_vecs; v += kCompute) {
+      float t8[8];
+      lds8(row + (size_t)v * 16, t8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float t = t8[j] * sc[j] + sf[j];
+        t8[j] = t > 0.f ? t : t * p.slope;
+      }
+      sts8(row + (size_t)v * 16, t8);
+    }
+    fence_async_smem();
+    mbar_arrive(norm_base + 8u * (k % S));
+    const long long g = z0 + k;
+    const int h = (int)(g % p.H);
+    if (!(h & 1) || (halo && k == 0)) continue;
+    // bottom row of pooled row g/2: its window rows k-2 (inside an image), k-1, k are normalised once everyone is here
+    asm volatile("bar.sync 1, %0;" ::"n"(kCompute) : "memory");
+    const int ho = h >> 1;
+    const bool has_top = ho > 0;
+    const uint8_t* const row_t = smem + (size_t)((k + S - 2) % S) * RB;
+    const uint8_t* const row_m = smem + (size_t)((k + S - 1) % S) * RB;
+    const long long out_row = (g >> 1) * (long long)Wo;
+    for (int it = threadIdx.x; it < items; it += kCompute) {
+      const int v = it % cv, wo = it / cv;
+      float best[8];
+      int bi[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = -1; }
+#pragma unroll
+      for (int kh = 0; kh < 3; ++kh) {
+        if (kh == 0 && !has_top) continue;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw) {
+          const int w = wo * 2 - 1 + kw;
+          if (w < 0) continue;                   // w < W always: W is even
+          float xv[8];
+          lds8((kh == 0 ? row_t : kh == 1 ? row_m : row) + ((size_t)w * C + v * 8) * 2, xv);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (bi[j] < 0) bi[j] = kh * 3 + kw;
+            if ((xv[j] > best[j]) || (xv[j] != xv[j])) { best[j] = xv[j]; bi[j] = kh * 3 + kw; }
+          }
+        }
+      }
+      const long long o = (out_row + wo) * C + v * 8;
+      *reinterpret_cast<uint4*>(p.y + o * 2) = make_uint4(pack_bf16x2(best[0], best[1]), pack_bf16x2(best[2], best[3]),
+                                                          pack_bf16x2(best[4], best[5]), pack_bf16x2(best[6], best[7]));
+      uint2 iv;
+      iv.x = (unsigned)bi[0] | ((unsigned)bi[1] << 8) | ((unsigned)bi[2] << 16) | ((unsigned)bi[3] << 24);
+      iv.y = (unsigned)bi[4] | ((unsigned)bi[5] << 8) | ((unsigned)bi[6] << 16) | ((unsigned)bi[7] << 24);
+      *reinterpret_cast<uint2*>(p.idx + o) = iv;
+    }
+    // the top and middle rows are finished; the bottom row is the next window's top row unless the image or the strip ends
+    if (has_top) mbar_arrive(done_base + 8u * ((k + S - 2) % S));
+    mbar_arrive(done_base + 8u * ((k + S - 1) % S));
+    if (ho == Ho - 1 || k == n - 1) mbar_arrive(done_base + 8u * (k % S));
+  }
+}
+
+}  // namespace
+
+int bn_apply_maxpool_stream(const void* x, void* a, void* y, unsigned char* idx, const double* sums,
+                            const bn::BnFwdFinal& fin, int B, int H, int W, int C, float slope, cudaStream_t st) {
+  const long long rb = (long long)W * C * 2;
+  if ((H & 1) || (W & 1) || C < 8 || C > 2048 || (C & (C - 1)) || rb > 64 * 1024) return UDA_ERR_UNSUPPORTED;
+  PoolParams p{};
+  p.x = (const uint8_t*)x; p.a = (uint8_t*)a; p.y = (uint8_t*)y; p.idx = idx; p.sums = sums; p.fin = fin;
+  p.B = B; p.H = H; p.W = W; p.C = C; p.row_bytes = (uint32_t)rb; p.slope = slope;
+  const size_t extra = 3 * 8 * kPoolMaxStages + 2 * (size_t)C * sizeof(float) + 128;
+  int S = (int)((208 * 1024 - extra) / (size_t)rb);
+  if (S > kPoolMaxStages) S = kPoolMaxStages;
+  if (S < 4) return UDA_ERR_UNSUPPORTED;
+  p.stages = S;
+  const long long NR = (long long)B * (H / 2);
+  const int grid = (int)(NR < num_sms() ? NR : num_sms());
+  static bool cfg = false;
+  if (!cfg) { if (int rc = set_smem_attr(bn_apply_maxpool_stream_kernel)) return rc; cfg = true; }
+  UDA_CUDA_OK(launch_pdl(bn_apply_maxpool_stream_kernel, dim3(grid), dim3(kCta), (size_t)S * rb + extra, st, p));
+  UDA_LAUNCH_OK("bn_apply_maxpool_stream_kernel");
+  return UDA_OK;
+}
+
 }  // namespace uda

@@ -670,8 +670,27 @@ def bias_act(ctx, zin, slope):
     return out
 
 
-def maxpool(ctx, xin):
-    y, idx = ops.maxpool_fwd(xin.t)
+def conv_bn_act_maxpool(ctx, xin, cp, bn, slope=0.0):
+    """The ResNet stem: ``a = act(BN(conv(x)))`` and ``y = maxpool3x3s2(a)``; returns both (``a`` is the first skip
+    connection).  Training on the bf16 path with the statistics from the conv epilogue: normalise + activation + pooling
+    as ONE pass over z (``ops.bn_apply_maxpool_fused``); the backward is the two ops' own."""
+    if ctx.training and ctx.dtype == torch.bfloat16 and ops.FUSE_BN_POOL and ops.FUSE_BN_STATS:
+        zin = conv(ctx, xin, cp, bn=bn)
+        r = None
+        if zin.sums is not None:
+            r = ops.bn_apply_maxpool_fused(zin.t, zin.sums, bn.weight, bn.bias, bn.running_mean, bn.running_var,
+                                           bn.eps, bn.momentum, slope)
+        if r is None:
+            f = bn_act(ctx, zin, bn, slope=slope)
+            return f, maxpool(ctx, f)
+        f = bn_act(ctx, zin, bn, slope=slope, _pre=r[:5])
+        return f, maxpool(ctx, f, _pre=r[5:])
+    f = conv_bn_act(ctx, xin, cp, bn, slope=slope)
+    return f, maxpool(ctx, f)
+
+
+def maxpool(ctx, xin, _pre=None):
+    y, idx = _pre if _pre is not None else ops.maxpool_fwd(xin.t)
     out = Var(y)
     if ctx.tape is not None:
         xin.uses += 1

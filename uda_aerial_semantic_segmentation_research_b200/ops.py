@@ -39,6 +39,9 @@ PREFETCH_WFT = os.environ.get("UDA_B200_PREFETCH_WFT", "1") != "0"
 #: layer2-4 and decoder blocks 0-1 at B=16, 512x512 (33 of the 46 BatchNorm layers).  Measured 8.37-8.43 vs 8.53 ms per
 #: step; UDA_B200_FUSE_BN_APPLY=0 runs the separate normalise pass everywhere
 FUSE_BN_APPLY = os.environ.get("UDA_B200_FUSE_BN_APPLY", "1") != "0"
+#: training: the stem's normalise + activation pass also produces the 3x3 stride-2 max-pool of its output (one pass over
+#: the largest tensor of the encoder instead of two; uda_bn_apply_maxpool_fused).  UDA_B200_FUSE_BN_POOL=0 = two launches
+FUSE_BN_POOL = os.environ.get("UDA_B200_FUSE_BN_POOL", "1") != "0"
 #: decoder conv1 as conv_transpose4x4(x) + conv3x3(skip): the upsampled / concatenated tensor is never materialised
 #: (UDA_B200_FUSE_UPCAT=0 runs the upsample+concat copy kernel and one 3x3 convolution over the concatenation)
 FUSE_UPCAT = os.environ.get("UDA_B200_FUSE_UPCAT", "1") != "0"
@@ -574,6 +577,28 @@ def bn_apply_fused(x, sums, gamma, beta, running_mean, running_var, eps=1e-5, mo
          float(momentum), float(slope), _stream())
     _count()
     return y, st[0], st[1], st[2], st[3]
+
+
+def bn_apply_maxpool_fused(x, sums, gamma, beta, running_mean, running_var, eps=1e-5, momentum=0.1, slope=0.0):
+    """``bn_apply_fused`` + ``maxpool_fwd`` of its output as ONE pass over x (the ResNet stem tail).  Returns
+    (a, mean, rstd, scale, shift, y, idx), or None when the launch declines (nothing ran)."""
+    if not FUSE_BN_POOL or x.dtype != torch.bfloat16:
+        return None
+    _chk(x, "bn_apply_maxpool_fused.x")
+    B, H, W, C = x.shape
+    if H % 2 or W % 2:
+        return None
+    st = torch.empty((4, C), dtype=torch.float32, device=x.device)
+    a = torch.empty_like(x)
+    y = torch.empty((B, H // 2, W // 2, C), dtype=x.dtype, device=x.device)
+    idx = torch.empty((B, H // 2, W // 2, C), dtype=torch.uint8, device=x.device)
+    ok = call("bn_apply_maxpool_fused", ptr(x), ptr(a), ptr(y), ptr(idx), ci(dt(x)), ptr(sums), ptr(gamma), ptr(beta),
+              ptr(running_mean), ptr(running_var), ptr(st[0]), ptr(st[1]), ptr(st[2]), ptr(st[3]), ci(B), ci(H), ci(W),
+              ci(C), float(eps), float(momentum), float(slope), _stream(), unsupported_ok=True)
+    if ok is False:
+        return None
+    _count()
+    return a, st[0], st[1], st[2], st[3], y, idx
 
 
 def bn_bwd(dy, x, a, gamma, mean, rstd, slope, dgamma, dbeta, dres=None, dres_accumulate=False,

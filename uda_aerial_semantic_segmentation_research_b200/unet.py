@@ -99,8 +99,7 @@ class ResNetEncoder(nn.Module):
                 nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
 
     def run(self, ctx, x):
-        f1 = E.conv_bn_act(ctx, x, self.conv1, self.bn1, slope=0.0)
-        y = E.maxpool(ctx, f1)
+        f1, y = E.conv_bn_act_maxpool(ctx, x, self.conv1, self.bn1, slope=0.0)
         feats = [x, f1]
         for li in range(1, 5):
             for blk in getattr(self, f"layer{li}"):
